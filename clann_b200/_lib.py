@@ -1,0 +1,92 @@
+"""ctypes binding of libclann_b200.so — the C ABI declared in include/clann_b200.h.
+
+This is the same stub a maintainer of the reference would write in Rust (`extern "C"` block);
+Python stands in because this environment has no cargo. The library is REQUIRED: a missing or unloadable .so raises,
+there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_vp, _u32, _u64, _i32, _i64, _f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int64, C.c_float
+
+
+class ClannConfig(C.Structure):
+    """clann_config (include/clann_b200.h) <- Config (src/core/config.rs:17-35)."""
+    _fields_ = [("num_tables", _u64), ("num_clusters_factor", _f32), ("k", _u64), ("delta", _f32)]
+
+
+# clann_status
+OK, ERR_DATA, ERR_CONFIG, ERR_CREATION, ERR_SEARCH, ERR_NOT_BUILT, ERR_BOUNDS, ERR_SERIALIZE, ERR_CUDA, ERR_ARG = (
+    0, -1, -2, -3, -4, -5, -6, -7, -8, -9)
+
+# clann_export_what
+(X_NUM_CLUSTERS, X_CENTERS, X_ASSIGNMENT, X_RADII, X_OFFSETS, X_PERM, X_Q15, X_SKETCHES, X_TABLE_HASHES, X_TABLE_INDICES,
+ X_BRUTE, X_NORMS, X_EST, X_QUERY_CODES, X_QUERY_SKETCHES, X_CLUSTER_ORDER, X_BUILD_MS) = range(17)
+
+EXPORTED_SYMBOLS = [
+    "clann_init_with_config", "clann_set_option", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
+    "clann_build", "clann_search", "clann_search_device", "clann_search_begin", "clann_search_step", "clann_state_bytes",
+    "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
+    "clann_last_search_profile", "clann_last_error", "clann_destroy",
+    "CPUFFINN_load_from_file", "CPUFFINN_index_create", "CPUFFINN_index_rebuild", "CPUFFINN_index_insert_cosine",
+    "CPUFFINN_search_cosine", "CPUFFINN_get_distance_computations", "CPUFFINN_clear_distance_computations",
+    "CPUFFINN_save_index",
+]
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (never build implicitly on a GPU box: the .so ships with the repository snapshot)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: run `python -m clann_b200.build` (nvcc, sm_100a). clann_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    L.clann_last_error.restype = C.c_char_p
+    L.clann_init_with_config.restype = _i32
+    L.clann_init_with_config.argtypes = [_vp, _u64, _u32, C.POINTER(ClannConfig), C.POINTER(_vp)]
+    L.clann_set_option.restype, L.clann_set_option.argtypes = _i32, [_vp, C.c_char_p, _i64]
+    L.clann_set_clustering.restype, L.clann_set_clustering.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]
+    L.clann_import_reference.restype, L.clann_import_reference.argtypes = _i32, [_vp, _u64, _vp, _u64]
+    L.clann_set_functions.restype, L.clann_set_functions.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]
+    L.clann_build.restype, L.clann_build.argtypes = _i32, [_vp]
+    L.clann_search.restype, L.clann_search.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp]
+    L.clann_search_device.restype, L.clann_search_device.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]
+    L.clann_search_begin.restype, L.clann_search_begin.argtypes = _i32, [_vp, _vp, _u64, _vp]
+    L.clann_search_step.restype, L.clann_search_step.argtypes = _i32, [_vp, _vp]
+    L.clann_state_bytes.restype, L.clann_state_bytes.argtypes = _u64, [_vp]
+    L.clann_state_ptr.restype, L.clann_state_ptr.argtypes = _vp, [_vp]
+    L.clann_search_merge.restype, L.clann_search_merge.argtypes = _i32, [_vp, _vp, _i32, C.POINTER(_u64), _vp]
+    L.clann_search_end.restype, L.clann_search_end.argtypes = _i32, [_vp, _vp, _vp, _vp, _vp]
+    L.clann_get_counters.restype, L.clann_get_counters.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]
+    L.clann_export.restype, L.clann_export.argtypes = _i32, [_vp, _i32, _u64, _vp, _u64, C.POINTER(_u64)]
+    L.clann_last_search_profile.restype, L.clann_last_search_profile.argtypes = _i32, [_vp, _vp, _vp]
+    L.clann_destroy.restype, L.clann_destroy.argtypes = None, [_vp]
+    # legacy ABI (libpuffinn-ffi/c_binder.h:14-26)
+    L.CPUFFINN_load_from_file.restype, L.CPUFFINN_load_from_file.argtypes = _vp, [C.c_char_p, C.c_char_p]
+    L.CPUFFINN_index_create.restype, L.CPUFFINN_index_create.argtypes = _vp, [C.c_char_p, _i32]
+    L.CPUFFINN_index_rebuild.restype, L.CPUFFINN_index_rebuild.argtypes = _u64, [_vp, C.c_uint]
+    L.CPUFFINN_index_insert_cosine.restype, L.CPUFFINN_index_insert_cosine.argtypes = None, [_vp, _vp, _i32]
+    L.CPUFFINN_search_cosine.restype = C.POINTER(_u32)
+    L.CPUFFINN_search_cosine.argtypes = [_vp, _vp, C.c_uint, _f32, _f32, _i32]
+    L.CPUFFINN_get_distance_computations.restype, L.CPUFFINN_get_distance_computations.argtypes = C.c_uint, []
+    L.CPUFFINN_clear_distance_computations.restype, L.CPUFFINN_clear_distance_computations.argtypes = None, []
+    L.CPUFFINN_save_index.restype, L.CPUFFINN_save_index.argtypes = None, [_vp, C.c_char_p, _i32]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return load().clann_last_error().decode("utf-8", "replace")

@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference's public API for the build + search hot path.
+
+Same names, argument meaning and error behaviour as the Rust crate (/root/reference/src/lib.rs:41-264):
+
+    config = Config(num_tables=84, num_clusters_factor=0.4, k=10, delta=0.9, dataset_name="glove")
+    index = init_with_config(AngularData(data), config)     # lib.rs:118   -> clann_init_with_config
+    build(index)                                            # lib.rs:142   -> clann_build
+    neighbours = search(index, query)                       # lib.rs:183   -> clann_search, [(distance, id), ...]
+
+plus `search_batch`, the call a GPU wants (many queries per FFI crossing). Everything here is a thin shim over the
+C ABI in include/clann_b200.h; no arithmetic of the hot path happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    "Config", "MetricsOutput", "AngularData", "ClusteredIndex", "ClusteredIndexError", "ConfigError", "DataError",
+    "PuffinnCreationError", "PuffinnSearchError", "IndexNotFound", "IndexOutOfBounds", "SerializeError", "MetricsError",
+    "CudaError", "init", "init_with_config", "build", "search", "search_batch", "PuffinnIndex", "get_recall_values",
+    "brute_force_search", "generate_random_unit_vectors",
+]
+
+
+# ------------------------------------------------------------------------------------------------ errors (core/errors.rs)
+
+class ClusteredIndexError(Exception):
+    """src/core/errors.rs:6-39"""
+
+
+class ConfigError(ClusteredIndexError):
+    def __str__(self):
+        return f"Configuration Error: {self.args[0]}"
+
+
+class DataError(ClusteredIndexError):
+    def __str__(self):
+        return f"Data Error: {self.args[0]}"
+
+
+class PuffinnCreationError(ClusteredIndexError):
+    def __str__(self):
+        return f"PUFFINN Creation Error: {self.args[0]}"
+
+
+class PuffinnSearchError(ClusteredIndexError):
+    def __str__(self):
+        return f"PUFFINN Search Error: {self.args[0]}"
+
+
+class IndexNotFound(ClusteredIndexError):
+    def __str__(self):
+        return "Index Not Found Error"
+
+
+class IndexOutOfBounds(ClusteredIndexError):
+    def __str__(self):
+        return f"Index Out of Bounds: {self.args[0]}"
+
+
+class SerializeError(ClusteredIndexError):
+    def __str__(self):
+        return f"Serialize Error: {self.args[0]}"
+
+
+class MetricsError(ClusteredIndexError):
+    def __str__(self):
+        return f"Metrics Error: {self.args[0]}"
+
+
+class CudaError(ClusteredIndexError):
+    """No reference counterpart: the reference has no GPU path. Raised when the device or the CUDA runtime fails."""
+
+
+_STATUS_TO_ERROR = {
+    _lib.ERR_DATA: DataError, _lib.ERR_CONFIG: ConfigError, _lib.ERR_CREATION: PuffinnCreationError,
+    _lib.ERR_SEARCH: PuffinnSearchError, _lib.ERR_NOT_BUILT: IndexNotFound, _lib.ERR_BOUNDS: IndexOutOfBounds,
+    _lib.ERR_SERIALIZE: SerializeError, _lib.ERR_CUDA: CudaError, _lib.ERR_ARG: ConfigError,
+}
+
+
+def _check(status: int) -> None:
+    if status != _lib.OK:
+        raise _STATUS_TO_ERROR.get(status, ClusteredIndexError)(_lib.last_error())
+
+
+# ------------------------------------------------------------------------------------------------ Config (core/config.rs)
+
+class MetricsOutput(enum.Enum):
+    """src/core/config.rs:4-7. The sqlite sink itself is out of scope."""
+    DB = "DB"
+    NONE = "None"
+
+
+@dataclass
+class Config:
+    """src/core/config.rs:17-35; defaults from :38-47."""
+    num_tables: int = 10
+    num_clusters_factor: float = 1.0
+    k: int = 10
+    delta: float = 0.9
+    dataset_name: str = ""
+    metrics_output: MetricsOutput = MetricsOutput.NONE
+
+    @classmethod
+    def new(cls, num_tables, num_clusters_factor, k, delta, dataset_name, metrics_output=MetricsOutput.NONE) -> "Config":
+        """Config::new (config.rs:50-67)."""
+        return cls(num_tables, num_clusters_factor, k, delta, dataset_name, metrics_output)
+
+    def to_json_dict(self) -> dict:
+        return {"num_tables": self.num_tables, "num_clusters_factor": self.num_clusters_factor, "k": self.k,
+                "delta": self.delta, "dataset_name": self.dataset_name, "metrics_output": self.metrics_output.value}
+
+
+# ------------------------------------------------------------------------------------------------ AngularData
+
+class AngularData:
+    """src/metricdata/angulardata.rs:6-62 — owns the n x d f32 matrix handed to the index. Norms and distances are
+    computed on the device inside the index (k_row_norms, distance_point); this class only carries the rows."""
+
+    def __init__(self, data):
+        arr = np.ascontiguousarray(data, dtype=np.float32)
+        if arr.ndim != 2:
+            raise DataError("data must be a 2-D array")
+        self.data = arr
+
+    def num_points(self) -> int:
+        return self.data.shape[0]
+
+    def dimensions(self) -> int:
+        return self.data.shape[1]
+
+    def get_point(self, i: int) -> np.ndarray:
+        return self.data[i]
+
+    def subset(self, indices: Sequence[int]) -> "AngularData":
+        return AngularData(self.data[np.asarray(indices, dtype=np.int64)])
+
+    @staticmethod
+    def similarity_type() -> str:
+        return "angular"  # puffinn_types.rs:42-44
+
+
+# ------------------------------------------------------------------------------------------------ ClusteredIndex
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class ClusteredIndex:
+    """ClusteredIndex<T> (src/core/index.rs:37-47), device resident behind the C ABI."""
+
+    def __init__(self, config: Config, data: AngularData):
+        if not isinstance(data, AngularData):
+            data = AngularData(data)
+        self.config = config
+        self.data = data
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        cfg = _lib.ClannConfig(int(config.num_tables), float(np.float32(config.num_clusters_factor)), int(config.k),
+                               float(np.float32(config.delta)))
+        n, d = data.data.shape if data.data.size else (data.data.shape[0], data.data.shape[1] if data.data.ndim == 2 else 0)
+        _check(self._lib.clann_init_with_config(_ptr(data.data) if n else None, n, d, C.byref(cfg), C.byref(self._h)))
+        self.built = False
+
+    # -- options / parity hooks (no counterpart in the reference API; used by tests and the multi-GPU driver)
+    def set_option(self, key: str, value: int) -> None:
+        _check(self._lib.clann_set_option(self._h, key.encode(), int(value)))
+
+    def set_clustering(self, centers, assignment, radii) -> None:
+        c = np.ascontiguousarray(centers, np.uint64)
+        a = np.ascontiguousarray(assignment, np.uint64)
+        r = np.ascontiguousarray(radii, np.float32)
+        _check(self._lib.clann_set_clustering(self._h, c.size, _ptr(c), _ptr(a), _ptr(r)))
+
+    def import_reference(self, cluster: int, stream: bytes) -> None:
+        buf = np.frombuffer(stream, np.uint8)
+        _check(self._lib.clann_import_reference(self._h, cluster, _ptr(buf), buf.size))
+
+    def set_functions(self, cluster: Optional[int], planes, signs, est) -> None:
+        p = np.ascontiguousarray(planes, np.int16) if planes is not None else None
+        s = np.ascontiguousarray(signs, np.int8) if signs is not None else None
+        e = np.ascontiguousarray(est, np.float32) if est is not None else None
+        cid = 0xFFFFFFFFFFFFFFFF if cluster is None else int(cluster)
+        _check(self._lib.clann_set_functions(self._h, cid, _ptr(p), _ptr(s), _ptr(e)))
+
+    # -- hot path
+    def build(self) -> None:
+        _check(self._lib.clann_build(self._h))
+        self.built = True
+
+    def search_batch(self, queries) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Returns (ids[nq,k] uint32 0xFFFFFFFF-padded, dists[nq,k] f32 +inf-padded, counts[nq])."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.data.dimensions():
+            raise PuffinnSearchError(f"query has {q.shape[1]} dimensions, index has {self.data.dimensions()}")
+        nq, k = q.shape[0], int(self.config.k)
+        ids = np.empty((nq, k), np.uint32)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.empty(nq, np.uint32)
+        _check(self._lib.clann_search(self._h, _ptr(q), nq, _ptr(ids), _ptr(dists), _ptr(counts)))
+        return ids, dists, counts
+
+    def search(self, query) -> List[Tuple[float, int]]:
+        """ClusteredIndex::search (index.rs:311-439): [(distance, point id)] ascending, possibly fewer than k."""
+        ids, dists, counts = self.search_batch(np.asarray(query, np.float32)[None, :])
+        c = int(counts[0])
+        return [(float(dists[0, i]), int(ids[0, i])) for i in range(c)]
+
+    def counters(self, nq: int):
+        cand, dc, vis = np.zeros(nq, np.uint64), np.zeros(nq, np.uint64), np.zeros(nq, np.uint32)
+        _check(self._lib.clann_get_counters(self._h, nq, _ptr(cand), _ptr(dc), _ptr(vis)))
+        return dict(candidates=cand, distance_computations=dc, clusters_visited=vis)
+
+    def search_profile(self):
+        ms = (C.c_float * 3)()
+        launches = C.c_uint32(0)
+        _check(self._lib.clann_last_search_profile(self._h, ms, C.byref(launches)))
+        return dict(prep_ms=ms[0], probe_ms=ms[1], finish_ms=ms[2], launches=launches.value)
+
+    def export(self, what: int, arg: int = 0, dtype=np.uint8) -> np.ndarray:
+        size = C.c_uint64(0)
+        _check(self._lib.clann_export(self._h, what, arg, None, 0, C.byref(size)))
+        buf = np.empty(size.value, np.uint8)
+        _check(self._lib.clann_export(self._h, what, arg, _ptr(buf), buf.size, C.byref(size)))
+        return buf.view(dtype)
+
+    @property
+    def num_clusters(self) -> int:
+        return int(self.export(_lib.X_NUM_CLUSTERS, 0, np.uint64)[0])
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.clann_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ lib.rs free functions
+
+def init(data) -> ClusteredIndex:
+    """lib.rs:76-82 — default Config."""
+    return ClusteredIndex(Config(), data if isinstance(data, AngularData) else AngularData(data))
+
+
+def init_with_config(data, config: Config) -> ClusteredIndex:
+    """lib.rs:118-124"""
+    return ClusteredIndex(config, data if isinstance(data, AngularData) else AngularData(data))
+
+
+def build(index: ClusteredIndex) -> None:
+    """lib.rs:142-148"""
+    index.build()
+
+
+def search(index: ClusteredIndex, query) -> List[Tuple[float, int]]:
+    """lib.rs:183-189"""
+    return index.search(query)
+
+
+def search_batch(index: ClusteredIndex, queries):
+    return index.search_batch(queries)
+
+
+# ------------------------------------------------------------------------------------------------ PuffinnIndex (legacy ABI)
+
+class PuffinnIndex:
+    """src/puffinn_binds/puffinn.rs:10-118 over the eight CPUFFINN_* symbols, exactly as the Rust crate drives them."""
+
+    def __init__(self, raw, dim):
+        self.raw, self.dim = raw, dim
+        self.memory = 0
+
+    @classmethod
+    def new(cls, metric_data: AngularData, num_maps: int) -> Tuple["PuffinnIndex", int]:
+        L = _lib.load()
+        raw = L.CPUFFINN_index_create(metric_data.similarity_type().encode(), metric_data.dimensions())
+        if not raw:
+            raise PuffinnCreationError("Failed to create PUFFINN index")  # puffinn.rs:34-36
+        self = cls(raw, metric_data.dimensions())
+        for i in range(metric_data.num_points()):  # puffinn.rs:41-46
+            row = np.ascontiguousarray(metric_data.get_point(i), np.float32)
+            L.CPUFFINN_index_insert_cosine(raw, _ptr(row), self.dim)
+        mem = L.CPUFFINN_index_rebuild(raw, num_maps)
+        if mem == 0:
+            raise PuffinnCreationError("Failed to create PUFFINN index, insufficient memory")  # puffinn.rs:52-54
+        self.memory = mem
+        return self, mem
+
+    def search(self, query, k: int, max_dist: float, recall: float) -> List[int]:
+        """puffinn.rs:77-118"""
+        L = _lib.load()
+        q = np.ascontiguousarray(query, np.float32)
+        max_sim = float(np.float32(1.0) - np.float32(max_dist) / np.float32(2.0))  # puffinn_types.rs:77-79
+        ptr = L.CPUFFINN_search_cosine(self.raw, _ptr(q), k, float(recall), max_sim, q.size)
+        if not ptr:
+            raise PuffinnSearchError("Search failed: returned null pointer.")
+        try:
+            if ptr[0] == 0xFFFFFFFF:
+                return []
+            return [int(ptr[i]) for i in range(k)]  # the crate reads exactly k words (puffinn.rs:108-114)
+        finally:
+            C.CDLL(None).free(ptr)
+
+
+def get_distance_computations() -> int:
+    return int(_lib.load().CPUFFINN_get_distance_computations())
+
+
+def clear_distance_computations() -> None:
+    _lib.load().CPUFFINN_clear_distance_computations()
+
+
+# ------------------------------------------------------------------------------------------------ measurement helpers (utils/mod.rs)
+
+def get_recall_values(dataset_distances: np.ndarray, run_distances: Sequence[Sequence[float]], count: int):
+    """src/utils/mod.rs:59-95 — a returned distance counts if it is <= the count-th true distance + 1e-3."""
+    recalls = []
+    for i, run in enumerate(run_distances):
+        t = np.float32(np.sort(np.asarray(dataset_distances[i], np.float32))[count - 1]) + np.float32(1e-3)
+        recalls.append(float(sum(1 for dd in list(run)[:count] if np.float32(dd) <= t)))
+    recalls_arr = np.asarray(recalls, np.float32)
+    mean = float(recalls_arr.sum() / (len(recalls) * count)) if len(recalls) else 0.0
+    std = float(recalls_arr.std() / count) if len(recalls) else 0.0
+    return mean, std, recalls
+
+
+def generate_random_unit_vectors(n: int, dimensions: int, seed: Optional[int] = None) -> np.ndarray:
+    """src/utils/mod.rs:101-114 — U[0,1) entries, normalised."""
+    rng = np.random.default_rng(seed)
+    v = rng.random((n, dimensions), dtype=np.float32)
+    return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+
+def brute_force_search(data: np.ndarray, query: np.ndarray, k: int) -> np.ndarray:
+    """src/utils/mod.rs:116-131 — exact neighbours for measuring recall (host-side measurement helper)."""
+    data = np.asarray(data, np.float32)
+    query = np.asarray(query, np.float32)
+    d = 1.0 - (data @ query) / (np.linalg.norm(data, axis=1) * np.linalg.norm(query))
+    return np.argsort(d, kind="stable")[:k].astype(np.uint32)

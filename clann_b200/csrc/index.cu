@@ -1,0 +1,1192 @@
+// Host side of libclann_b200: the device-resident clustered index, its build / search orchestration and the C ABI
+// declared in include/clann_b200.h. Citations are file:line into /root/reference.
+#include "../../include/clann_b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <numeric>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "kernels.h"
+
+namespace clann {
+
+static thread_local std::string g_last_error;
+
+struct StatusError : std::runtime_error {
+    int code;
+    StatusError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CLANN_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+    void zero(cudaStream_t s = 0) {
+        if (n) CLANN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void upload(const T* src, size_t count, cudaStream_t s = 0) {
+        ensure(count);
+        if (count) CLANN_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s = 0) { upload(v.data(), v.size(), s); }
+    std::vector<T> download(size_t count, size_t offset = 0) const {
+        std::vector<T> v(count);
+        if (count) CLANN_CUDA(cudaMemcpy(v.data(), p + offset, count * sizeof(T), cudaMemcpyDeviceToHost));
+        return v;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ host-side function sets
+
+// format/unit_vector.hpp:61-89 on the host (used for the SimHash hyperplanes, simhash.hpp:17-23); same arithmetic as
+// k_store_q15 (see the note there on the summation shape).
+static void store_q15_host(const float* v, uint32_t d, uint32_t sl, int16_t* out) {
+    float acc = 0.0f;
+    uint32_t body = d & ~3u;
+    for (uint32_t i = 0; i < body; i++) {
+        volatile float prod = v[i] * v[i];  // keep the product rounded (no contraction)
+        acc = acc + prod;
+    }
+    for (uint32_t i = body; i < d; i++) acc = fmaf(v[i], v[i], acc);
+    float len = sqrtf(acc);
+    for (uint32_t i = 0; i < d; i++) {
+        float x = v[i];
+        if (len != 0.0f) x = x / len;
+        float s = x * 32768.0f;
+        if (s > 32767.0f) s = 32767.0f;
+        out[i] = (int16_t)s;
+    }
+    for (uint32_t i = d; i < sl; i++) out[i] = 0;
+}
+
+struct FunctionSet {
+    std::vector<int16_t> planes;     // [2048][sl]
+    std::vector<uint32_t> signbits;  // [L*fph][3][W]
+    std::vector<float> est;          // [(m+2)][201]
+    bool have_est = false, have_fn = false;
+};
+
+static uint32_t sign_words(const HashGeom& g) { return (g.npts + 31) / 32; }
+
+static void pack_signs(const HashGeom& g, const int8_t* signs, std::vector<uint32_t>& out) {
+    const uint32_t W = sign_words(g);
+    const size_t nfunc = (size_t)g.L * g.fph;
+    out.assign(nfunc * kRotations * W, 0u);
+    for (size_t f = 0; f < nfunc; f++)
+        for (uint32_t r = 0; r < (uint32_t)kRotations; r++)
+            for (uint32_t i = 0; i < g.npts; i++)
+                if (signs[(f * kRotations + r) * g.npts + i] < 0) out[(f * kRotations + r) * W + i / 32] |= 1u << (i % 32);
+}
+
+// Fresh functions as the reference draws them: 2048 normalised Gaussian hyperplanes stored as Q15 (simhash.hpp:17-23,
+// unit_vector.hpp:91-100) and L*fph x 3 x 2^m uniform signs (crosspolytope.hpp:160-165).
+static void generate_functions(const HashGeom& g, uint64_t seed, FunctionSet& fs) {
+    std::mt19937_64 rng(seed);
+    std::normal_distribution<float> normal(0.0f, 1.0f);
+    fs.planes.resize((size_t)kNumPlanes * g.sl);
+    std::vector<float> v(g.d);
+    for (int f = 0; f < kNumPlanes; f++) {
+        for (uint32_t i = 0; i < g.d; i++) v[i] = normal(rng);
+        store_q15_host(v.data(), g.d, g.sl, fs.planes.data() + (size_t)f * g.sl);
+    }
+    const size_t nsign = (size_t)g.L * g.fph * kRotations * g.npts;
+    std::vector<int8_t> signs(nsign);
+    uint64_t bits = 0;
+    int left = 0;
+    for (size_t i = 0; i < nsign; i++) {
+        if (left == 0) {
+            bits = rng();
+            left = 64;
+        }
+        signs[i] = (bits & 1) ? 1 : -1;
+        bits >>= 1;
+        left--;
+    }
+    pack_signs(g, signs.data(), fs.signbits);
+    fs.have_fn = true;
+}
+
+// hash_source/hash_source.hpp:49-57 with crosspolytope.hpp:116-118, evaluated per similarity bin.
+static float concat_prob(const HashGeom& g, const float* est, uint32_t num_bits, uint32_t bin) {
+    uint32_t whole = num_bits / g.bpf, rem = num_bits % g.bpf;
+    float wp = est[(size_t)g.bpf * kEstBins + bin];
+    float rp = est[(size_t)rem * kEstBins + bin];
+    return (float)(pow((double)wp, (double)(int)whole) * (double)rp);
+}
+
+// The stop rule (collection.hpp:927-943) tabulated with the host's libm so that the device decision is bit-identical to
+// hash_source/independent.hpp:108-119: bit t of row (depth, bin) = failure_probability(depth, t, depth==24 ? t : L, sim) <= 1-recall.
+static void build_stop_table(const HashGeom& g, const float* est, float recall, uint32_t stop_words, uint32_t* out) {
+    const float thr = 1 - recall;
+    for (uint32_t depth = 1; depth <= (uint32_t)kMaxHashBits; depth++) {
+        for (uint32_t bin = 0; bin < (uint32_t)kEstBins; bin++) {
+            uint32_t* row = out + ((size_t)(depth - 1) * kEstBins + bin) * stop_words;
+            for (uint32_t w = 0; w < stop_words; w++) row[w] = 0;
+            float col = concat_prob(g, est, depth, bin);
+            float last = concat_prob(g, est, depth + 1, bin);
+            double one_minus_col = 1.0 - (double)col;
+            float one_minus_last = 1.0f - last;  // `1-last_prob` is evaluated in float (independent.hpp:118)
+            for (uint32_t t = 0; t <= g.L; t++) {
+                uint64_t max_tables = (depth == (uint32_t)kMaxHashBits) ? t : g.L;
+                double a = pow(one_minus_col, (double)(uint64_t)t);
+                double b = pow((double)one_minus_last, (double)(max_tables - t));
+                float fp = (float)(a * b);
+                if (fp <= thr) row[t >> 5] |= 1u << (t & 31);
+            }
+        }
+    }
+}
+
+// filterer.hpp:108-111 + simhash.hpp:96-102 tabulated over every value MaxBuffer::smallest_value() can take.
+static void build_msd_table(std::vector<uint8_t>& msd) {
+    msd.resize(65536);
+    for (uint32_t v = 0; v < 65536; v++) {
+        float sim = (float)v / 65536.0f;
+        float arg = 2.0f * sim - 1.0f;
+        float cp = (float)(1.0 - (double)acosf(arg) / M_PI);
+        float r = roundf((float)(64.0 * (1.0 - (double)cp)));
+        msd[v] = (uint8_t)r;
+    }
+}
+
+// --- Index::serialize reader (collection.hpp:185-203; field list in SURVEY.md section 8c): extracts the function set.
+struct Reader {
+    const uint8_t* p;
+    uint64_t len, off = 0;
+    void bytes(void* dst, uint64_t n) {
+        if (off + n > len) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");
+        if (dst) memcpy(dst, p + off, n);
+        off += n;
+    }
+    template <typename T>
+    T get() {
+        T v;
+        bytes(&v, sizeof(T));
+        return v;
+    }
+};
+
+static void parse_reference_stream(const uint8_t* blob, uint64_t len, const HashGeom& g, FunctionSet& fs, uint32_t* n_points) {
+    Reader r{blob, len};
+    uint32_t d = r.get<uint32_t>(), sl = r.get<uint32_t>(), n = r.get<uint32_t>();
+    if (d != g.d || sl != g.sl) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream has a different dimension");
+    r.bytes(nullptr, (uint64_t)n * sl * 2);                    // Dataset rows (dataset.hpp:79-86)
+    if (r.get<int32_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "sketch source is not IndependentHashSource");
+    r.get<uint32_t>(); r.get<uint32_t>();                      // SimHash dataset description
+    if (r.get<uint64_t>() != (uint64_t)kNumPlanes) throw StatusError(CLANN_ERR_SERIALIZE, "expected 2048 sketch functions");
+    fs.planes.resize((size_t)kNumPlanes * sl);
+    for (int f = 0; f < kNumPlanes; f++) {                     // simhash.hpp:33-38
+        if (r.get<uint32_t>() != sl) throw StatusError(CLANN_ERR_SERIALIZE, "hyperplane length mismatch");
+        r.bytes(fs.planes.data() + (size_t)f * sl, (uint64_t)sl * 2);
+    }
+    r.get<uint32_t>(); r.get<uint32_t>(); r.get<uint8_t>(); r.get<uint32_t>(); r.get<uint32_t>();  // independent.hpp:64-68
+    uint64_t n_sk = r.get<uint64_t>();
+    r.bytes(nullptr, n_sk * 8);                                // stored sketches (filterer.hpp:62-68)
+    if (r.get<int32_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "hash source is not IndependentHashSource");
+    uint32_t rot = r.get<uint32_t>();
+    r.get<uint32_t>(); r.get<float>();                         // estimation_repetitions, estimation_eps
+    if (rot != (uint32_t)kRotations) throw StatusError(CLANN_ERR_SERIALIZE, "expected 3 FHT rotations");
+    if (!r.get<uint8_t>()) throw StatusError(CLANN_ERR_SERIALIZE, "reference index was never rebuilt (no hash source)");
+    r.get<uint32_t>(); r.get<uint32_t>();                      // family: dataset description
+    r.get<uint32_t>(); r.get<uint32_t>(); r.get<float>();      // family: args
+    uint64_t rows = r.get<uint64_t>();                         // crosspolytope.hpp:104-114
+    if (rows != g.m + 2) throw StatusError(CLANN_ERR_SERIALIZE, "collision estimate table has the wrong height");
+    fs.est.resize((size_t)(g.m + 2) * kEstBins);
+    for (uint64_t b = 0; b < rows; b++) {
+        if (r.get<uint64_t>() != (uint64_t)kEstBins) throw StatusError(CLANN_ERR_SERIALIZE, "collision estimate table has the wrong width");
+        r.bytes(fs.est.data() + b * kEstBins, sizeof(float) * kEstBins);
+    }
+    r.get<float>();                                            // eps
+    uint64_t n_fn = r.get<uint64_t>();
+    if (n_fn != (uint64_t)g.L * g.fph) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream has a different number of tables");
+    std::vector<int8_t> signs((size_t)n_fn * kRotations * g.npts);
+    for (uint64_t f = 0; f < n_fn; f++) {                      // crosspolytope.hpp:178-184
+        int32_t dd = r.get<int32_t>(), mm = r.get<int32_t>();
+        uint32_t rr = r.get<uint32_t>();
+        if ((uint32_t)dd != g.d || (uint32_t)mm != g.m || rr != (uint32_t)kRotations) throw StatusError(CLANN_ERR_SERIALIZE, "FHT function header mismatch");
+        r.bytes(signs.data() + f * kRotations * g.npts, (uint64_t)kRotations * g.npts);
+    }
+    pack_signs(g, signs.data(), fs.signbits);
+    fs.have_fn = fs.have_est = true;
+    if (n_points) *n_points = n;
+}
+
+// ------------------------------------------------------------------------------------------------ the index
+
+}  // namespace clann
+
+using namespace clann;
+
+struct clann_index {
+    // configuration
+    clann_config cfg{};
+    uint64_t n = 0;
+    HashGeom g{};
+    uint32_t K = 0;
+    uint64_t seed = 0x5eedc1a7ull;
+    bool per_cluster_functions = false;
+    bool puffinn_mode = false;  // legacy single-index handle: one cluster, no CLANN layer
+    uint32_t shard_rank = 0, shard_count = 1;
+    bool clustering_imposed = false, built = false;
+
+    // host mirrors
+    std::vector<uint32_t> h_centers, h_sizes, h_assign;
+    std::vector<uint64_t> h_offsets;
+    std::vector<float> h_radii;
+    std::vector<uint8_t> h_brute, h_owner;
+    std::vector<uint32_t> h_fset_of;
+    std::vector<FunctionSet> fsets;  // 1 (shared) or K
+    std::vector<uint8_t> h_msd;
+    double build_ms[4] = {0, 0, 0, 0};
+
+    // device: dataset + CLANN layer
+    DevBuf<float> d_data, d_norms, d_dist, d_radii, d_center_rows, d_center_norms;
+    DevBuf<uint32_t> d_assign, d_centers, d_sizes, d_perm, d_fset_of;
+    DevBuf<uint64_t> d_keys, d_offsets;
+    DevBuf<uint8_t> d_brute, d_owner, d_msd;
+    // device: PUFFINN layer
+    DevBuf<int16_t> d_q15, d_planes;
+    DevBuf<uint64_t> d_sketches;
+    DevBuf<uint32_t> d_tbl_hash, d_tbl_idx, d_signbits, d_stop;
+    uint32_t stop_words = 0;
+    float stop_recall = -1.0f;
+
+    // search workspace
+    uint64_t ws_nq = 0;
+    DevBuf<float> w_queries, w_qnorm, w_cdist, w_out_dists;
+    DevBuf<int16_t> w_q15;
+    DevBuf<uint32_t> w_codes, w_corder, w_out_ids, w_out_counts, w_counter, w_vis;
+    DevBuf<uint64_t> w_sketches;
+    DevBuf<unsigned long long> w_cand, w_dc;
+    DevBuf<uint8_t> w_state;
+    DevBuf<RowTile> w_tiles;
+    uint32_t w_ntiles = 0;
+    uint64_t last_nq = 0;
+    const float* cur_queries = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t last_launches = 0;
+    bool profile_valid = false;
+
+    ~clann_index() {
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+
+    uint32_t n_fsets() const { return (uint32_t)fsets.size(); }
+
+    // index.rs:78-80
+    static uint32_t num_clusters(float factor, uint64_t n) {
+        double v = floor((double)factor * sqrt((double)n));
+        uint64_t k = v < 1.0 ? 1 : (uint64_t)v;
+        return (uint32_t)k;
+    }
+
+    void init(const float* data, uint64_t n_, uint32_t d, const clann_config& c) {
+        if (n_ == 0) throw StatusError(CLANN_ERR_DATA, "empty dataset");  // index.rs:72-74
+        if (!data || d == 0) throw StatusError(CLANN_ERR_ARG, "null data or zero dimension");
+        if (d > 1024) throw StatusError(CLANN_ERR_CONFIG, "dimension above 1024 is not supported");
+        if (c.num_tables == 0) throw StatusError(CLANN_ERR_CONFIG, "num tables should be >0");  // collection.hpp:242-244
+        if (c.k == 0) throw StatusError(CLANN_ERR_CONFIG, "k must be at least 1");
+        if (n_ > 0xfffffff0ull) throw StatusError(CLANN_ERR_CONFIG, "more than 2^32 points are not supported");
+        int dev_count = 0;
+        if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+            throw StatusError(CLANN_ERR_CUDA, "no CUDA device: libclann_b200 has no CPU fallback");
+        cfg = c;
+        n = n_;
+        g = make_geom(d, (uint32_t)c.num_tables);
+        K = puffinn_mode ? 1u : num_clusters(c.num_clusters_factor, n);
+        d_data.upload(data, (size_t)n * d);
+        for (auto& e : ev) CLANN_CUDA(cudaEventCreate(&e));
+    }
+
+    void set_clustering(uint64_t K_, const uint64_t* centers, const uint64_t* assignment, const float* radii) {
+        if (K_ == 0 || !centers || !assignment || !radii) throw StatusError(CLANN_ERR_ARG, "bad clustering");
+        K = (uint32_t)K_;
+        h_centers.resize(K);
+        h_radii.assign(radii, radii + K);
+        for (uint32_t c = 0; c < K; c++) {
+            if (centers[c] >= n) throw StatusError(CLANN_ERR_BOUNDS, "centre id out of range");
+            h_centers[c] = (uint32_t)centers[c];
+        }
+        h_assign.resize(n);
+        for (uint64_t i = 0; i < n; i++) {
+            if (assignment[i] >= K) throw StatusError(CLANN_ERR_BOUNDS, "assignment out of range");
+            h_assign[i] = (uint32_t)assignment[i];
+        }
+        clustering_imposed = true;
+        built = false;
+    }
+
+    void ensure_fsets() {
+        size_t want = per_cluster_functions ? K : 1;
+        if (fsets.size() != want) fsets.resize(want);
+    }
+
+    void import_reference(uint64_t cluster, const void* blob, uint64_t len) {
+        if (cluster >= K) throw StatusError(CLANN_ERR_BOUNDS, "cluster out of range");
+        per_cluster_functions = true;
+        ensure_fsets();
+        parse_reference_stream(static_cast<const uint8_t*>(blob), len, g, fsets[cluster], nullptr);
+        built = false;
+    }
+
+    void set_functions(uint64_t cluster, const int16_t* planes, const int8_t* signs, const float* est) {
+        FunctionSet* fs;
+        if (cluster == UINT64_MAX) {
+            per_cluster_functions = false;
+            ensure_fsets();
+            fs = &fsets[0];
+        } else {
+            if (cluster >= K) throw StatusError(CLANN_ERR_BOUNDS, "cluster out of range");
+            per_cluster_functions = true;
+            ensure_fsets();
+            fs = &fsets[cluster];
+        }
+        if (planes && signs) {
+            fs->planes.assign(planes, planes + (size_t)kNumPlanes * g.sl);
+            pack_signs(g, signs, fs->signbits);
+            fs->have_fn = true;
+        }
+        if (est) {
+            fs->est.assign(est, est + (size_t)(g.m + 2) * kEstBins);
+            fs->have_est = true;
+        }
+        built = false;
+    }
+
+    // ---- build -----------------------------------------------------------------------------------------------
+
+    void run_gmm(cudaStream_t s) {
+        // angulardata.rs:12-19
+        d_norms.alloc(n);
+        launch_row_norms(d_data.p, n, g.d, d_norms.p, s);
+        if (clustering_imposed) return;
+        if (n <= K) {  // gmm.rs:26-31: every point its own centre
+            K = (uint32_t)n;
+            h_centers.resize(K);
+            std::iota(h_centers.begin(), h_centers.end(), 0u);
+            h_assign.resize(n);
+            std::iota(h_assign.begin(), h_assign.end(), 0u);
+            h_radii.assign(K, 0.0f);
+            return;
+        }
+        d_dist.alloc(n);
+        d_assign.alloc(n);
+        d_keys.alloc(K);
+        d_keys.zero(s);
+        for (uint32_t c = 0; c < K; c++) launch_gmm_pass(d_data.p, d_norms.p, n, g.d, c, d_keys.p, d_dist.p, d_assign.p, s);
+        d_centers.alloc(K);
+        d_radii.alloc(K);
+        d_radii.zero(s);
+        d_sizes.alloc(K);
+        d_sizes.zero(s);
+        launch_gmm_finish(d_keys.p, K, n, d_dist.p, d_assign.p, d_centers.p, d_radii.p, d_sizes.p, s);
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        h_centers = d_centers.download(K);
+        h_radii = d_radii.download(K);
+        h_assign = d_assign.download(n);
+        d_dist.release();
+        d_keys.release();
+    }
+
+    // index.rs:188-192 — per-cluster member lists in ascending point order, laid out back to back.
+    void invert_assignment(cudaStream_t s) {
+        h_sizes.assign(K, 0);
+        for (uint64_t i = 0; i < n; i++) h_sizes[h_assign[i]]++;
+        h_offsets.assign(K + 1, 0);
+        for (uint32_t c = 0; c < K; c++) h_offsets[c + 1] = h_offsets[c] + h_sizes[c];
+        // stable partition by cluster id = the same radix sort the tables use, one segment of n keys
+        DevBuf<uint32_t> keys, scratch_k, scratch_i;
+        keys.upload(h_assign, s);
+        d_perm.alloc(n);
+        DevBuf<SortSegment> seg;
+        std::vector<SortSegment> hs(1);
+        hs[0] = SortSegment{0, 0, (uint32_t)n, 0};
+        seg.upload(hs, s);
+        if (n > segment_sort_smem_capacity()) {
+            scratch_k.alloc(n);
+            scratch_i.alloc(n);
+        }
+        launch_segment_sort(seg.p, 1, (uint32_t)n, keys.p, d_perm.p, scratch_k.p, scratch_i.p, s);
+        d_offsets.upload(h_offsets, s);
+        CLANN_CUDA(cudaStreamSynchronize(s));
+    }
+
+    void assign_owners() {
+        // longest-processing-time on cluster sizes; deterministic, so every rank derives the same map
+        h_owner.assign(K, 0);
+        if (shard_count <= 1) return;
+        std::vector<uint32_t> order(K);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_sizes[a] > h_sizes[b]; });
+        std::vector<uint64_t> load(shard_count, 0);
+        for (uint32_t c : order) {
+            uint32_t best = 0;
+            for (uint32_t r = 1; r < shard_count; r++)
+                if (load[r] < load[best]) best = r;
+            h_owner[c] = (uint8_t)best;
+            load[best] += h_sizes[c];
+        }
+    }
+
+    void prepare_functions(cudaStream_t s) {
+        ensure_fsets();
+        // collision estimates: one Monte-Carlo table per dimension, shared by every set that did not import its own
+        std::vector<float> shared_est;
+        auto need_est = [&]() -> const std::vector<float>& {
+            if (shared_est.empty()) {
+                DevBuf<float> d_est;
+                DevBuf<uint32_t> d_counts;
+                d_est.alloc((size_t)(g.m + 2) * kEstBins);
+                d_counts.alloc((size_t)(g.m + 2) * kEstBins);
+                launch_cp_estimates(g.m, 1000, seed ^ 0xC0111510ull, d_est.p, d_counts.p, s);  // crosspolytope.hpp:221-226
+                CLANN_CUDA(cudaStreamSynchronize(s));
+                shared_est = d_est.download((size_t)(g.m + 2) * kEstBins);
+            }
+            return shared_est;
+        };
+        for (size_t f = 0; f < fsets.size(); f++) {
+            FunctionSet& fs = fsets[f];
+            bool used = !per_cluster_functions || !h_brute[f];
+            if (!used) {
+                // keep array shapes uniform for unused slots
+                if (!fs.have_fn) {
+                    fs.planes.assign((size_t)kNumPlanes * g.sl, 0);
+                    fs.signbits.assign((size_t)g.L * g.fph * kRotations * sign_words(g), 0u);
+                }
+                if (!fs.have_est) fs.est.assign((size_t)(g.m + 2) * kEstBins, 1.0f);
+                continue;
+            }
+            if (!fs.have_fn) generate_functions(g, seed + 0x9E3779B97F4A7C15ull * (f + 1), fs);
+            if (!fs.have_est) {
+                fs.est = need_est();
+                fs.have_est = true;
+            }
+        }
+        // upload
+        const size_t plane_sz = (size_t)kNumPlanes * g.sl, sign_sz = (size_t)g.L * g.fph * kRotations * sign_words(g);
+        std::vector<int16_t> all_planes(plane_sz * fsets.size());
+        std::vector<uint32_t> all_signs(sign_sz * fsets.size());
+        for (size_t f = 0; f < fsets.size(); f++) {
+            memcpy(all_planes.data() + f * plane_sz, fsets[f].planes.data(), plane_sz * sizeof(int16_t));
+            memcpy(all_signs.data() + f * sign_sz, fsets[f].signbits.data(), sign_sz * sizeof(uint32_t));
+        }
+        d_planes.upload(all_planes, s);
+        d_signbits.upload(all_signs, s);
+        build_msd_table(h_msd);
+        d_msd.upload(h_msd, s);
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        stop_recall = -1.0f;
+    }
+
+    // Stop tables for a recall value (Config.delta for the batched ABI; per call for the legacy ABI).
+    void ensure_stop_table(float recall, cudaStream_t s) {
+        if (recall == stop_recall && d_stop.p) return;
+        stop_words = (g.L + 1 + 31) / 32;
+        const size_t per = (size_t)kMaxHashBits * kEstBins * stop_words;
+        std::vector<uint32_t> all(per * fsets.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                size_t f = next.fetch_add(1);
+                if (f >= fsets.size()) break;
+                build_stop_table(g, fsets[f].est.data(), recall, stop_words, all.data() + f * per);
+            }
+        };
+        unsigned nt = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), fsets.size());
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        d_stop.upload(all, s);
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        stop_recall = recall;
+    }
+
+    void build() {
+        cudaStream_t s = 0;
+        cudaEvent_t e0, e1, e2, e3;
+        CLANN_CUDA(cudaEventCreate(&e0)); CLANN_CUDA(cudaEventCreate(&e1)); CLANN_CUDA(cudaEventCreate(&e2)); CLANN_CUDA(cudaEventCreate(&e3));
+        CLANN_CUDA(cudaEventRecord(e0, s));
+        run_gmm(s);
+        invert_assignment(s);
+        // ClusterCenter records (index.rs:194-220)
+        h_brute.resize(K);
+        for (uint32_t c = 0; c < K; c++)
+            h_brute[c] = puffinn_mode ? 0 : (h_sizes[c] < 100 || h_sizes[c] < cfg.k);  // index.rs:204-205
+        h_fset_of.resize(K);
+        for (uint32_t c = 0; c < K; c++) h_fset_of[c] = per_cluster_functions ? c : 0;
+        assign_owners();
+        d_brute.upload(h_brute, s);
+        d_fset_of.upload(h_fset_of, s);
+        d_owner.upload(h_owner, s);
+        d_radii.upload(h_radii, s);
+        d_centers.upload(h_centers, s);
+        d_center_rows.alloc((size_t)K * g.d);
+        launch_gather_rows(d_data.p, d_centers.p, K, g.d, d_center_rows.p, s);
+        d_center_norms.alloc(K);
+        {
+            std::vector<float> norms = d_norms.download(n);
+            std::vector<float> cn(K);
+            for (uint32_t c = 0; c < K; c++) cn[c] = norms[h_centers[c]];
+            d_center_norms.upload(cn, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));
+        }
+        CLANN_CUDA(cudaEventRecord(e1, s));
+
+        prepare_functions(s);
+
+        // PUFFINN layer: Q15 rows in cluster order (puffinn.rs:41-46 -> dataset.hpp:109-124)
+        d_q15.alloc((size_t)n * g.sl);
+        launch_store_q15(d_data.p, d_perm.p, n, g.d, g.sl, d_q15.p, s);
+        std::vector<RowTile> tiles;
+        std::vector<SortSegment> segs;
+        uint32_t max_len = 0;
+        uint64_t scratch_total = 0;
+        const uint32_t cap = segment_sort_smem_capacity();
+        for (uint32_t c = 0; c < K; c++) {
+            if (h_brute[c] || h_sizes[c] == 0) continue;
+            if (shard_count > 1 && h_owner[c] != shard_rank) continue;  // other ranks build their own clusters
+            for (uint32_t r = 0; r < h_sizes[c]; r += 32) {
+                uint32_t row0 = (uint32_t)h_offsets[c] + r;
+                tiles.push_back(RowTile{row0, row0, std::min<uint32_t>(32, h_sizes[c] - r), h_fset_of[c]});
+            }
+            max_len = std::max(max_len, h_sizes[c]);
+        }
+        DevBuf<RowTile> d_tiles;
+        d_tiles.upload(tiles, s);
+        d_sketches.alloc((size_t)n * kNumSketches);
+        launch_sketch(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_planes.p, g.sl, d_sketches.p, s);
+        d_tbl_hash.alloc((size_t)g.L * n);
+        d_tbl_idx.alloc((size_t)g.L * n);
+        launch_codes(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_signbits.p, g, d_tbl_hash.p, n, 0, s);
+        CLANN_CUDA(cudaEventRecord(e2, s));
+        // collection.hpp:299-302 -> prefixmap.hpp:169-247: one stable radix sort per (cluster, table)
+        for (uint32_t c = 0; c < K; c++) {
+            if (h_brute[c] || h_sizes[c] == 0) continue;
+            if (shard_count > 1 && h_owner[c] != shard_rank) continue;
+            for (uint32_t t = 0; t < g.L; t++) {
+                SortSegment sg{(uint64_t)t * n + h_offsets[c], 0, h_sizes[c], 0};
+                if (h_sizes[c] > cap) {
+                    sg.scratch_base = scratch_total;
+                    scratch_total += h_sizes[c];
+                }
+                segs.push_back(sg);
+            }
+        }
+        DevBuf<SortSegment> d_segs;
+        DevBuf<uint32_t> scratch_k, scratch_i;
+        d_segs.upload(segs, s);
+        if (scratch_total) {
+            scratch_k.alloc(scratch_total);
+            scratch_i.alloc(scratch_total);
+        }
+        launch_segment_sort(d_segs.p, (uint32_t)segs.size(), max_len, d_tbl_hash.p, d_tbl_idx.p, scratch_k.p, scratch_i.p, s);
+        CLANN_CUDA(cudaEventRecord(e3, s));
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        CLANN_CUDA(cudaGetLastError());
+        float ms;
+        CLANN_CUDA(cudaEventElapsedTime(&ms, e0, e1)); build_ms[0] = ms;
+        CLANN_CUDA(cudaEventElapsedTime(&ms, e1, e2)); build_ms[1] = ms;
+        CLANN_CUDA(cudaEventElapsedTime(&ms, e2, e3)); build_ms[2] = ms;
+        CLANN_CUDA(cudaEventElapsedTime(&ms, e0, e3)); build_ms[3] = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+        ensure_stop_table(cfg.delta, s);
+        built = true;
+    }
+
+    // ---- search ----------------------------------------------------------------------------------------------
+
+    SearchParams params() const {
+        SearchParams p{};
+        p.g = g;
+        p.k = (uint32_t)cfg.k;
+        p.K = K;
+        p.n_fsets = n_fsets();
+        p.n = n;
+        p.stop_words = stop_words;
+        p.data = d_data.p;
+        p.norms = d_norms.p;
+        p.perm = d_perm.p;
+        p.offsets = d_offsets.p;
+        p.q15 = d_q15.p;
+        p.sketches = d_sketches.p;
+        p.tbl_hash = d_tbl_hash.p;
+        p.tbl_idx = d_tbl_idx.p;
+        p.center_rows = d_center_rows.p;
+        p.center_norms = d_center_norms.p;
+        p.radii = d_radii.p;
+        p.brute = d_brute.p;
+        p.fset_of = d_fset_of.p;
+        p.owner = d_owner.p;
+        p.stop = d_stop.p;
+        p.msd = d_msd.p;
+        p.shard_rank = shard_rank;
+        return p;
+    }
+
+    void ensure_workspace(uint64_t nq, cudaStream_t s) {
+        if (nq == ws_nq) return;
+        const uint32_t F = n_fsets();
+        const uint32_t k = (uint32_t)cfg.k;
+        w_qnorm.ensure(nq);
+        w_q15.ensure(nq * g.sl);
+        w_codes.ensure((size_t)F * g.L * nq);
+        w_sketches.ensure((size_t)F * nq * kNumSketches);
+        w_cdist.ensure(nq * K);
+        w_corder.ensure(nq * K);
+        w_state.ensure(nq * query_state_bytes(k));
+        w_counter.ensure(2);
+        w_cand.ensure(nq);
+        w_dc.ensure(nq);
+        w_vis.ensure(nq);
+        std::vector<RowTile> tiles;
+        for (uint32_t f = 0; f < F; f++)
+            for (uint64_t q0 = 0; q0 < nq; q0 += 32)
+                tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f});
+        w_tiles.upload(tiles, s);
+        w_ntiles = (uint32_t)tiles.size();
+        ws_nq = nq;
+    }
+
+    QueryBatch batch(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+        QueryBatch b{};
+        b.nq = nq;
+        b.queries = d_queries;
+        b.qnorm = w_qnorm.p;
+        b.q15 = w_q15.p;
+        b.codes = w_codes.p;
+        b.sketches = w_sketches.p;
+        b.cdist = w_cdist.p;
+        b.corder = w_corder.p;
+        b.state = w_state.p;
+        b.work_counter = w_counter.p;
+        b.out_ids = d_ids;
+        b.out_dists = d_dists;
+        b.out_counts = d_counts;
+        b.cnt_candidates = w_cand.p;
+        b.cnt_distcomp = w_dc.p;
+        b.cnt_visited = w_vis.p;
+        return b;
+    }
+
+    void require_built() const {
+        if (!built) throw StatusError(CLANN_ERR_NOT_BUILT, "index has not been built");
+    }
+
+    // hashing of the query batch with every function set in use, centre ordering, state reset
+    void search_begin(const float* d_queries, uint64_t nq, cudaStream_t s) {
+        require_built();
+        ensure_workspace(nq, s);
+        SearchParams p = params();
+        QueryBatch b = batch(d_queries, nq, nullptr, nullptr, nullptr);
+        launch_prep_queries(p, b, s);
+        // sketches are indexed by out_row = fset*nq + q (w_tiles); codes by fset*L*nq + t*nq + q (w_code_tiles)
+        launch_sketch(b.q15, w_tiles.p, w_ntiles, d_planes.p, g.sl, b.sketches, s);
+        launch_codes(b.q15, w_code_tiles(nq, s), w_ntiles, d_signbits.p, g, b.codes, nq, (uint64_t)g.L * nq, s);
+        launch_center_order(p, b, s);
+        launch_init_state(p, b, s);
+        cur_queries = d_queries;
+        last_nq = nq;
+        last_launches = 5;
+    }
+
+    DevBuf<RowTile> w_tiles_codes;
+    uint64_t w_tiles_codes_nq = 0;
+    const RowTile* w_code_tiles(uint64_t nq, cudaStream_t s) {
+        if (w_tiles_codes_nq != nq || !w_tiles_codes.p) {
+            std::vector<RowTile> tiles;
+            for (uint32_t f = 0; f < n_fsets(); f++)
+                for (uint64_t q0 = 0; q0 < nq; q0 += 32)
+                    tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)q0, (uint32_t)std::min<uint64_t>(32, nq - q0), f});
+            w_tiles_codes.upload(tiles, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));
+            w_tiles_codes_nq = nq;
+        }
+        return w_tiles_codes.p;
+    }
+
+    void search_device(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
+        require_built();
+        if (nq == 0) return;
+        CLANN_CUDA(cudaEventRecord(ev[0], s));
+        search_begin(d_queries, nq, s);
+        SearchParams p = params();
+        QueryBatch b = batch(d_queries, nq, d_ids, d_dists, d_counts);
+        CLANN_CUDA(cudaEventRecord(ev[1], s));
+        launch_probe(p, b, false, s);
+        CLANN_CUDA(cudaEventRecord(ev[2], s));
+        launch_finish(p, b, s);
+        CLANN_CUDA(cudaEventRecord(ev[3], s));
+        last_launches = 7;
+        profile_valid = true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ C ABI (batched)
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return CLANN_OK;
+    } catch (const StatusError& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const CudaError& e) {
+        g_last_error = e.what();
+        return CLANN_ERR_CUDA;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "out of host memory";
+        return CLANN_ERR_CREATION;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return CLANN_ERR_ARG;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return CLANN_ERR_ARG;
+    }
+}
+
+extern "C" {
+
+const char* clann_last_error(void) { return g_last_error.c_str(); }
+
+int clann_init_with_config(const float* data, uint64_t n, uint32_t d, const clann_config* config, clann_index** out) {
+    if (out) *out = nullptr;
+    return guarded([&] {
+        if (!config || !out) throw StatusError(CLANN_ERR_ARG, "null config or output pointer");
+        auto* ix = new clann_index();
+        try {
+            ix->init(data, n, d, *config);
+        } catch (...) {
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+int clann_set_option(clann_index* index, const char* key, int64_t value) {
+    return guarded([&] {
+        if (!index || !key) throw StatusError(CLANN_ERR_ARG, "null index or key");
+        std::string k(key);
+        if (k == "seed") index->seed = (uint64_t)value;
+        else if (k == "function_sets") index->per_cluster_functions = value != 0;
+        else if (k == "strict") { if (value != 1) throw StatusError(CLANN_ERR_ARG, "only strict mode is implemented"); }
+        else if (k == "shard_rank") index->shard_rank = (uint32_t)value;
+        else if (k == "shard_count") {
+            if (value < 1 || value > 255) throw StatusError(CLANN_ERR_ARG, "shard_count must be in 1..255");
+            index->shard_count = (uint32_t)value;
+        } else throw StatusError(CLANN_ERR_ARG, "unknown option '" + k + "'");
+        index->built = false;
+    });
+}
+
+int clann_set_clustering(clann_index* index, uint64_t K, const uint64_t* centers, const uint64_t* assignment, const float* radii) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->set_clustering(K, centers, assignment, radii);
+    });
+}
+
+int clann_import_reference(clann_index* index, uint64_t cluster, const void* blob, uint64_t len) {
+    return guarded([&] {
+        if (!index || !blob) throw StatusError(CLANN_ERR_ARG, "null index or blob");
+        index->import_reference(cluster, blob, len);
+    });
+}
+
+int clann_set_functions(clann_index* index, uint64_t cluster, const int16_t* planes, const int8_t* signs, const float* est) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->set_functions(cluster, planes, signs, est);
+    });
+}
+
+int clann_build(clann_index* index) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        try {
+            index->build();
+        } catch (const CudaError& e) {
+            throw StatusError(CLANN_ERR_CREATION, e.what());  // index.rs:267-273
+        }
+    });
+}
+
+int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts,
+                        void* stream) {
+    return guarded([&] {
+        if (!index || (nq && (!d_queries || !d_ids || !d_dists || !d_counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_device(d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search(clann_index* index, const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts) {
+    return guarded([&] {
+        if (!index || (nq && (!queries || !ids || !dists || !counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->require_built();
+        if (nq == 0) return;
+        const uint32_t k = (uint32_t)index->cfg.k;
+        cudaStream_t s = 0;
+        index->w_queries.ensure(nq * index->g.d);
+        index->w_out_ids.ensure(nq * k);
+        index->w_out_dists.ensure(nq * k);
+        index->w_out_counts.ensure(nq);
+        CLANN_CUDA(cudaMemcpyAsync(index->w_queries.p, queries, nq * index->g.d * sizeof(float), cudaMemcpyHostToDevice, s));
+        index->search_device(index->w_queries.p, nq, index->w_out_ids.p, index->w_out_dists.p, index->w_out_counts.p, s);
+        CLANN_CUDA(cudaMemcpyAsync(ids, index->w_out_ids.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaMemcpyAsync(dists, index->w_out_dists.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaMemcpyAsync(counts, index->w_out_counts.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        CLANN_CUDA(cudaGetLastError());
+    });
+}
+
+int clann_search_begin(clann_index* index, const float* d_queries, uint64_t nq, void* stream) {
+    return guarded([&] {
+        if (!index || !d_queries) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_begin(d_queries, nq, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search_step(clann_index* index, void* stream) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->require_built();
+        SearchParams p = index->params();
+        QueryBatch b = index->batch(index->cur_queries, index->last_nq, nullptr, nullptr, nullptr);
+        launch_probe(p, b, index->shard_count > 1, static_cast<cudaStream_t>(stream));
+        index->last_launches++;
+    });
+}
+
+uint64_t clann_state_bytes(const clann_index* index) { return index ? query_state_bytes((uint32_t)index->cfg.k) : 0; }
+void* clann_state_ptr(clann_index* index) { return index ? index->w_state.p : nullptr; }
+
+int clann_search_merge(clann_index* index, const void* d_all_states, int world, uint64_t* active_out, void* stream) {
+    return guarded([&] {
+        if (!index || !d_all_states || world < 1) throw StatusError(CLANN_ERR_ARG, "bad merge arguments");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        SearchParams p = index->params();
+        QueryBatch b = index->batch(index->cur_queries, index->last_nq, nullptr, nullptr, nullptr);
+        launch_merge_states(p, b, static_cast<const uint8_t*>(d_all_states), world, index->w_counter.p + 1, s);
+        index->last_launches++;
+        if (active_out) {
+            uint32_t a = 0;
+            CLANN_CUDA(cudaMemcpyAsync(&a, index->w_counter.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CLANN_CUDA(cudaStreamSynchronize(s));
+            *active_out = a;
+        }
+    });
+}
+
+int clann_search_end(clann_index* index, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, void* stream) {
+    return guarded([&] {
+        if (!index || !d_ids || !d_dists || !d_counts) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        SearchParams p = index->params();
+        QueryBatch b = index->batch(index->cur_queries, index->last_nq, d_ids, d_dists, d_counts);
+        launch_finish(p, b, static_cast<cudaStream_t>(stream));
+        index->last_launches++;
+    });
+}
+
+int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, uint64_t* distance_computations, uint32_t* clusters_visited) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        if (nq > index->last_nq) throw StatusError(CLANN_ERR_BOUNDS, "more counters requested than queries searched");
+        CLANN_CUDA(cudaDeviceSynchronize());
+        if (candidates) CLANN_CUDA(cudaMemcpy(candidates, index->w_cand.p, nq * 8, cudaMemcpyDeviceToHost));
+        if (distance_computations) CLANN_CUDA(cudaMemcpy(distance_computations, index->w_dc.p, nq * 8, cudaMemcpyDeviceToHost));
+        if (clusters_visited) CLANN_CUDA(cudaMemcpy(clusters_visited, index->w_vis.p, nq * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches) {
+    return guarded([&] {
+        if (!index || !index->profile_valid) throw StatusError(CLANN_ERR_ARG, "no profiled search yet");
+        CLANN_CUDA(cudaEventSynchronize(index->ev[3]));
+        if (ms) {
+            CLANN_CUDA(cudaEventElapsedTime(&ms[0], index->ev[0], index->ev[1]));
+            CLANN_CUDA(cudaEventElapsedTime(&ms[1], index->ev[1], index->ev[2]));
+            CLANN_CUDA(cudaEventElapsedTime(&ms[2], index->ev[2], index->ev[3]));
+        }
+        if (launches) *launches = index->last_launches;
+    });
+}
+
+int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        CLANN_CUDA(cudaDeviceSynchronize());
+        auto emit = [&](const void* src, uint64_t bytes) {
+            if (size) *size = bytes;
+            if (dst) {
+                if (cap < bytes) throw StatusError(CLANN_ERR_BOUNDS, "export buffer too small");
+                memcpy(dst, src, bytes);
+            }
+        };
+        auto emit_dev = [&](const void* src, uint64_t bytes) {
+            if (size) *size = bytes;
+            if (dst) {
+                if (cap < bytes) throw StatusError(CLANN_ERR_BOUNDS, "export buffer too small");
+                CLANN_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+            }
+        };
+        const uint32_t K = index->K;
+        auto need_cluster = [&]() {
+            index->require_built();
+            if (arg >= K) throw StatusError(CLANN_ERR_BOUNDS, "cluster out of range");
+        };
+        switch (what) {
+            case CLANN_X_NUM_CLUSTERS: {
+                uint64_t k64 = K;
+                emit(&k64, 8);
+                break;
+            }
+            case CLANN_X_CENTERS: {
+                index->require_built();
+                std::vector<uint64_t> v(index->h_centers.begin(), index->h_centers.end());
+                emit(v.data(), v.size() * 8);
+                break;
+            }
+            case CLANN_X_ASSIGNMENT: {
+                index->require_built();
+                std::vector<uint64_t> v(index->h_assign.begin(), index->h_assign.end());
+                emit(v.data(), v.size() * 8);
+                break;
+            }
+            case CLANN_X_RADII: index->require_built(); emit(index->h_radii.data(), (uint64_t)K * 4); break;
+            case CLANN_X_OFFSETS: index->require_built(); emit(index->h_offsets.data(), (uint64_t)(K + 1) * 8); break;
+            case CLANN_X_PERM: index->require_built(); emit_dev(index->d_perm.p, index->n * 4); break;
+            case CLANN_X_Q15:
+                need_cluster();
+                emit_dev(index->d_q15.p + index->h_offsets[arg] * index->g.sl, (uint64_t)index->h_sizes[arg] * index->g.sl * 2);
+                break;
+            case CLANN_X_SKETCHES:
+                need_cluster();
+                emit_dev(index->d_sketches.p + index->h_offsets[arg] * kNumSketches, (uint64_t)index->h_sizes[arg] * kNumSketches * 8);
+                break;
+            case CLANN_X_TABLE_HASHES:
+            case CLANN_X_TABLE_INDICES: {
+                need_cluster();
+                const uint32_t nc = index->h_sizes[arg], L = index->g.L;
+                const uint64_t bytes = (uint64_t)L * nc * 4;
+                if (size) *size = bytes;
+                if (dst) {
+                    if (cap < bytes) throw StatusError(CLANN_ERR_BOUNDS, "export buffer too small");
+                    const uint32_t* src = what == CLANN_X_TABLE_HASHES ? index->d_tbl_hash.p : index->d_tbl_idx.p;
+                    CLANN_CUDA(cudaMemcpy2D(dst, (size_t)nc * 4, src + index->h_offsets[arg], index->n * 4, (size_t)nc * 4, L,
+                                            cudaMemcpyDeviceToHost));
+                }
+                break;
+            }
+            case CLANN_X_BRUTE: index->require_built(); emit(index->h_brute.data(), K); break;
+            case CLANN_X_NORMS: index->require_built(); emit_dev(index->d_norms.p, index->n * 4); break;
+            case CLANN_X_EST: {
+                need_cluster();
+                const FunctionSet& fs = index->fsets[index->h_fset_of[arg]];
+                emit(fs.est.data(), fs.est.size() * 4);
+                break;
+            }
+            case CLANN_X_QUERY_CODES: {
+                need_cluster();
+                const uint64_t nq = index->last_nq, L = index->g.L;
+                const uint32_t f = index->h_fset_of[arg];
+                // device layout [L][nq] -> host layout [nq][L]
+                std::vector<uint32_t> tmp = index->w_codes.download(L * nq, (size_t)f * L * nq);
+                std::vector<uint32_t> outv(nq * L);
+                for (uint64_t t = 0; t < L; t++)
+                    for (uint64_t q = 0; q < nq; q++) outv[q * L + t] = tmp[t * nq + q];
+                emit(outv.data(), outv.size() * 4);
+                break;
+            }
+            case CLANN_X_QUERY_SKETCHES: {
+                need_cluster();
+                const uint64_t nq = index->last_nq;
+                const uint32_t f = index->h_fset_of[arg];
+                emit_dev(index->w_sketches.p + (size_t)f * nq * kNumSketches, nq * kNumSketches * 8);
+                break;
+            }
+            case CLANN_X_CLUSTER_ORDER: index->require_built(); emit_dev(index->w_corder.p, index->last_nq * K * 4); break;
+            case CLANN_X_BUILD_MS: emit(index->build_ms, sizeof(index->build_ms)); break;
+            default: throw StatusError(CLANN_ERR_ARG, "unknown export selector");
+        }
+    });
+}
+
+void clann_destroy(clann_index* index) { delete index; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ C ABI (legacy CPUFFINN_*)
+
+// One reference `puffinn::Index<CosineSimilarity>` handle: rows staged on the host until rebuild (dataset.hpp:109-124),
+// then a single-cluster device index searched by one warp per call.
+struct CPUFFINN {
+    int dim = 0;
+    std::vector<float> rows;
+    uint32_t count = 0;
+    clann_index* ix = nullptr;
+    uint32_t built_k = 0;
+    unsigned num_maps = 0;
+    DevBuf<float> d_query;
+    DevBuf<uint32_t> d_out;  // [k] ids, then count, then distance computations
+    ~CPUFFINN() { delete ix; }
+};
+
+static std::atomic<unsigned> g_legacy_distcomp{0};  // performance.hpp:65-80: counter of the last query, process-global
+
+extern "C" {
+
+CPUFFINN* CPUFFINN_index_create(const char* dataset_type, int dataset_args) {
+    if (!dataset_type || strcmp(dataset_type, "angular") != 0 || dataset_args <= 0) {
+        // c_binder.cpp:39-50 also accepts "jaccard" but every later call treats the handle as cosine; refuse it instead
+        fprintf(stderr, "Error: Unsupported dataset type '%s'. Only 'angular' is supported.\n", dataset_type ? dataset_type : "(null)");
+        return nullptr;
+    }
+    try {
+        auto* h = new CPUFFINN();
+        h->dim = dataset_args;
+        return h;
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+void CPUFFINN_index_insert_cosine(CPUFFINN* index, float* point, int dimension) {
+    if (!index || !point) return;
+    if (dimension != index->dim) {  // unit_vector.hpp:66-68 throws std::invalid_argument through extern "C"
+        fprintf(stderr, "CPUFFINN_index_insert_cosine: dimension %d != %d, point ignored\n", dimension, index->dim);
+        return;
+    }
+    try {
+        index->rows.insert(index->rows.end(), point, point + dimension);
+        index->count++;
+    } catch (...) {
+    }
+}
+
+static void legacy_build(CPUFFINN* h, uint32_t k) {
+    clann_config cfg{h->num_maps, 1.0f, k, 0.9f};
+    auto* ix = new clann_index();
+    try {
+        ix->puffinn_mode = true;
+        ix->init(h->rows.data(), h->count, (uint32_t)h->dim, cfg);
+        ix->seed = (uint64_t)std::random_device{}() << 32 | std::random_device{}();
+        // a second rebuild keeps the functions drawn by the first (collection.hpp:257-263)
+        if (h->ix && h->ix->g.L == ix->g.L && !h->ix->fsets.empty()) ix->fsets = h->ix->fsets;
+        ix->build();
+    } catch (...) {
+        delete ix;
+        throw;
+    }
+    delete h->ix;
+    h->ix = ix;
+    h->built_k = k;
+}
+
+uint64_t CPUFFINN_index_rebuild(CPUFFINN* index, unsigned int num_maps) {
+    if (!index) return 0;
+    try {
+        if (num_maps == 0) return 0;  // collection.hpp:242-244 throws -> c_binder.cpp:57-59 returns 0
+        if (index->count == 0) return 0;
+        index->num_maps = num_maps;
+        legacy_build(index, 10);
+        const HashGeom& g = index->ix->g;
+        // same quantity the reference returns (collection.hpp:249-254), for the device-resident layout
+        uint64_t per_point = (uint64_t)g.sl * 2 + kNumSketches * 8 + (uint64_t)g.L * 8;
+        return per_point * index->count + (uint64_t)kNumPlanes * g.sl * 2 + (uint64_t)g.L * g.fph * kRotations * g.npts;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 0;
+    } catch (...) {
+        return 0;
+    }
+}
+
+uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, float recall, float max_sim, int dimension) {
+    if (!query || dimension <= 0) {
+        fprintf(stderr, "Error: Query is null or empty.\n");
+        return nullptr;
+    }
+    if (!index || !index->ix || dimension != index->dim) return nullptr;
+    try {
+        const unsigned words = k > 1 ? k : 1;
+        uint32_t* result = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * words));
+        if (!result) return nullptr;
+        for (unsigned i = 0; i < words; i++) result[i] = 0xFFFFFFFFu;  // EMPTY_RESULT_SENTINEL, c_binder.h:8
+        if (k == 0) return result;
+        clann_index* ix = index->ix;
+        ix->cfg.k = k;
+        cudaStream_t s = 0;
+        ix->ensure_workspace(1, s);
+        ix->ensure_stop_table(recall, s);
+        index->d_query.upload(query, (size_t)dimension, s);
+        index->d_out.ensure((size_t)k + 2);
+        SearchParams p = ix->params();
+        QueryBatch b = ix->batch(index->d_query.p, 1, nullptr, nullptr, nullptr);
+        launch_prep_queries(p, b, s);
+        launch_sketch(b.q15, ix->w_tiles.p, ix->w_ntiles, ix->d_planes.p, ix->g.sl, b.sketches, s);
+        launch_codes(b.q15, ix->w_code_tiles(1, s), ix->w_ntiles, ix->d_signbits.p, ix->g, b.codes, 1, ix->g.L, s);
+        launch_puffinn_search(p, b, ix->d_stop.p, max_sim, index->d_out.p, index->d_out.p + k, index->d_out.p + k + 1, s);
+        std::vector<uint32_t> out(k + 2);
+        CLANN_CUDA(cudaMemcpyAsync(out.data(), index->d_out.p, sizeof(uint32_t) * (k + 2), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        CLANN_CUDA(cudaGetLastError());
+        const uint32_t cnt = out[k] < k ? out[k] : k;
+        for (uint32_t i = 0; i < cnt; i++) result[i] = out[i];
+        g_legacy_distcomp.store(out[k + 1]);
+        return result;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return nullptr;
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+unsigned int CPUFFINN_get_distance_computations(void) { return g_legacy_distcomp.load(); }
+void CPUFFINN_clear_distance_computations(void) { g_legacy_distcomp.store(0); }
+
+// Persistence (c_binder.cpp:4-36,106-146) rides on HDF5 in the reference; this environment has none, so the two entry
+// points exist for link compatibility and report failure the way the reference does (stderr / NULL). Round-trip of the
+// Index::serialize stream is SURVEY.md section 8(f) item 1.
+void CPUFFINN_save_index(CPUFFINN* index, const char* file_name, int index_number) {
+    (void)index;
+    fprintf(stderr, "Error opening HDF5 file: %s (index_%d): persistence is not available in libclann_b200\n",
+            file_name ? file_name : "(null)", index_number);
+}
+
+CPUFFINN* CPUFFINN_load_from_file(const char* file_name, const char* dataset_name) {
+    fprintf(stderr, "Failed to open HDF5 file %s (%s): persistence is not available in libclann_b200\n",
+            file_name ? file_name : "(null)", dataset_name ? dataset_name : "(null)");
+    return nullptr;
+}
+
+}  // extern "C"

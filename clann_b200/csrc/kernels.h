@@ -1,0 +1,107 @@
+// Host-callable launchers of the CUDA kernels (all asynchronous on `stream`). Device pointers unless noted.
+#pragma once
+
+#include "common.cuh"
+
+namespace clann {
+
+// ---- build: CLANN layer (gmm.rs, angulardata.rs)
+void launch_row_norms(const float* data, uint64_t n, uint32_t d, float* norms, cudaStream_t s);
+// One greedy k-center pass for centre number c (gmm.rs:40-53). keys[K]: packed arg-max of pass c is written to keys[c];
+// the centre of pass c (c > 0) is decoded from keys[c-1].
+void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t d, uint32_t c, uint64_t* keys,
+                     float* dist, uint32_t* assign, cudaStream_t s);
+void launch_gmm_finish(const uint64_t* keys, uint32_t K, uint64_t n, const float* dist, const uint32_t* assign,
+                       uint32_t* centers, float* radii, uint32_t* sizes, cudaStream_t s);
+void launch_gather_rows(const float* data, const uint32_t* rows, uint32_t count, uint32_t d, float* out, cudaStream_t s);
+
+// ---- build: PUFFINN layer
+// format/unit_vector.hpp:61-89 for rows perm[row] (perm may be null = identity) -> q15[row*sl..]
+void launch_store_q15(const float* data, const uint32_t* perm, uint64_t rows, uint32_t d, uint32_t sl, int16_t* q15, cudaStream_t s);
+// filterer.hpp:76-102: sketches[out_row*32 + s] for every row of every tile. planes: [fset][2048][sl] Q15.
+void launch_sketch(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const int16_t* planes, uint32_t sl,
+                   uint64_t* sketches, cudaStream_t s);
+// independent.hpp:70-86 over crosspolytope.hpp:187-209: codes[fset*fset_stride + t*code_stride + out_row].
+// signbits: [fset][L*fph][3][max(1, npts/32) words], bit i set = sign -1.
+void launch_codes(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const uint32_t* signbits, HashGeom g,
+                  uint32_t* codes, uint64_t code_stride, uint64_t fset_stride, cudaStream_t s);
+
+struct SortSegment {
+    uint64_t base;          // offset of the segment in keys / idx arrays
+    uint64_t scratch_base;  // offset in the scratch arrays (only used when len > smem capacity)
+    uint32_t len;
+    uint32_t pad;
+};
+// sorthash.hpp:133-194: stable LSD radix sort (3 byte passes) of every segment by its 24-bit key; payload = position in
+// the segment. keys are sorted in place, idx receives the payload. max_len = largest segment.
+void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_len, uint32_t* keys, uint32_t* idx,
+                         uint32_t* scratch_keys, uint32_t* scratch_idx, cudaStream_t s);
+uint32_t segment_sort_smem_capacity();  // segments up to this length are sorted entirely in shared memory
+
+// crosspolytope.hpp:16-88 Monte-Carlo collision estimates, est[(m+2)*201]
+void launch_cp_estimates(uint32_t m, uint32_t reps, uint64_t seed, float* est, uint32_t* scratch_counts, cudaStream_t s);
+
+// ---- search
+struct SearchParams {
+    // geometry
+    HashGeom g;
+    uint32_t k, K, n_fsets;
+    uint64_t n;
+    uint32_t stop_words;  // u32 words per (depth, bin) row of the stop table = ceil((L+1)/32)
+    // index (device)
+    const float* data;         // [n][d] original rows
+    const float* norms;        // [n]
+    const uint32_t* perm;      // [n] cluster-sorted row -> point id
+    const uint64_t* offsets;   // [K+1]
+    const int16_t* q15;        // [n][sl] cluster-sorted
+    const uint64_t* sketches;  // [n][32]
+    const uint32_t* tbl_hash;  // [L][n]
+    const uint32_t* tbl_idx;   // [L][n]
+    const float* center_rows;  // [K][d]
+    const float* center_norms; // [K]
+    const float* radii;        // [K]
+    const uint8_t* brute;      // [K]
+    const uint32_t* fset_of;   // [K]
+    const uint8_t* owner;      // [K] owning shard (multi-GPU), all 0 on one GPU
+    const uint32_t* stop;      // [n_fsets][24][201][stop_words] stop decision bit t (independent.hpp:108-119, host glibc pow)
+    const uint8_t* msd;        // [65536] max_sketch_diff by (dot + 32768) (filterer.hpp:108-111, host glibc acosf)
+    uint32_t shard_rank;
+};
+
+struct QueryBatch {
+    uint64_t nq;
+    const float* queries;   // [nq][d]
+    float* qnorm;           // [nq]
+    int16_t* q15;           // [nq][sl]
+    uint32_t* codes;        // [n_fsets][L][nq]   (table-major per function set)
+    uint64_t* sketches;     // [n_fsets][nq][32]
+    float* cdist;           // [nq][K] sorted ascending
+    uint32_t* corder;       // [nq][K]
+    // per-query running state (also the multi-GPU exchange unit): see kernels_search.cu
+    uint8_t* state;
+    uint32_t* work_counter; // [1]
+    // outputs
+    uint32_t* out_ids;      // [nq][k]
+    float* out_dists;       // [nq][k]
+    uint32_t* out_counts;   // [nq]
+    // counters [nq]
+    unsigned long long* cnt_candidates;
+    unsigned long long* cnt_distcomp;
+    uint32_t* cnt_visited;
+};
+
+uint64_t query_state_bytes(uint32_t k);
+void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+// Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).
+void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
+void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
+void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+
+// Single PUFFINN index query (legacy CPUFFINN_search_cosine): one cluster, explicit recall / max_sim, Q15 brute force
+// when n < 100 (collection.hpp:550-555). out_ids[k] local ids best first, out_count.
+void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim,
+                           uint32_t* out_ids, uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s);
+
+}  // namespace clann

@@ -1,0 +1,542 @@
+// Build-side kernels: greedy k-center (gmm.rs), Q15 store, SimHash sketches, FHT cross-polytope table codes,
+// segmented stable radix sort of the hash tables, Monte-Carlo collision estimates.
+// Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#include "kernels.h"
+
+namespace clann {
+
+// ------------------------------------------------------------------------------------------------ CLANN layer
+
+// src/metricdata/angulardata.rs:12-19 — norms[i] = sqrt(row.dot(row)); 8 lanes per row.
+__global__ void __launch_bounds__(256) k_row_norms(const float* __restrict__ data, uint64_t n, uint32_t d, float* __restrict__ norms) {
+    uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    uint64_t r = row < n ? row : n - 1;
+    const float* x = data + r * d;
+    float dot = ndarray_dot_group8(x, x, d);
+    if (row < n && (threadIdx.x & 7) == 0) norms[row] = __fsqrt_rn(dot);
+}
+
+__device__ __forceinline__ uint64_t gmm_key(float dist, uint64_t i) {
+    // arg-max with first-max tie rule (src/core/gmm.rs:5-15): larger distance wins, then the smaller index.
+    return ((uint64_t)float_order_bits(dist) << 32) | (uint64_t)(0xffffffffu - (uint32_t)i);
+}
+__device__ __forceinline__ uint32_t gmm_key_index(uint64_t key) { return 0xffffffffu - (uint32_t)(key & 0xffffffffu); }
+
+// src/core/gmm.rs:40-53 — one pass: distances of all points to centre c, strict-< reassignment, arg-max of the updated
+// distances (which selects centre c+1). Memory-bound: streams n*d floats once.
+__global__ void __launch_bounds__(256) k_gmm_pass(const float* __restrict__ data, const float* __restrict__ norms, uint64_t n,
+                                                  uint32_t d, uint32_t c, uint64_t* __restrict__ keys, float* __restrict__ dist,
+                                                  uint32_t* __restrict__ assign) {
+    __shared__ uint64_t s_key[8];
+    const uint32_t ci = (c == 0) ? 0u : gmm_key_index(keys[c - 1]);
+    uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const bool valid = row < n;
+    uint64_t r = valid ? row : n - 1;
+    const float* x = data + r * d;
+    const float* y = data + (uint64_t)ci * d;
+    float dot = ndarray_dot_group8(x, y, d);
+    // angulardata.rs:25-27: 1.0 - (dot / (norms[i] * norms[j]))
+    float nd = __fsub_rn(1.0f, __fdiv_rn(dot, __fmul_rn(norms[r], norms[ci])));
+    uint64_t key = 0;
+    if (valid && (threadIdx.x & 7) == 0) {
+        float cur;
+        if (c == 0) {
+            cur = nd;
+            dist[row] = nd;
+            assign[row] = 0;
+        } else {
+            cur = dist[row];
+            if (nd < cur) {  // gmm.rs:49
+                cur = nd;
+                dist[row] = nd;
+                assign[row] = c;
+            }
+        }
+        key = gmm_key(cur, row);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        uint64_t other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane_id() == 0) s_key[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t best = s_key[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) best = s_key[w] > best ? s_key[w] : best;
+        atomicMax((unsigned long long*)&keys[c], (unsigned long long)best);
+    }
+}
+
+// gmm.rs:56-60 radii, cluster sizes, and decoding of the centre list.
+__global__ void k_gmm_finish(const uint64_t* __restrict__ keys, uint32_t K, uint64_t n, const float* __restrict__ dist,
+                             const uint32_t* __restrict__ assign, uint32_t* __restrict__ centers, float* __restrict__ radii,
+                             uint32_t* __restrict__ sizes) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) centers[i] = (i == 0) ? 0u : gmm_key_index(keys[i - 1]);
+    if (i < n) {
+        uint32_t a = assign[i];
+        // radii start at 0.0 and take f32::max: as signed ints, negative floats order below 0 and positives order naturally.
+        atomicMax((int*)&radii[a], __float_as_int(dist[i]));
+        atomicAdd(&sizes[a], 1u);
+    }
+}
+
+__global__ void k_gather_rows(const float* __restrict__ data, const uint32_t* __restrict__ rows, uint32_t count, uint32_t d,
+                              float* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint64_t)count * d) {
+        uint32_t r = (uint32_t)(i / d), j = (uint32_t)(i % d);
+        out[i] = data[(uint64_t)rows[r] * d + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Q15 store
+
+// format/unit_vector.hpp:61-89. The sum of squares follows the shape g++ -O3 gives the reference loop (:71-74):
+// products rounded then added in order for the first d - d%4 elements, FMAs for the last d%4 (see oracle/clann_oracle.c).
+__global__ void __launch_bounds__(256) k_store_q15(const float* __restrict__ data, const uint32_t* __restrict__ perm, uint64_t rows,
+                                                   uint32_t d, uint32_t sl, int16_t* __restrict__ q15) {
+    uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const float* v = data + (uint64_t)(perm ? perm[row] : row) * d;
+    float acc = 0.0f;
+    const uint32_t body = d & ~3u;
+    for (uint32_t i = 0; i < body; i++) acc = __fadd_rn(acc, __fmul_rn(v[i], v[i]));
+    for (uint32_t i = body; i < d; i++) acc = __fmaf_rn(v[i], v[i], acc);
+    const float len = __fsqrt_rn(acc);
+    int16_t* out = q15 + row * sl;
+    for (uint32_t i = 0; i < d; i++) {
+        float x = v[i];
+        if (len != 0.0f) x = __fdiv_rn(x, len);
+        out[i] = to_q15(x);
+    }
+    for (uint32_t i = d; i < sl; i++) out[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ SimHash sketches
+
+// filterer.hpp:76-102 + simhash.hpp:41-44 + independent.hpp:70-86 (function 64*s+b -> bit 63-b of sketch s).
+// One CTA = one tile of <=32 rows x 256 hyperplanes (4 sketches). Thread = hyperplane; rows live in shared memory as
+// int32 so that each 16-element unit costs 4 broadcast LDS.128 + 48 integer ops per row.
+__global__ void __launch_bounds__(256) k_sketch(const int16_t* __restrict__ q15, const RowTile* __restrict__ tiles,
+                                                const int16_t* __restrict__ planes, uint32_t sl, uint64_t* __restrict__ sketches) {
+    extern __shared__ int s_rows[];  // [32][sl]
+    const RowTile tile = tiles[blockIdx.x];
+    for (uint32_t e = threadIdx.x; e < 32 * sl; e += blockDim.x) {
+        uint32_t p = e / sl, i = e % sl;
+        s_rows[e] = (p < tile.count) ? (int)q15[(uint64_t)(tile.in_row0 + p) * sl + i] : 0;
+    }
+    __syncthreads();
+    const uint32_t f = blockIdx.y * 256 + threadIdx.x;  // hyperplane 0..2047
+    const uint4* prow = reinterpret_cast<const uint4*>(planes + ((uint64_t)tile.fset * kNumPlanes + f) * sl);
+    int acc[32];
+#pragma unroll
+    for (int p = 0; p < 32; p++) acc[p] = 0;
+    for (uint32_t u = 0; u < sl / 16; u++) {
+        uint4 w0 = __ldg(prow + 2 * u), w1 = __ldg(prow + 2 * u + 1);
+        int a[16];
+        a[0] = unpack_lo(w0.x); a[1] = unpack_hi(w0.x); a[2] = unpack_lo(w0.y); a[3] = unpack_hi(w0.y);
+        a[4] = unpack_lo(w0.z); a[5] = unpack_hi(w0.z); a[6] = unpack_lo(w0.w); a[7] = unpack_hi(w0.w);
+        a[8] = unpack_lo(w1.x); a[9] = unpack_hi(w1.x); a[10] = unpack_lo(w1.y); a[11] = unpack_hi(w1.y);
+        a[12] = unpack_lo(w1.z); a[13] = unpack_hi(w1.z); a[14] = unpack_lo(w1.w); a[15] = unpack_hi(w1.w);
+#pragma unroll
+        for (int p = 0; p < 32; p++) {
+            const int4* pv = reinterpret_cast<const int4*>(s_rows + p * sl + u * 16);
+            int4 v0 = pv[0], v1 = pv[1], v2 = pv[2], v3 = pv[3];
+            int s = acc[p];
+            s += q15_mul(a[0], v0.x); s += q15_mul(a[1], v0.y); s += q15_mul(a[2], v0.z); s += q15_mul(a[3], v0.w);
+            s += q15_mul(a[4], v1.x); s += q15_mul(a[5], v1.y); s += q15_mul(a[6], v1.z); s += q15_mul(a[7], v1.w);
+            s += q15_mul(a[8], v2.x); s += q15_mul(a[9], v2.y); s += q15_mul(a[10], v2.z); s += q15_mul(a[11], v2.w);
+            s += q15_mul(a[12], v3.x); s += q15_mul(a[13], v3.y); s += q15_mul(a[14], v3.z); s += q15_mul(a[15], v3.w);
+            acc[p] = s;
+        }
+    }
+    // bit = dot >= 0 on the wrapping int16 accumulator (math.hpp:37-44, simhash.hpp:43)
+    uint32_t mine = 0;
+#pragma unroll
+    for (int p = 0; p < 32; p++) {
+        uint32_t bal = __ballot_sync(0xffffffffu, (int16_t)acc[p] >= 0);
+        if ((int)lane_id() == p) mine = __brev(bal);  // lane (plane b) -> bit 31-b of this 32-bit half
+    }
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t sk = blockIdx.y * 4 + (warp >> 1);
+    const uint32_t half = warp & 1;  // planes 0..31 of the sketch are its high word
+    if (lane_id() < tile.count) {
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(sketches);
+        out32[((uint64_t)(tile.out_row0 + lane_id()) * kNumSketches + sk) * 2 + (half ? 0 : 1)] = mine;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FHT cross-polytope codes
+
+// external/ffht/fht_avx.c:107-195,375-567: unnormalised in-place WHT, strides 1,2,4,... in that order, fl(u+v), fl(u-v).
+template <int N, bool UNROLL>
+__device__ __forceinline__ void fht_inplace(float* x) {
+    if constexpr (UNROLL) {
+#pragma unroll
+        for (int h = 1; h < N; h <<= 1) {
+#pragma unroll
+            for (int i = 0; i < N; i += 2 * h) {
+#pragma unroll
+                for (int j = i; j < i + h; j++) {
+                    float u = x[j], v = x[j + h];
+                    x[j] = __fadd_rn(u, v);
+                    x[j + h] = __fsub_rn(u, v);
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int h = 1; h < N; h <<= 1) {
+#pragma unroll 1
+            for (int i = 0; i < N; i += 2 * h) {
+#pragma unroll 4
+                for (int j = i; j < i + h; j++) {
+                    float u = x[j], v = x[j + h];
+                    x[j] = __fadd_rn(u, v);
+                    x[j + h] = __fsub_rn(u, v);
+                }
+            }
+        }
+    }
+}
+
+// One FHT-CP function value (crosspolytope.hpp:187-209, encode_closest_axis :131-144) for the row held by this lane.
+// sb: sign bits of this function, [3][W] words, bit i set = sign -1 (random_signs, :160-165).
+template <int M>
+__device__ __forceinline__ uint32_t fht_cp_hash(const int16_t* row, uint32_t d, const uint32_t* __restrict__ sb) {
+    constexpr int N = 1 << M;
+    constexpr int W = (N + 31) / 32;
+    constexpr bool UNROLL = (M <= 7);
+    float x[N];
+    if constexpr (UNROLL) {
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = (i < (int)d) ? __fmul_rn((float)row[i], 1.0f / 32768.0f) : 0.0f;
+    } else {
+        for (int i = 0; i < N; i++) x[i] = (i < (int)d) ? __fmul_rn((float)row[i], 1.0f / 32768.0f) : 0.0f;
+    }
+#pragma unroll 1
+    for (int r = 0; r < kRotations; r++) {
+        if constexpr (UNROLL) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                uint32_t w = __ldg(sb + r * W + (i >> 5));
+                x[i] = __uint_as_float(__float_as_uint(x[i]) ^ ((w << (31 - (i & 31))) & 0x80000000u));
+            }
+        } else {
+            for (int i = 0; i < N; i++) {
+                uint32_t w = __ldg(sb + r * W + (i >> 5));
+                x[i] = __uint_as_float(__float_as_uint(x[i]) ^ ((w << (31 - (i & 31))) & 0x80000000u));
+            }
+        }
+        fht_inplace<N, UNROLL>(x);
+    }
+    int res = 0;
+    float best = 0.0f;
+    if constexpr (UNROLL) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            float v = x[i];
+            if (v > best) { res = i; best = v; }
+            else if (-v > best) { res = i + N; best = -v; }
+        }
+    } else {
+        for (int i = 0; i < N; i++) {
+            float v = x[i];
+            if (v > best) { res = i; best = v; }
+            else if (-v > best) { res = i + N; best = -v; }
+        }
+    }
+    return (uint32_t)res;
+}
+
+// independent.hpp:70-86: table code = fph function values concatenated MSB-first, >> bits_to_cut.
+// CTA = one tile of <=32 rows; lane = row, warp = table (so sign bits are warp-uniform loads).
+template <int M>
+__global__ void __launch_bounds__(256) k_codes(const int16_t* __restrict__ q15, const RowTile* __restrict__ tiles,
+                                               const uint32_t* __restrict__ signbits, HashGeom g, uint32_t* __restrict__ codes,
+                                               uint64_t code_stride, uint64_t fset_stride) {
+    extern __shared__ int16_t s_q[];  // [32][sl + 2] (odd word stride: conflict-free column reads)
+    constexpr int N = 1 << M;
+    constexpr int W = (N + 31) / 32;
+    const RowTile tile = tiles[blockIdx.x];
+    const uint32_t stride = g.sl + 2;
+    for (uint32_t e = threadIdx.x; e < 32 * g.sl; e += blockDim.x) {
+        uint32_t p = e / g.sl, i = e % g.sl;
+        s_q[p * stride + i] = (p < tile.count) ? q15[(uint64_t)(tile.in_row0 + p) * g.sl + i] : (int16_t)0;
+    }
+    __syncthreads();
+    const uint32_t t = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= g.L) return;
+    const int16_t* row = s_q + lane_id() * stride;
+    uint64_t code = 0;
+    for (uint32_t f = 0; f < g.fph; f++) {
+        const uint32_t func = t * g.fph + f;
+        const uint32_t* sb = signbits + ((uint64_t)tile.fset * (g.L * g.fph) + func) * (kRotations * W);
+        uint32_t h = fht_cp_hash<M>(row, g.d, sb);
+        code = (code << g.bpf) | h;
+    }
+    code >>= g.cut;
+    if (lane_id() < tile.count)
+        codes[(uint64_t)tile.fset * fset_stride + (uint64_t)t * code_stride + tile.out_row0 + lane_id()] = (uint32_t)code;
+}
+
+// ------------------------------------------------------------------------------------------------ segmented radix sort
+
+constexpr uint32_t kSortThreads = 512;
+constexpr uint32_t kSortWarps = kSortThreads / 32;
+constexpr uint32_t kSortSmemCapSmall = 4096;   // 16 B/entry -> 64 KB + 36 KB bookkeeping: 2 CTAs / SM
+constexpr uint32_t kSortSmemCapLarge = 11264;  // 176 KB + 36 KB: 1 CTA / SM
+constexpr uint32_t kSortBookWords = 3 * 256 + 2 * kSortWarps * 256 + 256;
+
+uint32_t segment_sort_smem_capacity() { return kSortSmemCapLarge; }
+
+// sorthash.hpp:133-194 — stable LSD radix sort with three byte passes over (hash, payload) pairs; one CTA per segment.
+// Stability inside a pass: elements are taken 512 at a time in order; __match_any gives each element its rank among
+// the equal digits of its warp, per-warp digit counts are prefix-summed across warps on top of the running bin offset.
+// Segments longer than `cap` ping-pong through a global scratch pair instead of shared memory.
+__global__ void __launch_bounds__(kSortThreads) k_segment_sort(const SortSegment* __restrict__ segs, uint32_t cap, uint32_t* keys,
+                                                               uint32_t* idx, uint32_t* scratch_keys, uint32_t* scratch_idx) {
+    extern __shared__ uint32_t s_mem[];
+    uint32_t* s_hist = s_mem;                           // [3][256]
+    uint32_t* s_cnt = s_hist + 3 * 256;                 // [warps][256]
+    uint32_t* s_off = s_cnt + kSortWarps * 256;         // [warps][256]
+    uint32_t* s_bin = s_off + kSortWarps * 256;         // [256]
+    uint32_t* s_buf = s_bin + 256;                      // [4][cap]
+
+    const SortSegment seg = segs[blockIdx.x];
+    const uint32_t len = seg.len;
+    if (len == 0) return;
+    uint32_t* gk = keys + seg.base;
+    uint32_t* gi = idx + seg.base;
+    const bool in_smem = len <= cap;
+    uint32_t *b0k, *b0i, *b1k, *b1i;
+    if (in_smem) {
+        b0k = s_buf; b0i = s_buf + cap; b1k = s_buf + 2 * cap; b1i = s_buf + 3 * cap;
+    } else {
+        // one global scratch pair: pass 1 -> scratch, pass 2 -> (keys, idx) in place, pass 3 -> scratch, then copy back
+        b0k = scratch_keys + seg.scratch_base; b0i = scratch_idx + seg.scratch_base; b1k = gk; b1i = gi;
+    }
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (uint32_t i = tid; i < 3 * 256 + kSortWarps * 256; i += kSortThreads) s_mem[i] = 0;  // s_hist and s_cnt
+    __syncthreads();
+    for (uint32_t i = tid; i < len; i += kSortThreads) {
+        uint32_t h = gk[i];
+        atomicAdd(&s_hist[h & 0xff], 1u);
+        atomicAdd(&s_hist[256 + ((h >> 8) & 0xff)], 1u);
+        atomicAdd(&s_hist[512 + ((h >> 16) & 0xff)], 1u);
+    }
+    __syncthreads();
+
+    for (int pass = 0; pass < 3; pass++) {
+        const uint32_t *sk, *si;
+        uint32_t *dk, *di;
+        if (pass == 0) { sk = gk; si = nullptr; dk = b0k; di = b0i; }
+        else if (pass == 1) { sk = b0k; si = b0i; dk = b1k; di = b1i; }
+        else { sk = b1k; si = b1i; dk = in_smem ? gk : b0k; di = in_smem ? gi : b0i; }
+        const int shift = 8 * pass;
+        // exclusive prefix of this pass's histogram -> running bin offsets (warp 0)
+        if (warp == 0) {
+            uint32_t run = 0;
+            for (int c = 0; c < 8; c++) {
+                uint32_t v = s_hist[pass * 256 + c * 32 + lane];
+                uint32_t incl = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += t;
+                }
+                s_bin[c * 32 + lane] = run + incl - v;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        for (uint32_t base = 0; base < len; base += kSortThreads) {
+            const uint32_t i = base + tid;
+            const bool valid = i < len;
+            uint32_t key = 0, payload = 0, digit = 0xffffu;
+            if (valid) {
+                key = sk[i];
+                payload = si ? si[i] : i;
+                digit = (key >> shift) & 0xff;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+            if (valid && rank == 0) s_cnt[warp * 256 + digit] = __popc(peers);
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = s_bin[tid];
+#pragma unroll 8
+                for (uint32_t w = 0; w < kSortWarps; w++) {
+                    uint32_t c = s_cnt[w * 256 + tid];
+                    s_cnt[w * 256 + tid] = 0;
+                    s_off[w * 256 + tid] = run;
+                    run += c;
+                }
+                s_bin[tid] = run;
+            }
+            __syncthreads();
+            if (valid) {
+                uint32_t pos = s_off[warp * 256 + digit] + rank;
+                dk[pos] = key;
+                di[pos] = payload;
+            }
+        }
+        __syncthreads();
+    }
+    if (!in_smem) {
+        for (uint32_t i = tid; i < len; i += kSortThreads) {
+            gk[i] = b0k[i];
+            gi[i] = b0i[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ collision estimates
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// crosspolytope.hpp:16-88 — Monte-Carlo estimate of the probability that a random rotation maps x = e1 and
+// y = (alpha, sqrt(1-alpha^2), 0, ...) to cross-polytope hashes that agree in their top `used_bits` bits.
+// One thread per (alpha bin, repetition); any good RNG is statistically equivalent to the reference's clock-seeded one.
+__global__ void k_cp_trials(uint32_t m, uint32_t reps, uint64_t seed, float eps, uint32_t* __restrict__ counts) {
+    const uint32_t bin = blockIdx.x;
+    const uint32_t rep = blockIdx.y * blockDim.x + threadIdx.x;
+    if (rep >= reps) return;
+    // alpha advances by 2*eps in double starting from -1 (crosspolytope.hpp:31-34,86)
+    double alpha = -1.0;
+    const double step = (double)(2 * eps);
+    for (uint32_t i = 0; i < bin; i++) alpha += step;
+    const double beta = sqrt(1.0 - alpha * alpha);
+    const uint32_t dims = 1u << m;
+    uint32_t hx = 0, hy = 0;
+    double vx = 0.0, vy = 0.0;
+    uint64_t ctr = splitmix64(seed ^ (((uint64_t)bin << 40) | ((uint64_t)rep << 16)));
+    for (uint32_t j = 0; j < dims; j++) {
+        uint64_t r1 = splitmix64(ctr + 2 * j), r2 = splitmix64(ctr + 2 * j + 1);
+        double u1 = ((double)(r1 >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0,1]
+        double u2 = (double)(r2 >> 11) * (1.0 / 9007199254740992.0);          // [0,1)
+        double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        double z1 = rad * cs, z2 = rad * sn;
+        if (fabs(z1) > vx) {
+            vx = fabs(z1);
+            hx = j;
+            if (z1 < 0) hx |= (1u << m);
+        }
+        double h = alpha * z1 + beta * z2;
+        if (fabs(h) > vy) {
+            vy = fabs(h);
+            hy = j;
+            if (h < 0) hy |= (1u << m);
+        }
+    }
+    for (uint32_t used = 0; used <= m + 1; used++) {
+        uint32_t shift = m + 1 - used;
+        if ((hx >> shift) == (hy >> shift)) atomicAdd(&counts[used * kEstBins + bin], 1u);
+    }
+}
+
+__global__ void k_cp_finalize(uint32_t m, uint32_t reps, const uint32_t* __restrict__ counts, float* __restrict__ est) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (m + 2) * kEstBins) est[i] = (float)counts[i] / (float)reps;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+
+void launch_row_norms(const float* data, uint64_t n, uint32_t d, float* norms, cudaStream_t s) {
+    uint64_t threads = n * 8;
+    k_row_norms<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, n, d, norms);
+}
+
+void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t d, uint32_t c, uint64_t* keys, float* dist,
+                     uint32_t* assign, cudaStream_t s) {
+    uint64_t threads = n * 8;
+    k_gmm_pass<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, norms, n, d, c, keys, dist, assign);
+}
+
+void launch_gmm_finish(const uint64_t* keys, uint32_t K, uint64_t n, const float* dist, const uint32_t* assign, uint32_t* centers,
+                       float* radii, uint32_t* sizes, cudaStream_t s) {
+    uint64_t threads = n > K ? n : K;
+    k_gmm_finish<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(keys, K, n, dist, assign, centers, radii, sizes);
+}
+
+void launch_gather_rows(const float* data, const uint32_t* rows, uint32_t count, uint32_t d, float* out, cudaStream_t s) {
+    uint64_t threads = (uint64_t)count * d;
+    if (threads == 0) return;
+    k_gather_rows<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, rows, count, d, out);
+}
+
+void launch_store_q15(const float* data, const uint32_t* perm, uint64_t rows, uint32_t d, uint32_t sl, int16_t* q15, cudaStream_t s) {
+    if (rows == 0) return;
+    k_store_q15<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(data, perm, rows, d, sl, q15);
+}
+
+void launch_sketch(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const int16_t* planes, uint32_t sl, uint64_t* sketches,
+                   cudaStream_t s) {
+    if (n_tiles == 0) return;
+    size_t smem = (size_t)32 * sl * sizeof(int);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_sketch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(n_tiles, kNumPlanes / 256);
+    k_sketch<<<grid, 256, smem, s>>>(q15, tiles, planes, sl, sketches);
+}
+
+template <int M>
+static void launch_codes_m(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const uint32_t* signbits, HashGeom g,
+                           uint32_t* codes, uint64_t code_stride, uint64_t fset_stride, cudaStream_t s) {
+    size_t smem = (size_t)32 * (g.sl + 2) * sizeof(int16_t);
+    if (smem > 48 * 1024) CLANN_CUDA(cudaFuncSetAttribute(k_codes<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_tiles, (g.L + 7) / 8);
+    k_codes<M><<<grid, 256, smem, s>>>(q15, tiles, signbits, g, codes, code_stride, fset_stride);
+}
+
+void launch_codes(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const uint32_t* signbits, HashGeom g, uint32_t* codes,
+                  uint64_t code_stride, uint64_t fset_stride, cudaStream_t s) {
+    if (n_tiles == 0) return;
+    switch (g.m) {
+        case 0: launch_codes_m<0>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 1: launch_codes_m<1>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 2: launch_codes_m<2>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 3: launch_codes_m<3>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 4: launch_codes_m<4>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 5: launch_codes_m<5>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 6: launch_codes_m<6>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 7: launch_codes_m<7>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 8: launch_codes_m<8>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 9: launch_codes_m<9>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        case 10: launch_codes_m<10>(q15, tiles, n_tiles, signbits, g, codes, code_stride, fset_stride, s); break;
+        default: throw std::invalid_argument("dimension above 1024 is not supported");
+    }
+}
+
+void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_len, uint32_t* keys, uint32_t* idx,
+                         uint32_t* scratch_keys, uint32_t* scratch_idx, cudaStream_t s) {
+    if (n_segs == 0) return;
+    const uint32_t cap = (max_len <= kSortSmemCapSmall) ? kSortSmemCapSmall : kSortSmemCapLarge;
+    size_t smem = ((size_t)kSortBookWords + (size_t)4 * cap) * sizeof(uint32_t);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_segment_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_segment_sort<<<n_segs, kSortThreads, smem, s>>>(segs, cap, keys, idx, scratch_keys, scratch_idx);
+}
+
+void launch_cp_estimates(uint32_t m, uint32_t reps, uint64_t seed, float* est, uint32_t* scratch_counts, cudaStream_t s) {
+    CLANN_CUDA(cudaMemsetAsync(scratch_counts, 0, sizeof(uint32_t) * (m + 2) * kEstBins, s));
+    dim3 grid(kEstBins, (reps + 127) / 128);
+    k_cp_trials<<<grid, 128, 0, s>>>(m, reps, seed, 5e-3f, scratch_counts);
+    k_cp_finalize<<<((m + 2) * kEstBins + 255) / 256, 256, 0, s>>>(m, reps, scratch_counts, est);
+}
+
+}  // namespace clann

@@ -1,0 +1,953 @@
+// Search-side kernels: query preparation, centre ordering, and the probe kernel (one warp per query) that walks the
+// clusters in centre-distance order and, inside each cluster, reproduces puffinn::Index::search_maps exactly:
+// anchors, per-depth ranges, the 32-slot sketch-filter ring (ring slot == warp lane), the 128-entry passing buffer,
+// the Q15 rerank gather, the 2k-slot MaxBuffer, the filter threshold update and the delta stop rule.
+// Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#include "kernels.h"
+
+namespace clann {
+
+// ------------------------------------------------------------------------------------------------ query state
+
+// Per-query running state; also the unit exchanged between ranks in the multi-GPU stepping mode.
+struct QueryStateHeader {
+    uint32_t next_pos;   // next position in the cluster visiting order
+    uint32_t done;       // 1 = search finished (early exit or all clusters seen)
+    uint32_t heap_len;   // entries in the TopKClosestHeap
+    uint32_t visited;    // clusters probed
+    unsigned long long candidates;  // performance.hpp:82-86 summed over visits
+    unsigned long long distcomp;    // performance.hpp:72-76 summed over visits
+    // followed by k x u64 heap keys: (order_bits(distance) << 32) | point id
+};
+
+uint64_t query_state_bytes(uint32_t k) { return sizeof(QueryStateHeader) + (uint64_t)k * 8; }
+
+// ------------------------------------------------------------------------------------------------ query prep
+
+// Q15 form of the query (collection.hpp:331-333 -> unit_vector.hpp:61-89) and its fp32 norm as distance_point derives it
+// (src/metricdata/angulardata.rs:31: sequential sum of squares, no FMA).
+__global__ void __launch_bounds__(128) k_prep_queries(const float* __restrict__ queries, uint64_t nq, uint32_t d, uint32_t sl,
+                                                      int16_t* __restrict__ q15, float* __restrict__ qnorm) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float* v = queries + q * d;
+    float acc = 0.0f, accn = 0.0f;
+    const uint32_t body = d & ~3u;
+    for (uint32_t i = 0; i < d; i++) {
+        float x = v[i];
+        accn = __fadd_rn(accn, __fmul_rn(x, x));
+        acc = (i < body) ? __fadd_rn(acc, __fmul_rn(x, x)) : __fmaf_rn(x, x, acc);
+    }
+    qnorm[q] = __fsqrt_rn(accn);
+    const float len = __fsqrt_rn(acc);
+    int16_t* out = q15 + q * sl;
+    for (uint32_t i = 0; i < d; i++) {
+        float x = v[i];
+        if (len != 0.0f) x = __fdiv_rn(x, len);
+        out[i] = to_q15(x);
+    }
+    for (uint32_t i = d; i < sl; i++) out[i] = 0;
+}
+
+// angulardata.rs:29-35
+__device__ __forceinline__ float distance_point(const float* __restrict__ row, float row_norm, const float* __restrict__ q, float qn,
+                                                uint32_t d) {
+    float dot = ndarray_dot_thread(row, q, d);
+    float cs = __fdiv_rn(dot, __fmul_rn(row_norm, qn));
+    return __fsub_rn(1.0f, cs);
+}
+
+// src/core/index.rs:592-616 — distance from the query to every centre, then a stable ascending sort.
+// One CTA per query; bitonic sort of (order_bits(dist), cluster) keys, which is the stable order.
+__global__ void __launch_bounds__(256) k_center_order(const float* __restrict__ queries, const float* __restrict__ qnorm,
+                                                      const float* __restrict__ center_rows, const float* __restrict__ center_norms,
+                                                      uint32_t K, uint32_t d, uint32_t P, float* __restrict__ cdist,
+                                                      uint32_t* __restrict__ corder) {
+    extern __shared__ unsigned long long s_keys[];  // [P], P = next pow2 >= K
+    const uint64_t q = blockIdx.x;
+    const float* qv = queries + q * d;
+    const float qn = qnorm[q];
+    for (uint32_t c = threadIdx.x; c < P; c += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (c < K) {
+            float dist = distance_point(center_rows + (uint64_t)c * d, center_norms[c], qv, qn, d);
+            key = ((unsigned long long)float_order_bits(dist) << 32) | c;
+        }
+        s_keys[c] = key;
+    }
+    __syncthreads();
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = s_keys[i], b = s_keys[ixj];
+                    bool up = (i & kk) == 0;
+                    if ((a > b) == up) {
+                        s_keys[i] = b;
+                        s_keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t c = threadIdx.x; c < K; c += blockDim.x) {
+        unsigned long long key = s_keys[c];
+        cdist[q * K + c] = float_from_order_bits((uint32_t)(key >> 32));
+        corder[q * K + c] = (uint32_t)key;
+    }
+}
+
+__global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t state_bytes, uint32_t* work_counter) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *work_counter = 0;
+    if (q >= nq) return;
+    QueryStateHeader* h = reinterpret_cast<QueryStateHeader*>(state + q * state_bytes);
+    h->next_pos = 0;
+    h->done = 0;
+    h->heap_len = 0;
+    h->visited = 0;
+    h->candidates = 0;
+    h->distcomp = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ warp helpers
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// Bitonic sort (descending) of P (power of two) u64 keys in shared memory by one warp.
+__device__ __forceinline__ void warp_sort_desc(unsigned long long* keys, uint32_t P) {
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane_id(); i < P; i += 32) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool desc = (i & kk) == 0;
+                    if ((a < b) == desc) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Per-warp scratch carved out of dynamic shared memory.
+struct WarpSmem {
+    uint32_t* pass_idx;        // [kPassingCap] passing-filter ids (collection.hpp:783)
+    uint16_t* pass_sim;        // [kPassingCap] their Q15 similarity as dot + 32768
+    uint32_t* anchor;          // [L] lower bound of the query code in each table (prefixmap.hpp:36-57), unpadded position
+    uint2* lcp_up;             // [L] 8 bytes: common-prefix length with the code at anchor + 12 j, j = 0..7
+    uint2* lcp_dn;             // [L] 8 bytes: same at anchor - 1 - 12 j
+    uint32_t* code;            // [L] query code per table
+    uint32_t* start;           // [L] range start of the current depth
+    uint32_t* segbase;         // [L+1] exclusive prefix of 4-entry segment counts of the current depth
+    unsigned long long* mb;    // [P2K] MaxBuffer slots (maxbuffer.hpp:20): (sim16 << 32) | local id
+    unsigned long long* heap;  // [k] TopKClosestHeap (src/core/heap.rs): (order_bits(dist) << 32) | point id
+    unsigned long long* loc;   // [k] local heap of a brute-force cluster (index.rs:671)
+};
+
+__host__ __device__ inline uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+__host__ __device__ inline uint32_t warp_smem_bytes(uint32_t L, uint32_t k) {
+    uint32_t p2k = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    uint32_t b = kPassingCap * 4 + kPassingCap * 2;  // pass_idx, pass_sim
+    b += L * 4;                                       // anchor
+    b += L * 8 * 2;                                   // lcp_up, lcp_dn
+    b += L * 4 * 2;                                   // code, start
+    b += (L + 1) * 4;                                 // segbase
+    b = (b + 15) & ~15u;
+    b += p2k * 8 + k * 8 * 2;
+    return (b + 15) & ~15u;
+}
+
+__device__ __forceinline__ WarpSmem carve(uint8_t* base, uint32_t L, uint32_t k) {
+    WarpSmem w;
+    uint32_t p2k = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    uint8_t* p = base;
+    w.lcp_up = reinterpret_cast<uint2*>(p); p += L * 8;
+    w.lcp_dn = reinterpret_cast<uint2*>(p); p += L * 8;
+    w.pass_idx = reinterpret_cast<uint32_t*>(p); p += kPassingCap * 4;
+    w.anchor = reinterpret_cast<uint32_t*>(p); p += L * 4;
+    w.code = reinterpret_cast<uint32_t*>(p); p += L * 4;
+    w.start = reinterpret_cast<uint32_t*>(p); p += L * 4;
+    w.segbase = reinterpret_cast<uint32_t*>(p); p += (L + 1) * 4;
+    w.pass_sim = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
+    p = base + (((uint32_t)(p - base) + 15) & ~15u);
+    w.mb = reinterpret_cast<unsigned long long*>(p); p += p2k * 8;
+    w.heap = reinterpret_cast<unsigned long long*>(p); p += k * 8;
+    w.loc = reinterpret_cast<unsigned long long*>(p);
+    return w;
+}
+
+// heap.rs:23-36 — bounded max-heap on (distance, index): push while not full, else replace the maximum iff the new
+// distance is strictly smaller. Executed by the whole warp; `len` is warp-uniform.
+__device__ __forceinline__ void topk_add(unsigned long long* heap, uint32_t& len, uint32_t cap, float dist, uint32_t id) {
+    unsigned long long key = ((unsigned long long)float_order_bits(dist) << 32) | id;
+    if (len < cap) {
+        if (lane_id() == 0) heap[len] = key;
+        len++;
+        __syncwarp();
+        return;
+    }
+    unsigned long long best = 0;
+    uint32_t where = 0;
+    for (uint32_t i = lane_id(); i < len; i += 32) {
+        unsigned long long v = heap[i];
+        if (v >= best) {
+            best = v;
+            where = i;
+        }
+    }
+    unsigned long long mx = warp_max_u64(best);
+    // strict comparison on the distance only (heap.rs:27)
+    if ((uint32_t)(key >> 32) < (uint32_t)(mx >> 32)) {
+        uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == mx && lane_id() < len)) - 1;
+        if (lane_id() == owner) heap[where] = key;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long topk_peek(const unsigned long long* heap, uint32_t len) {
+    unsigned long long best = 0;
+    for (uint32_t i = lane_id(); i < len; i += 32) {
+        unsigned long long v = heap[i];
+        best = v > best ? v : best;
+    }
+    return warp_max_u64(best);
+}
+
+// maxbuffer.hpp:25-46 — filter(): sort by (value desc, id desc), drop adjacent duplicate ids, keep k,
+// minval = k-th value iff k entries survive. mb holds `inserted` keys; slots up to P are scratch.
+__device__ __forceinline__ void maxbuffer_filter(unsigned long long* mb, uint32_t P, uint32_t k, uint32_t& inserted, uint32_t& minval16) {
+    for (uint32_t i = inserted + lane_id(); i < P; i += 32) mb[i] = 0;  // pad sorts last
+    __syncwarp();
+    warp_sort_desc(mb, P);
+    uint32_t kept = 0;
+    uint32_t prev_id = 0xffffffffu;
+    bool have_prev = false;
+    for (uint32_t base = 0; base < inserted; base += 32) {
+        uint32_t i = base + lane_id();
+        unsigned long long key = (i < inserted) ? mb[i] : 0;
+        uint32_t id = (uint32_t)key;
+        uint32_t left = __shfl_up_sync(0xffffffffu, id, 1);
+        bool keep = i < inserted;
+        if (lane_id() == 0) {
+            if (have_prev && id == prev_id) keep = false;
+        } else if (id == left) {
+            keep = false;
+        }
+        uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        uint32_t pos = kept + __popc(bal & ((1u << lane_id()) - 1));
+        __syncwarp();
+        if (keep) mb[pos] = key;
+        kept += __popc(bal);
+        uint32_t last_valid = (inserted - base) < 32 ? (inserted - base - 1) : 31;
+        prev_id = __shfl_sync(0xffffffffu, id, last_valid);
+        have_prev = true;
+        __syncwarp();
+    }
+    inserted = kept < k ? kept : k;
+    if (inserted == k && k != 0) minval16 = (uint32_t)(mb[k - 1] >> 32);
+    __syncwarp();
+}
+
+// maxbuffer.hpp:64-76 for a list of candidates in order: reject sim <= minval; an accepted entry that finds all 2k slots
+// taken first runs filter() and is then stored WITHOUT being re-checked against the new minval (:68-75).
+__device__ __forceinline__ void maxbuffer_insert_list(unsigned long long* mb, uint32_t P, uint32_t k, uint32_t& inserted,
+                                                      uint32_t& minval16, const uint32_t* ids, const uint16_t* sims, uint32_t count) {
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = (i < count) ? sims[i] : 0;
+        const uint32_t id = (i < count) ? ids[i] : 0;
+        const unsigned long long key = ((unsigned long long)v << 32) | id;
+        uint32_t todo = __ballot_sync(0xffffffffu, i < count);
+        while (todo) {
+            const bool accept = ((todo >> lane) & 1u) && v > minval16;
+            const uint32_t acc = __ballot_sync(0xffffffffu, accept);
+            if (!acc) break;
+            const uint32_t space = 2 * k - inserted;
+            const uint32_t nacc = __popc(acc);
+            const uint32_t rank = __popc(acc & ((1u << lane) - 1));
+            if (nacc <= space) {
+                if (accept) mb[inserted + rank] = key;
+                inserted += nacc;
+                __syncwarp();
+                break;
+            }
+            if (accept && rank < space) mb[inserted + rank] = key;
+            inserted += space;
+            __syncwarp();
+            const uint32_t trig = __fns(acc, 0, space + 1);  // lane of the accepted entry that finds the buffer full
+            maxbuffer_filter(mb, P, k, inserted, minval16);
+            if (lane == trig) mb[inserted] = key;
+            inserted += 1;
+            __syncwarp();
+            todo &= ~((2u << trig) - 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ probe of one cluster
+
+struct ProbeCounters {
+    unsigned long long candidates, distcomp;
+};
+
+__device__ __forceinline__ uint32_t lcp24(uint32_t a, uint32_t b) {
+    uint32_t x = (a ^ b) & 0xffffffu;
+    return x ? (uint32_t)(__clz(x) - 8) : 24u;
+}
+
+// number of leading samples (of 8 byte-packed lcp values) that are >= depth
+__device__ __forceinline__ uint32_t lead_count(uint2 packed, uint32_t depth) {
+    uint32_t rep = depth * 0x01010101u;
+    uint32_t m0 = __vcmpgeu4(packed.x, rep), m1 = __vcmpgeu4(packed.y, rep);
+    return (uint32_t)(__popc(m0) + __popc(m1)) >> 3;
+}
+
+// Q15 similarities (as dot + 32768) of the first `count` ids in sm.pass_idx -> sm.pass_sim.
+// G lanes cooperate on one row with 128-bit loads (the HBM-bound rerank gather, cosine.hpp:19-23 / math.hpp:11-44).
+template <int G>
+__device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const int16_t* __restrict__ rows, uint32_t sl,
+                                       const int16_t* __restrict__ qrow_smem, const int (&qreg)[8], bool qreg_valid) {
+    constexpr int CPI = 32 / G;  // candidates per warp iteration
+    const uint32_t sub = lane_id() % G;
+    const uint32_t grp = lane_id() / G;
+    const uint32_t cpr = sl / 8;  // 16-byte chunks per row
+    for (uint32_t base = 0; base < count; base += CPI * 4) {
+        int part[4];
+        uint4 w[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t cand = base + u * CPI + grp;
+            ok[u] = cand < count && sub < cpr;
+            w[u] = make_uint4(0, 0, 0, 0);
+            if (ok[u]) {
+                const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[cand] * sl) + sub;
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w)
+                             : "l"(src));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int s = 0;
+            if (qreg_valid) {
+                s += q15_mul(unpack_lo(w[u].x), qreg[0]); s += q15_mul(unpack_hi(w[u].x), qreg[1]);
+                s += q15_mul(unpack_lo(w[u].y), qreg[2]); s += q15_mul(unpack_hi(w[u].y), qreg[3]);
+                s += q15_mul(unpack_lo(w[u].z), qreg[4]); s += q15_mul(unpack_hi(w[u].z), qreg[5]);
+                s += q15_mul(unpack_lo(w[u].w), qreg[6]); s += q15_mul(unpack_hi(w[u].w), qreg[7]);
+            }
+            part[u] = s;
+        }
+        if (!qreg_valid) {
+            // rows wider than 32 chunks (d > 256): loop over the remaining chunks with the query read from shared memory
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t cand = base + u * CPI + grp;
+                int s = 0;
+                if (cand < count) {
+                    const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[cand] * sl);
+                    for (uint32_t ch = sub; ch < cpr; ch += G) {
+                        uint4 a = __ldg(src + ch);
+                        uint4 b = *reinterpret_cast<const uint4*>(qrow_smem + ch * 8);
+                        s += q15_mul(unpack_lo(a.x), unpack_lo(b.x)); s += q15_mul(unpack_hi(a.x), unpack_hi(b.x));
+                        s += q15_mul(unpack_lo(a.y), unpack_lo(b.y)); s += q15_mul(unpack_hi(a.y), unpack_hi(b.y));
+                        s += q15_mul(unpack_lo(a.z), unpack_lo(b.z)); s += q15_mul(unpack_hi(a.z), unpack_hi(b.z));
+                        s += q15_mul(unpack_lo(a.w), unpack_lo(b.w)); s += q15_mul(unpack_hi(a.w), unpack_hi(b.w));
+                    }
+                }
+                part[u] = s;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int s = part[u];
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            uint32_t cand = base + u * CPI + grp;
+            if (sub == 0 && cand < count) sm.pass_sim[cand] = (uint16_t)(s + 32768);
+        }
+    }
+    __syncwarp();
+}
+
+// One PUFFINN query against cluster c (collection.hpp:543-601 -> search_maps :768-948). On return sm.mb[0..cnt) holds the
+// best entries, best first (maxbuffer.hpp:79-96). `codes` points at this query's code of table 0 (stride code_stride).
+template <int G>
+__device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
+                                  uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
+                                  const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, ProbeCounters& ctr) {
+    const uint32_t L = p.g.L, k = p.k;
+    const uint32_t lane = lane_id();
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    const int16_t* rows = p.q15 + off * p.g.sl;
+    const uint64_t* sk = p.sketches + off * kNumSketches;
+
+    uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;  // maxbuffer.hpp:53-55, filterer.hpp:101
+
+    // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
+    for (uint32_t t = lane; t < L; t += 32) {
+        const uint32_t h = codes[(uint64_t)t * code_stride];
+        const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
+        uint32_t lo = 0, len = nc;  // lower_bound == the reference's hinted halving search
+        while (len > 0) {
+            uint32_t half = len >> 1;
+            uint32_t mid = lo + half;
+            if (__ldg(H + mid) < h) {
+                lo = mid + 1;
+                len -= half + 1;
+            } else {
+                len = half;
+            }
+        }
+        sm.code[t] = h;
+        sm.anchor[t] = lo;
+        uint32_t up[8], dn[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t pu = lo + kSegment * j;
+            up[j] = pu < nc ? lcp24(__ldg(H + pu), h) : 0u;  // beyond the data lie the 0xffffffff sentinels (prefixmap.hpp:215-226)
+            int64_t pd = (int64_t)lo - 1 - kSegment * j;
+            dn[j] = pd >= 0 ? lcp24(__ldg(H + pd), h) : 0u;
+        }
+        sm.lcp_up[t] = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
+        sm.lcp_dn[t] = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
+    }
+    __syncwarp();
+
+    bool stopped = false;
+    for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
+        // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
+        const uint32_t it = kMaxHashBits + 1 - depth;              // iteration 1..24
+        const uint32_t dir_bit = 1u << (it >= 2 ? it - 2 : 0);     // removed bit (prefixmap.hpp:268-274)
+        uint32_t running = 0;
+        for (uint32_t t0 = 0; t0 < L; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            uint32_t nseg = 0;
+            if (t < L) {
+                const uint32_t h = sm.code[t];
+                const uint32_t A = sm.anchor[t];
+                const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
+                int64_t start, end;
+                if ((h & dir_bit) == 0) {  // upward (prefixmap.hpp:277-290)
+                    uint32_t j = lead_count(sm.lcp_up[t], depth);
+                    if (j == 8) {
+                        // run longer than the samples: first position >= A + 96 whose prefix differs, rounded up to the stride
+                        uint32_t lo = A + 8 * kSegment, len = nc > lo ? nc - lo : 0;
+                        while (len > 0) {
+                            uint32_t half = len >> 1, mid = lo + half;
+                            if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                        }
+                        j = (lo - A + kSegment - 1) / kSegment;
+                    }
+                    start = A;
+                    end = (int64_t)A + (int64_t)kSegment * j;
+                    if (end >= (int64_t)nc) end = (end - kSegment) > start ? (end - kSegment) : start;
+                } else {  // downward (prefixmap.hpp:291-303)
+                    uint32_t j = lead_count(sm.lcp_dn[t], depth);
+                    if (j == 8) {
+                        // first position of the matching run below A - 96
+                        uint32_t hi = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [0, hi) undecided
+                        uint32_t lo = 0, len = hi;
+                        while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
+                            uint32_t half = len >> 1, mid = lo + half;
+                            if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                        }
+                        j = (A - lo + kSegment - 1) / kSegment;
+                    }
+                    end = A;
+                    start = (int64_t)A - (int64_t)kSegment * j;
+                    if (start < 0) start = (start + kSegment) < end ? (start + kSegment) : end;
+                }
+                sm.start[t] = (uint32_t)start;
+                nseg = (uint32_t)(end - start) >> 2;
+            }
+            uint32_t total;
+            uint32_t ex = warp_excl_scan(nseg, total);
+            if (t < L) sm.segbase[t] = running + ex;
+            running += total;
+        }
+        if (lane == 0) sm.segbase[L] = running;
+        __syncwarp();
+        const uint32_t S = running;
+        if (S <= kRing) continue;  // the initial ring fill swallows the whole stream (collection.hpp:802-810)
+
+        // segment number -> (table, position)
+        auto locate = [&](uint32_t s, uint32_t& t_out) -> uint64_t {
+            uint32_t lo = 0, len = L;  // upper_bound(segbase, s) - 1 over segbase[0..L)
+            while (len > 0) {
+                uint32_t half = len >> 1, mid = lo + half;
+                if (sm.segbase[mid] <= s) { lo = mid + 1; len -= half + 1; } else { len = half; }
+            }
+            uint32_t t = lo - 1;
+            t_out = t;
+            return (uint64_t)t * p.n + off + sm.start[t] + 4 * (s - sm.segbase[t]);
+        };
+
+        uint32_t base = 0;  // first stream segment held by the ring
+        do {
+            uint32_t np = 0;
+            uint32_t missing = (base + kRing > S) ? (base + kRing - S > kRing ? kRing : base + kRing - S) : 0;
+            while (np < kFilterBuffer && missing == 0) {  // collection.hpp:813-866: a full ring sweep, slot == lane
+                uint32_t t;
+                const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
+                uint32_t v0 = __ldg(seg), v1 = __ldg(seg + 1), v2 = __ldg(seg + 2), v3 = __ldg(seg + 3);
+                uint64_t s0 = __ldg(sk + ((uint64_t)v0 << 5 | lane)), s1 = __ldg(sk + ((uint64_t)v1 << 5 | lane));
+                uint64_t s2 = __ldg(sk + ((uint64_t)v2 << 5 | lane)), s3 = __ldg(sk + ((uint64_t)v3 << 5 | lane));
+                uint32_t p0 = (uint32_t)__popcll(s0 ^ my_sketch) <= max_diff, p1 = (uint32_t)__popcll(s1 ^ my_sketch) <= max_diff;
+                uint32_t p2 = (uint32_t)__popcll(s2 ^ my_sketch) <= max_diff, p3 = (uint32_t)__popcll(s3 ^ my_sketch) <= max_diff;
+                uint32_t cnt = p0 + p1 + p2 + p3, total;
+                uint32_t pos = np + warp_excl_scan(cnt, total);
+                if (p0) sm.pass_idx[pos++] = v0;
+                if (p1) sm.pass_idx[pos++] = v1;
+                if (p2) sm.pass_idx[pos++] = v2;
+                if (p3) sm.pass_idx[pos++] = v3;
+                np += total;
+                ctr.candidates += kRing * 4;
+                base += kRing;
+                missing = (base + kRing > S) ? (base + kRing - S > kRing ? kRing : base + kRing - S) : 0;
+            }
+            // tail (collection.hpp:869-903): the not-yet-tested ring slots, in descending slot order, tested with the point
+            // index itself in place of its sketch (:890-893)
+            {
+                const uint32_t live = kRing - missing;  // slots 0..live-1 hold real segments base+slot
+                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+                if (lane < live) {
+                    uint32_t t;
+                    const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
+                    v0 = __ldg(seg); v1 = __ldg(seg + 1); v2 = __ldg(seg + 2); v3 = __ldg(seg + 3);
+                    p0 = (uint32_t)__popcll((uint64_t)v0 ^ my_sketch) <= max_diff;
+                    p1 = (uint32_t)__popcll((uint64_t)v1 ^ my_sketch) <= max_diff;
+                    p2 = (uint32_t)__popcll((uint64_t)v2 ^ my_sketch) <= max_diff;
+                    p3 = (uint32_t)__popcll((uint64_t)v3 ^ my_sketch) <= max_diff;
+                }
+                uint32_t cnt = p0 + p1 + p2 + p3, total;
+                uint32_t ex = warp_excl_scan(cnt, total);
+                uint32_t pos = np + (total - ex - cnt);  // entries of higher slots come first
+                if (p0) sm.pass_idx[pos++] = v0;
+                if (p1) sm.pass_idx[pos++] = v1;
+                if (p2) sm.pass_idx[pos++] = v2;
+                if (p3) sm.pass_idx[pos++] = v3;
+                np += total;
+                ctr.candidates += 4 * live;
+            }
+            __syncwarp();
+            // empty the buffer (collection.hpp:909-925)
+            rerank<G>(sm, np, rows, p.g.sl, qrow_smem, qreg, qreg_valid);
+            maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, np);
+            ctr.distcomp += np;
+            max_diff = p.msd[minval16 < 65536u ? minval16 : 65535u];  // filterer.hpp:108-111
+            // stop rule (collection.hpp:927-943)
+            uint32_t pulled = base + kRing;
+            uint32_t table_idx = L;
+            if (pulled < S) {
+                uint32_t lo = 0, len = L;
+                while (len > 0) {
+                    uint32_t half = len >> 1, mid = lo + half;
+                    if (sm.segbase[mid] <= pulled) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                }
+                table_idx = lo - 1;
+            }
+            float kth = __fdiv_rn((float)minval16, 65536.0f);
+            float sim = kth < max_sim ? max_sim : kth;  // std::max(kth, max_sim)
+            uint32_t bin = (uint32_t)__fdiv_rn(sim, 0.005f);  // crosspolytope.hpp:116-118
+            bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
+            uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (table_idx >> 5));
+            if ((word >> (table_idx & 31)) & 1u) {
+                stopped = true;
+                break;
+            }
+        } while (base + kRing < S);
+    }
+    // best_indices (collection.hpp:598, maxbuffer.hpp:79-96)
+    maxbuffer_filter(sm.mb, P, k, inserted, minval16);
+    return inserted;
+}
+
+// Q15 brute force of a whole cluster (collection.hpp:524-541), used by the legacy ABI when n < 100 (:550-555).
+template <int G>
+__device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& sm, uint32_t c, const int16_t* qrow_smem,
+                                         const int (&qreg)[8], bool qreg_valid) {
+    const uint32_t k = p.k;
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    const int16_t* rows = p.q15 + off * p.g.sl;
+    uint32_t inserted = 0, minval16 = 0;
+    for (uint32_t base = 0; base < nc; base += kFilterBuffer) {
+        uint32_t cnt = nc - base < (uint32_t)kFilterBuffer ? nc - base : (uint32_t)kFilterBuffer;
+        for (uint32_t i = lane_id(); i < cnt; i += 32) sm.pass_idx[i] = base + i;
+        __syncwarp();
+        rerank<G>(sm, cnt, rows, p.g.sl, qrow_smem, qreg, qreg_valid);
+        maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, cnt);
+    }
+    maxbuffer_filter(sm.mb, P, k, inserted, minval16);
+    return inserted;
+}
+
+// ------------------------------------------------------------------------------------------------ CLANN search loop
+
+// src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
+// for expensive ones). Warps are persistent; grid = multiple of the SM count.
+template <int G>
+__global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    uint8_t* wbase = s_dyn + (size_t)warp * (warp_bytes + p.g.sl * 2);
+    const WarpSmem sm = carve(wbase + p.g.sl * 2, p.g.L, p.k);
+    int16_t* qrow = reinterpret_cast<int16_t*>(wbase);  // this warp's query in Q15
+    const uint64_t state_bytes = sizeof(QueryStateHeader) + (uint64_t)p.k * 8;
+    const uint32_t cpr = p.g.sl / 8;
+    const bool qreg_valid = cpr <= 32;
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(b.work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= b.nq) break;
+        QueryStateHeader* st = reinterpret_cast<QueryStateHeader*>(b.state + (uint64_t)q * state_bytes);
+        if (st->done) continue;
+        unsigned long long* st_heap = reinterpret_cast<unsigned long long*>(st + 1);
+        uint32_t heap_len = st->heap_len;
+        uint32_t pos = st->next_pos;
+        uint32_t visited = st->visited;
+        ProbeCounters ctr{st->candidates, st->distcomp};
+        for (uint32_t i = lane; i < heap_len; i += 32) sm.heap[i] = st_heap[i];
+        // query row -> shared memory and this lane's 16-byte chunk -> registers
+        for (uint32_t i = lane; i < p.g.sl / 2; i += 32)
+            reinterpret_cast<uint32_t*>(qrow)[i] = reinterpret_cast<const uint32_t*>(b.q15 + (uint64_t)q * p.g.sl)[i];
+        __syncwarp();
+        int qreg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (qreg_valid && (lane % G) < cpr) {
+            uint4 w = *reinterpret_cast<const uint4*>(qrow + (lane % G) * 8);
+            qreg[0] = unpack_lo(w.x); qreg[1] = unpack_hi(w.x); qreg[2] = unpack_lo(w.y); qreg[3] = unpack_hi(w.y);
+            qreg[4] = unpack_lo(w.z); qreg[5] = unpack_hi(w.z); qreg[6] = unpack_lo(w.w); qreg[7] = unpack_hi(w.w);
+        }
+        const float* qv = b.queries + (uint64_t)q * p.g.d;
+        const float qn = b.qnorm[q];
+        bool done = false, foreign = false;
+
+        for (; pos < p.K; pos++) {
+            const uint32_t c = b.corder[(uint64_t)q * p.K + pos];
+            float max_dist = INFINITY;
+            if (heap_len > 0) {  // index.rs:342-361
+                unsigned long long top = topk_peek(sm.heap, heap_len);
+                max_dist = float_from_order_bits((uint32_t)(top >> 32));
+                float cmin = __fsub_rn(b.cdist[(uint64_t)q * p.K + pos], p.radii[c]);
+                if (cmin > max_dist) {
+                    done = true;
+                    break;
+                }
+            }
+            if (stop_at_foreign && p.owner[c] != p.shard_rank) {
+                foreign = true;
+                break;
+            }
+            visited++;
+            const uint64_t off = p.offsets[c];
+            const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+            if (p.brute[c]) {
+                // index.rs:364-378 with brute_force_search :666-685: members in assignment order into a local top-k, then merge
+                uint32_t loc_len = 0;
+                for (uint32_t base = 0; base < nc; base += 32) {
+                    uint32_t j = base + lane;
+                    float dist = 0.0f;
+                    uint32_t pid = 0;
+                    if (j < nc) {
+                        pid = p.perm[off + j];
+                        dist = distance_point(p.data + (uint64_t)pid * p.g.d, p.norms[pid], qv, qn, p.g.d);
+                    }
+                    uint32_t lim = nc - base < 32 ? nc - base : 32;
+                    for (uint32_t l = 0; l < lim; l++) {
+                        float dl = __shfl_sync(0xffffffffu, dist, l);
+                        uint32_t il = __shfl_sync(0xffffffffu, pid, l);
+                        topk_add(sm.loc, loc_len, p.k, dl, il);
+                    }
+                }
+                // to_list (heap.rs:42-48): ascending by distance; ties are in std's heap order there, by id here
+                const uint32_t P = next_pow2(2 * p.k) < 32 ? 32 : next_pow2(2 * p.k);
+                for (uint32_t i = lane; i < P; i += 32) sm.mb[i] = i < loc_len ? ~sm.loc[i] : 0ull;  // ~ turns asc into desc
+                __syncwarp();
+                warp_sort_desc(sm.mb, P);
+                for (uint32_t i = 0; i < loc_len; i++) {
+                    unsigned long long key = ~sm.mb[i];
+                    topk_add(sm.heap, heap_len, p.k, float_from_order_bits((uint32_t)(key >> 32)), (uint32_t)key);
+                }
+            } else {
+                const uint32_t fs = p.fset_of[c];
+                const float max_sim = __fsub_rn(1.0f, __fdiv_rn(max_dist, 2.0f));  // puffinn_types.rs:77-79
+                const uint32_t* codes = b.codes + (uint64_t)fs * p.g.L * b.nq + q;
+                const uint64_t my_sketch = b.sketches[((uint64_t)fs * b.nq + q) * kNumSketches + lane];
+                const uint32_t* stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
+                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, ctr);
+                // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
+                for (uint32_t base = 0; base < cnt; base += 32) {
+                    uint32_t j = base + lane;
+                    float dist = 0.0f;
+                    uint32_t pid = 0;
+                    if (j < cnt) {
+                        pid = p.perm[off + (uint32_t)sm.mb[j]];
+                        dist = distance_point(p.data + (uint64_t)pid * p.g.d, p.norms[pid], qv, qn, p.g.d);
+                    }
+                    uint32_t lim = cnt - base < 32 ? cnt - base : 32;
+                    for (uint32_t l = 0; l < lim; l++) {
+                        float dl = __shfl_sync(0xffffffffu, dist, l);
+                        uint32_t il = __shfl_sync(0xffffffffu, pid, l);
+                        topk_add(sm.heap, heap_len, p.k, dl, il);
+                    }
+                }
+            }
+        }
+        if (pos >= p.K) done = true;
+        (void)foreign;
+        __syncwarp();
+        for (uint32_t i = lane; i < heap_len; i += 32) st_heap[i] = sm.heap[i];
+        if (lane == 0) {
+            st->heap_len = heap_len;
+            st->next_pos = pos;
+            st->visited = visited;
+            st->done = done ? 1u : 0u;
+            st->candidates = ctr.candidates;
+            st->distcomp = ctr.distcomp;
+        }
+        __syncwarp();
+    }
+}
+
+// Multi-GPU: adopt, for every query, the state of the rank that advanced it furthest (exactly one rank advances a
+// query per step: the owner of its next cluster).
+__global__ void k_merge_states(uint8_t* __restrict__ mine, const uint8_t* __restrict__ all, int world, uint64_t nq,
+                               uint64_t state_bytes, uint32_t* __restrict__ active, uint32_t* work_counter) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) *work_counter = 0;
+    if (q >= nq) return;
+    int best = 0;
+    uint32_t best_pos = 0, best_done = 0;
+    for (int r = 0; r < world; r++) {
+        const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(all + ((uint64_t)r * nq + q) * state_bytes);
+        if (r == 0 || h->done > best_done || (h->done == best_done && h->next_pos > best_pos)) {
+            best = r;
+            best_pos = h->next_pos;
+            best_done = h->done;
+        }
+    }
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(all + ((uint64_t)best * nq + q) * state_bytes);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(mine + q * state_bytes);
+    for (uint64_t i = 0; i < state_bytes / 8; i++) dst[i] = src[i];
+    if (!best_done) atomicAdd(active, 1u);
+}
+
+// heap.rs:42-48 — results ascending by distance; pads with 0xFFFFFFFF / +inf.
+__global__ void __launch_bounds__(128) k_finish(const uint8_t* __restrict__ state, uint64_t nq, uint32_t k, uint64_t state_bytes,
+                                                uint32_t* __restrict__ out_ids, float* __restrict__ out_dists,
+                                                uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ cnt_cand,
+                                                unsigned long long* __restrict__ cnt_dc, uint32_t* __restrict__ cnt_vis) {
+    // one warp per query; selection sort by repeated minimum is fine for small k, bitonic otherwise is unnecessary here
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(state + q * state_bytes);
+    const unsigned long long* heap = reinterpret_cast<const unsigned long long*>(h + 1);
+    const uint32_t len = h->heap_len;
+    const uint32_t lane = lane_id();
+    // rank of each entry = number of strictly smaller keys (keys are unique unless an id repeats; ties broken by slot)
+    for (uint32_t i = lane; i < len; i += 32) {
+        unsigned long long key = heap[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < len; j++) {
+            unsigned long long o = heap[j];
+            rank += (o < key) || (o == key && j < i);
+        }
+        out_ids[q * k + rank] = (uint32_t)key;
+        out_dists[q * k + rank] = float_from_order_bits((uint32_t)(key >> 32));
+    }
+    for (uint32_t i = len + lane; i < k; i += 32) {
+        out_ids[q * k + i] = 0xffffffffu;
+        out_dists[q * k + i] = INFINITY;
+    }
+    if (lane == 0) {
+        out_counts[q] = len;
+        if (cnt_cand) cnt_cand[q] = h->candidates;
+        if (cnt_dc) cnt_dc[q] = h->distcomp;
+        if (cnt_vis) cnt_vis[q] = h->visited;
+    }
+}
+
+// Legacy single-index query (c_binder.cpp:69-96 -> collection.hpp:324-334): one warp, cluster 0, explicit max_sim.
+template <int G>
+__global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatch b, const uint32_t* stop, float max_sim,
+                                                       uint32_t warp_bytes, uint32_t* out_ids, uint32_t* out_count,
+                                                       uint32_t* out_distcomp) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const uint32_t lane = lane_id();
+    const WarpSmem sm = carve(s_dyn + p.g.sl * 2, p.g.L, p.k);
+    (void)warp_bytes;
+    int16_t* qrow = reinterpret_cast<int16_t*>(s_dyn);
+    for (uint32_t i = lane; i < p.g.sl / 2; i += 32) reinterpret_cast<uint32_t*>(qrow)[i] = reinterpret_cast<const uint32_t*>(b.q15)[i];
+    __syncwarp();
+    const uint32_t cpr = p.g.sl / 8;
+    const bool qreg_valid = cpr <= 32;
+    int qreg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (qreg_valid && (lane % G) < cpr) {
+        uint4 w = *reinterpret_cast<const uint4*>(qrow + (lane % G) * 8);
+        qreg[0] = unpack_lo(w.x); qreg[1] = unpack_hi(w.x); qreg[2] = unpack_lo(w.y); qreg[3] = unpack_hi(w.y);
+        qreg[4] = unpack_lo(w.z); qreg[5] = unpack_hi(w.z); qreg[6] = unpack_lo(w.w); qreg[7] = unpack_hi(w.w);
+    }
+    ProbeCounters ctr{0, 0};
+    uint32_t cnt;
+    if (p.n < 100) {  // collection.hpp:550-555
+        cnt = probe_bruteforce_q15<G>(p, sm, 0, qrow, qreg, qreg_valid);
+    } else {
+        const uint64_t my_sketch = b.sketches[lane];
+        cnt = probe_cluster<G>(p, sm, 0, b.codes, 1, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, ctr);
+    }
+    for (uint32_t i = lane; i < cnt; i += 32) out_ids[i] = (uint32_t)sm.mb[i];
+    if (lane == 0) {
+        *out_count = cnt;
+        *out_distcomp = (uint32_t)ctr.distcomp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+
+void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0) return;
+    k_prep_queries<<<(unsigned)((b.nq + 127) / 128), 128, 0, s>>>(b.queries, b.nq, p.g.d, p.g.sl, b.q15, b.qnorm);
+}
+
+void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0) return;
+    uint32_t P = next_pow2(p.K);
+    size_t smem = (size_t)P * 8;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_center_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_center_order<<<(unsigned)b.nq, 256, smem, s>>>(b.queries, b.qnorm, p.center_rows, p.center_norms, p.K, p.g.d, P, b.cdist, b.corder);
+}
+
+void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    uint64_t threads = b.nq > 0 ? b.nq : 1;
+    k_init_state<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(b.state, b.nq, query_state_bytes(p.k), b.work_counter);
+}
+
+static int rerank_group(uint32_t sl) {
+    uint32_t cpr = sl / 8;
+    int g = 2;
+    while ((uint32_t)g < cpr && g < 32) g <<= 1;
+    return g;
+}
+
+template <int G>
+static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev;
+        CLANN_CUDA(cudaGetDevice(&dev));
+        CLANN_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
+    const uint32_t per_warp = wb + p.g.sl * 2;
+    // warps per CTA: as many as fit in ~100 KB so that two CTAs share an SM, at most 8
+    uint32_t warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp > 100 * 1024) warps >>= 1;
+    size_t smem = (size_t)warps * per_warp;
+    if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int ctas_per_sm = 0;
+    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G>, warps * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    uint64_t want = (b.nq + warps - 1) / warps;
+    uint64_t grid = (uint64_t)sm_count * ctas_per_sm;
+    if (want < grid) grid = want ? want : 1;
+    k_probe<G><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0);
+}
+
+void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+    if (b.nq == 0) return;
+    switch (rerank_group(p.g.sl)) {
+        case 2: launch_probe_g<2>(p, b, stop_at_foreign, s); break;
+        case 4: launch_probe_g<4>(p, b, stop_at_foreign, s); break;
+        case 8: launch_probe_g<8>(p, b, stop_at_foreign, s); break;
+        case 16: launch_probe_g<16>(p, b, stop_at_foreign, s); break;
+        default: launch_probe_g<32>(p, b, stop_at_foreign, s); break;
+    }
+}
+
+void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active,
+                         cudaStream_t s) {
+    CLANN_CUDA(cudaMemsetAsync(active, 0, sizeof(uint32_t), s));
+    uint64_t threads = b.nq > 0 ? b.nq : 1;
+    k_merge_states<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(b.state, all_states, world, b.nq, query_state_bytes(p.k), active,
+                                                                      b.work_counter);
+}
+
+void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0) return;
+    uint64_t threads = b.nq * 32;
+    k_finish<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(b.state, b.nq, p.k, query_state_bytes(p.k), b.out_ids, b.out_dists,
+                                                               b.out_counts, b.cnt_candidates, b.cnt_distcomp, b.cnt_visited);
+}
+
+template <int G>
+static void launch_puffinn_g(const SearchParams& p, const QueryBatch& b, const uint32_t* stop, float max_sim, uint32_t* out_ids,
+                             uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s) {
+    const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
+    size_t smem = (size_t)wb + p.g.sl * 2;
+    if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_puffinn_search<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_puffinn_search<G><<<1, 32, smem, s>>>(p, b, stop, max_sim, wb, out_ids, out_count, out_distcomp);
+}
+
+void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim, uint32_t* out_ids,
+                           uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s) {
+    switch (rerank_group(p.g.sl)) {
+        case 2: launch_puffinn_g<2>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+        case 4: launch_puffinn_g<4>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+        case 8: launch_puffinn_g<8>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+        case 16: launch_puffinn_g<16>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+        default: launch_puffinn_g<32>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+    }
+}
+
+}  // namespace clann

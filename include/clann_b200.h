@@ -1,0 +1,154 @@
+/* clann_b200 — C ABI of the B200-native CLANN build + search hot path.
+ *
+ * This header is the drop-in boundary. It has two halves:
+ *
+ *  (1) The eight legacy `CPUFFINN_*` symbols, byte-compatible with the reference's
+ *      /root/reference/libpuffinn-ffi/c_binder.h:10-27 (Rust declarations: src/puffinn_binds/puffinn_sys.rs:8-52),
+ *      so the unmodified Rust crate can link `libclann_b200.so` instead of compiling c_binder.cpp.
+ *  (2) A batched `clann_*` ABI that moves all of ClusteredIndex::{new,build,search}
+ *      (/root/reference/src/core/index.rs:71-91,177-289,311-439) behind the boundary, because one FFI call per
+ *      (query, cluster) with a host-side early exit between calls cannot feed a GPU. lib.rs's init_with_config / build /
+ *      search (src/lib.rs:118,142,183) become one-line wrappers over it.
+ *
+ * Plain pointers and sizes only; no C++ or torch types. Every entry point returns 0 on success or a negative
+ * clann_status; clann_last_error() gives the message (thread-local). No exception crosses this boundary.
+ * There is no CPU fallback: every call needs a CUDA device and fails with CLANN_ERR_CUDA without one.
+ */
+#ifndef CLANN_B200_H
+#define CLANN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (2) batched ABI
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+typedef struct clann_index clann_index; /* opaque; owns device memory */
+
+/* Mirrors the hot-path fields of Config (src/core/config.rs:17-35). dataset_name / metrics_output are host-side
+ * concerns of the Rust crate and stay there. */
+typedef struct {
+    uint64_t num_tables;       /* L, PUFFINN tables per cluster                                  (config.rs:19) */
+    float num_clusters_factor; /* K = max(1, floor(f64(factor) * sqrt(n)))        (config.rs:22, index.rs:78-80) */
+    uint64_t k;                /* neighbours returned                                            (config.rs:25) */
+    float delta;               /* target recall                                                  (config.rs:28) */
+} clann_config;
+
+typedef enum {
+    CLANN_OK = 0,
+    CLANN_ERR_DATA = -1,       /* ClusteredIndexError::DataError            (errors.rs:10-11) e.g. empty dataset */
+    CLANN_ERR_CONFIG = -2,     /* ClusteredIndexError::ConfigError          (errors.rs:7-8)                      */
+    CLANN_ERR_CREATION = -3,   /* ClusteredIndexError::PuffinnCreationError (errors.rs:19-20)                    */
+    CLANN_ERR_SEARCH = -4,     /* ClusteredIndexError::PuffinnSearchError   (errors.rs:22-23)                    */
+    CLANN_ERR_NOT_BUILT = -5,  /* ClusteredIndexError::IndexNotFound        (errors.rs:25-26)                    */
+    CLANN_ERR_BOUNDS = -6,     /* ClusteredIndexError::IndexOutOfBounds     (errors.rs:28-29)                    */
+    CLANN_ERR_SERIALIZE = -7,  /* ClusteredIndexError::SerializeError       (errors.rs:34-35)                    */
+    CLANN_ERR_CUDA = -8,       /* no device / CUDA runtime failure (no reference counterpart: it has no GPU path) */
+    CLANN_ERR_ARG = -9         /* null pointer or malformed argument                                             */
+} clann_status;
+
+/* ClusteredIndex::new (index.rs:71-91) behind init_with_config (lib.rs:118-124). `data` is n x d row-major f32 in HOST
+ * memory; it is copied to the device. n == 0 -> CLANN_ERR_DATA ("empty dataset"). Uses the current CUDA device. */
+int clann_init_with_config(const float* data, uint64_t n, uint32_t d, const clann_config* config, clann_index** out);
+
+/* Options, to be set between init and build. Unknown key -> CLANN_ERR_ARG.
+ *   "seed"            seed of the function generator (the reference seeds from the wall clock, typedefs.hpp:17)
+ *   "function_sets"   0 (default) = one hash/sketch function set shared by all clusters (query hashed once);
+ *                     1 = one set per cluster, as the reference does (collection.hpp:128-135,265-268)
+ *   "strict"          1 (default) = reproduce search_maps' candidate order and quirks exactly;
+ *   "shard_rank", "shard_count"   cluster ownership for multi-GPU: this index only probes clusters c with
+ *                     owner(c) == shard_rank (longest-processing-time assignment on cluster sizes), default 0 / 1  */
+int clann_set_option(clann_index* index, const char* key, int64_t value);
+
+/* Parity mode: impose a clustering instead of running greedy k-center (centers[K] = point ids, assignment[n] = cluster
+ * of every point, radii[K]); and import the function set (SimHash planes, FHT signs, collision estimates) of one
+ * cluster from the bytes of puffinn::Index::serialize (collection.hpp:185-203). Importing implies function_sets = 1. */
+int clann_set_clustering(clann_index* index, uint64_t K, const uint64_t* centers, const uint64_t* assignment, const float* radii);
+int clann_import_reference(clann_index* index, uint64_t cluster, const void* blob, uint64_t len);
+/* Same, from raw arrays: planes[2048*SL] Q15, signs[L*fph*3*2^m] (+1/-1), est[(m+2)*201]. cluster == UINT64_MAX sets
+ * the shared set. */
+int clann_set_functions(clann_index* index, uint64_t cluster, const int16_t* planes, const int8_t* signs, const float* est);
+
+/* ClusteredIndex::build (index.rs:177-289): greedy k-center, per-cluster Q15 rows, sketches, table codes, sorted tables. */
+int clann_build(clann_index* index);
+
+/* ClusteredIndex::search (index.rs:311-439) for a batch of nq queries (HOST pointers, nq x d row-major f32).
+ * ids[nq*k] (0xFFFFFFFF pad), dists[nq*k] (+inf pad), counts[nq] = pairs returned per query (<= k), ascending distance. */
+int clann_search(clann_index* index, const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts);
+/* Same with DEVICE pointers (queries and outputs already resident in HBM); asynchronous on `stream` (a cudaStream_t). */
+int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
+                        uint32_t* d_counts, void* stream);
+
+/* Multi-GPU stepping (one process per GPU, clusters sharded by owner). clann_search_begin prepares the batch (query
+ * hashing, centre ordering); each clann_search_step advances every unfinished query through the consecutive clusters
+ * this rank owns and stops at the first cluster owned by another rank; the caller then exchanges the per-query state
+ * (clann_state_bytes() bytes per query, device pointer from clann_state_ptr) with an all-gather and calls
+ * clann_search_merge, which adopts for every query the state of the rank that advanced it. *active_out = queries not
+ * yet finished anywhere. clann_search_end writes the results. */
+int clann_search_begin(clann_index* index, const float* d_queries, uint64_t nq, void* stream);
+int clann_search_step(clann_index* index, void* stream);
+uint64_t clann_state_bytes(const clann_index* index);
+void* clann_state_ptr(clann_index* index);
+int clann_search_merge(clann_index* index, const void* d_all_states, int world, uint64_t* active_out, void* stream);
+int clann_search_end(clann_index* index, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, void* stream);
+
+/* Per-query counters of the last search, the same quantities the reference keeps (performance.hpp:72-86 plus the
+ * cluster count): any pointer may be NULL. Arrays of nq. */
+int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, uint64_t* distance_computations,
+                       uint32_t* clusters_visited);
+
+/* Golden-dump access for parity tests (device -> host copies). *size receives the byte size; dst may be NULL to query it. */
+typedef enum {
+    CLANN_X_NUM_CLUSTERS = 0, /* u64 K */
+    CLANN_X_CENTERS = 1,      /* u64[K]  centre point ids */
+    CLANN_X_ASSIGNMENT = 2,   /* u64[n]  cluster of every point */
+    CLANN_X_RADII = 3,        /* f32[K] */
+    CLANN_X_OFFSETS = 4,      /* u64[K+1] cluster c owns rows [off[c], off[c+1]) of the cluster-sorted arrays */
+    CLANN_X_PERM = 5,         /* u32[n]  cluster-sorted row -> point id (the concatenated ClusterCenter.assignment) */
+    CLANN_X_Q15 = 6,          /* i16[n_c*SL] of cluster `arg` */
+    CLANN_X_SKETCHES = 7,     /* u64[n_c*32] of cluster `arg` */
+    CLANN_X_TABLE_HASHES = 8, /* u32[L*n_c] sorted hashes of cluster `arg`, table-major, unpadded */
+    CLANN_X_TABLE_INDICES = 9,/* u32[L*n_c] matching local point indices */
+    CLANN_X_BRUTE = 10,       /* u8[K] brute-force flag (index.rs:204-205) */
+    CLANN_X_NORMS = 11,       /* f32[n] row norms (angulardata.rs:12-19) */
+    CLANN_X_EST = 12,         /* f32[(m+2)*201] collision estimates of function set of cluster `arg` */
+    CLANN_X_QUERY_CODES = 13, /* u32[nq*L] table codes of the last search batch for the function set of cluster `arg` */
+    CLANN_X_QUERY_SKETCHES = 14, /* u64[nq*32] likewise */
+    CLANN_X_CLUSTER_ORDER = 15,  /* u32[nq*K] visiting order of the last search batch (index.rs:592-616) */
+    CLANN_X_BUILD_MS = 16     /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
+} clann_export_what;
+int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size);
+
+/* Kernel-level timing of the last clann_search / clann_search_device call: ms[0] = query prep + hashing + ordering,
+ * ms[1] = probe kernel (the roofline kernel), launches = kernels launched. Measured with CUDA events on the call's stream. */
+int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches);
+
+const char* clann_last_error(void);
+void clann_destroy(clann_index* index);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (1) legacy per-cluster ABI (c_binder.h:14-26). Same signatures, same ownership, two hardening deviations:
+ *     results are always max(k,1) words, 0xFFFFFFFF-padded (the reference lets Rust over-read, puffinn.rs:108-114),
+ *     and no C++ exception crosses the boundary (the reference throws through extern "C", c_binder.cpp:8,15).
+ * ------------------------------------------------------------------------------------------------------------------ */
+struct CPUFFINN;
+typedef struct CPUFFINN CPUFFINN;
+
+CPUFFINN* CPUFFINN_load_from_file(const char* file_name, const char* dataset_name);          /* c_binder.cpp:4-36   */
+CPUFFINN* CPUFFINN_index_create(const char* dataset_type, int dataset_args);                 /* c_binder.cpp:39-50  */
+uint64_t CPUFFINN_index_rebuild(CPUFFINN* index, unsigned int num_maps);                     /* c_binder.cpp:53-60  */
+void CPUFFINN_index_insert_cosine(CPUFFINN* index, float* point, int dimension);             /* c_binder.cpp:63-66  */
+uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, float recall, float max_sim,
+                                 int dimension);                                             /* c_binder.cpp:69-96  */
+unsigned int CPUFFINN_get_distance_computations(void);                                       /* c_binder.cpp:98-100 */
+void CPUFFINN_clear_distance_computations(void);                                             /* c_binder.cpp:102-104*/
+void CPUFFINN_save_index(CPUFFINN* index, const char* file_name, int index_number);          /* c_binder.cpp:106-146*/
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLANN_B200_H */

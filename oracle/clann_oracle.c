@@ -938,7 +938,7 @@ int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out
             }
             qsort(loc.e, loc.len, sizeof(hp_elem), hp_cmp);
             for (uint32_t j = 0; j < loc.len; j++) hp_add(&pq, loc.e[j]);
-            distcomp += c->sizes[ci];
+            /* counters follow PUFFINN's own (performance.hpp:72-86): brute-force clusters add nothing */
         } else {
             if (!c->indices[ci]) { /* index.rs:386-388 IndexNotFound */
                 err = -1;

@@ -487,7 +487,7 @@ int ref_clann_search(void* h, const float* q, uint64_t* out_ids, float* out_dist
             }
             std::stable_sort(l.begin(), l.end(), [](const Elem& a, const Elem& b) { return a.dist < b.dist; });
             for (auto& e : l) pq.add(e);
-            c->last_distcomp += c->members[ci].size();
+            // counters follow PUFFINN's own (performance.hpp:72-86): brute-force clusters add nothing
         } else {
             ensure_index(*c, ci);
             float max_sim = 1.0f - max_dist / 2.0f;  // puffinn_types.rs:77-79

@@ -1,0 +1,196 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle and the real reference.
+
+Bar (BASELINE.json north_star): hash codes, sketches, tables ("bucket contents") and candidate sets bit-exact;
+returned ids identical up to ties within 1e-5 cosine. Candidate sets are compared through the counters that depend on
+every candidate in order (candidates, distance computations, clusters visited) plus the returned ids and distances.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _import_cluster_streams(ref_clann, K):
+    streams = {}
+    for ci in range(K):
+        s = ref_clann.cluster_stream(ci)
+        if s:
+            streams[ci] = s
+    return streams
+
+
+class Scenario:
+    """Reference-built CLANN state + the GPU index built from the same clustering and the same functions."""
+
+    def __init__(self, oracle, reflib, n, d, L, k, delta, seed, kind="planted", factor=0.4):
+        import clann_b200 as cb
+        from clann_b200 import _lib as cl
+        self.cb, self.cl = cb, cl
+        self.n, self.d, self.L, self.k, self.delta = n, d, L, k, delta
+        self.data = util.planted(n, d, seed) if kind == "planted" else util.uniform_sphere(n, d, seed)
+        cfg = cb.Config(L, factor, k, delta, "parity")
+        # 1. stand-alone GPU build: its own greedy k-center
+        self.gpu_own = cb.init_with_config(self.data, cfg)
+        self.gpu_own.set_option("seed", 7)
+        self.gpu_own.build()
+        self.K = self.gpu_own.num_clusters
+        self.centers = self.gpu_own.export(cl.X_CENTERS, 0, np.uint64).copy()
+        self.assignment = self.gpu_own.export(cl.X_ASSIGNMENT, 0, np.uint64).copy()
+        self.radii = self.gpu_own.export(cl.X_RADII, 0, np.float32).copy()
+        # 2. the reference over that clustering (real PUFFINN per cluster, seeded)
+        self.ref = reflib.clann(self.data, L, k, delta, self.centers, self.assignment, self.radii, seed_base=4321)
+        self.ref.build_all()
+        self.streams = _import_cluster_streams(self.ref, self.K)
+        # 3. the oracle restatement over the same streams
+        self.orc = oracle.clann(self.data, k, delta, self.centers, self.assignment, self.radii)
+        for ci, s in self.streams.items():
+            self.orc.set_cluster_stream(ci, s)
+        self.oracle = oracle
+        # 4. GPU index with the imposed clustering and the imported per-cluster functions
+        self.gpu = cb.init_with_config(self.data, cfg)
+        self.gpu.set_clustering(self.centers, self.assignment, self.radii)
+        for ci, s in self.streams.items():
+            self.gpu.import_reference(ci, s)
+        self.gpu.build()
+
+
+@pytest.fixture(scope="module")
+def sc25(oracle, reflib):
+    return Scenario(oracle, reflib, n=6000, d=25, L=24, k=10, delta=0.9, seed=11)
+
+
+@pytest.fixture(scope="module")
+def sc100(oracle, reflib):
+    return Scenario(oracle, reflib, n=2500, d=100, L=84, k=10, delta=0.9, seed=12)
+
+
+@pytest.fixture(scope="module")
+def sc128u(oracle, reflib):
+    # uniform data: every cluster is visited, deep stop depths, long ranges (the overflow path of the range finder)
+    return Scenario(oracle, reflib, n=1600, d=128, L=16, k=5, delta=0.95, seed=13, kind="uniform")
+
+
+SCENARIOS = ["sc25", "sc100", "sc128u"]
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_gmm_matches_oracle(name, request, oracle):
+    """gmm.rs:21-62 on the device == the restatement, bit for bit (centres, assignment, radii)."""
+    sc = request.getfixturevalue(name)
+    centers, assign, radii = oracle.gmm(sc.data, sc.K)
+    assert np.array_equal(centers, sc.centers)
+    assert np.array_equal(assign, sc.assignment)
+    assert np.array_equal(radii.view(np.uint32), sc.radii.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_build_matches_reference_streams(name, request, oracle):
+    """Q15 rows, sketches and sorted tables built by the kernels == the bytes the reference serialises."""
+    sc = request.getfixturevalue(name)
+    cl = sc.cl
+    brute = sc.gpu.export(cl.X_BRUTE, 0, np.uint8)
+    checked = 0
+    for ci, stream in sc.streams.items():
+        assert not brute[ci]
+        oi = oracle.index_import(stream)
+        nc = oi.n
+        q15 = sc.gpu.export(cl.X_Q15, ci, np.int16).reshape(nc, oi.sl)
+        assert np.array_equal(q15, oi.q15), f"cluster {ci}: Q15 rows differ"
+        sk = sc.gpu.export(cl.X_SKETCHES, ci, np.uint64).reshape(nc, 32)
+        assert np.array_equal(sk, oi.sketches), f"cluster {ci}: sketches differ"
+        th = sc.gpu.export(cl.X_TABLE_HASHES, ci, np.uint32).reshape(sc.L, nc)
+        ti = sc.gpu.export(cl.X_TABLE_INDICES, ci, np.uint32).reshape(sc.L, nc)
+        assert np.array_equal(th, oi.hashes[:, 12:-12]), f"cluster {ci}: table hashes differ"
+        assert np.array_equal(ti, oi.indices[:, 12:-12]), f"cluster {ci}: table indices differ"
+        oi.free()
+        checked += 1
+    assert checked > 0
+    # brute-force flags follow index.rs:204-205
+    sizes = np.bincount(sc.assignment.astype(np.int64), minlength=sc.K)
+    assert np.array_equal(brute.astype(bool), (sizes < 100) | (sizes < sc.k))
+
+
+def _queries(sc, nq, seed):
+    qa = util.planted_queries(sc.data, nq // 2, seed)
+    qb = util.uniform_sphere(nq - nq // 2, sc.d, seed + 1) * 3.0  # unnormalised on purpose
+    return np.concatenate([qa, qb]).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_query_hashing_matches_oracle(name, request, oracle):
+    sc = request.getfixturevalue(name)
+    cl = sc.cl
+    q = _queries(sc, 64, 100)
+    sc.gpu.search_batch(q)
+    q15 = oracle.store_q15(q)
+    for ci, stream in list(sc.streams.items())[:4]:
+        oi = oracle.index_import(stream)
+        codes = sc.gpu.export(cl.X_QUERY_CODES, ci, np.uint32).reshape(len(q), sc.L)
+        sks = sc.gpu.export(cl.X_QUERY_SKETCHES, ci, np.uint64).reshape(len(q), 32)
+        for i in range(len(q)):
+            assert np.array_equal(codes[i], oi.codes(q15[i])), f"cluster {ci} query {i}: codes differ"
+            assert np.array_equal(sks[i], oi.sketch(q15[i])), f"cluster {ci} query {i}: sketches differ"
+        oi.free()
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_search_matches_oracle_and_reference(name, request):
+    sc = request.getfixturevalue(name)
+    cl = sc.cl
+    q = _queries(sc, 200, 200)
+    ids, dists, counts = sc.gpu.search_batch(q)
+    ctr = sc.gpu.counters(len(q))
+    order = sc.gpu.export(cl.X_CLUSTER_ORDER, 0, np.uint32).reshape(len(q), sc.K)
+    bad = []
+    for i in range(len(q)):
+        o_ids, o_d, o_order, o_ctr = sc.orc.search(q[i])
+        r_ids, r_d, r_order, r_ctr = sc.ref.search(q[i])
+        # the restatement and the real reference agree with each other first
+        assert list(o_ids) == list(r_ids) and o_ctr == r_ctr, f"query {i}: oracle and reference disagree"
+        c = int(counts[i])
+        g_ids, g_d = ids[i, :c], dists[i, :c]
+        ok = (
+            np.array_equal(order[i], o_order.astype(np.uint32))
+            and int(ctr["clusters_visited"][i]) == o_ctr["visited"]
+            and int(ctr["candidates"][i]) == o_ctr["candidates"]
+            and int(ctr["distance_computations"][i]) == o_ctr["distance_computations"]
+            and util.same_ids_up_to_ties(g_ids, g_d, o_ids.astype(np.uint32), o_d)
+            and np.array_equal(np.sort(g_d).view(np.uint32), np.sort(o_d).view(np.uint32))
+        )
+        if not ok:
+            bad.append((i, c, len(o_ids), int(ctr["clusters_visited"][i]), o_ctr["visited"], int(ctr["candidates"][i]),
+                        o_ctr["candidates"], int(ctr["distance_computations"][i]), o_ctr["distance_computations"]))
+        # padding contract
+        assert np.all(ids[i, c:] == 0xFFFFFFFF) and np.all(np.isinf(dists[i, c:]))
+    assert not bad, f"{len(bad)} of {len(q)} queries differ (i, n_gpu, n_orc, vis_gpu, vis_orc, cand_gpu, cand_orc, dc_gpu, dc_orc): {bad[:10]}"
+
+
+@pytest.mark.parametrize("name", ["sc25", "sc100"])
+def test_standalone_index_recall(name, request):
+    """Own functions, shared by all clusters: recall@k >= delta-ish on planted data (utils/mod.rs:59-95)."""
+    sc = request.getfixturevalue(name)
+    q = util.planted_queries(sc.data, 300, 300)
+    ids, dists, counts = sc.gpu_own.search_batch(q)
+    rec = util.recall_at_k(sc.data, q, dists, counts, sc.k)
+    assert rec >= 0.9, rec
+    # the reference at the same delta on the same clustering, for comparison
+    hits = 0
+    ex = np.sort(util.exact_distances(sc.data, q), axis=1)[:, : sc.k]
+    for i in range(60):
+        _, r_d, _, _ = sc.ref.search(q[i])
+        hits += int(np.sum(r_d <= ex[i, sc.k - 1] + 1e-3))
+    ref_rec = hits / (60 * sc.k)
+    assert rec >= ref_rec - 0.03, (rec, ref_rec)
+
+
+def test_idempotent_and_batch_independent(sc25):
+    q = _queries(sc25, 96, 400)
+    a = sc25.gpu.search_batch(q)
+    b = sc25.gpu.search_batch(q)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    c = sc25.gpu.search_batch(q[:17])
+    assert np.array_equal(a[0][:17], c[0]) and np.array_equal(a[1][:17].view(np.uint32), c[1].view(np.uint32))
+    one = sc25.gpu.search(q[5])
+    assert [i for _, i in one] == list(a[0][5, : a[2][5]])
