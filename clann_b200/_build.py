@@ -1,6 +1,6 @@
 """In-tree build of libclann_b200.so (hand-written CUDA for sm_100a + the C ABI of include/clann_b200.h).
 
-`python -m clann_b200.build` or `clann_b200.build.build_library()`. The .so lands in clann_b200/lib/ so that it travels
+`python -m clann_b200._build` or `clann_b200._build.build_library()`. The .so lands in clann_b200/lib/ so that it travels
 with the repository snapshot to the GPU box; nothing is installed into site-packages.
 """
 from __future__ import annotations

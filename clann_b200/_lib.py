@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from . import build as _build
+from . import _build
 
 _vp, _u32, _u64, _i32, _i64, _f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_int64, C.c_float
 
@@ -52,7 +52,7 @@ def load() -> C.CDLL:
     path = library_path()
     if not os.path.exists(path):
         raise ImportError(
-            f"{path} is missing: run `python -m clann_b200.build` (nvcc, sm_100a). clann_b200 has no CPU fallback.")
+            f"{path} is missing: run `python -m clann_b200._build` (nvcc, sm_100a). clann_b200 has no CPU fallback.")
     L = C.CDLL(path)
     L.clann_last_error.restype = C.c_char_p
     L.clann_init_with_config.restype = _i32
