@@ -279,7 +279,8 @@ struct clann_index {
     uint64_t ws_nq = 0;
     DevBuf<float> w_queries, w_qnorm, w_cdist, w_out_dists;
     DevBuf<int16_t> w_q15;
-    DevBuf<uint32_t> w_codes, w_corder, w_out_ids, w_out_counts, w_counter, w_vis;
+    DevBuf<uint32_t> w_codes, w_first, w_qperm, w_out_ids, w_out_counts, w_counter, w_vis, w_sort_k, w_sort_i;
+    DevBuf<SortSegment> w_sort_seg;
     DevBuf<uint64_t> w_sketches;
     DevBuf<unsigned long long> w_cand, w_dc;
     DevBuf<uint8_t> w_state;
@@ -658,7 +659,16 @@ struct clann_index {
         w_codes.ensure((size_t)F * g.L * nq);
         w_sketches.ensure((size_t)F * nq * kNumSketches);
         w_cdist.ensure(nq * K);
-        w_corder.ensure(nq * K);
+        w_first.ensure(nq);
+        w_qperm.ensure(nq);
+        if (nq > segment_sort_smem_capacity()) {
+            w_sort_k.ensure(nq);
+            w_sort_i.ensure(nq);
+        }
+        {
+            std::vector<SortSegment> seg(1, SortSegment{0, 0, (uint32_t)nq, 0});
+            w_sort_seg.upload(seg, s);
+        }
         w_state.ensure(nq * query_state_bytes(k));
         w_counter.ensure(2);
         w_cand.ensure(nq);
@@ -682,7 +692,8 @@ struct clann_index {
         b.codes = w_codes.p;
         b.sketches = w_sketches.p;
         b.cdist = w_cdist.p;
-        b.corder = w_corder.p;
+        b.first = w_first.p;
+        b.qperm = w_qperm.p;
         b.state = w_state.p;
         b.work_counter = w_counter.p;
         b.out_ids = d_ids;
@@ -709,10 +720,12 @@ struct clann_index {
         launch_sketch(b.q15, w_tiles.p, w_ntiles, d_planes.p, g.sl, b.sketches, s);
         launch_codes(b.q15, w_code_tiles(nq, s), w_ntiles, d_signbits.p, g, b.codes, nq, (uint64_t)g.L * nq, s);
         launch_center_order(p, b, s);
+        // work order: stable sort of the queries by nearest cluster (same radix sort as the tables)
+        launch_segment_sort(w_sort_seg.p, 1, (uint32_t)nq, b.first, b.qperm, w_sort_k.p, w_sort_i.p, s);
         launch_init_state(p, b, s);
         cur_queries = d_queries;
         last_nq = nq;
-        last_launches = 5;
+        last_launches = 7;
     }
 
     DevBuf<RowTile> w_tiles_codes;
@@ -742,7 +755,7 @@ struct clann_index {
         CLANN_CUDA(cudaEventRecord(ev[2], s));
         launch_finish(p, b, s);
         CLANN_CUDA(cudaEventRecord(ev[3], s));
-        last_launches = 7;
+        last_launches = 9;
         profile_valid = true;
     }
 };
@@ -1033,7 +1046,21 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 emit_dev(index->w_sketches.p + (size_t)f * nq * kNumSketches, nq * kNumSketches * 8);
                 break;
             }
-            case CLANN_X_CLUSTER_ORDER: index->require_built(); emit_dev(index->w_corder.p, index->last_nq * K * 4); break;
+            case CLANN_X_CLUSTER_ORDER: {
+                // index.rs:592-616: stable ascending order of the centre distances, derived on the host for the tests
+                index->require_built();
+                const uint64_t nq = index->last_nq;
+                std::vector<float> cd = index->w_cdist.download(nq * K);
+                std::vector<uint32_t> order(nq * K);
+                for (uint64_t q = 0; q < nq; q++) {
+                    uint32_t* o = order.data() + q * K;
+                    std::iota(o, o + K, 0u);
+                    const float* dq = cd.data() + q * K;
+                    std::stable_sort(o, o + K, [&](uint32_t a, uint32_t b) { return dq[a] < dq[b]; });
+                }
+                emit(order.data(), order.size() * 4);
+                break;
+            }
             case CLANN_X_BUILD_MS: emit(index->build_ms, sizeof(index->build_ms)); break;
             default: throw StatusError(CLANN_ERR_ARG, "unknown export selector");
         }

@@ -75,8 +75,9 @@ struct QueryBatch {
     int16_t* q15;           // [nq][sl]
     uint32_t* codes;        // [n_fsets][L][nq]   (table-major per function set)
     uint64_t* sketches;     // [n_fsets][nq][32]
-    float* cdist;           // [nq][K] sorted ascending
-    uint32_t* corder;       // [nq][K]
+    float* cdist;           // [nq][K] distance to every centre (unsorted; the probe kernel walks it in key order)
+    uint32_t* first;        // [nq] nearest cluster (scratch: sorted in place to derive qperm)
+    uint32_t* qperm;        // [nq] work order: queries sorted by nearest cluster
     // per-query running state (also the multi-GPU exchange unit): see kernels_search.cu
     uint8_t* state;
     uint32_t* work_counter; // [1]
@@ -92,6 +93,7 @@ struct QueryBatch {
 
 uint64_t query_state_bytes(uint32_t k);
 void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+// cdist + first (nearest cluster); the caller then sorts `first` with launch_segment_sort to obtain qperm.
 void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).

@@ -3,6 +3,8 @@
 // anchors, per-depth ranges, the 32-slot sketch-filter ring (ring slot == warp lane), the 128-entry passing buffer,
 // the Q15 rerank gather, the 2k-slot MaxBuffer, the filter threshold update and the delta stop rule.
 // Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace clann {
@@ -11,12 +13,14 @@ namespace clann {
 
 // Per-query running state; also the unit exchanged between ranks in the multi-GPU stepping mode.
 struct QueryStateHeader {
-    uint32_t next_pos;   // next position in the cluster visiting order
+    uint32_t next_pos;   // number of clusters of the visiting order already consumed
     uint32_t done;       // 1 = search finished (early exit or all clusters seen)
     uint32_t heap_len;   // entries in the TopKClosestHeap
     uint32_t visited;    // clusters probed
     unsigned long long candidates;  // performance.hpp:82-86 summed over visits
     unsigned long long distcomp;    // performance.hpp:72-76 summed over visits
+    unsigned long long last_key;    // (order_bits(centre distance) << 32 | cluster) of the last consumed cluster, 0 = none
+    unsigned long long pad;
     // followed by k x u64 heap keys: (order_bits(distance) << 32) | point id
 };
 
@@ -57,46 +61,70 @@ __device__ __forceinline__ float distance_point(const float* __restrict__ row, f
     return __fsub_rn(1.0f, cs);
 }
 
-// src/core/index.rs:592-616 — distance from the query to every centre, then a stable ascending sort.
-// One CTA per query; bitonic sort of (order_bits(dist), cluster) keys, which is the stable order.
-__global__ void __launch_bounds__(256) k_center_order(const float* __restrict__ queries, const float* __restrict__ qnorm,
-                                                      const float* __restrict__ center_rows, const float* __restrict__ center_norms,
-                                                      uint32_t K, uint32_t d, uint32_t P, float* __restrict__ cdist,
-                                                      uint32_t* __restrict__ corder) {
-    extern __shared__ unsigned long long s_keys[];  // [P], P = next pow2 >= K
-    const uint64_t q = blockIdx.x;
-    const float* qv = queries + q * d;
-    const float qn = qnorm[q];
-    for (uint32_t c = threadIdx.x; c < P; c += blockDim.x) {
-        unsigned long long key = ~0ull;
-        if (c < K) {
-            float dist = distance_point(center_rows + (uint64_t)c * d, center_norms[c], qv, qn, d);
-            key = ((unsigned long long)float_order_bits(dist) << 32) | c;
+// src/core/index.rs:592-600 — distance from every query to every centre (the "GEMM" of the CLANN layer, computed in the
+// exact fp32 order of angulardata.rs:29-35). One CTA = 32 queries x all centres; centre rows stream through shared
+// memory in chunks of 64; lane = centre (padded rows: conflict-free), query row = warp-uniform broadcast.
+// The stable ascending order of index.rs:609-613 is NOT materialised: the probe kernel picks "the smallest
+// (distance, cluster) key above the last one" on demand, which is the same order.
+__global__ void __launch_bounds__(256) k_center_dist(const float* __restrict__ queries, const float* __restrict__ qnorm, uint64_t nq,
+                                                     const float* __restrict__ center_rows, const float* __restrict__ center_norms,
+                                                     uint32_t K, uint32_t d, float* __restrict__ cdist) {
+    extern __shared__ float s_f[];
+    const uint32_t stride = d | 1;        // odd row stride
+    float* s_q = s_f;                      // [32][stride]
+    float* s_c = s_f + 32 * stride;        // [64][stride]
+    const uint64_t q0 = (uint64_t)blockIdx.x * 32;
+    const uint32_t nqt = (uint32_t)((nq - q0) < 32 ? (nq - q0) : 32);
+    for (uint32_t e = threadIdx.x; e < 32 * d; e += blockDim.x) {
+        uint32_t j = e / d, i = e % d;
+        s_q[j * stride + i] = j < nqt ? queries[(q0 + j) * d + i] : 0.0f;
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    for (uint32_t cb = 0; cb < K; cb += 64) {
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < 64 * d; e += blockDim.x) {
+            uint32_t c = e / d, i = e % d;
+            s_c[c * stride + i] = (cb + c) < K ? center_rows[(uint64_t)(cb + c) * d + i] : 0.0f;
         }
-        s_keys[c] = key;
-    }
-    __syncthreads();
-    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
-        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-                uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = s_keys[i], b = s_keys[ixj];
-                    bool up = (i & kk) == 0;
-                    if ((a > b) == up) {
-                        s_keys[i] = b;
-                        s_keys[ixj] = a;
-                    }
-                }
-            }
-            __syncthreads();
+        __syncthreads();
+#pragma unroll
+        for (uint32_t h = 0; h < 2; h++) {
+            const uint32_t c = cb + h * 32 + lane;
+            if (c >= K) continue;
+            const float cn = center_norms[c];
+            for (uint32_t j = warp; j < nqt; j += 8)
+                cdist[(q0 + j) * K + c] = distance_point(s_c + (h * 32 + lane) * stride, cn, s_q + j * stride, qnorm[q0 + j], d);
         }
     }
-    for (uint32_t c = threadIdx.x; c < K; c += blockDim.x) {
-        unsigned long long key = s_keys[c];
-        cdist[q * K + c] = float_from_order_bits((uint32_t)(key >> 32));
-        corder[q * K + c] = (uint32_t)key;
+}
+
+// Fallback for very wide rows (the tiles above would not fit in shared memory): one thread per (query, centre).
+__global__ void __launch_bounds__(256) k_center_dist_simple(const float* __restrict__ queries, const float* __restrict__ qnorm, uint64_t nq,
+                                                            const float* __restrict__ center_rows, const float* __restrict__ center_norms,
+                                                            uint32_t K, uint32_t d, float* __restrict__ cdist) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * K) return;
+    uint64_t q = i / K;
+    uint32_t c = (uint32_t)(i % K);
+    cdist[i] = distance_point(center_rows + (uint64_t)c * d, center_norms[c], queries + q * d, qnorm[q], d);
+}
+
+// Nearest centre of every query (first cluster of its visiting order); used only to schedule queries that start in
+// the same cluster next to each other so that the cluster's rows, sketches and tables are shared through L2.
+__global__ void __launch_bounds__(256) k_first_cluster(const float* __restrict__ cdist, uint64_t nq, uint32_t K, uint32_t* __restrict__ first) {
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    unsigned long long best = ~0ull;
+    for (uint32_t c = lane_id(); c < K; c += 32) {
+        unsigned long long key = ((unsigned long long)float_order_bits(cdist[q * K + c]) << 32) | c;
+        best = key < best ? key : best;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t < best ? t : best;
+    }
+    if (lane_id() == 0) first[q] = (uint32_t)best;
 }
 
 __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t state_bytes, uint32_t* work_counter) {
@@ -110,6 +138,8 @@ __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t 
     h->visited = 0;
     h->candidates = 0;
     h->distcomp = 0;
+    h->last_key = 0;
+    h->pad = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ warp helpers
@@ -621,8 +651,8 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
 
 // src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
 // for expensive ones). Warps are persistent; grid = multiple of the SM count.
-template <int G>
-__global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign) {
+template <int G, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint8_t* wbase = s_dyn + (size_t)warp * (warp_bytes + p.g.sl * 2);
@@ -637,11 +667,13 @@ __global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uin
         if (lane == 0) q = atomicAdd(b.work_counter, 1u);
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= b.nq) break;
+        q = b.qperm[q];  // queries sorted by their nearest cluster
         QueryStateHeader* st = reinterpret_cast<QueryStateHeader*>(b.state + (uint64_t)q * state_bytes);
         if (st->done) continue;
         unsigned long long* st_heap = reinterpret_cast<unsigned long long*>(st + 1);
         uint32_t heap_len = st->heap_len;
         uint32_t pos = st->next_pos;
+        unsigned long long last_key = st->last_key;
         uint32_t visited = st->visited;
         ProbeCounters ctr{st->candidates, st->distcomp};
         for (uint32_t i = lane; i < heap_len; i += 32) sm.heap[i] = st_heap[i];
@@ -659,13 +691,25 @@ __global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uin
         const float qn = b.qnorm[q];
         bool done = false, foreign = false;
 
+        const float* cd = b.cdist + (uint64_t)q * p.K;
         for (; pos < p.K; pos++) {
-            const uint32_t c = b.corder[(uint64_t)q * p.K + pos];
+            // next cluster of the stable ascending centre-distance order (index.rs:592-616): smallest key above last_key
+            unsigned long long nk = ~0ull;
+            for (uint32_t cc = lane; cc < p.K; cc += 32) {
+                unsigned long long key = ((unsigned long long)float_order_bits(cd[cc]) << 32) | cc;
+                if ((pos == 0 || key > last_key) && key < nk) nk = key;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long t = __shfl_xor_sync(0xffffffffu, nk, o);
+                nk = t < nk ? t : nk;
+            }
+            const uint32_t c = (uint32_t)nk;
             float max_dist = INFINITY;
             if (heap_len > 0) {  // index.rs:342-361
                 unsigned long long top = topk_peek(sm.heap, heap_len);
                 max_dist = float_from_order_bits((uint32_t)(top >> 32));
-                float cmin = __fsub_rn(b.cdist[(uint64_t)q * p.K + pos], p.radii[c]);
+                float cmin = __fsub_rn(float_from_order_bits((uint32_t)(nk >> 32)), p.radii[c]);
                 if (cmin > max_dist) {
                     done = true;
                     break;
@@ -675,6 +719,7 @@ __global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uin
                 foreign = true;
                 break;
             }
+            last_key = nk;
             visited++;
             const uint64_t off = p.offsets[c];
             const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
@@ -737,6 +782,7 @@ __global__ void __launch_bounds__(256) k_probe(SearchParams p, QueryBatch b, uin
         if (lane == 0) {
             st->heap_len = heap_len;
             st->next_pos = pos;
+            st->last_key = last_key;
             st->visited = visited;
             st->done = done ? 1u : 0u;
             st->candidates = ctr.candidates;
@@ -848,14 +894,21 @@ void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_
 
 void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
     if (b.nq == 0) return;
-    uint32_t P = next_pow2(p.K);
-    size_t smem = (size_t)P * 8;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_center_order, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    const uint32_t stride = p.g.d | 1;
+    size_t smem = (size_t)96 * stride * sizeof(float);
+    if (smem <= 160 * 1024) {
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            CLANN_CUDA(cudaFuncSetAttribute(k_center_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        k_center_dist<<<(unsigned)((b.nq + 31) / 32), 256, smem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms, p.K,
+                                                                     p.g.d, b.cdist);
+    } else {
+        k_center_dist_simple<<<(unsigned)((b.nq * p.K + 255) / 256), 256, 0, s>>>(b.queries, b.qnorm, b.nq, p.center_rows,
+                                                                                 p.center_norms, p.K, p.g.d, b.cdist);
     }
-    k_center_order<<<(unsigned)b.nq, 256, smem, s>>>(b.queries, b.qnorm, p.center_rows, p.center_norms, p.K, p.g.d, P, b.cdist, b.corder);
+    k_first_cluster<<<(unsigned)((b.nq * 32 + 255) / 256), 256, 0, s>>>(b.cdist, b.nq, p.K, b.first);
 }
 
 void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
@@ -870,8 +923,8 @@ static int rerank_group(uint32_t sl) {
     return g;
 }
 
-template <int G>
-static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+template <int G, int OCC>
+static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev;
@@ -880,23 +933,36 @@ static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop
     }
     const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
     const uint32_t per_warp = wb + p.g.sl * 2;
-    // warps per CTA: as many as fit in ~100 KB so that two CTAs share an SM, at most 8
+    // warps per CTA: as many as keep OCC CTAs of shared memory on one SM, at most 8
     uint32_t warps = 8;
-    while (warps > 1 && (size_t)warps * per_warp > 100 * 1024) warps >>= 1;
+    while (warps > 1 && (size_t)warps * per_warp * OCC > 200 * 1024) warps >>= 1;
     size_t smem = (size_t)warps * per_warp;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     int ctas_per_sm = 0;
-    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G>, warps * 32, smem));
+    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC>, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     uint64_t want = (b.nq + warps - 1) / warps;
-    uint64_t grid = (uint64_t)sm_count * ctas_per_sm;
+    uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want ? want : 1;
-    k_probe<G><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0);
+    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0);
+}
+
+template <int G>
+static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+    static int occ = 0;
+    if (occ == 0) {
+        const char* e = getenv("CLANN_PROBE_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
+        occ = e ? atoi(e) : 3;
+        if (occ < 2 || occ > 4) occ = 3;
+    }
+    if (occ == 2) launch_probe_go<G, 2>(p, b, stop_at_foreign, s);
+    else if (occ == 4) launch_probe_go<G, 4>(p, b, stop_at_foreign, s);
+    else launch_probe_go<G, 3>(p, b, stop_at_foreign, s);
 }
 
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {

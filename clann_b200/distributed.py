@@ -59,7 +59,7 @@ class ShardedSearcher:
         if self.world == 1:
             _check(self.lib.clann_search_device(h, d_queries.data_ptr(), nq, d_ids.data_ptr(), d_dists.data_ptr(),
                                                 d_counts.data_ptr(), stream))
-            self.last_launches, self.last_steps = 7, 1
+            self.last_launches, self.last_steps = 9, 1
             return
         import torch.distributed as dist
         _check(self.lib.clann_search_begin(h, d_queries.data_ptr(), nq, stream))
@@ -67,7 +67,7 @@ class ShardedSearcher:
         local = torch.as_tensor(_DeviceBytes(self.lib.clann_state_ptr(h), nq * sb), device=d_queries.device)
         if self._gather is None or self._gather.numel() != self.world * nq * sb:
             self._gather = torch.empty(self.world * nq * sb, dtype=torch.uint8, device=d_queries.device)
-        launches = [5]
+        launches = [7]
 
         def step():
             _check(self.lib.clann_search_step(h, stream))

@@ -828,6 +828,56 @@ static int hp_cmp(const void* a, const void* b) {
     return 0;
 }
 
+typedef struct {
+    uint64_t ci;
+    float dist;
+} cd_t;
+
+/* Drives the TopKClosestHeap restatement for the reference's own unit tests (heap.rs:52-161): n adds, then to_list.
+ * added[i] = return value of add; top_* = get_top() after all adds (id, distance), valid if the count is > 0. */
+int orc_topk_run(uint32_t k, const float* dists, const uint64_t* ids, int n, float* out_d, uint64_t* out_ids, uint8_t* added,
+                 uint64_t* top_id, float* top_dist) {
+    topk h = {(hp_elem*)malloc(sizeof(hp_elem) * (k + 1)), 0, k};
+    for (int i = 0; i < n; i++) {
+        hp_elem e = {dists[i], ids[i]};
+        added[i] = (uint8_t)hp_add(&h, e);
+    }
+    if (h.len > 0) {
+        hp_elem t = h.e[hp_max(&h)];
+        *top_id = t.idx;
+        *top_dist = t.dist;
+    }
+    qsort(h.e, h.len, sizeof(hp_elem), hp_cmp);
+    for (uint32_t i = 0; i < h.len; i++) {
+        out_d[i] = h.e[i].dist;
+        out_ids[i] = h.e[i].idx;
+    }
+    int r = (int)h.len;
+    free(h.e);
+    return r;
+}
+
+/* index.rs:592-616 on its own: stable ascending order of the centres by distance_point to the query. */
+void orc_sort_clusters(const float* data, uint32_t d, const uint64_t* centers, uint64_t K, const float* q, uint64_t* order) {
+    cd_t* cd = (cd_t*)malloc(sizeof(cd_t) * K);
+    for (uint64_t ci = 0; ci < K; ci++) {
+        const float* row = data + centers[ci] * d;
+        cd[ci].ci = ci;
+        cd[ci].dist = orc_distance_point(row, sqrtf(orc_ndarray_dot(row, row, d)), q, d);
+    }
+    for (uint64_t i = 1; i < K; i++) {
+        cd_t x = cd[i];
+        uint64_t j = i;
+        while (j > 0 && x.dist < cd[j - 1].dist) {
+            cd[j] = cd[j - 1];
+            j--;
+        }
+        cd[j] = x;
+    }
+    for (uint64_t i = 0; i < K; i++) order[i] = cd[i].ci;
+    free(cd);
+}
+
 struct orc_clann {
     const float* data;
     uint64_t n, K;
@@ -888,11 +938,6 @@ int orc_clann_build_cluster(orc_clann* c, uint64_t ci, const orc_functions* fn) 
     free(sub);
     return 0;
 }
-
-typedef struct {
-    uint64_t ci;
-    float dist;
-} cd_t;
 
 /* index.rs:311-439 */
 int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out, uint64_t* counters) {

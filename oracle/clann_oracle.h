@@ -84,6 +84,10 @@ float orc_ndarray_dot(const float* x, const float* y, size_t len);
 float orc_distance_point(const float* row, float row_norm, const float* q, uint32_t d);
 uint64_t orc_gmm(const float* data, uint64_t n, uint32_t d, uint64_t K, uint64_t* centers, uint64_t* assignment, float* radii);
 
+int orc_topk_run(uint32_t k, const float* dists, const uint64_t* ids, int n, float* out_d, uint64_t* out_ids, uint8_t* added,
+                 uint64_t* top_id, float* top_dist);
+void orc_sort_clusters(const float* data, uint32_t d, const uint64_t* centers, uint64_t K, const float* q, uint64_t* order);
+
 typedef struct orc_clann orc_clann;
 /* fns: either 1 shared function set or K per-cluster sets (n_fns in {1, K}); streams: optional per-cluster Index::serialize
    blobs (then fns is ignored for those clusters). data is borrowed. */

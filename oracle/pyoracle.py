@@ -194,6 +194,9 @@ class OracleLib:
         L.orc_ndarray_dot.restype, L.orc_ndarray_dot.argtypes = _f32, [_vp, _vp, C.c_size_t]
         L.orc_distance_point.restype, L.orc_distance_point.argtypes = _f32, [_vp, _f32, _vp, _u32]
         L.orc_gmm.restype, L.orc_gmm.argtypes = _u64, [_vp, _u64, _u32, _u64, _vp, _vp, _vp]
+        L.orc_topk_run.restype = _i32
+        L.orc_topk_run.argtypes = [_u32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]
+        L.orc_sort_clusters.argtypes = [_vp, _u32, _vp, _u64, _vp, _vp]
         L.orc_clann_create.restype = _vp
         L.orc_clann_create.argtypes = [_vp, _u64, _u32, _u32, _f32, _u64, _vp, _vp, _vp]
         L.orc_clann_set_cluster_stream.restype = _i32
@@ -268,6 +271,23 @@ class OracleLib:
         row, q = np.ascontiguousarray(row, np.float32), np.ascontiguousarray(q, np.float32)
         norm = np.float32(np.sqrt(np.float32(self.lib.orc_ndarray_dot(_ptr(row), _ptr(row), row.size))))
         return float(self.lib.orc_distance_point(_ptr(row), float(norm), _ptr(q), row.size))
+
+    def topk_run(self, k, dists, ids):
+        """TopKClosestHeap (heap.rs): returns (to_list as [(dist, id)], added flags, get_top as (id, dist) or None)."""
+        dists, ids = np.ascontiguousarray(dists, np.float32), np.ascontiguousarray(ids, np.uint64)
+        od, oi = np.zeros(max(k, 1), np.float32), np.zeros(max(k, 1), np.uint64)
+        added = np.zeros(max(len(ids), 1), np.uint8)
+        tid, td = _u64(0), _f32(0)
+        c = self.lib.orc_topk_run(k, _ptr(dists), _ptr(ids), len(ids), _ptr(od), _ptr(oi), _ptr(added), C.byref(tid), C.byref(td))
+        top = (int(tid.value), float(td.value)) if c > 0 else None
+        return [(float(od[i]), int(oi[i])) for i in range(c)], added[: len(ids)].astype(bool), top
+
+    def sort_clusters(self, data, centers, q):
+        data, q = np.ascontiguousarray(data, np.float32), np.ascontiguousarray(q, np.float32)
+        centers = np.ascontiguousarray(centers, np.uint64)
+        order = np.zeros(centers.size, np.uint64)
+        self.lib.orc_sort_clusters(_ptr(data), data.shape[1], _ptr(centers), centers.size, _ptr(q), _ptr(order))
+        return order
 
     def clann(self, data, k, delta, centers, assignment, radii) -> "OracleClann":
         return OracleClann(self, data, k, delta, centers, assignment, radii)

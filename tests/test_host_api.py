@@ -1,0 +1,46 @@
+"""Host-side mirror of the Rust API (clann_b200/api.py): Config semantics, error mapping, recall helper."""
+import numpy as np
+import pytest
+
+import clann_b200 as cb
+
+
+def test_default_config():  # src/core/config.rs:38-47 (the reference's own test asserts num_tables == 1 and fails)
+    c = cb.Config()
+    assert (c.num_tables, c.num_clusters_factor, c.k, c.delta, c.dataset_name) == (10, 1.0, 10, 0.9, "")
+    assert c.metrics_output is cb.MetricsOutput.NONE
+
+
+def test_new_config_and_json():  # config.rs:85-126
+    c = cb.Config.new(2048, 10.0, 100, 0.95, "test_dataset", cb.MetricsOutput.NONE)
+    assert (c.num_tables, c.num_clusters_factor, c.k, c.delta, c.dataset_name) == (2048, 10.0, 100, 0.95, "test_dataset")
+    j = c.to_json_dict()
+    assert j["num_tables"] == 2048 and j["num_clusters_factor"] == 10.0 and j["metrics_output"] == "None"
+
+
+def test_empty_dataset_is_data_error():  # index.rs:72-74
+    with pytest.raises(cb.DataError, match="empty dataset"):
+        cb.init_with_config(np.zeros((0, 8), np.float32), cb.Config(4, 1.0, 3, 0.9))
+
+
+def test_bad_config_is_config_error():
+    with pytest.raises(cb.ConfigError):
+        cb.init_with_config(np.zeros((5, 8), np.float32), cb.Config(0, 1.0, 3, 0.9))
+
+
+def test_error_messages_follow_errors_rs():  # src/core/errors.rs:6-39
+    assert str(cb.DataError("empty dataset")) == "Data Error: empty dataset"
+    assert str(cb.PuffinnCreationError("x")) == "PUFFINN Creation Error: x"
+    assert str(cb.IndexNotFound()) == "Index Not Found Error"
+
+
+def test_recall_values():  # src/utils/mod.rs:59-95
+    truth = np.array([[0.1, 0.2, 0.3, 0.9], [0.0, 0.5, 0.6, 0.7]], np.float32)
+    run = [[0.1, 0.2, 0.3005], [0.0, 0.5, 0.8]]
+    mean, std, per = cb.get_recall_values(truth, run, 3)
+    assert per == [3.0, 2.0] and abs(mean - 5 / 6) < 1e-6
+
+
+def test_unit_vector_helper():
+    v = cb.generate_random_unit_vectors(50, 16, seed=1)
+    assert v.shape == (50, 16) and np.allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-5) and (v >= 0).all()

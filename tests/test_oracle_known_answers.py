@@ -1,0 +1,124 @@
+"""The oracle against every known-answer test the reference holds for this path:
+format_test.hpp:10-33, similarity_measure_test.hpp:13-41, maxbuffer_test.hpp:10-73, dataset_test.hpp:13-30,
+math_test.hpp:13-30, hash_test.hpp:140-151, filterer_test.hpp:12-42, src/core/heap.rs:55-161, src/core/index.rs:695-748.
+"""
+import numpy as np
+import pytest
+
+
+def test_to_16bit_fixed_point(oracle):  # format_test.hpp:10-17
+    f = oracle.lib.orc_to_q15
+    assert f(0.99999) == 32767 and f(1.0) == 32767 and f(-1.0) == -32768 and f(0.0) == 0
+    assert f(0.5) == 0x4000 and f(-0.5) == np.int16(np.uint16(0xC000))
+
+
+def test_from_16bit_fixed_point(oracle):  # format_test.hpp:19-26
+    f = oracle.lib.orc_from_q15
+    assert f(0) == 0.0 and f(0x4000) == 0.5
+    assert f(int(np.int16(np.uint16(0xA000)))) == -0.75 and f(int(np.int16(np.uint16(0x8000)))) == -1.0
+    assert f(0x7FFF) == np.float32(32767) / np.float32(32768)
+
+
+def test_pad_dimensions(oracle):  # format_test.hpp:28-33
+    assert [oracle.lib.orc_storage_len(d) for d in (0, 1, 16, 17)] == [0, 16, 16, 32]
+
+
+def test_compute_similarity_known_answer(oracle):  # similarity_measure_test.hpp:13-41
+    a = oracle.store_q15(np.array([0.2, 0.4, 0.0, 0.8, 0.4], np.float32))
+    b = oracle.store_q15(np.array([0.4, 0.0, 0.8, 0.2, 0.4], np.float32))
+    assert abs(oracle.similarity(a, b) - 0.7) <= 1e-4
+    l1, l2 = np.zeros(64, np.float32), np.zeros(64, np.float32)
+    l1[[2, 16, 27, 63]] = [0.2, 0.4, 0.8, 0.4]
+    l2[[2, 27, 51, 63]] = [0.4, 0.2, 0.8, 0.4]
+    assert abs(oracle.similarity(oracle.store_q15(l1), oracle.store_q15(l2)) - 0.7) <= 1e-4
+
+
+MAXBUFFER_CASES = [  # maxbuffer_test.hpp:10-73 (k, inserts, best_entries, smallest_value or None)
+    (0, [(1, 0.5)], [], None),
+    (2, [], [], None),
+    (2, [(2, 0.6)], [(2, 0.6)], 0.0),
+    (2, [(100, 0.1)], [(100, 0.1)], 0.0),
+    (2, [(100, 0.1), (50, 0.2), (105, 0.3)], [(105, 0.3), (50, 0.2)], None),
+    (2, [(1, 0.1), (2, 0.5), (3, 0.05), (4, 0.07), (5, 0.5), (6, 0.9), (7, 0.7), (8, 0.8)], [(6, 0.9), (8, 0.8)], None),
+    (2, [(1, 0.1), (1, 0.1), (1, 0.1)], [(1, 0.1)], None),
+    (2, [(1, -5.0), (2, 1.2)], [(2, 1.0)], None),
+]
+
+
+@pytest.mark.parametrize("k,inserts,expected,minval", MAXBUFFER_CASES)
+def test_maxbuffer_known_answers(oracle, k, inserts, expected, minval):
+    ids = [i for i, _ in inserts]
+    vals = [v for _, v in inserts]
+    oi, ov, mv = oracle.maxbuffer_run(k, ids, vals)
+    assert list(oi) == [i for i, _ in expected]
+    assert np.allclose(ov, [v for _, v in expected])
+    if minval is not None:
+        assert mv == minval
+
+
+def test_maxbuffer_minval_after_filter(oracle):
+    # maxbuffer_test.hpp:37-45,47-60: smallest_value() is read after best_entries() there, i.e. after a filter
+    _, ov, _ = oracle.maxbuffer_run(2, [100, 50, 105], [0.1, 0.2, 0.3])
+    assert ov[-1] == np.float32(0.2)
+    _, ov, _ = oracle.maxbuffer_run(2, [1, 2, 3, 4, 5, 6, 7, 8], [0.1, 0.5, 0.05, 0.07, 0.5, 0.9, 0.7, 0.8])
+    assert ov[-1] == np.float32(0.8)
+
+
+def test_dataset_accessor(oracle):  # dataset_test.hpp:13-30
+    assert oracle.lib.orc_storage_len(3) == 16
+    rows = oracle.store_q15(np.array([[1, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32))
+    assert rows.shape == (3, 16)
+    assert rows[0, 0] == 32767 and rows[1, 2] == -32768 and rows[2, 1] == 32767
+    assert not rows[:, 3:].any()
+
+
+def test_dot_simple_equals_avx2(oracle, reflib):  # math_test.hpp:13-30
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        a = oracle.store_q15(rng.standard_normal(100).astype(np.float32))
+        b = oracle.store_q15(rng.standard_normal(100).astype(np.float32))
+        assert reflib.dot_i16(a, b) == reflib.dot_i16(a, b, simple=True) == oracle.dot_i16(a, b)
+
+
+def test_bits_per_function(oracle):  # hash_test.hpp:140-151
+    assert oracle.lib.orc_ceil_log(100) + 1 == 8
+    assert oracle.lib.orc_ceil_log(25) + 1 == 6 and oracle.lib.orc_ceil_log(128) + 1 == 8
+
+
+def test_sketch_filter_semantics(oracle):  # filterer_test.hpp:12-42
+    # equal vectors have sketch distance 0 <= max_sketch_diff(1.0); opposite vectors differ in every bit
+    assert oracle.lib.orc_max_sketch_diff(1.0) == 0
+    assert oracle.lib.orc_max_sketch_diff(0.0) == 64
+    assert oracle.lib.orc_max_sketch_diff(0.5) == 32
+
+
+def test_heap_rs_unit_tests(oracle):  # src/core/heap.rs:55-161
+    lst, added, _ = oracle.topk_run(3, [2.5, 1.5], [0, 1])
+    assert lst == [(1.5, 1), (2.5, 0)] and added.all()
+    lst, _, _ = oracle.topk_run(3, [3.0, 2.0, 1.0, 0.5], [0, 1, 2, 3])
+    assert len(lst) == 3 and (1.0, 2) in lst and (2.0, 1) in lst and (0.5, 3) in lst
+    lst, added, _ = oracle.topk_run(3, [3.0, 2.0, 1.0, 4.0], [0, 1, 2, 3])
+    assert not added[3] and len(lst) == 3 and (4.0, 3) not in lst
+    _, _, top = oracle.topk_run(2, [2.0, 1.0], [1, 2])
+    assert top == (1, 2.0)
+    _, _, top = oracle.topk_run(2, [2.0, 1.0, 0.5], [1, 2, 3])
+    assert top == (2, 1.0)
+    lst, _, top = oracle.topk_run(3, [], [])
+    assert lst == [] and top is None
+
+
+def test_sort_cluster_known_answer(oracle):  # src/core/index.rs:695-748 — the only known-answer test of the CLANN layer
+    pts = np.array([
+        [0.1, 0.9, 0.4], [0.7, 0.2, 0.6], [0.5, 0.3, 0.9], [0.8, 0.4, 0.1], [0.2, 0.1, 0.8], [0.9, 0.8, 0.3], [0.3, 0.6, 0.5],
+        [0.4, 0.3, 0.7], [0.1, 0.2, 0.9], [0.6, 0.7, 0.8], [0.2, 0.8, 0.1], [0.9, 0.2, 0.4], [0.3, 0.5, 0.6], [0.1, 0.9, 0.2],
+        [0.7, 0.4, 0.6], [0.8, 0.3, 0.2], [0.4, 0.6, 0.3], [0.2, 0.7, 0.9], [0.9, 0.4, 0.8], [0.5, 0.1, 0.3]], np.float32)
+    order = oracle.sort_clusters(pts, [6, 3, 17], [0.1, 0.0, 0.7])
+    assert list(order) == [2, 0, 1]
+
+
+def test_num_clusters_rule(oracle):  # src/core/index.rs:78-80
+    assert oracle.num_clusters(0.4, 10_000) == 40
+    assert oracle.num_clusters(0.4, 1_183_514) == 435
+    assert oracle.num_clusters(0.4, 10_000_000) == 1264
+    assert oracle.num_clusters(0.4, 100_000_000) == 4000
+    assert oracle.num_clusters(0.0001, 10) == 1
