@@ -14,12 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libclann_b200.so")
-SOURCES = ["index.cu", "kernels_build.cu", "kernels_search.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "clann_b200.h")]
+SOURCES = ["index.cu", "kernels_build.cu", "kernels_search.cu", "kernels_probe_cta.cu"]
+HEADERS = ["common.cuh", "kernels.h", "probe_common.cuh", os.path.join("..", "..", "include", "clann_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
 
 
 def _nvcc() -> str:
@@ -29,19 +30,38 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libclann_b200.so cannot be built (there is no CPU fallback)")
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in deps)
+
+
+def needs_build() -> bool:
+    return _stale(LIB_PATH, SOURCES + HEADERS)
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if force or _stale(obj, [src] + HEADERS):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+
+    # one nvcc per translation unit, in parallel (each takes tens of seconds), then one link
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     tmp = LIB_PATH + ".tmp"
-    cmd = [_nvcc(), *NVCC_FLAGS, *[os.path.join(CSRC, f) for f in SOURCES], "-o", tmp]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", tmp]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

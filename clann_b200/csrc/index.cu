@@ -647,6 +647,7 @@ struct clann_index {
         p.stop = d_stop.p;
         p.msd = d_msd.p;
         p.shard_rank = shard_rank;
+        p.max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
         return p;
     }
 

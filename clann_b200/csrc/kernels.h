@@ -66,6 +66,7 @@ struct SearchParams {
     const uint32_t* stop;      // [n_fsets][24][201][stop_words] stop decision bit t (independent.hpp:108-119, host glibc pow)
     const uint8_t* msd;        // [65536] max_sketch_diff by (dot + 32768) (filterer.hpp:108-111, host glibc acosf)
     uint32_t shard_rank;
+    uint32_t max_cluster;      // largest cluster size (sizes the per-CTA similarity memo)
 };
 
 struct QueryBatch {
@@ -98,6 +99,8 @@ void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_
 void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
+void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query
+void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);   // one CTA per query
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 

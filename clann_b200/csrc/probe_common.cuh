@@ -1,0 +1,238 @@
+// Device helpers shared by the probe kernels (kernels_search.cu: one warp per query; kernels_probe_cta.cu: one CTA per
+// query): per-query state, fp32 distance, warp primitives, TopKClosestHeap and MaxBuffer emulation, range helpers.
+// Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#pragma once
+
+#include "kernels.h"
+
+namespace clann {
+
+// ------------------------------------------------------------------------------------------------ query state
+
+// Per-query running state; also the unit exchanged between ranks in the multi-GPU stepping mode.
+struct QueryStateHeader {
+    uint32_t next_pos;   // number of clusters of the visiting order already consumed
+    uint32_t done;       // 1 = search finished (early exit or all clusters seen)
+    uint32_t heap_len;   // entries in the TopKClosestHeap
+    uint32_t visited;    // clusters probed
+    unsigned long long candidates;  // performance.hpp:82-86 summed over visits
+    unsigned long long distcomp;    // performance.hpp:72-76 summed over visits
+    unsigned long long last_key;    // (order_bits(centre distance) << 32 | cluster) of the last consumed cluster, 0 = none
+    unsigned long long pad;
+    // followed by k x u64 heap keys: (order_bits(distance) << 32) | point id
+};
+
+
+
+// angulardata.rs:29-35
+__device__ __forceinline__ float distance_point(const float* __restrict__ row, float row_norm, const float* __restrict__ q, float qn,
+                                                uint32_t d) {
+    float dot = ndarray_dot_thread(row, q, d);
+    float cs = __fdiv_rn(dot, __fmul_rn(row_norm, qn));
+    return __fsub_rn(1.0f, cs);
+}
+
+
+__host__ __device__ inline uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+
+// ------------------------------------------------------------------------------------------------ warp helpers
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t& total) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// Bitonic sort (descending) of 32 u64 keys held one per lane: 15 shuffle steps, no shared memory.
+__device__ __forceinline__ unsigned long long warp_sort_desc32(unsigned long long key) {
+    unsigned long long x = ~key;  // ascending sort of the complement
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (uint32_t kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, x, j);
+            const bool up = (lane & kk) == 0;
+            const bool keep_min = ((lane & j) == 0) == up;
+            const unsigned long long lo = x < other ? x : other, hi = x < other ? other : x;
+            x = keep_min ? lo : hi;
+        }
+    }
+    return ~x;
+}
+
+// Bitonic sort (descending) of P (power of two) u64 keys in shared memory by one warp.
+__device__ __forceinline__ void warp_sort_desc(unsigned long long* keys, uint32_t P) {
+    if (P == 32) {
+        unsigned long long k = keys[lane_id()];
+        __syncwarp();
+        keys[lane_id()] = warp_sort_desc32(k);
+        __syncwarp();
+        return;
+    }
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane_id(); i < P; i += 32) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool desc = (i & kk) == 0;
+                    if ((a < b) == desc) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+
+// heap.rs:23-36 — bounded max-heap on (distance, index): push while not full, else replace the maximum iff the new
+// distance is strictly smaller. Executed by the whole warp; `len` is warp-uniform.
+__device__ __forceinline__ void topk_add(unsigned long long* heap, uint32_t& len, uint32_t cap, float dist, uint32_t id) {
+    unsigned long long key = ((unsigned long long)float_order_bits(dist) << 32) | id;
+    if (len < cap) {
+        if (lane_id() == 0) heap[len] = key;
+        len++;
+        __syncwarp();
+        return;
+    }
+    unsigned long long best = 0;
+    uint32_t where = 0;
+    for (uint32_t i = lane_id(); i < len; i += 32) {
+        unsigned long long v = heap[i];
+        if (v >= best) {
+            best = v;
+            where = i;
+        }
+    }
+    unsigned long long mx = warp_max_u64(best);
+    // strict comparison on the distance only (heap.rs:27)
+    if ((uint32_t)(key >> 32) < (uint32_t)(mx >> 32)) {
+        uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == mx && lane_id() < len)) - 1;
+        if (lane_id() == owner) heap[where] = key;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ unsigned long long topk_peek(const unsigned long long* heap, uint32_t len) {
+    unsigned long long best = 0;
+    for (uint32_t i = lane_id(); i < len; i += 32) {
+        unsigned long long v = heap[i];
+        best = v > best ? v : best;
+    }
+    return warp_max_u64(best);
+}
+
+// maxbuffer.hpp:25-46 — filter(): sort by (value desc, id desc), drop adjacent duplicate ids, keep k,
+// minval = k-th value iff k entries survive. mb holds `inserted` keys; slots up to P are scratch.
+__device__ __forceinline__ void maxbuffer_filter(unsigned long long* mb, uint32_t P, uint32_t k, uint32_t& inserted, uint32_t& minval16) {
+    for (uint32_t i = inserted + lane_id(); i < P; i += 32) mb[i] = 0;  // pad sorts last
+    __syncwarp();
+    warp_sort_desc(mb, P);
+    uint32_t kept = 0;
+    uint32_t prev_id = 0xffffffffu;
+    bool have_prev = false;
+    for (uint32_t base = 0; base < inserted; base += 32) {
+        uint32_t i = base + lane_id();
+        unsigned long long key = (i < inserted) ? mb[i] : 0;
+        uint32_t id = (uint32_t)key;
+        uint32_t left = __shfl_up_sync(0xffffffffu, id, 1);
+        bool keep = i < inserted;
+        if (lane_id() == 0) {
+            if (have_prev && id == prev_id) keep = false;
+        } else if (id == left) {
+            keep = false;
+        }
+        uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        uint32_t pos = kept + __popc(bal & ((1u << lane_id()) - 1));
+        __syncwarp();
+        if (keep) mb[pos] = key;
+        kept += __popc(bal);
+        uint32_t last_valid = (inserted - base) < 32 ? (inserted - base - 1) : 31;
+        prev_id = __shfl_sync(0xffffffffu, id, last_valid);
+        have_prev = true;
+        __syncwarp();
+    }
+    inserted = kept < k ? kept : k;
+    if (inserted == k && k != 0) minval16 = (uint32_t)(mb[k - 1] >> 32);
+    __syncwarp();
+}
+
+// maxbuffer.hpp:64-76 for a list of candidates in order: reject sim <= minval; an accepted entry that finds all 2k slots
+// taken first runs filter() and is then stored WITHOUT being re-checked against the new minval (:68-75).
+__device__ __forceinline__ void maxbuffer_insert_list(unsigned long long* mb, uint32_t P, uint32_t k, uint32_t& inserted,
+                                                      uint32_t& minval16, const uint32_t* ids, const uint16_t* sims, uint32_t count) {
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = (i < count) ? sims[i] : 0;
+        const uint32_t id = (i < count) ? ids[i] : 0;
+        const unsigned long long key = ((unsigned long long)v << 32) | id;
+        uint32_t todo = __ballot_sync(0xffffffffu, i < count);
+        while (todo) {
+            const bool accept = ((todo >> lane) & 1u) && v > minval16;
+            const uint32_t acc = __ballot_sync(0xffffffffu, accept);
+            if (!acc) break;
+            const uint32_t space = 2 * k - inserted;
+            const uint32_t nacc = __popc(acc);
+            const uint32_t rank = __popc(acc & ((1u << lane) - 1));
+            if (nacc <= space) {
+                if (accept) mb[inserted + rank] = key;
+                inserted += nacc;
+                __syncwarp();
+                break;
+            }
+            if (accept && rank < space) mb[inserted + rank] = key;
+            inserted += space;
+            __syncwarp();
+            const uint32_t trig = __fns(acc, 0, space + 1);  // lane of the accepted entry that finds the buffer full
+            maxbuffer_filter(mb, P, k, inserted, minval16);
+            if (lane == trig) mb[inserted] = key;
+            inserted += 1;
+            __syncwarp();
+            todo &= ~((2u << trig) - 1);
+        }
+    }
+}
+
+
+struct ProbeCounters {
+    unsigned long long candidates, distcomp;
+};
+
+__device__ __forceinline__ uint32_t lcp24(uint32_t a, uint32_t b) {
+    uint32_t x = (a ^ b) & 0xffffffu;
+    return x ? (uint32_t)(__clz(x) - 8) : 24u;
+}
+
+// number of leading samples (of 8 byte-packed lcp values) that are >= depth
+__device__ __forceinline__ uint32_t lead_count(uint2 packed, uint32_t depth) {
+    uint32_t rep = depth * 0x01010101u;
+    uint32_t m0 = __vcmpgeu4(packed.x, rep), m1 = __vcmpgeu4(packed.y, rep);
+    return (uint32_t)(__popc(m0) + __popc(m1)) >> 3;
+}
+
+
+}  // namespace clann

@@ -798,7 +798,16 @@ typedef struct {
     hp_elem* e;
     uint32_t len, cap;
 } topk;
-static int hp_less(hp_elem a, hp_elem b) { return a.dist < b.dist || (a.dist == b.dist && a.idx < b.idx); }
+/* ordered-float 4.6.0 total order (Cargo.lock): NaN is greater than every number and equal to itself */
+static int of_cmp(float a, float b) {
+    int an = a != a, bn = b != b;
+    if (an || bn) return an - bn;
+    return (a > b) - (a < b);
+}
+static int hp_less(hp_elem a, hp_elem b) {
+    int c = of_cmp(a.dist, b.dist);
+    return c < 0 || (c == 0 && a.idx < b.idx);
+}
 static uint32_t hp_max(const topk* h) {
     uint32_t m = 0;
     for (uint32_t i = 1; i < h->len; i++)
@@ -812,7 +821,7 @@ static int hp_add(topk* h, hp_elem x) { /* heap.rs:23-36 */
     }
     if (h->len == 0) return 1; /* k == 0: `else if let Some(max)` is skipped and true is returned */
     uint32_t m = hp_max(h);
-    if (x.dist < h->e[m].dist) {
+    if (of_cmp(x.dist, h->e[m].dist) < 0) {
         h->e[m] = x;
         return 1;
     }
@@ -821,8 +830,8 @@ static int hp_add(topk* h, hp_elem x) { /* heap.rs:23-36 */
 static int hp_cmp(const void* a, const void* b) {
     const hp_elem* x = (const hp_elem*)a;
     const hp_elem* y = (const hp_elem*)b;
-    if (x->dist < y->dist) return -1;
-    if (x->dist > y->dist) return 1;
+    int c = of_cmp(x->dist, y->dist); /* to_list's partial_cmp().unwrap() would panic on a NaN; here NaN sorts last */
+    if (c) return c;
     if (x->idx < y->idx) return -1; /* tie order inside std's BinaryHeap::iter() is unspecified; ids ascending here */
     if (x->idx > y->idx) return 1;
     return 0;
