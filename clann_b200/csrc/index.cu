@@ -268,6 +268,7 @@ struct clann_index {
     DevBuf<uint32_t> d_assign, d_centers, d_sizes, d_perm, d_fset_of;
     DevBuf<uint64_t> d_keys, d_offsets;
     DevBuf<uint8_t> d_brute, d_owner, d_msd;
+    DevBuf<uint32_t> d_msd_thr;
     // device: PUFFINN layer
     DevBuf<int16_t> d_q15, d_planes;
     DevBuf<uint64_t> d_sketches;
@@ -500,6 +501,16 @@ struct clann_index {
         d_signbits.upload(all_signs, s);
         build_msd_table(h_msd);
         d_msd.upload(h_msd, s);
+        {
+            // threshold form of the same table for the probe kernel: the table is non-increasing in v, so
+            // msd[v] = #{m in [0,64) : thr[m] > v} with thr[m] = smallest v whose entry is <= m
+            std::vector<uint32_t> thr(64, 65536u);
+            for (uint32_t v = 65536; v-- > 0;) {
+                if (v + 1 < 65536 && h_msd[v] < h_msd[v + 1]) throw StatusError(CLANN_ERR_CUDA, "max_sketch_diff table is not monotone");
+                for (uint32_t m = h_msd[v]; m < 64; m++) thr[m] = v;
+            }
+            d_msd_thr.upload(thr, s);
+        }
         CLANN_CUDA(cudaStreamSynchronize(s));
         stop_recall = -1.0f;
     }
@@ -646,6 +657,7 @@ struct clann_index {
         p.owner = d_owner.p;
         p.stop = d_stop.p;
         p.msd = d_msd.p;
+        p.msd_thr = d_msd_thr.p;
         p.shard_rank = shard_rank;
         p.max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
         return p;

@@ -65,6 +65,7 @@ struct SearchParams {
     const uint8_t* owner;      // [K] owning shard (multi-GPU), all 0 on one GPU
     const uint32_t* stop;      // [n_fsets][24][201][stop_words] stop decision bit t (independent.hpp:108-119, host glibc pow)
     const uint8_t* msd;        // [65536] max_sketch_diff by (dot + 32768) (filterer.hpp:108-111, host glibc acosf)
+    const uint32_t* msd_thr;   // [64] msd_thr[m] = smallest v with msd[v] <= m (msd is non-increasing): msd[v] = #{m : msd_thr[m] > v}
     uint32_t shard_rank;
     uint32_t max_cluster;      // largest cluster size (sizes the per-CTA similarity memo)
 };
