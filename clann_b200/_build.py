@@ -50,7 +50,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         if force or _stale(obj, [src] + HEADERS):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+            extra = os.environ.get("CLANN_NVCC_EXTRA", "").split()  # e.g. -DCLANN_TIMING for the instrumented debug build
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.run(cmd, check=True, cwd=CSRC)

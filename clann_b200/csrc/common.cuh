@@ -39,7 +39,20 @@ struct RowTile {
     uint32_t out_row0;  // first row in the output array
     uint32_t count;     // 1..32
     uint32_t fset;      // function set id
+    // table codes only: when code_stride != 0 the code of table t for row r of the tile goes to codes[code_base + t*code_stride + r]
+    // (index build: cluster-major tables), otherwise to the launcher's [fset][table][row] layout (query batches)
+    uint32_t code_stride;
+    uint32_t pad;
+    uint64_t code_base;
 };
+
+// Cluster-major table layout: the L tables of a cluster are adjacent, so that everything one (query, cluster) visit touches
+// lies in a handful of 2 MB pages (measured on B200: random reads over an L2-resident working set drop from 288 to 37 G
+// sectors/s once it is spread over more pages than the TLB covers — profiles/micro/tlb_spread.cu). Entry i of table t of the
+// cluster whose rows start at `off` (nc rows) is at L*off + t*nc + i; its directory at (c*L + t)*kDirEntries.
+__host__ __device__ inline uint64_t table_base(uint64_t off, uint32_t nc, uint32_t L, uint32_t t) {
+    return (uint64_t)L * off + (uint64_t)t * nc;
+}
 
 // Geometry of the hash family for dimension d (independent.hpp:29-33, crosspolytope.hpp:301-303, generic.hpp:34-40).
 struct HashGeom {

@@ -272,7 +272,7 @@ struct clann_index {
     // device: PUFFINN layer
     DevBuf<int16_t> d_q15, d_planes;
     DevBuf<uint64_t> d_sketches;
-    DevBuf<uint32_t> d_tbl_hash, d_tbl_idx, d_signbits, d_stop;
+    DevBuf<uint32_t> d_tbl_hash, d_tbl_idx, d_tbl_dir, d_signbits, d_stop;
     uint32_t stop_words = 0;
     float stop_recall = -1.0f;
 
@@ -585,7 +585,8 @@ struct clann_index {
             if (shard_count > 1 && h_owner[c] != shard_rank) continue;  // other ranks build their own clusters
             for (uint32_t r = 0; r < h_sizes[c]; r += 32) {
                 uint32_t row0 = (uint32_t)h_offsets[c] + r;
-                tiles.push_back(RowTile{row0, row0, std::min<uint32_t>(32, h_sizes[c] - r), h_fset_of[c]});
+                tiles.push_back(RowTile{row0, row0, std::min<uint32_t>(32, h_sizes[c] - r), h_fset_of[c], h_sizes[c], 0,
+                                        (uint64_t)g.L * h_offsets[c] + r});
             }
             max_len = std::max(max_len, h_sizes[c]);
         }
@@ -602,7 +603,7 @@ struct clann_index {
             if (h_brute[c] || h_sizes[c] == 0) continue;
             if (shard_count > 1 && h_owner[c] != shard_rank) continue;
             for (uint32_t t = 0; t < g.L; t++) {
-                SortSegment sg{(uint64_t)t * n + h_offsets[c], 0, h_sizes[c], 0};
+                SortSegment sg{table_base(h_offsets[c], h_sizes[c], g.L, t), 0, h_sizes[c], 0};
                 if (h_sizes[c] > cap) {
                     sg.scratch_base = scratch_total;
                     scratch_total += h_sizes[c];
@@ -618,6 +619,17 @@ struct clann_index {
             scratch_i.alloc(scratch_total);
         }
         launch_segment_sort(d_segs.p, (uint32_t)segs.size(), max_len, d_tbl_hash.p, d_tbl_idx.p, scratch_k.p, scratch_i.p, s);
+        {
+            // bucket directory over the top 8 code bits of every table this rank built
+            std::vector<uint8_t> skip(K);
+            for (uint32_t c = 0; c < K; c++)
+                skip[c] = h_brute[c] || h_sizes[c] == 0 || (shard_count > 1 && h_owner[c] != shard_rank);
+            DevBuf<uint8_t> d_skip;
+            d_skip.upload(skip, s);
+            d_tbl_dir.alloc((size_t)g.L * K * kDirEntries);
+            launch_build_dir(d_tbl_hash.p, n, d_offsets.p, d_skip.p, K, g.L, d_tbl_dir.p, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));
+        }
         CLANN_CUDA(cudaEventRecord(e3, s));
         CLANN_CUDA(cudaStreamSynchronize(s));
         CLANN_CUDA(cudaGetLastError());
@@ -649,6 +661,7 @@ struct clann_index {
         p.sketches = d_sketches.p;
         p.tbl_hash = d_tbl_hash.p;
         p.tbl_idx = d_tbl_idx.p;
+        p.tbl_dir = d_tbl_dir.p;
         p.center_rows = d_center_rows.p;
         p.center_norms = d_center_norms.p;
         p.radii = d_radii.p;
@@ -690,7 +703,7 @@ struct clann_index {
         std::vector<RowTile> tiles;
         for (uint32_t f = 0; f < F; f++)
             for (uint64_t q0 = 0; q0 < nq; q0 += 32)
-                tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f});
+                tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
         w_tiles.upload(tiles, s);
         w_ntiles = (uint32_t)tiles.size();
         ws_nq = nq;
@@ -748,7 +761,7 @@ struct clann_index {
             std::vector<RowTile> tiles;
             for (uint32_t f = 0; f < n_fsets(); f++)
                 for (uint64_t q0 = 0; q0 < nq; q0 += 32)
-                    tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)q0, (uint32_t)std::min<uint64_t>(32, nq - q0), f});
+                    tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)q0, (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
             w_tiles_codes.upload(tiles, s);
             CLANN_CUDA(cudaStreamSynchronize(s));
             w_tiles_codes_nq = nq;
@@ -1027,8 +1040,8 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 if (dst) {
                     if (cap < bytes) throw StatusError(CLANN_ERR_BOUNDS, "export buffer too small");
                     const uint32_t* src = what == CLANN_X_TABLE_HASHES ? index->d_tbl_hash.p : index->d_tbl_idx.p;
-                    CLANN_CUDA(cudaMemcpy2D(dst, (size_t)nc * 4, src + index->h_offsets[arg], index->n * 4, (size_t)nc * 4, L,
-                                            cudaMemcpyDeviceToHost));
+                    // cluster-major layout: the L tables of the cluster are adjacent
+                    CLANN_CUDA(cudaMemcpy(dst, src + table_base(index->h_offsets[arg], nc, L, 0), bytes, cudaMemcpyDeviceToHost));
                 }
                 break;
             }

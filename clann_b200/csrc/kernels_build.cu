@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(256) k_codes(const int16_t* __restrict__ q15, 
         code = (code << g.bpf) | h;
     }
     code >>= g.cut;
-    if (lane_id() < tile.count)
-        codes[(uint64_t)tile.fset * fset_stride + (uint64_t)t * code_stride + tile.out_row0 + lane_id()] = (uint32_t)code;
+    if (lane_id() < tile.count) {
+        if (tile.code_stride) codes[tile.code_base + (uint64_t)t * tile.code_stride + lane_id()] = (uint32_t)code;
+        else codes[(uint64_t)tile.fset * fset_stride + (uint64_t)t * code_stride + tile.out_row0 + lane_id()] = (uint32_t)code;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ segmented radix sort
@@ -530,6 +532,30 @@ void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_
         configured = smem;
     }
     k_segment_sort<<<n_segs, kSortThreads, smem, s>>>(segs, cap, keys, idx, scratch_keys, scratch_idx);
+}
+
+// One CTA per (table, cluster): thread b finds the lower bound of (b << 16) in the sorted 24-bit codes of the segment.
+__global__ void __launch_bounds__(320) k_build_dir(const uint32_t* __restrict__ tbl_hash, uint64_t n, const uint64_t* __restrict__ offsets,
+                                                   const uint8_t* __restrict__ skip, uint32_t K, uint32_t* __restrict__ dir) {
+    const uint32_t c = blockIdx.x, t = blockIdx.y, b = threadIdx.x;
+    if (b >= kDirEntries || skip[c]) return;
+    const uint64_t off = offsets[c];
+    const uint32_t nc = (uint32_t)(offsets[c + 1] - off);
+    const uint32_t* H = tbl_hash + table_base(off, nc, gridDim.y, t);
+    const uint32_t key = b << (kMaxHashBits - kDirBits);
+    uint32_t lo = 0, len = nc;
+    while (len > 0) {
+        uint32_t half = len >> 1, mid = lo + half;
+        if (__ldg(H + mid) < key) { lo = mid + 1; len -= half + 1; } else { len = half; }
+    }
+    dir[((uint64_t)c * gridDim.y + t) * kDirEntries + b] = lo;
+}
+
+void launch_build_dir(const uint32_t* tbl_hash, uint64_t n, const uint64_t* offsets, const uint8_t* skip, uint32_t K, uint32_t L,
+                      uint32_t* dir, cudaStream_t s) {
+    if (K == 0 || L == 0) return;
+    dim3 grid(K, L);
+    k_build_dir<<<grid, 320, 0, s>>>(tbl_hash, n, offsets, skip, K, dir);
 }
 
 void launch_cp_estimates(uint32_t m, uint32_t reps, uint64_t seed, float* est, uint32_t* scratch_counts, cudaStream_t s) {

@@ -1,29 +1,32 @@
-// k_probe_cta — the CLANN search loop with ONE CTA (4 warps) PER QUERY, organised so that no global-memory latency sits
-// on the sequential part of puffinn::Index::search_maps.
+// k_probe_cta — the CLANN search loop with ONE CTA (4 warps) PER QUERY, warp-specialised so that no global-memory latency
+// sits on the sequential part of puffinn::Index::search_maps and the sequential part overlaps the memory-bound part.
 //
 // Same results, bit for bit, as the one-warp-per-query kernel in kernels_search.cu (which stays as the plain
-// restatement and serves the legacy single-query ABI). What changes is the schedule of one (query, cluster) visit:
+// restatement and serves the legacy single-query ABI). What changes is the schedule of one (query, cluster) visit.
+// Per depth the segment stream is cut into CHUNKS of 384 segments (12 ring sweeps, 1536 candidates); chunk boundaries
+// do not depend on the data (every batch of the reference ends on a ring boundary), so chunks can be prepared ahead:
 //
-//   per depth, the segment stream is consumed in CHUNKS of 512 segments (16 ring sweeps, 2048 candidates):
-//   phase A  all 128 threads: table indices of the chunk, the sketch word of every candidate (ring slot = segment
-//            number mod 32) -> its Hamming distance to the query sketch, one byte per candidate in shared memory.
-//            The distance is kept instead of a pass/fail bit because the filter threshold only ever tightens during a
-//            visit (filterer.hpp:108-111 is monotone in the k-th similarity), so any later threshold can be applied
-//            without touching global memory again.
-//   phase B  Q15 similarity of every candidate that passes the threshold in force at the start of the chunk. A per-CTA
-//            memo (one u16 per local id) returns similarities already computed during this visit — the reference
-//            rescans nested ranges at every depth, so more than half of its distance computations are repeats (the
-//            counter still counts them). Missing rows are gathered by the TMA unit, one bulk asynchronous copy per row
-//            (cp.async.bulk global -> shared, completion on an mbarrier) into bank-conflict-free padded slots, and two
-//            threads reduce each row against the query.
-//   phase C  warp 0 replays the reference's sequential loop over the chunk out of shared memory only: ring sweeps in
-//            order (lane = ring slot), the 128-entry passing buffer, the index-as-sketch tail (collection.hpp:890-893),
-//            MaxBuffer inserts, threshold update, stop rule. A batch may straddle chunks; the stop rule may end the
-//            visit in the middle of a chunk (the rest of the chunk was speculative work).
+//   PRODUCERS (warps 1-3, 96 threads), one chunk ahead of the consumer through a two-slot ring in shared memory
+//   ranges   per depth: get_next_range in closed form for every table, prefix sum -> segment stream
+//   phase A  table indices of the chunk and the sketch word of every candidate (ring slot = segment number mod 32) ->
+//            its Hamming distance to the query sketch, one byte per candidate. The distance is kept instead of a
+//            pass/fail bit because the filter threshold only ever tightens during a visit (filterer.hpp:108-111 is
+//            monotone in the k-th similarity): the consumer applies whatever threshold is in force when it gets there.
+//   phase B  Q15 similarity of every candidate that passes the (possibly stale, hence looser) threshold the producers
+//            last saw. A per-CTA memo (one u16 per local id) returns similarities already computed during this visit —
+//            the reference rescans nested ranges at every depth, so more than half of its distance computations are
+//            repeats (the counter still counts them). Missing rows are read with 128-bit loads, four lanes per row.
+//   CONSUMER (warp 0) replays the reference's sequential loop out of shared memory only: ring sweeps in order (lane =
+//            ring slot), the 128-entry passing buffer, the index-as-sketch tail (collection.hpp:890-893), MaxBuffer
+//            inserts, threshold update, stop rule. A batch may straddle chunks; the stop rule may end the visit in the
+//            middle of a chunk (what the producers prepared beyond that point was speculative).
+//   Hand-over: one mbarrier pair (full / empty) per slot; an END record closes every visit so both sides always see
+//            the same number of chunks and the barrier phases stay in step across visits.
 //
 // Queries are scheduled in nearest-cluster order and only (SMs x CTAs/SM) of them are in flight, so the clusters being
 // probed at any moment (rows + sketches + tables, ~3 MB each at the glove-100 shape) stay resident in the 126 MB L2.
 // Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -31,67 +34,100 @@
 
 namespace clann {
 
+#ifdef CLANN_TIMING
+// Debug build only (-DCLANN_TIMING): clock64 totals per phase, summed over CTAs, printed by the launcher.
+enum { T_SETUP, T_RANGES, T_WAIT_EMPTY, T_A, T_B, T_HAND, T_WAIT_FULL, T_C, T_VISIT, T_QUERY, T_SELECT, T_FINAL, T_CHUNKS, T_VISITS, T_N };
+__device__ unsigned long long g_timing[T_N];
+#define TSTART(var) long long var = clock64()
+#define TADD(slot, var) do { long long _n = clock64(); t_acc[slot] += (unsigned long long)(_n - var); var = _n; } while (0)
+#define TDECL unsigned long long t_acc[T_N] = {0}
+#define TARG , unsigned long long* t_acc
+#define TPASS , t_acc
+#else
+#define TSTART(var)
+#define TADD(slot, var)
+#define TDECL
+#define TARG
+#define TPASS
+#endif
+
 constexpr int kCtaWarps = 4;
 constexpr int kCtaThreads = kCtaWarps * 32;
-constexpr uint32_t kSegPerThread = 4;                              // consecutive segments handled by one thread in phase A
-constexpr uint32_t kChunkSegs = kCtaThreads * kSegPerThread;       // 512 segments = 16 ring sweeps per chunk
-constexpr uint32_t kChunkCand = kChunkSegs * 4;                    // 2048 candidates
-constexpr uint32_t kStageRows = 64;                                // Q15 rows gathered per bulk-copy round (2 threads per row)
-constexpr uint32_t kNeedMore = 1u;
+constexpr uint32_t kProducers = kCtaThreads - 32;                  // warps 1..3
+constexpr uint32_t kSegPerThread = 4;                              // consecutive segments handled by one producer in phase A
+constexpr uint32_t kChunkSegs = kProducers * kSegPerThread;        // 384 segments = 12 ring sweeps per chunk
+constexpr uint32_t kChunkCand = kChunkSegs * 4;                    // 1536 candidates
+constexpr uint32_t kRowsPerIter = kProducers / 4;                  // phase B: four lanes per row
+constexpr uint32_t kSlots = 2;
+constexpr uint32_t kNeedMore = 1u, kDepthDone = 0u, kStopped = 2u;
 
 struct CtaCtrl {
     unsigned long long nk, top;
-    unsigned long long mbar;  // mbarrier of the bulk row copies
-    unsigned long long candidates, distcomp;  // performance.hpp:72-86, running totals of the query
+    unsigned long long full[kSlots], empty[kSlots];  // mbarriers of the chunk ring
+    unsigned long long candidates, distcomp;         // performance.hpp:72-86, running totals of the query
     uint32_t work, heap_len, result_cnt;
-    uint32_t inserted, minval16, max_diff, stopped;  // search_maps state carried between chunks
-    uint32_t base, np, status;
+    uint32_t inserted, minval16;                     // MaxBuffer state at the end of the visit (consumer -> everyone)
+    volatile uint32_t max_diff, stopped;             // consumer -> producers (advisory threshold, stop flag)
+    uint32_t p_md, p_stop;                           // the producers' uniform copy of the two, refreshed once per chunk
     uint32_t unk_cnt, tail_unk;
     uint32_t warp_tot[kCtaWarps];
 };
 static_assert(sizeof(CtaCtrl) <= 128, "CtaCtrl must fit its 128-byte slot");
 
+// Chunk record: what the producers hand to the consumer.
+struct SlotMeta {
+    uint32_t depth;  // 0 = END of the visit
+    uint32_t S;      // segments in the stream of this depth
+    uint32_t cb, ce; // stream segments [cb, ce) are in the slot
+    uint32_t md;     // every candidate with Hamming distance <= md has its similarity in csim
+    uint32_t pad[3];
+};
+
 struct CtaSmem {
     CtaCtrl* ctrl;
     uint64_t* qsk;              // [32] query sketches of the function set in use
     int* qrow2;                 // [sl] query in Q15, doubled (see q15_mul_hi)
-    uint8_t* stage;             // [kStageRows][stage_stride] gathered Q15 rows
-    uint32_t* cid;              // [kChunkCand] local ids of the chunk's candidates, stream order
-    uint16_t* csim;             // [kChunkCand] similarity (dot + 32768) of the candidates that pass the chunk threshold
+    // chunk ring
+    uint8_t* ring;              // kSlots records of slot_bytes each:
+    uint32_t slot_bytes;
+    //   cid  [kChunkCand] u32  local ids of the chunk's candidates, stream order
+    //   csim [kChunkCand] u16  similarity (dot + 32768) of the candidates with distance <= meta.md
+    //   cpc  [kChunkCand] u8   Hamming distances
+    //   segb [L+1] u32         copy of segbase for the stop rule's table lookup
+    //   meta SlotMeta
+    __device__ __forceinline__ uint32_t* cid(uint32_t slot) const { return reinterpret_cast<uint32_t*>(ring + slot * slot_bytes); }
+    __device__ __forceinline__ uint16_t* csim(uint32_t slot) const { return reinterpret_cast<uint16_t*>(ring + slot * slot_bytes + kChunkCand * 4); }
+    __device__ __forceinline__ uint32_t* cpc(uint32_t slot) const { return reinterpret_cast<uint32_t*>(ring + slot * slot_bytes + kChunkCand * 6); }
+    __device__ __forceinline__ uint32_t* segb(uint32_t slot) const { return reinterpret_cast<uint32_t*>(ring + slot * slot_bytes + kChunkCand * 7); }
+    __device__ __forceinline__ SlotMeta* meta(uint32_t slot) const { return reinterpret_cast<SlotMeta*>(ring + (slot + 1) * slot_bytes - 32); }
+    // producers
     uint16_t* unk;              // [kChunkCand] chunk positions whose similarity is not memoised yet
-    uint32_t* cpc;              // [kChunkCand / 4] Hamming distances, one byte per candidate
     uint2* lcp_up;              // [L]
     uint2* lcp_dn;              // [L]
-    unsigned long long* mb;     // [P2K] MaxBuffer slots
-    unsigned long long* heap;   // [k]
-    unsigned long long* loc;    // [k]
     uint32_t* anchor;           // [L]
     uint32_t* code;             // [L]
     uint32_t* start;            // [L]
     uint32_t* segbase;          // [L+1]
+    // consumer
+    unsigned long long* mb;     // [P2K] MaxBuffer slots
+    unsigned long long* heap;   // [k]
+    unsigned long long* loc;    // [k]
     uint32_t* pass_idx;         // [kPassingCap]
     uint16_t* pass_sim;         // [kPassingCap]
+    uint16_t* tunk;             // [4 * kRing] passing-list positions of tail entries without a prefetched similarity
 };
 
-// Row slots are padded to a number of 16-byte units that is 2 modulo 8: two threads per row reading alternate units
-// then hit eight distinct bank groups per quarter warp.
-__host__ __device__ inline uint32_t stage_stride_units(uint32_t sl) {
-    uint32_t u = sl / 8;
-    while ((u & 7u) != 2u) u++;
-    return u;
-}
+__host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 __host__ __device__ inline uint32_t cta_smem_bytes(uint32_t L, uint32_t k, uint32_t sl) {
     uint32_t p2k = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
-    uint32_t b = 128 + 32 * 8;                            // ctrl, qsk
-    b += sl * 4;                                          // qrow2
-    b += kStageRows * stage_stride_units(sl) * 16;        // stage
-    b += kChunkCand * 4;                                  // cid
-    b += L * 8 * 2 + p2k * 8 + k * 8 * 2;                 // lcp_up, lcp_dn, mb, heap, loc
-    b += L * 4 * 3 + (L + 1) * 4 + kPassingCap * 4;       // anchor, code, start, segbase, pass_idx
-    b += kChunkCand;                                      // cpc
-    b += kChunkCand * 2 * 2 + kPassingCap * 2;            // csim, unk, pass_sim
-    return (b + 15) & ~15u;
+    uint32_t b = 128 + 32 * 8 + sl * 4;                                                        // ctrl, qsk, qrow2
+    b += kSlots * (kChunkCand * 4 + kChunkCand * 2 + kChunkCand + align16((L + 1) * 4) + 32);  // ring
+    b += kChunkCand * 2;                                                                       // unk
+    b += L * 8 * 2 + p2k * 8 + k * 8 * 2;                                                      // lcp_up, lcp_dn, mb, heap, loc
+    b += L * 4 * 3 + (L + 1) * 4 + kPassingCap * 4;                                            // anchor, code, start, segbase, pass_idx
+    b += kPassingCap * 2 + 4 * kRing * 2;                                                      // pass_sim, tunk
+    return align16(b);
 }
 
 __device__ __forceinline__ CtaSmem carve_cta(uint8_t* base, uint32_t L, uint32_t k, uint32_t sl) {
@@ -101,11 +137,10 @@ __device__ __forceinline__ CtaSmem carve_cta(uint8_t* base, uint32_t L, uint32_t
     s.ctrl = reinterpret_cast<CtaCtrl*>(p); p += 128;
     s.qsk = reinterpret_cast<uint64_t*>(p); p += 32 * 8;
     s.qrow2 = reinterpret_cast<int*>(p); p += sl * 4;
-    s.stage = p; p += kStageRows * stage_stride_units(sl) * 16;
-    s.cid = reinterpret_cast<uint32_t*>(p); p += kChunkCand * 4;
-    s.csim = reinterpret_cast<uint16_t*>(p); p += kChunkCand * 2;
+    s.ring = p;
+    s.slot_bytes = kChunkCand * 7 + align16((L + 1) * 4) + 32;
+    p += kSlots * s.slot_bytes;
     s.unk = reinterpret_cast<uint16_t*>(p); p += kChunkCand * 2;
-    s.cpc = reinterpret_cast<uint32_t*>(p); p += kChunkCand;
     s.lcp_up = reinterpret_cast<uint2*>(p); p += L * 8;
     s.lcp_dn = reinterpret_cast<uint2*>(p); p += L * 8;
     s.mb = reinterpret_cast<unsigned long long*>(p); p += p2k * 8;
@@ -116,34 +151,31 @@ __device__ __forceinline__ CtaSmem carve_cta(uint8_t* base, uint32_t L, uint32_t
     s.start = reinterpret_cast<uint32_t*>(p); p += L * 4;
     s.segbase = reinterpret_cast<uint32_t*>(p); p += (L + 1) * 4;
     s.pass_idx = reinterpret_cast<uint32_t*>(p); p += kPassingCap * 4;
-    s.pass_sim = reinterpret_cast<uint16_t*>(p);
+    s.pass_sim = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
+    s.tunk = reinterpret_cast<uint16_t*>(p);
     return s;
 }
 
-// --- mbarrier + bulk asynchronous copy (TMA unit, SASS: UBLKCP / SYNCS)
+// --- mbarriers (SASS: SYNCS) and the producers' named barrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok;
+    uint32_t ok, spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();  // watchdog: a broken hand-over protocol must fail loudly, not hang the GPU
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
 
 __device__ __forceinline__ uint32_t ldg_nc_na_u32(const uint32_t* p) {
     uint32_t v;
@@ -155,9 +187,40 @@ __device__ __forceinline__ uint64_t ldg_nc_na_u64(const uint64_t* p) {
     asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ldg_nc_na_v4(const uint4* p) {
+    uint4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// Ask the TMA unit to stream [ptr, ptr+bytes) into L2 (SASS: UBLKPF). The range is widened to 16-byte boundaries.
+__device__ __forceinline__ void l2_prefetch_range(const void* ptr, uint64_t bytes) {
+    uint64_t a = reinterpret_cast<uint64_t>(ptr);
+    const uint64_t end = (a + bytes + 15ull) & ~15ull;
+    a &= ~15ull;
+    const uint32_t sz = (uint32_t)(end - a);
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(sz) : "memory");
+}
+
+// Streams everything a visit of cluster c can touch (Q15 rows, sketches, the cluster's slice of every table) into L2:
+// sequential DRAM traffic at full bandwidth instead of the random 32-byte reads the probe itself would issue.
+__device__ __forceinline__ void l2_prefetch_cluster(const SearchParams& p, uint32_t c) {
+    if (p.brute[c]) return;
+    const uint64_t off = p.offsets[c];
+    const uint64_t nc = p.offsets[c + 1] - off;
+    constexpr uint64_t kPiece = 32 * 1024;
+    const uint8_t* base[4] = {reinterpret_cast<const uint8_t*>(p.q15 + off * p.g.sl), reinterpret_cast<const uint8_t*>(p.sketches + off * kNumSketches),
+                              reinterpret_cast<const uint8_t*>(p.tbl_hash + (uint64_t)p.g.L * off),
+                              reinterpret_cast<const uint8_t*>(p.tbl_idx + (uint64_t)p.g.L * off)};
+    const uint64_t len[4] = {nc * p.g.sl * 2, nc * kNumSketches * 8, nc * p.g.L * 4, nc * p.g.L * 4};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+        for (uint64_t lo = (uint64_t)threadIdx.x * kPiece; lo < len[a]; lo += (uint64_t)blockDim.x * kPiece)
+            l2_prefetch_range(base[a] + lo, lo + kPiece < len[a] ? kPiece : len[a] - lo);
+}
 
 // One term of math.hpp:37-44, (a*b + 2^14) >> 15, for a given in the HIGH half of a 32-bit word and b doubled:
-// (a*2^16) * (2b) + 2^31 = 2^17 (a*b + 2^14), whose upper word is the term. One IMAD.WIDE, no shift.
+// (a*2^16) * (2b) + 2^31 = 2^17 (a*b + 2^14), whose upper word is the term (one IMAD.HI with a 64-bit addend, no shift).
 __device__ __forceinline__ int q15_mul_hi(int a_hi16, int b2) {
     return (int)(((long long)a_hi16 * (long long)b2 + 0x80000000ll) >> 32);
 }
@@ -196,134 +259,80 @@ __device__ __forceinline__ uint32_t warp_excl_scan3(uint32_t cnt, uint32_t& tota
     return __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
 }
 
-// One PUFFINN query against cluster c by the whole CTA (collection.hpp:543-601 -> search_maps :768-948).
-// Returns the number of results; sm.mb[0..cnt) holds them best first.
-__device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
-                                      uint64_t code_stride, const uint32_t* __restrict__ stop, float max_sim, uint16_t* memo,
-                                      uint32_t& phase) {
-    const uint32_t L = p.g.L, k = p.k, sl = p.g.sl;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t off = p.offsets[c];
-    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
-    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+struct VisitArgs {
+    uint32_t c;                 // cluster
+    const uint32_t* codes;      // this query's code of table 0 (stride code_stride)
+    uint64_t code_stride;
+    const uint32_t* stop;       // stop table of the function set
+    float max_sim;
+    uint16_t* memo;             // per-CTA similarity memo or null
+};
+
+// ------------------------------------------------------------------------------------------------ producers (warps 1-3)
+__device__ __forceinline__ void produce_visit(const SearchParams& p, const CtaSmem& sm, const VisitArgs& a, uint32_t& it TARG) {
+    const uint32_t L = p.g.L, sl = p.g.sl;
+    const uint32_t ptid = threadIdx.x - 32, pwarp = ptid >> 5, lane = threadIdx.x & 31;
+    const uint64_t off = p.offsets[a.c];
+    const uint32_t nc = (uint32_t)(p.offsets[a.c + 1] - off);
     const int16_t* rows = p.q15 + off * sl;
     const uint64_t* sk = p.sketches + off * kNumSketches;
+    uint16_t* memo = a.memo;
     CtaCtrl* ctrl = sm.ctrl;
     const uint32_t cpr = sl / 8;
-    const uint32_t sunits = stage_stride_units(sl);
+    bool stop_seen = false;
+    TSTART(tp);
 
-    if (memo) {
-        uint4* mz = reinterpret_cast<uint4*>(memo);
-        for (uint32_t i = tid; i < (nc + 7) / 8; i += kCtaThreads) mz[i] = make_uint4(0, 0, 0, 0);
-    }
-    // --- SearchBuffers ctor (collection.hpp:642-645): one thread per table
-    for (uint32_t t = tid; t < L; t += kCtaThreads) {
-        const uint32_t h = codes[(uint64_t)t * code_stride];
-        const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
-        uint32_t lo = 0, len = nc;  // lower_bound == the reference's hinted halving search
-        while (len > 0) {
-            uint32_t half = len >> 1, mid = lo + half;
-            if (__ldg(H + mid) < h) { lo = mid + 1; len -= half + 1; } else { len = half; }
-        }
-        sm.code[t] = h;
-        sm.anchor[t] = lo;
-        uint32_t up[8], dn[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t pu = lo + kSegment * j;
-            up[j] = pu < nc ? lcp24(__ldg(H + pu), h) : 0u;  // beyond the data lie the 0xffffffff sentinels (prefixmap.hpp:215-226)
-            int64_t pd = (int64_t)lo - 1 - kSegment * j;
-            dn[j] = pd >= 0 ? lcp24(__ldg(H + pd), h) : 0u;
-        }
-        sm.lcp_up[t] = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
-        sm.lcp_dn[t] = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
-    }
-    if (tid == 0) {
-        ctrl->inserted = 0;            // maxbuffer.hpp:53-55
-        ctrl->minval16 = 0;
-        ctrl->max_diff = kSketchBits;  // filterer.hpp:101
-        ctrl->stopped = 0;
-    }
-    __syncthreads();
-    const uint64_t my_sketch = sm.qsk[lane];  // ring slot == lane (used by warp 0 for the tail)
-
-    for (uint32_t depth = kMaxHashBits; depth > 0; depth--) {
-        if (ctrl->stopped) break;
+    for (uint32_t depth = kMaxHashBits; depth > 0 && !stop_seen; depth--) {
         // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
-        const uint32_t it = kMaxHashBits + 1 - depth;              // iteration 1..24
-        const uint32_t dir_bit = 1u << (it >= 2 ? it - 2 : 0);     // removed bit (prefixmap.hpp:268-274)
         uint32_t running = 0;
-        for (uint32_t t0 = 0; t0 < L; t0 += kCtaThreads) {
-            const uint32_t t = t0 + tid;
+        for (uint32_t t0 = 0; t0 < L; t0 += kProducers) {
+            const uint32_t t = t0 + ptid;
             uint32_t nseg = 0;
-            if (t < L) {
-                const uint32_t h = sm.code[t];
-                const uint32_t A = sm.anchor[t];
-                const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
-                int64_t start, end;
-                if ((h & dir_bit) == 0) {  // upward (prefixmap.hpp:277-290)
-                    uint32_t j = lead_count(sm.lcp_up[t], depth);
-                    if (j == 8) {
-                        // run longer than the samples: first position >= A + 96 whose prefix differs, rounded up to the stride
-                        uint32_t lo = A + 8 * kSegment, len = nc > lo ? nc - lo : 0;
-                        while (len > 0) {
-                            uint32_t half = len >> 1, mid = lo + half;
-                            if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
-                        }
-                        j = (lo - A + kSegment - 1) / kSegment;
-                    }
-                    start = A;
-                    end = (int64_t)A + (int64_t)kSegment * j;
-                    if (end >= (int64_t)nc) end = (end - kSegment) > start ? (end - kSegment) : start;
-                } else {  // downward (prefixmap.hpp:291-303)
-                    uint32_t j = lead_count(sm.lcp_dn[t], depth);
-                    if (j == 8) {
-                        uint32_t hi = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [0, hi) undecided
-                        uint32_t lo = 0, len = hi;
-                        while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
-                            uint32_t half = len >> 1, mid = lo + half;
-                            if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
-                        }
-                        j = (A - lo + kSegment - 1) / kSegment;
-                    }
-                    end = A;
-                    start = (int64_t)A - (int64_t)kSegment * j;
-                    if (start < 0) start = (start + kSegment) < end ? (start + kSegment) : end;
-                }
-                sm.start[t] = (uint32_t)start;
-                nseg = (uint32_t)(end - start) >> 2;
-            }
+            if (t < L)
+                sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)a.c * L + t) * kDirEntries, nc,
+                                          sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
             uint32_t total;
             const uint32_t ex = warp_excl_scan(nseg, total);
-            if (lane == 0) ctrl->warp_tot[warp] = total;
-            __syncthreads();
+            if (lane == 0) ctrl->warp_tot[pwarp] = total;
+            producers_sync();
             uint32_t prefix = running, tile_total = 0;
 #pragma unroll
-            for (int w = 0; w < kCtaWarps; w++) {
+            for (uint32_t w = 0; w < kProducers / 32; w++) {
                 uint32_t wt = ctrl->warp_tot[w];
-                if ((uint32_t)w < warp) prefix += wt;
+                if (w < pwarp) prefix += wt;
                 tile_total += wt;
             }
             if (t < L) sm.segbase[t] = prefix + ex;
             running += tile_total;
-            __syncthreads();
+            producers_sync();
         }
         const uint32_t S = running;
+        TADD(T_RANGES, tp);
         if (S <= (uint32_t)kRing) continue;  // the initial ring fill swallows the whole stream (collection.hpp:802-810)
-        if (tid == 0) {
-            sm.segbase[L] = running;
-            ctrl->base = 0;
-            ctrl->np = 0;
-        }
-        __syncthreads();
+        if (ptid == 0) sm.segbase[L] = S;
 
-        for (;;) {  // chunks of the segment stream of this depth
-            const uint32_t cb = ctrl->base;                                         // first stream segment of the chunk
-            const uint32_t ce = S - cb < kChunkSegs ? S : cb + kChunkSegs;          // one past the last
-            const uint32_t md = ctrl->max_diff;                                     // threshold in force at the start of the chunk
+        for (uint32_t cb = 0; cb < S; cb += kChunkSegs) {  // chunk boundaries are data independent (see the header)
+            const uint32_t slot = it & 1u;
+            mbar_wait(&ctrl->empty[slot], ((it >> 1) & 1u) ^ 1u);
+            TADD(T_WAIT_EMPTY, tp);
+            if (ptid == 0) {
+                ctrl->p_stop = ctrl->stopped;
+                ctrl->p_md = ctrl->max_diff;
+                ctrl->unk_cnt = 0;
+            }
+            producers_sync();  // also orders phase B of the previous chunk (memo writes) before this chunk's memo reads
+            if (ctrl->p_stop) {
+                stop_seen = true;
+                break;
+            }
+            const uint32_t md = ctrl->p_md;
+            const uint32_t ce = S - cb < kChunkSegs ? S : cb + kChunkSegs;
+            uint32_t* cid = sm.cid(slot);
+            uint16_t* csim = sm.csim(slot);
+            uint32_t* cpc = sm.cpc(slot);
             // ---------------------------------------------------------------- phase A: indices, Hamming distances, memo
             {
-                const uint32_t s0 = cb + tid * kSegPerThread;
+                const uint32_t s0 = cb + ptid * kSegPerThread;
                 uint32_t ids[kSegPerThread][4];
                 uint32_t nmine = 0;
                 if (s0 < ce) {
@@ -340,9 +349,9 @@ __device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, 
                         if (j < nmine) {
                             const uint32_t s = s0 + j;
                             while (t + 1 < L && sm.segbase[t + 1] <= s) t++;
-                            const uint32_t* seg = p.tbl_idx + (uint64_t)t * p.n + off + sm.start[t] + 4 * (s - sm.segbase[t]);
-                            ids[j][0] = ldg_nc_na_u32(seg); ids[j][1] = ldg_nc_na_u32(seg + 1);
-                            ids[j][2] = ldg_nc_na_u32(seg + 2); ids[j][3] = ldg_nc_na_u32(seg + 3);
+                            const uint32_t* seg = p.tbl_idx + table_base(off, nc, L, t) + sm.start[t] + 4 * (s - sm.segbase[t]);
+                            ids[j][0] = __ldg(seg); ids[j][1] = __ldg(seg + 1);  // L1-allocating: the four words share a sector
+                            ids[j][2] = __ldg(seg + 2); ids[j][3] = __ldg(seg + 3);
                         }
                     }
                 }
@@ -352,9 +361,9 @@ __device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, 
 #pragma unroll
                 for (uint32_t j = 0; j < kSegPerThread; j++) {
                     if (j < nmine) {
-                        const uint32_t slot = (s0 + j) & 31u;  // chunks start on a multiple of the ring size
+                        const uint32_t slot_r = (s0 + j) & 31u;  // chunks start on a multiple of the ring size
 #pragma unroll
-                        for (int e = 0; e < 4; e++) w[j][e] = ldg_nc_na_u64(sk + ((uint64_t)ids[j][e] << 5 | slot));
+                        for (int e = 0; e < 4; e++) w[j][e] = ldg_nc_na_u64(sk + ((uint64_t)ids[j][e] << 5 | slot_r));
 #pragma unroll
                         for (int e = 0; e < 4; e++) mm[j][e] = memo ? (uint32_t)memo[ids[j][e]] : 0u;
                     }
@@ -374,15 +383,15 @@ __device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, 
                             pcs |= pc << (8 * e);
                             if (pc <= md) {
                                 if (mm[j][e]) {
-                                    sm.csim[ci + e] = (uint16_t)mm[j][e];
+                                    csim[ci + e] = (uint16_t)mm[j][e];
                                 } else {
                                     my_unk |= 1u << (4 * j + e);
                                     n_unk++;
                                 }
                             }
                         }
-                        sm.cpc[ci >> 2] = pcs;
-                        *reinterpret_cast<uint4*>(sm.cid + ci) = make_uint4(ids[j][0], ids[j][1], ids[j][2], ids[j][3]);
+                        cpc[ci >> 2] = pcs;
+                        *reinterpret_cast<uint4*>(cid + ci) = make_uint4(ids[j][0], ids[j][1], ids[j][2], ids[j][3]);
                     }
                 }
                 if (n_unk) {
@@ -395,159 +404,276 @@ __device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, 
                     }
                 }
             }
-            __syncthreads();
+            producers_sync();
+            TADD(T_A, tp);
             // ---------------------------------------------------------------- phase B: Q15 rerank of the missing rows
-            const uint32_t nunk = ctrl->unk_cnt;
-            for (uint32_t rb = 0; rb < nunk; rb += kStageRows) {
-                const uint32_t nrows = nunk - rb < kStageRows ? nunk - rb : kStageRows;
-                if (tid == 0) mbar_arrive_expect_tx(&ctrl->mbar, nrows * sl * 2);
-                if (tid < nrows) {
-                    const uint32_t id = sm.cid[sm.unk[rb + tid]];
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot vs the async write
-                    bulk_copy_g2s(sm.stage + tid * sunits * 16, rows + (uint64_t)id * sl, sl * 2, &ctrl->mbar);
-                }
-                mbar_wait(&ctrl->mbar, phase);
-                phase ^= 1u;
-                {
-                    const uint32_t r = tid >> 1, half = tid & 1u;
+            {
+                const uint32_t nunk = ctrl->unk_cnt;
+                const uint32_t sub = ptid & 3u;
+                const int4* qv = reinterpret_cast<const int4*>(sm.qrow2);
+                for (uint32_t rb = 0; rb < nunk; rb += kRowsPerIter) {
+                    const uint32_t r = rb + (ptid >> 2);
+                    const bool valid = r < nunk;
                     int s = 0;
-                    if (r < nrows) {
-                        const uint4* row = reinterpret_cast<const uint4*>(sm.stage + r * sunits * 16);
-                        const int4* qv = reinterpret_cast<const int4*>(sm.qrow2);
-                        for (uint32_t ch = half; ch < cpr; ch += 2) s += q15_dot_unit(row[ch], qv[2 * ch], qv[2 * ch + 1]);
+                    uint32_t pos = 0, id = 0;
+                    if (valid) {
+                        pos = sm.unk[r];
+                        id = cid[pos];
+                        const uint4* row = reinterpret_cast<const uint4*>(rows + (uint64_t)id * sl);
+                        if (cpr <= 16) {  // d <= 128: at most four 16-byte units per lane, all requested before the first is used
+                            uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0, u2 = u0, u3 = u0;
+                            if (sub < cpr) u0 = ldg_nc_na_v4(row + sub);
+                            if (sub + 4 < cpr) u1 = ldg_nc_na_v4(row + sub + 4);
+                            if (sub + 8 < cpr) u2 = ldg_nc_na_v4(row + sub + 8);
+                            if (sub + 12 < cpr) u3 = ldg_nc_na_v4(row + sub + 12);
+                            if (sub < cpr) s += q15_dot_unit(u0, qv[2 * sub], qv[2 * sub + 1]);
+                            if (sub + 4 < cpr) s += q15_dot_unit(u1, qv[2 * sub + 8], qv[2 * sub + 9]);
+                            if (sub + 8 < cpr) s += q15_dot_unit(u2, qv[2 * sub + 16], qv[2 * sub + 17]);
+                            if (sub + 12 < cpr) s += q15_dot_unit(u3, qv[2 * sub + 24], qv[2 * sub + 25]);
+                        } else {
+                            for (uint32_t ch = sub; ch < cpr; ch += 4) s += q15_dot_unit(ldg_nc_na_v4(row + ch), qv[2 * ch], qv[2 * ch + 1]);
+                        }
                     }
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    if (r < nrows && half == 0) {
-                        const uint32_t pos = sm.unk[rb + r];
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (valid && sub == 0) {
                         const uint16_t sim16 = (uint16_t)(s + 32768);
-                        sm.csim[pos] = sim16;
-                        if (memo) memo[sm.cid[pos]] = sim16;
+                        csim[pos] = sim16;
+                        if (memo) memo[id] = sim16;
                     }
-                }
-                __syncthreads();
-            }
-            // ---------------------------------------------------------------- phase C: the sequential loop, warp 0
-            if (warp == 0) {
-                uint32_t base = ctrl->base, np = ctrl->np;
-                uint32_t inserted = ctrl->inserted, minval16 = ctrl->minval16, max_diff = md;
-                unsigned long long cand = 0, dcomp = 0;
-                uint32_t status = 0, stopped = 0;
-                for (;;) {
-                    bool need = false;
-                    // full ring sweeps (collection.hpp:813-866): slot == lane, real sketches
-                    while (np < (uint32_t)kFilterBuffer && base + kRing <= S) {
-                        if (base + kRing > ce) { need = true; break; }
-                        const uint32_t ci = (base - cb + lane) * 4;
-                        const uint32_t pcs = sm.cpc[ci >> 2];
-                        const uint32_t mask = __vcmpleu4(pcs, max_diff * 0x01010101u);
-                        const uint32_t cnt = (uint32_t)__popc(mask) >> 3;
-                        uint32_t total;
-                        uint32_t pos = np + warp_excl_scan3(cnt, total);
-                        if (cnt) {
-                            const uint4 v = *reinterpret_cast<const uint4*>(sm.cid + ci);
-                            const uint2 sv = *reinterpret_cast<const uint2*>(sm.csim + ci);
-                            if (mask & 0x000000ffu) { sm.pass_idx[pos] = v.x; sm.pass_sim[pos] = (uint16_t)(sv.x & 0xffffu); pos++; }
-                            if (mask & 0x0000ff00u) { sm.pass_idx[pos] = v.y; sm.pass_sim[pos] = (uint16_t)(sv.x >> 16); pos++; }
-                            if (mask & 0x00ff0000u) { sm.pass_idx[pos] = v.z; sm.pass_sim[pos] = (uint16_t)(sv.y & 0xffffu); pos++; }
-                            if (mask & 0xff000000u) { sm.pass_idx[pos] = v.w; sm.pass_sim[pos] = (uint16_t)(sv.y >> 16); pos++; }
-                        }
-                        np += total;
-                        cand += kRing * 4;
-                        base += kRing;
-                    }
-                    if (need) { status = kNeedMore; break; }
-                    // tail (collection.hpp:869-903): the not-yet-tested ring slots, in descending slot order, tested with the
-                    // point index itself in place of its sketch (:890-893)
-                    const uint32_t live = base + kRing > S ? (S > base ? S - base : 0u) : (uint32_t)kRing;
-                    if (base + live > ce) { status = kNeedMore; break; }
-                    {
-                        uint32_t cnt = 0, pm = 0, um = 0;
-                        uint4 v = make_uint4(0, 0, 0, 0);
-                        uint2 sv = make_uint2(0, 0);
-                        if (lane < live) {
-                            const uint32_t ci = (base - cb + lane) * 4;
-                            v = *reinterpret_cast<const uint4*>(sm.cid + ci);
-                            sv = *reinterpret_cast<const uint2*>(sm.csim + ci);
-                            const uint32_t pcs = sm.cpc[ci >> 2];
-                            const uint32_t known = __vcmpleu4(pcs, md * 0x01010101u);  // similarity was prefetched in phase B
-                            pm |= ((uint32_t)__popcll((uint64_t)v.x ^ my_sketch) <= max_diff) ? 1u : 0u;
-                            pm |= ((uint32_t)__popcll((uint64_t)v.y ^ my_sketch) <= max_diff) ? 2u : 0u;
-                            pm |= ((uint32_t)__popcll((uint64_t)v.z ^ my_sketch) <= max_diff) ? 4u : 0u;
-                            pm |= ((uint32_t)__popcll((uint64_t)v.w ^ my_sketch) <= max_diff) ? 8u : 0u;
-                            cnt = __popc(pm);
-                            um = pm & ~((known & 1u) | ((known >> 7) & 2u) | ((known >> 14) & 4u) | ((known >> 21) & 8u));
-                        }
-                        uint32_t total;
-                        const uint32_t ex = warp_excl_scan3(cnt, total);
-                        uint32_t pos = np + (total - ex - cnt);  // entries of higher slots come first
-                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-                        const uint32_t ss[4] = {sv.x & 0xffffu, sv.x >> 16, sv.y & 0xffffu, sv.y >> 16};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (pm & (1u << e)) {
-                                sm.pass_idx[pos] = vv[e];
-                                sm.pass_sim[pos] = (uint16_t)ss[e];
-                                if (um & (1u << e)) sm.unk[atomicAdd(&ctrl->tail_unk, 1u)] = (uint16_t)pos;
-                                pos++;
-                            }
-                        }
-                        np += total;
-                        cand += 4ull * live;
-                        __syncwarp();
-                        // tail entries that failed the sketch filter of phase A but pass the index-as-sketch test: compute now
-                        const uint32_t ntu = ctrl->tail_unk;
-                        if (ntu) {
-                            for (uint32_t i = 0; i < ntu; i++) {
-                                const uint32_t pp = sm.unk[i];
-                                const uint32_t sim16 = warp_row_sim(rows + (uint64_t)sm.pass_idx[pp] * sl, sm.qrow2, sl);
-                                if (lane == 0) sm.pass_sim[pp] = (uint16_t)sim16;
-                            }
-                            __syncwarp();
-                            if (lane == 0) ctrl->tail_unk = 0;
-                            __syncwarp();
-                        }
-                    }
-                    // empty the buffer (collection.hpp:909-925)
-                    dcomp += np;
-                    maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, np);
-                    max_diff = p.msd[minval16 < 65536u ? minval16 : 65535u];  // filterer.hpp:108-111
-                    np = 0;
-                    // stop rule (collection.hpp:927-943)
-                    const uint32_t pulled = base + kRing;
-                    uint32_t table_idx = L;
-                    if (pulled < S) {
-                        uint32_t lo = 0, len = L;
-                        while (len > 0) {
-                            uint32_t half = len >> 1, mid = lo + half;
-                            if (sm.segbase[mid] <= pulled) { lo = mid + 1; len -= half + 1; } else { len = half; }
-                        }
-                        table_idx = lo - 1;
-                    }
-                    const float kth = __fdiv_rn((float)minval16, 65536.0f);
-                    const float sim = kth < max_sim ? max_sim : kth;  // std::max(kth, max_sim)
-                    uint32_t bin = (uint32_t)__fdiv_rn(sim, 0.005f);  // crosspolytope.hpp:116-118
-                    bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
-                    const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (table_idx >> 5));
-                    if ((word >> (table_idx & 31)) & 1u) { stopped = 1; break; }
-                    if (!(base + kRing < S)) break;  // status 0: depth finished
-                }
-                if (lane == 0) {
-                    ctrl->base = base;
-                    ctrl->np = np;
-                    ctrl->inserted = inserted;
-                    ctrl->minval16 = minval16;
-                    ctrl->max_diff = max_diff;
-                    ctrl->stopped = stopped;
-                    ctrl->status = status;
-                    ctrl->unk_cnt = 0;
-                    ctrl->candidates += cand;
-                    ctrl->distcomp += dcomp;
                 }
             }
-            __syncthreads();
-            if (ctrl->status != kNeedMore) break;
+            TADD(T_B, tp);
+            // ---------------------------------------------------------------- hand the slot over
+            for (uint32_t i = ptid; i <= L; i += kProducers) sm.segb(slot)[i] = sm.segbase[i];
+            if (ptid == 0) {
+                SlotMeta* m = sm.meta(slot);
+                m->depth = depth;
+                m->S = S;
+                m->cb = cb;
+                m->ce = ce;
+                m->md = md;
+            }
+            mbar_arrive(&ctrl->full[slot]);  // release: this thread's writes to the slot are visible to whoever sees the phase complete
+            it++;
+            TADD(T_HAND, tp);
+#ifdef CLANN_TIMING
+            t_acc[T_CHUNKS]++;
+#endif
         }
     }
+    // END record: closes the visit for the consumer whatever happened above
+    {
+        const uint32_t slot = it & 1u;
+        mbar_wait(&ctrl->empty[slot], ((it >> 1) & 1u) ^ 1u);
+        if (ptid == 0) sm.meta(slot)->depth = 0;
+        mbar_arrive(&ctrl->full[slot]);
+        it++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ consumer (warp 0)
+__device__ __forceinline__ void consume_visit(const SearchParams& p, const CtaSmem& sm, const VisitArgs& a, uint32_t thr_lo,
+                                              uint32_t thr_hi, uint32_t& it TARG) {
+    const uint32_t L = p.g.L, k = p.k, sl = p.g.sl;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t off = p.offsets[a.c];
+    const int16_t* rows = p.q15 + off * sl;
+    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    CtaCtrl* ctrl = sm.ctrl;
+    const uint64_t my_sketch = sm.qsk[lane];  // ring slot == lane
+    const float max_sim = a.max_sim;
+
+    uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;  // maxbuffer.hpp:53-55, filterer.hpp:101
+    uint32_t base = 0, np = 0, cur_depth = 0, status = kDepthDone;
+    unsigned long long cand = 0, dcomp = 0;
+    uint32_t stop_key = 0xffffffffu, stop_word = 0;  // lane w < stop_words caches word w of the stop row (depth, bin)
+    TSTART(tc);
+
+    for (;;) {
+        const uint32_t slot = it & 1u;
+        mbar_wait(&ctrl->full[slot], (it >> 1) & 1u);
+        TADD(T_WAIT_FULL, tc);
+        const SlotMeta m = *sm.meta(slot);
+        if (m.depth == 0 || status == kStopped) {  // END, or draining what the producers prepared past the stop
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctrl->empty[slot]);
+            it++;
+            if (m.depth == 0) break;
+            continue;
+        }
+        const uint32_t S = m.S, cb = m.cb, ce = m.ce, md = m.md, depth = m.depth;
+        if ((depth != cur_depth) == (status == kNeedMore)) __trap();  // a depth ends exactly when the replay stops asking for more
+        if (depth != cur_depth) {
+            cur_depth = depth;
+            base = 0;
+            np = 0;
+        }
+        const uint32_t* cid = sm.cid(slot);
+        const uint16_t* csim = sm.csim(slot);
+        const uint32_t* cpc = sm.cpc(slot);
+        const uint32_t* segb = sm.segb(slot);
+        for (;;) {
+            bool need = false;
+            // full ring sweeps (collection.hpp:813-866): slot == lane, real sketches
+            while (np < (uint32_t)kFilterBuffer && base + kRing <= S) {
+                if (base + kRing > ce) { need = true; break; }
+                const uint32_t ci = (base - cb + lane) * 4;
+                const uint32_t pcs = cpc[ci >> 2];
+                const uint32_t mask = __vcmpleu4(pcs, max_diff * 0x01010101u);
+                const uint32_t cnt = (uint32_t)__popc(mask) >> 3;
+                uint32_t total;
+                uint32_t pos = np + warp_excl_scan3(cnt, total);
+                if (cnt) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(cid + ci);
+                    const uint2 sv = *reinterpret_cast<const uint2*>(csim + ci);
+                    if (mask & 0x000000ffu) { sm.pass_idx[pos] = v.x; sm.pass_sim[pos] = (uint16_t)(sv.x & 0xffffu); pos++; }
+                    if (mask & 0x0000ff00u) { sm.pass_idx[pos] = v.y; sm.pass_sim[pos] = (uint16_t)(sv.x >> 16); pos++; }
+                    if (mask & 0x00ff0000u) { sm.pass_idx[pos] = v.z; sm.pass_sim[pos] = (uint16_t)(sv.y & 0xffffu); pos++; }
+                    if (mask & 0xff000000u) { sm.pass_idx[pos] = v.w; sm.pass_sim[pos] = (uint16_t)(sv.y >> 16); pos++; }
+                }
+                np += total;
+                cand += kRing * 4;
+                base += kRing;
+            }
+            if (need) { status = kNeedMore; break; }
+            // tail (collection.hpp:869-903): the not-yet-tested ring slots, in descending slot order, tested with the
+            // point index itself in place of its sketch (:890-893)
+            const uint32_t live = base + kRing > S ? (S > base ? S - base : 0u) : (uint32_t)kRing;
+            if (base + live > ce) { status = kNeedMore; break; }
+            {
+                uint32_t cnt = 0, pm = 0, um = 0;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                uint2 sv = make_uint2(0, 0);
+                if (lane < live) {
+                    const uint32_t ci = (base - cb + lane) * 4;
+                    v = *reinterpret_cast<const uint4*>(cid + ci);
+                    sv = *reinterpret_cast<const uint2*>(csim + ci);
+                    const uint32_t pcs = cpc[ci >> 2];
+                    const uint32_t known = __vcmpleu4(pcs, md * 0x01010101u);  // similarity was prefetched in phase B
+                    pm |= ((uint32_t)__popcll((uint64_t)v.x ^ my_sketch) <= max_diff) ? 1u : 0u;
+                    pm |= ((uint32_t)__popcll((uint64_t)v.y ^ my_sketch) <= max_diff) ? 2u : 0u;
+                    pm |= ((uint32_t)__popcll((uint64_t)v.z ^ my_sketch) <= max_diff) ? 4u : 0u;
+                    pm |= ((uint32_t)__popcll((uint64_t)v.w ^ my_sketch) <= max_diff) ? 8u : 0u;
+                    cnt = __popc(pm);
+                    um = pm & ~((known & 1u) | ((known >> 7) & 2u) | ((known >> 14) & 4u) | ((known >> 21) & 8u));
+                }
+                uint32_t total;
+                const uint32_t ex = warp_excl_scan3(cnt, total);
+                uint32_t pos = np + (total - ex - cnt);  // entries of higher slots come first
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t ss[4] = {sv.x & 0xffffu, sv.x >> 16, sv.y & 0xffffu, sv.y >> 16};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (pm & (1u << e)) {
+                        sm.pass_idx[pos] = vv[e];
+                        sm.pass_sim[pos] = (uint16_t)ss[e];
+                        if (um & (1u << e)) sm.tunk[atomicAdd(&ctrl->tail_unk, 1u)] = (uint16_t)pos;
+                        pos++;
+                    }
+                }
+                np += total;
+                cand += 4ull * live;
+                __syncwarp();
+                // tail entries that failed the sketch filter of phase A but pass the index-as-sketch test: compute now
+                const uint32_t ntu = __any_sync(0xffffffffu, um != 0) ? ctrl->tail_unk : 0u;
+                if (ntu) {
+                    for (uint32_t i = 0; i < ntu; i++) {
+                        const uint32_t pp = sm.tunk[i];
+                        const uint32_t sim16 = warp_row_sim(rows + (uint64_t)sm.pass_idx[pp] * sl, sm.qrow2, sl);
+                        if (lane == 0) sm.pass_sim[pp] = (uint16_t)sim16;
+                    }
+                    __syncwarp();
+                    if (lane == 0) ctrl->tail_unk = 0;
+                    __syncwarp();
+                }
+            }
+            // empty the buffer (collection.hpp:909-925)
+            dcomp += np;
+            const uint32_t minval_before = minval16;
+            maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, np);
+            np = 0;
+            if (minval16 != minval_before) {
+                // filterer.hpp:108-111 through the threshold form of the host table: #{m : thr[m] > minval}
+                max_diff = __popc(__ballot_sync(0xffffffffu, thr_lo > minval16)) + __popc(__ballot_sync(0xffffffffu, thr_hi > minval16));
+                if (lane == 0) ctrl->max_diff = max_diff;  // advisory, for the producers
+            }
+            // stop rule (collection.hpp:927-943)
+            const uint32_t pulled = base + kRing;
+            uint32_t table_idx = L;
+            if (pulled < S) {
+                // upper_bound(segbase[0..L), pulled) - 1 by counting, 32 tables per ballot
+                uint32_t cnt_le = 0;
+                for (uint32_t t0 = 0; t0 < L; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    cnt_le += __popc(__ballot_sync(0xffffffffu, t < L && segb[t] <= pulled));
+                }
+                table_idx = cnt_le - 1;
+            }
+            const float kth = __fdiv_rn((float)minval16, 65536.0f);
+            const float sim = kth < max_sim ? max_sim : kth;  // std::max(kth, max_sim)
+            uint32_t bin = (uint32_t)__fdiv_rn(sim, 0.005f);  // crosspolytope.hpp:116-118
+            bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
+            const uint32_t key = (depth - 1) * kEstBins + bin;
+            if (key != stop_key) {
+                stop_key = key;
+                stop_word = lane < p.stop_words ? __ldg(a.stop + (uint64_t)key * p.stop_words + lane) : 0u;
+            }
+            const uint32_t word = __shfl_sync(0xffffffffu, stop_word, (table_idx >> 5) & 31u);
+            if ((word >> (table_idx & 31)) & 1u) { status = kStopped; break; }
+            if (!(base + kRing < S)) { status = kDepthDone; break; }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (status == kStopped) ctrl->stopped = 1;
+            mbar_arrive(&ctrl->empty[slot]);
+        }
+        it++;
+        TADD(T_C, tc);
+    }
+    if (lane == 0) {
+        ctrl->inserted = inserted;
+        ctrl->minval16 = minval16;
+        ctrl->candidates += cand;
+        ctrl->distcomp += dcomp;
+    }
+}
+
+// One PUFFINN query against cluster c by the whole CTA (collection.hpp:543-601 -> search_maps :768-948).
+// Returns the number of results; sm.mb[0..cnt) holds them best first.
+__device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, const VisitArgs& a, uint32_t thr_lo, uint32_t thr_hi,
+                                      uint32_t& it TARG) {
+    const uint32_t L = p.g.L, k = p.k;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t off = p.offsets[a.c];
+    const uint32_t nc = (uint32_t)(p.offsets[a.c + 1] - off);
+    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    CtaCtrl* ctrl = sm.ctrl;
+    TSTART(t0);
+
+    if (a.memo) {
+        uint4* mz = reinterpret_cast<uint4*>(a.memo);
+        for (uint32_t i = tid; i < (nc + 7) / 8; i += kCtaThreads) mz[i] = make_uint4(0, 0, 0, 0);
+    }
+    // --- SearchBuffers ctor (collection.hpp:642-645): one thread per table
+    for (uint32_t t = tid; t < L; t += kCtaThreads) {
+        const uint32_t h = a.codes[(uint64_t)t * a.code_stride];
+        uint32_t A;
+        uint2 up, dn;
+        table_anchor(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)a.c * L + t) * kDirEntries, nc, h, A, up, dn);
+        sm.code[t] = h;
+        sm.anchor[t] = A;
+        sm.lcp_up[t] = up;
+        sm.lcp_dn[t] = dn;
+    }
+    if (tid == 0) {
+        ctrl->max_diff = kSketchBits;  // filterer.hpp:101
+        ctrl->stopped = 0;
+    }
+    __syncthreads();
+    TADD(T_SETUP, t0);
+    if (warp == 0) consume_visit(p, sm, a, thr_lo, thr_hi, it TPASS);
+    else produce_visit(p, sm, a, it TPASS);
     __syncthreads();
     if (warp == 0) {  // best_indices (collection.hpp:598, maxbuffer.hpp:79-96)
         uint32_t inserted = ctrl->inserted, minval16 = ctrl->minval16;
@@ -560,7 +686,7 @@ __device__ uint32_t probe_cluster_cta(const SearchParams& p, const CtaSmem& sm, 
 
 template <int OCC>
 __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, QueryBatch b, int stop_at_foreign, uint16_t* memo_base,
-                                                                uint64_t memo_stride) {
+                                                                uint64_t memo_stride, uint32_t prefetch_ahead) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const CtaSmem sm = carve_cta(s_dyn, p.g.L, p.k, p.g.sl);
     CtaCtrl* ctrl = sm.ctrl;
@@ -569,11 +695,17 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
     uint16_t* memo = memo_base ? memo_base + (uint64_t)blockIdx.x * memo_stride : nullptr;
     const uint32_t P = next_pow2(2 * p.k) < 32 ? 32 : next_pow2(2 * p.k);
     if (tid == 0) {
-        mbar_init(&ctrl->mbar, 1);
+        for (uint32_t i = 0; i < kSlots; i++) {
+            mbar_init(&ctrl->full[i], kProducers);
+            mbar_init(&ctrl->empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ctrl->unk_cnt = 0;
         ctrl->tail_unk = 0;
     }
-    uint32_t phase = 0;
+    const uint32_t thr_lo = p.msd_thr[lane], thr_hi = p.msd_thr[lane + 32];
+    uint32_t it = 0;  // chunks handed over so far (identical in producers and consumer at every visit boundary)
+    TDECL;
     __syncthreads();
 
     for (;;) {
@@ -582,9 +714,18 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
         const uint32_t w = ctrl->work;
         __syncthreads();
         if (w >= b.nq) break;
-        const uint32_t q = b.qperm[w];  // queries sorted by their nearest cluster
+        const uint32_t q = (stop_at_foreign & 2) ? w : b.qperm[w];  // queries sorted by their nearest cluster (bit 1: debug, unsorted)
+        if (prefetch_ahead) {
+            // b.first holds the nearest cluster of every work item, in work order: whoever takes the first query of a
+            // cluster prefetches it (cold start), and the cluster that comes up `prefetch_ahead` work items later
+            if (w < prefetch_ahead && (w == 0 || b.first[w] != b.first[w - 1])) l2_prefetch_cluster(p, b.first[w]);
+            const uint64_t wa = (uint64_t)w + prefetch_ahead;
+            if (wa < b.nq && b.first[wa] != b.first[wa - 1]) l2_prefetch_cluster(p, b.first[wa]);
+        }
         QueryStateHeader* st = reinterpret_cast<QueryStateHeader*>(b.state + (uint64_t)q * state_bytes);
         if (st->done) continue;
+        TSTART(tq);
+        TSTART(tm);
         unsigned long long* st_heap = reinterpret_cast<unsigned long long*>(st + 1);
         uint32_t pos = st->next_pos;
         unsigned long long last_key = st->last_key;
@@ -634,7 +775,7 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
                     break;
                 }
             }
-            if (stop_at_foreign && p.owner[c] != p.shard_rank) break;
+            if ((stop_at_foreign & 1) && p.owner[c] != p.shard_rank) break;
             last_key = nk;
             visited++;
             const uint64_t off = p.offsets[c];
@@ -642,8 +783,8 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
             __syncthreads();  // everyone has read ctrl->nk / top before warp 0 may overwrite them
             if (p.brute[c]) {
                 // index.rs:364-378 with brute_force_search :666-685: members in assignment order into a local top-k, then merge
-                float* s_dist = reinterpret_cast<float*>(sm.cid);
-                uint32_t* s_pid = sm.cid + kCtaThreads;
+                float* s_dist = reinterpret_cast<float*>(sm.cid(0));
+                uint32_t* s_pid = sm.cid(0) + kCtaThreads;
                 uint32_t loc_len = 0;
                 for (uint32_t base = 0; base < nc; base += kCtaThreads) {
                     const uint32_t j = base + tid;
@@ -672,12 +813,20 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
                 }
             } else {
                 const uint32_t fs = p.fset_of[c];
-                const float max_sim = __fsub_rn(1.0f, __fdiv_rn(max_dist, 2.0f));  // puffinn_types.rs:77-79
-                const uint32_t* codes = b.codes + (uint64_t)fs * p.g.L * b.nq + q;
+                VisitArgs a;
+                a.c = c;
+                a.codes = b.codes + (uint64_t)fs * p.g.L * b.nq + q;
+                a.code_stride = b.nq;
+                a.stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
+                a.max_sim = __fsub_rn(1.0f, __fdiv_rn(max_dist, 2.0f));  // puffinn_types.rs:77-79
+                a.memo = (memo && nc <= memo_stride) ? memo : nullptr;
                 if (tid < kNumSketches) sm.qsk[tid] = b.sketches[((uint64_t)fs * b.nq + q) * kNumSketches + tid];
-                const uint32_t* stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
-                uint16_t* use_memo = (memo && nc <= memo_stride) ? memo : nullptr;
-                const uint32_t cnt = probe_cluster_cta(p, sm, c, codes, b.nq, stop, max_sim, use_memo, phase);
+                TADD(T_SELECT, tm);
+                const uint32_t cnt = probe_cluster_cta(p, sm, a, thr_lo, thr_hi, it TPASS);
+                TADD(T_VISIT, tm);
+#ifdef CLANN_TIMING
+                t_acc[T_VISITS]++;
+#endif
                 if (warp == 0) {  // map_candidates + fp32 distance + heap (index.rs:392-416), best first
                     uint32_t hl = ctrl->heap_len;
                     for (uint32_t base = 0; base < cnt; base += 32) {
@@ -697,6 +846,7 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
                     }
                     if (lane == 0) ctrl->heap_len = hl;
                 }
+                TADD(T_FINAL, tm);
             }
             __syncthreads();
         }
@@ -714,7 +864,19 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
             st->distcomp = ctrl->distcomp;
         }
         __syncthreads();
+        TADD(T_QUERY, tq);
     }
+#ifdef CLANN_TIMING
+    // representative threads: tid 0 (consumer lane 0 + CTA-level), tid 32 (producer 0)
+    if (tid == 0) {
+        const int slots[] = {T_SETUP, T_WAIT_FULL, T_C, T_VISIT, T_QUERY, T_SELECT, T_FINAL, T_VISITS};
+        for (int i : slots) atomicAdd(&g_timing[i], t_acc[i]);
+    }
+    if (tid == 32) {
+        const int slots[] = {T_RANGES, T_WAIT_EMPTY, T_A, T_B, T_HAND, T_CHUNKS};
+        for (int i : slots) atomicAdd(&g_timing[i], t_acc[i]);
+    }
+#endif
 }
 
 template <int OCC>
@@ -757,7 +919,29 @@ static void launch_probe_cta_occ(const SearchParams& p, const QueryBatch& b, boo
         }
         use = memo;
     }
-    k_probe_cta<OCC><<<(unsigned)grid, kCtaThreads, smem, s>>>(p, b, stop_at_foreign ? 1 : 0, use, stride);
+    static int nosort = -1;
+    if (nosort < 0) nosort = getenv("CLANN_PROBE_NOSORT") ? 2 : 0;  // debug: measure what the nearest-cluster work order buys
+    static int pf = -1;
+    if (pf < 0) {
+        const char* e = getenv("CLANN_PROBE_PREFETCH");  // work items of lookahead for the L2 cluster prefetch; 0 = off, unset = one grid
+        pf = e ? atoi(e) : -2;
+    }
+    // the prefetch follows the nearest-cluster work order, which only exists for a fresh batch (not for multi-GPU re-entry)
+    const uint32_t ahead = stop_at_foreign ? 0u : (pf == -2 ? (uint32_t)grid : (uint32_t)pf);
+    k_probe_cta<OCC><<<(unsigned)grid, kCtaThreads, smem, s>>>(p, b, (stop_at_foreign ? 1 : 0) | nosort, use, stride, ahead);
+#ifdef CLANN_TIMING
+    {
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        unsigned long long h[T_N], z[T_N] = {0};
+        CLANN_CUDA(cudaMemcpyFromSymbol(h, g_timing, sizeof(h)));
+        CLANN_CUDA(cudaMemcpyToSymbol(g_timing, z, sizeof(z)));
+        const char* names[T_N] = {"setup", "ranges", "wait_empty", "A", "B", "hand", "wait_full", "C", "visit", "query", "select", "final", "chunks", "visits"};
+        const double nqd = (double)b.nq;
+        fprintf(stderr, "[clann timing] grid=%llu per-query kcycles:", (unsigned long long)grid);
+        for (int i = 0; i < T_N; i++) fprintf(stderr, " %s=%.2f", names[i], i >= T_CHUNKS ? h[i] / nqd : h[i] / nqd / 1e3);
+        fprintf(stderr, "\n");
+    }
+#endif
 }
 
 void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {

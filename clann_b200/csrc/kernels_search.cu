@@ -124,6 +124,7 @@ __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t 
 struct WarpSmem {
     uint32_t* pass_idx;        // [kPassingCap] passing-filter ids (collection.hpp:783)
     uint16_t* pass_sim;        // [kPassingCap] their Q15 similarity as dot + 32768
+    uint16_t* unk;             // [kPassingCap] positions of the passing list whose similarity is not memoised yet
     uint32_t* anchor;          // [L] lower bound of the query code in each table (prefixmap.hpp:36-57), unpadded position
     uint2* lcp_up;             // [L] 8 bytes: common-prefix length with the code at anchor + 12 j, j = 0..7
     uint2* lcp_dn;             // [L] 8 bytes: same at anchor - 1 - 12 j
@@ -137,7 +138,7 @@ struct WarpSmem {
 
 __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t L, uint32_t k) {
     uint32_t p2k = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
-    uint32_t b = kPassingCap * 4 + kPassingCap * 2;  // pass_idx, pass_sim
+    uint32_t b = kPassingCap * 4 + kPassingCap * 2 * 2;  // pass_idx, pass_sim, unk
     b += L * 4;                                       // anchor
     b += L * 8 * 2;                                   // lcp_up, lcp_dn
     b += L * 4 * 2;                                   // code, start
@@ -159,6 +160,7 @@ __device__ __forceinline__ WarpSmem carve(uint8_t* base, uint32_t L, uint32_t k)
     w.start = reinterpret_cast<uint32_t*>(p); p += L * 4;
     w.segbase = reinterpret_cast<uint32_t*>(p); p += (L + 1) * 4;
     w.pass_sim = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
+    w.unk = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
     p = base + (((uint32_t)(p - base) + 15) & ~15u);
     w.mb = reinterpret_cast<unsigned long long*>(p); p += p2k * 8;
     w.heap = reinterpret_cast<unsigned long long*>(p); p += k * 8;
@@ -169,25 +171,41 @@ __device__ __forceinline__ WarpSmem carve(uint8_t* base, uint32_t L, uint32_t k)
 // ------------------------------------------------------------------------------------------------ probe of one cluster
 
 // Q15 similarities (as dot + 32768) of the first `count` ids in sm.pass_idx -> sm.pass_sim.
-// G lanes cooperate on one row with 128-bit loads (the HBM-bound rerank gather, cosine.hpp:19-23 / math.hpp:11-44).
+// memo (one u16 per local id, 0 = unknown; may be null) returns similarities already computed during this visit: the
+// reference rescans nested ranges at every depth, so more than half of its distance computations are repeats. The rows
+// that are missing are gathered with 128-bit loads, G lanes per row (the HBM-bound rerank gather, cosine.hpp:19-23 /
+// math.hpp:11-44).
 template <int G>
 __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const int16_t* __restrict__ rows, uint32_t sl,
-                                       const int16_t* __restrict__ qrow_smem, const int (&qreg)[8], bool qreg_valid) {
+                                       const int16_t* __restrict__ qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo) {
     constexpr int CPI = 32 / G;  // candidates per warp iteration
-    const uint32_t sub = lane_id() % G;
-    const uint32_t grp = lane_id() / G;
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane % G;
+    const uint32_t grp = lane / G;
     const uint32_t cpr = sl / 8;  // 16-byte chunks per row
-    for (uint32_t base = 0; base < count; base += CPI * 4) {
+    uint32_t nunk = 0;
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < count;
+        const uint32_t m = (valid && memo) ? (uint32_t)memo[sm.pass_idx[i]] : 0u;
+        const bool need = valid && m == 0;
+        if (valid && m) sm.pass_sim[i] = (uint16_t)m;
+        const uint32_t bal = __ballot_sync(0xffffffffu, need);
+        if (need) sm.unk[nunk + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+        nunk += __popc(bal);
+    }
+    __syncwarp();
+    for (uint32_t base = 0; base < nunk; base += CPI * 4) {
         int part[4];
         uint4 w[4];
-        bool ok[4];
+        uint32_t pos[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            uint32_t cand = base + u * CPI + grp;
-            ok[u] = cand < count && sub < cpr;
+            const uint32_t cand = base + u * CPI + grp;
+            pos[u] = cand < nunk ? sm.unk[cand] : 0xffffffffu;
             w[u] = make_uint4(0, 0, 0, 0);
-            if (ok[u]) {
-                const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[cand] * sl) + sub;
+            if (pos[u] != 0xffffffffu && sub < cpr) {
+                const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[pos[u]] * sl) + sub;
                 asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w)
                              : "l"(src));
@@ -208,10 +226,9 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
             // rows wider than 32 chunks (d > 256): loop over the remaining chunks with the query read from shared memory
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                uint32_t cand = base + u * CPI + grp;
                 int s = 0;
-                if (cand < count) {
-                    const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[cand] * sl);
+                if (pos[u] != 0xffffffffu) {
+                    const uint4* src = reinterpret_cast<const uint4*>(rows + (uint64_t)sm.pass_idx[pos[u]] * sl);
                     for (uint32_t ch = sub; ch < cpr; ch += G) {
                         uint4 a = __ldg(src + ch);
                         uint4 b = *reinterpret_cast<const uint4*>(qrow_smem + ch * 8);
@@ -229,8 +246,11 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
             int s = part[u];
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            uint32_t cand = base + u * CPI + grp;
-            if (sub == 0 && cand < count) sm.pass_sim[cand] = (uint16_t)(s + 32768);
+            if (sub == 0 && pos[u] != 0xffffffffu) {
+                const uint16_t sim16 = (uint16_t)(s + 32768);
+                sm.pass_sim[pos[u]] = sim16;
+                if (memo) memo[sm.pass_idx[pos[u]]] = sim16;
+            }
         }
     }
     __syncwarp();
@@ -241,7 +261,7 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
 template <int G>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
-                                  const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, ProbeCounters& ctr) {
+                                  const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr) {
     const uint32_t L = p.g.L, k = p.k;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -251,84 +271,34 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     const uint64_t* sk = p.sketches + off * kNumSketches;
 
     uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;  // maxbuffer.hpp:53-55, filterer.hpp:101
+    if (memo) {
+        uint4* mz = reinterpret_cast<uint4*>(memo);
+        for (uint32_t i = lane; i < (nc + 7) / 8; i += 32) mz[i] = make_uint4(0, 0, 0, 0);
+    }
 
     // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
     for (uint32_t t = lane; t < L; t += 32) {
         const uint32_t h = codes[(uint64_t)t * code_stride];
-        const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
-        uint32_t lo = 0, len = nc;  // lower_bound == the reference's hinted halving search
-        while (len > 0) {
-            uint32_t half = len >> 1;
-            uint32_t mid = lo + half;
-            if (__ldg(H + mid) < h) {
-                lo = mid + 1;
-                len -= half + 1;
-            } else {
-                len = half;
-            }
-        }
+        uint32_t A;
+        uint2 up, dn;
+        table_anchor(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc, h, A, up, dn);
         sm.code[t] = h;
-        sm.anchor[t] = lo;
-        uint32_t up[8], dn[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            uint32_t pu = lo + kSegment * j;
-            up[j] = pu < nc ? lcp24(__ldg(H + pu), h) : 0u;  // beyond the data lie the 0xffffffff sentinels (prefixmap.hpp:215-226)
-            int64_t pd = (int64_t)lo - 1 - kSegment * j;
-            dn[j] = pd >= 0 ? lcp24(__ldg(H + pd), h) : 0u;
-        }
-        sm.lcp_up[t] = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
-        sm.lcp_dn[t] = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
+        sm.anchor[t] = A;
+        sm.lcp_up[t] = up;
+        sm.lcp_dn[t] = dn;
     }
     __syncwarp();
 
     bool stopped = false;
     for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
         // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
-        const uint32_t it = kMaxHashBits + 1 - depth;              // iteration 1..24
-        const uint32_t dir_bit = 1u << (it >= 2 ? it - 2 : 0);     // removed bit (prefixmap.hpp:268-274)
         uint32_t running = 0;
         for (uint32_t t0 = 0; t0 < L; t0 += 32) {
             const uint32_t t = t0 + lane;
             uint32_t nseg = 0;
-            if (t < L) {
-                const uint32_t h = sm.code[t];
-                const uint32_t A = sm.anchor[t];
-                const uint32_t* H = p.tbl_hash + (uint64_t)t * p.n + off;
-                int64_t start, end;
-                if ((h & dir_bit) == 0) {  // upward (prefixmap.hpp:277-290)
-                    uint32_t j = lead_count(sm.lcp_up[t], depth);
-                    if (j == 8) {
-                        // run longer than the samples: first position >= A + 96 whose prefix differs, rounded up to the stride
-                        uint32_t lo = A + 8 * kSegment, len = nc > lo ? nc - lo : 0;
-                        while (len > 0) {
-                            uint32_t half = len >> 1, mid = lo + half;
-                            if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
-                        }
-                        j = (lo - A + kSegment - 1) / kSegment;
-                    }
-                    start = A;
-                    end = (int64_t)A + (int64_t)kSegment * j;
-                    if (end >= (int64_t)nc) end = (end - kSegment) > start ? (end - kSegment) : start;
-                } else {  // downward (prefixmap.hpp:291-303)
-                    uint32_t j = lead_count(sm.lcp_dn[t], depth);
-                    if (j == 8) {
-                        // first position of the matching run below A - 96
-                        uint32_t hi = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [0, hi) undecided
-                        uint32_t lo = 0, len = hi;
-                        while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
-                            uint32_t half = len >> 1, mid = lo + half;
-                            if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
-                        }
-                        j = (A - lo + kSegment - 1) / kSegment;
-                    }
-                    end = A;
-                    start = (int64_t)A - (int64_t)kSegment * j;
-                    if (start < 0) start = (start + kSegment) < end ? (start + kSegment) : end;
-                }
-                sm.start[t] = (uint32_t)start;
-                nseg = (uint32_t)(end - start) >> 2;
-            }
+            if (t < L)
+                sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc,
+                                          sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
             uint32_t total;
             uint32_t ex = warp_excl_scan(nseg, total);
             if (t < L) sm.segbase[t] = running + ex;
@@ -348,7 +318,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             }
             uint32_t t = lo - 1;
             t_out = t;
-            return (uint64_t)t * p.n + off + sm.start[t] + 4 * (s - sm.segbase[t]);
+            return table_base(off, nc, L, t) + sm.start[t] + 4 * (s - sm.segbase[t]);
         };
 
         uint32_t base = 0;  // first stream segment held by the ring
@@ -400,7 +370,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             }
             __syncwarp();
             // empty the buffer (collection.hpp:909-925)
-            rerank<G>(sm, np, rows, p.g.sl, qrow_smem, qreg, qreg_valid);
+            rerank<G>(sm, np, rows, p.g.sl, qrow_smem, qreg, qreg_valid, memo);
             maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, np);
             ctr.distcomp += np;
             max_diff = p.msd[minval16 < 65536u ? minval16 : 65535u];  // filterer.hpp:108-111
@@ -445,7 +415,7 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
         uint32_t cnt = nc - base < (uint32_t)kFilterBuffer ? nc - base : (uint32_t)kFilterBuffer;
         for (uint32_t i = lane_id(); i < cnt; i += 32) sm.pass_idx[i] = base + i;
         __syncwarp();
-        rerank<G>(sm, cnt, rows, p.g.sl, qrow_smem, qreg, qreg_valid);
+        rerank<G>(sm, cnt, rows, p.g.sl, qrow_smem, qreg, qreg_valid, nullptr);
         maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, cnt);
     }
     maxbuffer_filter(sm.mb, P, k, inserted, minval16);
@@ -457,7 +427,8 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
 // src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
 // for expensive ones). Warps are persistent; grid = multiple of the SM count.
 template <int G, int OCC>
-__global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign) {
+__global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign,
+                                                    uint16_t* memo_base, uint64_t memo_stride) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint8_t* wbase = s_dyn + (size_t)warp * (warp_bytes + p.g.sl * 2);
@@ -466,6 +437,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
     const uint64_t state_bytes = sizeof(QueryStateHeader) + (uint64_t)p.k * 8;
     const uint32_t cpr = p.g.sl / 8;
     const bool qreg_valid = cpr <= 32;
+    uint16_t* memo = memo_base ? memo_base + ((uint64_t)blockIdx.x * (blockDim.x >> 5) + warp) * memo_stride : nullptr;
 
     for (;;) {
         uint32_t q = 0;
@@ -561,7 +533,8 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 const uint32_t* codes = b.codes + (uint64_t)fs * p.g.L * b.nq + q;
                 const uint64_t my_sketch = b.sketches[((uint64_t)fs * b.nq + q) * kNumSketches + lane];
                 const uint32_t* stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
-                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, ctr);
+                uint16_t* use_memo = (memo && nc <= memo_stride) ? memo : nullptr;
+                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr);
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
                     uint32_t j = base + lane;
@@ -681,7 +654,7 @@ __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatc
         cnt = probe_bruteforce_q15<G>(p, sm, 0, qrow, qreg, qreg_valid);
     } else {
         const uint64_t my_sketch = b.sketches[lane];
-        cnt = probe_cluster<G>(p, sm, 0, b.codes, 1, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, ctr);
+        cnt = probe_cluster<G>(p, sm, 0, b.codes, 1, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, nullptr, ctr);
     }
     for (uint32_t i = lane; i < cnt; i += 32) out_ids[i] = (uint32_t)sm.mb[i];
     if (lane == 0) {
@@ -754,7 +727,23 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     uint64_t want = (b.nq + warps - 1) / warps;
     uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want ? want : 1;
-    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0);
+    // per-warp similarity memo (u16 per local id of the cluster being probed); skipped when it would not fit in ~1 GiB
+    static uint16_t* memo = nullptr;
+    static size_t memo_cap = 0;
+    const uint64_t stride = ((uint64_t)p.max_cluster + 7) & ~7ull;
+    const size_t need = (size_t)grid * warps * stride;
+    uint16_t* use = nullptr;
+    static int no_memo = -1;
+    if (no_memo < 0) no_memo = getenv("CLANN_PROBE_NOMEMO") ? 1 : 0;  // A/B knob
+    if (!no_memo && stride > 0 && need * sizeof(uint16_t) <= ((size_t)1 << 30)) {
+        if (need > memo_cap) {
+            if (memo) CLANN_CUDA(cudaFree(memo));
+            CLANN_CUDA(cudaMalloc(&memo, need * sizeof(uint16_t)));
+            memo_cap = need;
+        }
+        use = memo;
+    }
+    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0, use, stride);
 }
 
 template <int G>

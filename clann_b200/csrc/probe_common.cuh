@@ -235,4 +235,97 @@ __device__ __forceinline__ uint32_t lead_count(uint2 packed, uint32_t depth) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------------ per-table probe state
+
+// SearchBuffers ctor for one table (collection.hpp:642-645 -> prefixmap.hpp:36-57,250-260): the anchor A = lower bound of
+// the query code h in the cluster's sorted codes H[0..nc), found inside bucket [dir[b], dir[b+1]) of its top byte b
+// (lower_bound == the reference's hinted halving search), plus the common-prefix length with the codes at
+// A + 12 j and A - 1 - 12 j, j = 0..7, packed one byte each (beyond the data lie the 0xffffffff sentinels,
+// prefixmap.hpp:215-226, which match nothing).
+__device__ __forceinline__ void table_anchor(const uint32_t* __restrict__ H, const uint32_t* __restrict__ dir, uint32_t nc, uint32_t h,
+                                             uint32_t& anchor, uint2& lcp_up, uint2& lcp_dn) {
+    const uint32_t b = h >> (kMaxHashBits - kDirBits);
+    uint32_t lo = __ldg(dir + b), len = __ldg(dir + b + 1) - lo;
+    while (len > 8) {
+        uint32_t half = len >> 1, mid = lo + half;
+        if (__ldg(H + mid) < h) { lo = mid + 1; len -= half + 1; } else { len = half; }
+    }
+    uint32_t below = 0;  // the codes are sorted: the lower bound is the number of entries below h
+#pragma unroll
+    for (uint32_t j = 0; j < 8; j++)
+        if (j < len) below += __ldg(H + lo + j) < h ? 1u : 0u;
+    lo += below;
+    anchor = lo;
+    uint32_t up[8], dn[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t pu = lo + kSegment * j;
+        up[j] = pu < nc ? lcp24(__ldg(H + pu), h) : 0u;
+        int64_t pd = (int64_t)lo - 1 - kSegment * j;
+        dn[j] = pd >= 0 ? lcp24(__ldg(H + pd), h) : 0u;
+    }
+    lcp_up = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
+    lcp_dn = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
+}
+
+// PrefixMap::get_next_range (prefixmap.hpp:267-304) in closed form for one table at `depth`: with [lo, hi)
+// the block of codes sharing the query's `depth`-bit prefix, upward [A, A + 12 ceil((hi - A)/12)) then the `>= len-12`
+// clamp, downward [A - 12 ceil((A - lo)/12), A) then the `< 12` clamp; the anchors are never advanced (:278,292).
+// The block comes from the directory when depth <= 8 bits, from the stride-12 samples otherwise (a block longer than the
+// samples is resolved by a binary search confined to the code's bucket). Returns the range start; nseg = 4-entry segments.
+__device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, const uint32_t* __restrict__ dir, uint32_t nc, uint32_t h,
+                                                uint32_t A, uint2 lcp_up, uint2 lcp_dn, uint32_t depth, uint32_t& nseg) {
+    const uint32_t it = kMaxHashBits + 1 - depth;              // iteration 1..24
+    const uint32_t dir_bit = 1u << (it >= 2 ? it - 2 : 0);     // removed bit (prefixmap.hpp:268-274)
+    const bool upward = (h & dir_bit) == 0;
+    const uint32_t b = h >> (kMaxHashBits - kDirBits);
+    uint32_t j;
+    if (depth <= kDirBits) {
+        const uint32_t sh = kDirBits - depth, pb = b >> sh;
+        if (upward) {
+            const uint32_t hi = __ldg(dir + ((pb + 1) << sh));
+            j = hi > A ? (hi - A + kSegment - 1) / kSegment : 0u;
+        } else {
+            const uint32_t lo = __ldg(dir + (pb << sh));
+            j = A > lo ? (A - lo + kSegment - 1) / kSegment : 0u;
+        }
+    } else if (upward) {
+        j = lead_count(lcp_up, depth);
+        if (j == 8) {  // first position >= A + 96 whose prefix differs; it cannot lie beyond the bucket of the top byte
+            uint32_t lo = A + 8 * kSegment, end = __ldg(dir + b + 1);
+            uint32_t len = end > lo ? end - lo : 0;
+            while (len > 0) {
+                uint32_t half = len >> 1, mid = lo + half;
+                if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+            }
+            j = (lo - A + kSegment - 1) / kSegment;
+        }
+    } else {
+        j = lead_count(lcp_dn, depth);
+        if (j == 8) {  // first position of the matching block below A - 96, not before the bucket start
+            const uint32_t beg = __ldg(dir + b);
+            const uint32_t top = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [beg, top) undecided
+            uint32_t lo = beg, len = top > beg ? top - beg : 0;
+            while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
+                uint32_t half = len >> 1, mid = lo + half;
+                if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+            }
+            j = (A - lo + kSegment - 1) / kSegment;
+        }
+    }
+    int64_t start, end;
+    if (upward) {  // prefixmap.hpp:277-290
+        start = A;
+        end = (int64_t)A + (int64_t)kSegment * j;
+        if (end >= (int64_t)nc) end = (end - kSegment) > start ? (end - kSegment) : start;
+    } else {       // prefixmap.hpp:291-303
+        end = A;
+        start = (int64_t)A - (int64_t)kSegment * j;
+        if (start < 0) start = (start + kSegment) < end ? (start + kSegment) : end;
+    }
+    nseg = (uint32_t)(end - start) >> 2;
+    return (uint32_t)start;
+}
+
 }  // namespace clann
