@@ -219,12 +219,6 @@ __device__ __forceinline__ void l2_prefetch_cluster(const SearchParams& p, uint3
             l2_prefetch_range(base[a] + lo, lo + kPiece < len[a] ? kPiece : len[a] - lo);
 }
 
-// One term of math.hpp:37-44, (a*b + 2^14) >> 15, for a given in the HIGH half of a 32-bit word and b doubled:
-// (a*2^16) * (2b) + 2^31 = 2^17 (a*b + 2^14), whose upper word is the term (one IMAD.HI with a 64-bit addend, no shift).
-__device__ __forceinline__ int q15_mul_hi(int a_hi16, int b2) {
-    return (int)(((long long)a_hi16 * (long long)b2 + 0x80000000ll) >> 32);
-}
-
 // Sum of the terms of one 16-byte unit (8 elements) against 8 doubled query elements.
 __device__ __forceinline__ int q15_dot_unit(uint4 w, int4 a, int4 b) {
     int s = 0;

@@ -76,6 +76,79 @@ __global__ void __launch_bounds__(256) k_center_dist(const float* __restrict__ q
     }
 }
 
+// Register-tiled version of the same computation (d <= 256): a warp owns four queries, a lane two centres of the 64-centre
+// chunk, so eight dot products advance together and every shared-memory word read feeds several of them (the plain tile
+// above spends two LDS per multiply-add and is bound by shared-memory bandwidth). Centre rows are stored transposed with a
+// 65-word pitch (conflict-free for the transposing store and for the lane-contiguous read); query rows are read as
+// float4 broadcasts. The arithmetic and its order are those of ndarray's unrolled_dot (common.cuh), per (query, centre).
+__global__ void __launch_bounds__(256) k_center_dist_tiled(const float* __restrict__ queries, const float* __restrict__ qnorm, uint64_t nq,
+                                                           const float* __restrict__ center_rows, const float* __restrict__ center_norms,
+                                                           uint32_t K, uint32_t d, float* __restrict__ cdist) {
+    extern __shared__ __align__(16) float s_f[];
+    const uint32_t dq = (d + 3) & ~3u;     // query pitch (16-byte aligned rows)
+    float* s_q = s_f;                       // [32][dq]
+    float* s_ct = s_f + 32 * dq;            // [d][65]
+    const uint64_t q0 = (uint64_t)blockIdx.x * 32;
+    const uint32_t nqt = (uint32_t)((nq - q0) < 32 ? (nq - q0) : 32);
+    for (uint32_t e = threadIdx.x; e < 32 * dq; e += blockDim.x) {
+        uint32_t j = e / dq, i = e % dq;
+        s_q[e] = (j < nqt && i < d) ? queries[(q0 + j) * d + i] : 0.0f;
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t full = d & ~7u;
+    for (uint32_t cb = 0; cb < K; cb += 64) {
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < 64 * d; e += blockDim.x) {
+            uint32_t c = e / d, i = e % d;
+            s_ct[i * 65 + c] = (cb + c) < K ? center_rows[(uint64_t)(cb + c) * d + i] : 0.0f;
+        }
+        __syncthreads();
+        float p[4][2][8];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int u = 0; u < 8; u++) p[j][h][u] = 0.0f;
+        for (uint32_t i0 = 0; i0 < full; i0 += 8) {
+            float cv[2][8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                cv[0][u] = s_ct[(i0 + u) * 65 + lane];
+                cv[1][u] = s_ct[(i0 + u) * 65 + lane + 32];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 qa = *reinterpret_cast<const float4*>(s_q + (warp * 4 + j) * dq + i0);
+                const float4 qb = *reinterpret_cast<const float4*>(s_q + (warp * 4 + j) * dq + i0 + 4);
+                const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int u = 0; u < 8; u++) p[j][h][u] = __fadd_rn(p[j][h][u], __fmul_rn(cv[h][u], qv[u]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t jq = warp * 4 + j;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t c = cb + h * 32 + lane;
+                float sum = 0.0f;
+                sum = __fadd_rn(sum, __fadd_rn(p[j][h][0], p[j][h][4]));
+                sum = __fadd_rn(sum, __fadd_rn(p[j][h][1], p[j][h][5]));
+                sum = __fadd_rn(sum, __fadd_rn(p[j][h][2], p[j][h][6]));
+                sum = __fadd_rn(sum, __fadd_rn(p[j][h][3], p[j][h][7]));
+                for (uint32_t i = full; i < d; i++) sum = __fadd_rn(sum, __fmul_rn(s_ct[i * 65 + h * 32 + lane], s_q[jq * dq + i]));
+                if (jq < nqt && c < K) {
+                    const float cs = __fdiv_rn(sum, __fmul_rn(center_norms[c], qnorm[q0 + jq]));  // angulardata.rs:29-35
+                    cdist[(q0 + jq) * K + c] = __fsub_rn(1.0f, cs);
+                }
+            }
+        }
+    }
+}
+
 // Fallback for very wide rows (the tiles above would not fit in shared memory): one thread per (query, centre).
 __global__ void __launch_bounds__(256) k_center_dist_simple(const float* __restrict__ queries, const float* __restrict__ qnorm, uint64_t nq,
                                                             const float* __restrict__ center_rows, const float* __restrict__ center_norms,
@@ -674,7 +747,16 @@ void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_
     if (b.nq == 0) return;
     const uint32_t stride = p.g.d | 1;
     size_t smem = (size_t)96 * stride * sizeof(float);
-    if (smem <= 160 * 1024) {
+    if (p.g.d <= 256) {
+        const size_t tsmem = ((size_t)32 * ((p.g.d + 3) & ~3u) + (size_t)p.g.d * 65) * sizeof(float);
+        static size_t tconfigured = 0;
+        if (tsmem > 48 * 1024 && tsmem > tconfigured) {
+            CLANN_CUDA(cudaFuncSetAttribute(k_center_dist_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
+            tconfigured = tsmem;
+        }
+        k_center_dist_tiled<<<(unsigned)((b.nq + 31) / 32), 256, tsmem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms,
+                                                                             p.K, p.g.d, b.cdist);
+    } else if (smem <= 160 * 1024) {
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             CLANN_CUDA(cudaFuncSetAttribute(k_center_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
