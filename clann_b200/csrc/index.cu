@@ -1088,6 +1088,12 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 break;
             }
             case CLANN_X_BUILD_MS: emit(index->build_ms, sizeof(index->build_ms)); break;
+            case CLANN_X_TABLE_DIR: {
+                need_cluster();
+                const uint64_t L = index->g.L;
+                emit_dev(index->d_tbl_dir.p + (uint64_t)arg * L * kDirEntries, L * kDirEntries * 4);
+                break;
+            }
             default: throw StatusError(CLANN_ERR_ARG, "unknown export selector");
         }
     });

@@ -119,7 +119,9 @@ typedef enum {
     CLANN_X_QUERY_CODES = 13, /* u32[nq*L] table codes of the last search batch for the function set of cluster `arg` */
     CLANN_X_QUERY_SKETCHES = 14, /* u64[nq*32] likewise */
     CLANN_X_CLUSTER_ORDER = 15,  /* u32[nq*K] visiting order of the last search batch (index.rs:592-616) */
-    CLANN_X_BUILD_MS = 16     /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
+    CLANN_X_BUILD_MS = 16,    /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
+    CLANN_X_TABLE_DIR = 17    /* u32[L*257] bucket directory of cluster `arg`: first position per top code byte (the role of
+                                 PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 8 bits), table-major */
 } clann_export_what;
 int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size);
 

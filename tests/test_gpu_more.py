@@ -265,3 +265,62 @@ def test_sharded_search_equals_single_gpu(big):
     assert steps >= 2  # at least one hand-over happened
     for ix in shards:
         ix.close()
+
+
+def test_bucket_directory_matches_tables(big):
+    """The bucket directory (role of PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 8 bits): entry b of table t is the
+    lower bound of (b << 16) in that table's sorted codes; entry 256 is the cluster size."""
+    from clann_b200 import _lib as cl
+    _, ix = big
+    off = ix.export(cl.X_OFFSETS, 0, np.uint64)
+    brute = ix.export(cl.X_BRUTE, 0, np.uint8)
+    keys = (np.arange(257, dtype=np.uint32) << np.uint32(16))
+    for ci in np.flatnonzero(brute == 0)[:4]:
+        nc = int(off[ci + 1] - off[ci])
+        th = ix.export(cl.X_TABLE_HASHES, int(ci), np.uint32).reshape(84, nc)
+        dr = ix.export(cl.X_TABLE_DIR, int(ci), np.uint32).reshape(84, 257)
+        for t in range(84):
+            assert np.array_equal(dr[t], np.searchsorted(th[t], keys, side="left").astype(np.uint32))
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from tests import util
+import clann_b200 as cb
+data = util.planted(60_000, 100, 31)
+q = np.concatenate([util.planted_queries(data, 400, 32), util.uniform_sphere(40, 100, 33)])
+ix = cb.init_with_config(data, cb.Config(84, 0.4, 10, 0.9, "variant"))
+ix.set_option("seed", 77)
+ix.build()
+ids, dists, counts = ix.search_batch(q)
+ctr = ix.counters(len(q))
+np.savez(sys.argv[2], ids=ids, dists=dists, counts=counts, cand=ctr["candidates"], dc=ctr["distance_computations"],
+         vis=ctr["clusters_visited"])
+"""
+
+
+def test_probe_kernel_variants_agree(tmp_path):
+    """The probe kernel is selected once per process (CLANN_PROBE / CLANN_PROBE_NOMEMO): the one-warp-per-query kernel with
+    and without the similarity memo and the warp-specialised one-CTA-per-query kernel must return identical ids, distance
+    bits and reference counters (candidates, distance_computations, clusters visited) for the same index and queries —
+    planted queries plus uniform ones that walk many clusters."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for name, env in (("warp", {}), ("warp_nomemo", {"CLANN_PROBE_NOMEMO": "1"}), ("cta", {"CLANN_PROBE": "cta"})):
+        out = str(tmp_path / (name + ".npz"))
+        e = dict(os.environ)
+        e.pop("CLANN_PROBE", None)
+        e.pop("CLANN_PROBE_NOMEMO", None)
+        e.update(env)
+        subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root, out], check=True, env=e, timeout=600)
+        outs[name] = np.load(out)
+    ref = outs["warp"]
+    assert ref["vis"].max() > 3  # the uniform queries do walk several clusters
+    for name in ("warp_nomemo", "cta"):
+        o = outs[name]
+        for key in ("ids", "counts", "cand", "dc", "vis"):
+            assert np.array_equal(ref[key], o[key]), (name, key)
+        assert np.array_equal(ref["dists"].view(np.uint32), o["dists"].view(np.uint32)), name
