@@ -206,6 +206,10 @@ def main():
     ap.add_argument("--workload", default="glove100", choices=["glove100", "glove25", "readme"],
                     help="glove100 (default) is the configuration the metric is quoted on; the others are BASELINE.json's parity-size configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="queries", choices=["queries", "clusters"],
+                    help="N > 1: 'queries' = the index is replicated and every rank searches its own batch (weak scaling, no "
+                         "data-path collective); 'clusters' = clusters are sharded by owner and one fixed batch is stepped "
+                         "through the ranks with an all-gather per step (strong scaling; for indices beyond one GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -257,12 +261,27 @@ def main():
 
     data, queries, src = make_data(w, args.dist)
     nq, k, d = w["nq"], w["k"], w["d"]
+    shard_clusters = world > 1 and args.shard == "clusters"
+    if world > 1 and not shard_clusters:
+        # weak scaling: every rank owns a full replica and its own batch of nq queries (same distribution, its own seed)
+        rq = np.random.default_rng(43 + 1000 * rank)
+        if args.dist == "planted":
+            src = rq.integers(0, w["n"], nq)
+            queries = data[src] + np.float32(0.05) * rq.standard_normal((nq, d), dtype=np.float32)
+        else:
+            queries = rq.standard_normal((nq, d), dtype=np.float32)
+        queries /= np.linalg.norm(queries, axis=1, keepdims=True)
+        queries = np.ascontiguousarray(queries, np.float32)
+    cfg_json["parallelism"] = ("single GPU" if world == 1 else
+                               f"clusters sharded over {world} GPUs, one batch stepped with an all-gather of query states per step"
+                               if shard_clusters else
+                               f"index replicated on {world} GPUs, {nq} queries per GPU per step (global batch {nq * world}), no data-path collective")
 
     # ---- build (untimed setup of the search benchmark; reported on its own)
     t0 = time.time()
     index = cb.init_with_config(data, cb.Config(w["L"], w["factor"], w["k"], w["delta"], "bench"))
     index.set_option("seed", 1234)
-    if world > 1:
+    if shard_clusters:
         index.set_option("shard_count", world)
         index.set_option("shard_rank", rank)
     index.build()
@@ -279,7 +298,8 @@ def main():
     d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
     d_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
     d_counts = torch.empty(nq, dtype=torch.int32, device=dev)
-    searcher = ShardedSearcher(index, world, rank)
+    searcher = ShardedSearcher(index, world, rank) if shard_clusters else ShardedSearcher(index, 1, 0)
+    single = not shard_clusters  # this rank runs the whole single-GPU path on its own batch
 
     def step_device():
         searcher.search_device(d_q, d_ids, d_dists, d_counts)
@@ -291,7 +311,7 @@ def main():
     h_counts = torch.empty(nq, dtype=torch.int32).pin_memory()
 
     def step_e2e():
-        if world == 1:
+        if single:
             # the reference-facing call: host pointers in, host pointers out (copies inside clann_search)
             st = index._lib.clann_search(index.handle, h_q.data_ptr(), nq, h_ids.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr())
             if st != 0:
@@ -349,7 +369,7 @@ def main():
     clocks = sampler.stop()
     launches_per_step = searcher.last_launches
     # per-kernel split from a separate pass (events inside the library); same stream, same inputs
-    if world == 1:
+    if single:
         for _ in range(args.steps):
             step_device()
             prof = index.search_profile()
@@ -360,13 +380,14 @@ def main():
         probe_ms = prep_ms = None
 
     ms_per_step = total_ms / args.steps
-    value = nq / (ms_per_step / 1000.0)
+    global_nq = nq if (world == 1 or shard_clusters) else nq * world   # queries the whole job answers per step
+    value = global_nq / (ms_per_step / 1000.0)
 
     # end to end
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps) / args.steps
-    e2e_value = nq / (e2e_ms / 1000.0)
+    e2e_value = global_nq / (e2e_ms / 1000.0)
 
     # ---- correctness of what was timed: recall@k against exact fp32 neighbours (utils/mod.rs:59-95)
     step_device()
@@ -386,7 +407,7 @@ def main():
 
     line = None
     if rank == 0:
-        ctr = index.counters(nq) if world == 1 else searcher.counters(nq)
+        ctr = index.counters(nq) if single else searcher.counters(nq)
         cand = float(ctr["candidates"].sum()); dc = float(ctr["distance_computations"].sum()); vis = float(ctr["clusters_visited"].sum())
         sl = (d + 15) // 16 * 16
         rerank_bytes = dc * 2 * sl + vis * k * 4 * d
@@ -409,7 +430,7 @@ def main():
                         "algorithmic_bytes_per_launch": rerank_bytes + filter_bytes,
                         "rerank_gbs": rerank_bytes / (probe_ms / 1000.0) / 1e9, "filter_gbs": filter_bytes / (probe_ms / 1000.0) / 1e9}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N=1 only
             try:
                 ref = run_reference(w, data, queries, src, centers, assignment, radii, threads=1)
                 cpu = {"value": ref["qps_1thread"], "unit": UNIT, "cores": 1, "kind": ref["kind"], "sample": ref["sample"],
@@ -419,11 +440,13 @@ def main():
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i16",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (shard_clusters or world == 1) else "weak",
+            "vs_baseline": None, "dtype": "i16",
             "data": "synthetic", "config": cfg_json, "recall_at_k": recall, "recall_queries_checked": nchk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 8 + nq * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,
+                    "d2h_bytes_per_step": global_nq * k * 8 + global_nq * 4,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches_per_step * args.steps * (1 if (world == 1 or shard_clusters) else world)), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "build": {"wall_s": build_wall, "gmm_ms": build_ms[0], "hash_ms": build_ms[1], "sort_ms": build_ms[2], "device_ms": build_ms[3],
                       "clusters": int(K)},
             "per_query": {"clusters_visited": vis / nq, "candidates": cand / nq, "distance_computations": dc / nq},
