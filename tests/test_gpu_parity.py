@@ -72,7 +72,13 @@ def sc128u(oracle, reflib):
     return Scenario(oracle, reflib, n=1600, d=128, L=16, k=5, delta=0.95, seed=13, kind="uniform")
 
 
-SCENARIOS = ["sc25", "sc100", "sc128u"]
+@pytest.fixture(scope="module")
+def sc96k100(oracle, reflib):
+    # BASELINE.json configs[4] style: d=96, k=100, delta=0.8 (256-slot MaxBuffer, larger per-warp state)
+    return Scenario(oracle, reflib, n=3000, d=96, L=20, k=100, delta=0.8, seed=14, factor=0.1)
+
+
+SCENARIOS = ["sc25", "sc100", "sc128u", "sc96k100"]
 
 
 @pytest.mark.parametrize("name", SCENARIOS)
