@@ -285,6 +285,9 @@ struct clann_index {
     DevBuf<uint64_t> w_sketches;
     DevBuf<unsigned long long> w_cand, w_dc;
     DevBuf<uint8_t> w_state;
+    DevBuf<uint16_t> w_memo;  // similarity memo scratch of the probe kernels
+    uint64_t w_memo_stride = 0;
+    uint32_t w_memo_slots = 0;
     DevBuf<RowTile> w_tiles;
     uint32_t w_ntiles = 0;
     uint64_t last_nq = 0;
@@ -541,6 +544,7 @@ struct clann_index {
 
     void build() {
         cudaStream_t s = 0;
+        ws_nq = 0;  // the search workspace (memo stride, tiles) depends on the clustering
         cudaEvent_t e0, e1, e2, e3;
         CLANN_CUDA(cudaEventCreate(&e0)); CLANN_CUDA(cudaEventCreate(&e1)); CLANN_CUDA(cudaEventCreate(&e2)); CLANN_CUDA(cudaEventCreate(&e3));
         CLANN_CUDA(cudaEventRecord(e0, s));
@@ -696,6 +700,15 @@ struct clann_index {
             w_sort_seg.upload(seg, s);
         }
         w_state.ensure(nq * query_state_bytes(k));
+        {
+            // one memo region (u16 per local id of the largest cluster) per resident probe warp; skipped beyond 1 GiB
+            const uint32_t max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
+            w_memo_stride = ((uint64_t)max_cluster + 7) & ~7ull;
+            w_memo_slots = probe_memo_slots();
+            const uint64_t need = w_memo_stride * w_memo_slots;
+            if (need > 0 && need * sizeof(uint16_t) <= (1ull << 30)) w_memo.ensure(need);
+            else w_memo_slots = 0;
+        }
         w_counter.ensure(2);
         w_cand.ensure(nq);
         w_dc.ensure(nq);
@@ -722,6 +735,9 @@ struct clann_index {
         b.qperm = w_qperm.p;
         b.state = w_state.p;
         b.work_counter = w_counter.p;
+        b.memo = w_memo_slots ? w_memo.p : nullptr;
+        b.memo_stride = w_memo_stride;
+        b.memo_slots = w_memo_slots;
         b.out_ids = d_ids;
         b.out_dists = d_dists;
         b.out_counts = d_counts;

@@ -92,6 +92,11 @@ struct QueryBatch {
     // per-query running state (also the multi-GPU exchange unit): see kernels_search.cu
     uint8_t* state;
     uint32_t* work_counter; // [1]
+    // similarity memo scratch owned by the index workspace: memo_slots regions of memo_stride u16 (one per resident warp /
+    // CTA of the probe kernel); null = no memo (the largest cluster would make it too big)
+    uint16_t* memo;
+    uint64_t memo_stride;
+    uint32_t memo_slots;
     // outputs
     uint32_t* out_ids;      // [nq][k]
     float* out_dists;       // [nq][k]
@@ -113,6 +118,7 @@ void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_
 void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);   // one CTA per query
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+uint32_t probe_memo_slots();  // upper bound on the memo regions any probe launch uses on the current device
 
 // Single PUFFINN index query (legacy CPUFFINN_search_cosine): one cluster, explicit recall / max_sim, Q15 brute force
 // when n < 100 (collection.hpp:550-555). out_ids[k] local ids best first, out_count.

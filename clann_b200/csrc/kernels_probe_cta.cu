@@ -899,20 +899,9 @@ static void launch_probe_cta_occ(const SearchParams& p, const QueryBatch& b, boo
     if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = cap;
     uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (b.nq < grid) grid = b.nq;
-    // per-CTA similarity memo (u16 per local id of the cluster being probed); skipped when it would not fit in ~1 GiB
-    static uint16_t* memo = nullptr;
-    static size_t memo_cap = 0;
-    uint64_t stride = ((uint64_t)p.max_cluster + 7) & ~7ull;
-    size_t need = (size_t)grid * stride;
-    uint16_t* use = nullptr;
-    if (stride > 0 && need * sizeof(uint16_t) <= ((size_t)1 << 30)) {
-        if (need > memo_cap) {
-            if (memo) CLANN_CUDA(cudaFree(memo));
-            CLANN_CUDA(cudaMalloc(&memo, need * sizeof(uint16_t)));
-            memo_cap = need;
-        }
-        use = memo;
-    }
+    // per-CTA similarity memo (u16 per local id of the cluster being probed), from the index workspace
+    uint16_t* use = (b.memo && grid <= b.memo_slots) ? b.memo : nullptr;
+    const uint64_t stride = b.memo_stride;
     static int nosort = -1;
     if (nosort < 0) nosort = getenv("CLANN_PROBE_NOSORT") ? 2 : 0;  // debug: measure what the nearest-cluster work order buys
     static int pf = -1;

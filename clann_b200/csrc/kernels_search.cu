@@ -809,22 +809,11 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     uint64_t want = (b.nq + warps - 1) / warps;
     uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want ? want : 1;
-    // per-warp similarity memo (u16 per local id of the cluster being probed); skipped when it would not fit in ~1 GiB
-    static uint16_t* memo = nullptr;
-    static size_t memo_cap = 0;
-    const uint64_t stride = ((uint64_t)p.max_cluster + 7) & ~7ull;
-    const size_t need = (size_t)grid * warps * stride;
-    uint16_t* use = nullptr;
+    // per-warp similarity memo (u16 per local id of the cluster being probed), from the index workspace
     static int no_memo = -1;
     if (no_memo < 0) no_memo = getenv("CLANN_PROBE_NOMEMO") ? 1 : 0;  // A/B knob
-    if (!no_memo && stride > 0 && need * sizeof(uint16_t) <= ((size_t)1 << 30)) {
-        if (need > memo_cap) {
-            if (memo) CLANN_CUDA(cudaFree(memo));
-            CLANN_CUDA(cudaMalloc(&memo, need * sizeof(uint16_t)));
-            memo_cap = need;
-        }
-        use = memo;
-    }
+    uint16_t* use = (!no_memo && b.memo && (uint64_t)grid * warps <= b.memo_slots) ? b.memo : nullptr;
+    const uint64_t stride = b.memo_stride;
     k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0, use, stride);
 }
 
@@ -860,6 +849,13 @@ void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_
         case 16: launch_probe_g<16>(p, b, stop_at_foreign, s); break;
         default: launch_probe_g<32>(p, b, stop_at_foreign, s); break;
     }
+}
+
+uint32_t probe_memo_slots() {
+    int dev = 0, sms = 0;
+    CLANN_CUDA(cudaGetDevice(&dev));
+    CLANN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return (uint32_t)sms * 32u;  // at most 32 resident probe warps (warp kernel) or 8 CTAs (CTA kernel) per SM
 }
 
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active,
