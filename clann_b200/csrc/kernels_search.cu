@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) k_center_dist_tiled(const float* __restri
     }
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t full = d & ~7u;
-    for (uint32_t cb = 0; cb < K; cb += 64) {
+    // blockIdx.y strides over the 64-centre chunks: small CTAs keep the last wave of the grid short
+    for (uint32_t cb = blockIdx.y * 64; cb < K; cb += gridDim.y * 64) {
         __syncthreads();
         for (uint32_t e = threadIdx.x; e < 64 * d; e += blockDim.x) {
             uint32_t c = e / d, i = e % d;
@@ -754,7 +755,9 @@ void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_
             CLANN_CUDA(cudaFuncSetAttribute(k_center_dist_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
             tconfigured = tsmem;
         }
-        k_center_dist_tiled<<<(unsigned)((b.nq + 31) / 32), 256, tsmem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms,
+        const uint32_t nchunks = (p.K + 63) / 64;
+        dim3 tgrid((unsigned)((b.nq + 31) / 32), nchunks < 8 ? nchunks : 8);
+        k_center_dist_tiled<<<tgrid, 256, tsmem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms,
                                                                              p.K, p.g.d, b.cdist);
     } else if (smem <= 160 * 1024) {
         static size_t configured = 0;
