@@ -235,6 +235,96 @@ static void parse_reference_stream(const uint8_t* blob, uint64_t len, const Hash
     if (n_points) *n_points = n;
 }
 
+// --- Index::serialize writer (collection.hpp:185-203): the byte stream a puffinn::Index<CosineSimilarity> built over the
+// same rows, with the same functions, would write — so that an index built here can be loaded by the CPU reference
+// (Index(std::istream&), collection.hpp:147-170) and vice versa (parse_reference_stream). Field list in SURVEY.md 8c.
+struct Writer {
+    std::vector<uint8_t> out;
+    template <typename T>
+    void put(T v) {
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&v);
+        out.insert(out.end(), b, b + sizeof(T));
+    }
+    void bytes(const void* src, uint64_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(src);
+        out.insert(out.end(), b, b + n);
+    }
+};
+
+static std::vector<uint8_t> write_reference_stream(const HashGeom& g, const FunctionSet& fs, uint32_t nc, const int16_t* q15,
+                                                   const uint64_t* sketches, const uint32_t* tbl_hash, const uint32_t* tbl_idx) {
+    Writer w;
+    const uint32_t d = g.d, sl = g.sl, L = g.L;
+    w.out.reserve((size_t)nc * (sl * 2 + kNumSketches * 8 + (size_t)L * 8) + (size_t)kNumPlanes * (sl * 2 + 4) + (size_t)L * 8200 * 4 + 65536);
+    // Dataset (dataset.hpp:79-86): description {args = d, storage_len}, inserted_vectors, rows
+    w.put<uint32_t>(d); w.put<uint32_t>(sl); w.put<uint32_t>(nc);
+    w.bytes(q15, (uint64_t)nc * sl * 2);
+    // Filterer (filterer.hpp:62-68): sketch args, SimHash source, sketches
+    w.put<int32_t>(0);                                   // HashSourceType::Independent (independent.hpp:135-139); SimHash args are empty
+    w.put<uint32_t>(d); w.put<uint32_t>(sl);             // family: dataset description
+    w.put<uint64_t>((uint64_t)kNumPlanes);
+    for (int f = 0; f < kNumPlanes; f++) {               // simhash.hpp:33-38
+        w.put<uint32_t>(sl);
+        w.bytes(fs.planes.data() + (size_t)f * sl, (uint64_t)sl * 2);
+    }
+    w.put<uint32_t>(kNumSketches); w.put<uint32_t>(kSketchBits); w.put<uint8_t>(1);  // num_hashers, functions_per_hasher, bits_per_function
+    w.put<uint32_t>(0); w.put<uint32_t>(0);                                          // next_function, bits_to_cut (independent.hpp:64-68)
+    w.put<uint64_t>((uint64_t)nc * kNumSketches);
+    w.bytes(sketches, (uint64_t)nc * kNumSketches * 8);
+    // hash args (independent.hpp:135-139 + crosspolytope.hpp:234-238)
+    w.put<int32_t>(0); w.put<int32_t>(kRotations); w.put<uint32_t>(1000); w.put<float>(0.005f);
+    w.put<uint8_t>(1);                                   // has_hash_source
+    // IndependentHashSource<FHTCrossPolytopeHash> (independent.hpp:56-68): family (crosspolytope.hpp:291-295) ...
+    w.put<uint32_t>(d); w.put<uint32_t>(sl);
+    w.put<int32_t>(kRotations); w.put<uint32_t>(1000); w.put<float>(0.005f);
+    w.put<uint64_t>((uint64_t)g.m + 2);                  // estimates (crosspolytope.hpp:104-114)
+    for (uint32_t b = 0; b < g.m + 2; b++) {
+        w.put<uint64_t>((uint64_t)kEstBins);
+        w.bytes(fs.est.data() + (size_t)b * kEstBins, sizeof(float) * kEstBins);
+    }
+    w.put<float>(0.005f);
+    // ... functions (crosspolytope.hpp:178-184): ±1 signs per rotation
+    const uint64_t n_fn = (uint64_t)L * g.fph;
+    const uint32_t W = sign_words(g);
+    w.put<uint64_t>(n_fn);
+    std::vector<int8_t> signs((size_t)kRotations * g.npts);
+    for (uint64_t f = 0; f < n_fn; f++) {
+        w.put<int32_t>((int32_t)d); w.put<int32_t>((int32_t)g.m); w.put<uint32_t>(kRotations);
+        for (uint32_t r = 0; r < (uint32_t)kRotations; r++)
+            for (uint32_t i = 0; i < g.npts; i++)
+                signs[(size_t)r * g.npts + i] = (fs.signbits[(f * kRotations + r) * W + i / 32] >> (i % 32)) & 1u ? -1 : 1;
+        w.bytes(signs.data(), signs.size());
+    }
+    w.put<uint32_t>(L); w.put<uint32_t>(g.fph); w.put<uint8_t>((uint8_t)g.bpf); w.put<uint32_t>(0); w.put<uint32_t>(g.cut);
+    // tables (collection.hpp:196-201 -> prefixmap.hpp:128-154): 12 + n_c + 12 entries, sentinels (0, 0xffffffff), prefix_index
+    w.put<uint64_t>((uint64_t)L);
+    w.put<uint8_t>(0);                                   // use_chunks
+    const uint32_t len = nc + 2 * kSegment;
+    std::vector<uint32_t> padded(len), pidx((1u << 13) + 1);
+    for (uint32_t t = 0; t < L; t++) {
+        const uint32_t* H = tbl_hash + (size_t)t * nc;
+        const uint32_t* I = tbl_idx + (size_t)t * nc;
+        w.put<uint64_t>((uint64_t)len);
+        for (uint32_t i = 0; i < (uint32_t)kSegment; i++) padded[i] = padded[len - 1 - i] = 0u;
+        memcpy(padded.data() + kSegment, I, (size_t)nc * 4);
+        w.bytes(padded.data(), (uint64_t)len * 4);
+        for (uint32_t i = 0; i < (uint32_t)kSegment; i++) padded[i] = padded[len - 1 - i] = 0xffffffffu;  // IMPOSSIBLE_PREFIX
+        memcpy(padded.data() + kSegment, H, (size_t)nc * 4);
+        w.bytes(padded.data(), (uint64_t)len * 4);
+        w.put<uint64_t>(0);                              // rebuilding data
+        w.put<uint32_t>(kMaxHashBits);                   // hash_length
+        uint32_t idx = 0;                                // prefixmap.hpp:231-240: first position per 13-bit prefix
+        for (uint32_t prefix = 0; prefix < (1u << 13); prefix++) {
+            while (idx < nc && (H[idx] >> (kMaxHashBits - 13)) < prefix) idx++;
+            pidx[prefix] = kSegment + idx;
+        }
+        pidx[1u << 13] = kSegment + nc;
+        w.bytes(pidx.data(), pidx.size() * 4);
+    }
+    w.put<uint32_t>(nc);                                 // last_rebuild = points present at the last rebuild (collection.hpp:304)
+    return std::move(w.out);
+}
+
 // ------------------------------------------------------------------------------------------------ the index
 
 }  // namespace clann
@@ -1104,6 +1194,21 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 break;
             }
             case CLANN_X_BUILD_MS: emit(index->build_ms, sizeof(index->build_ms)); break;
+            case CLANN_X_REFERENCE_STREAM: {
+                need_cluster();
+                if (index->h_brute[arg] || index->h_sizes[arg] == 0)
+                    throw StatusError(CLANN_ERR_SERIALIZE, "brute-force clusters have no PUFFINN index (index.rs:204-205)");
+                const uint32_t nc = index->h_sizes[arg], L = index->g.L;
+                const uint64_t off = index->h_offsets[arg];
+                std::vector<int16_t> rows = index->d_q15.download((size_t)nc * index->g.sl, off * index->g.sl);
+                std::vector<uint64_t> sks = index->d_sketches.download((size_t)nc * kNumSketches, off * kNumSketches);
+                std::vector<uint32_t> th = index->d_tbl_hash.download((size_t)L * nc, table_base(off, nc, L, 0));
+                std::vector<uint32_t> ti = index->d_tbl_idx.download((size_t)L * nc, table_base(off, nc, L, 0));
+                std::vector<uint8_t> blob = write_reference_stream(index->g, index->fsets[index->h_fset_of[arg]], nc, rows.data(), sks.data(),
+                                                                   th.data(), ti.data());
+                emit(blob.data(), blob.size());
+                break;
+            }
             case CLANN_X_TABLE_DIR: {
                 need_cluster();
                 const uint64_t L = index->g.L;

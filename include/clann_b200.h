@@ -120,8 +120,11 @@ typedef enum {
     CLANN_X_QUERY_SKETCHES = 14, /* u64[nq*32] likewise */
     CLANN_X_CLUSTER_ORDER = 15,  /* u32[nq*K] visiting order of the last search batch (index.rs:592-616) */
     CLANN_X_BUILD_MS = 16,    /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
-    CLANN_X_TABLE_DIR = 17    /* u32[L*257] bucket directory of cluster `arg`: first position per top code byte (the role of
+    CLANN_X_TABLE_DIR = 17,   /* u32[L*257] bucket directory of cluster `arg`: first position per top code byte (the role of
                                  PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 8 bits), table-major */
+    CLANN_X_REFERENCE_STREAM = 18 /* bytes of puffinn::Index::serialize (collection.hpp:185-203) for cluster `arg`: what the CPU
+                                 reference would write for the same rows and functions, loadable by Index(std::istream&) —
+                                 persistence compatible with the reference without HDF5 (CPUFFINN_save_index's payload) */
 } clann_export_what;
 int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size);
 

@@ -495,6 +495,17 @@ class RefLib:
                 raise RuntimeError("reference rebuild failed")
         return ix
 
+    def index_from_stream(self, stream: bytes) -> RefIndex:
+        """puffinn::Index(std::istream&) (collection.hpp:147-170) over a serialized stream."""
+        buf = np.frombuffer(stream, np.uint8)
+        self.lib.ref_index_deserialize.restype = _vp
+        self.lib.ref_index_deserialize.argtypes = [_vp, _u64]
+        h = self.lib.ref_index_deserialize(_ptr(buf), buf.size)
+        if not h:
+            raise RuntimeError("the reference could not deserialize the stream")
+        d = int(np.frombuffer(stream[:4], np.uint32)[0])
+        return RefIndex(self, h, d)
+
     def fht(self, buf, m):
         buf = np.ascontiguousarray(buf, np.float32).copy()
         self.lib.ref_fht(_ptr(buf), m)

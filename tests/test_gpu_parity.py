@@ -200,3 +200,43 @@ def test_idempotent_and_batch_independent(sc25):
     assert np.array_equal(a[0][:17], c[0]) and np.array_equal(a[1][:17].view(np.uint32), c[1].view(np.uint32))
     one = sc25.gpu.search(q[5])
     assert [i for _, i in one] == list(a[0][5, : a[2][5]])
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_serialized_stream_equals_reference(name, request):
+    """Persistence compatible with the reference: for an index built on the device from the same rows and
+    the same functions, CLANN_X_REFERENCE_STREAM is byte for byte what puffinn::Index::serialize wrote on the CPU
+    (collection.hpp:185-203: Q15 rows, hyperplanes, sketches, estimates, signs, padded tables, prefix_index)."""
+    sc = request.getfixturevalue(name)
+    checked = 0
+    for ci, ref_stream in sc.streams.items():
+        mine = sc.gpu.export(sc.cl.X_REFERENCE_STREAM, int(ci), np.uint8).tobytes()
+        assert len(mine) == len(ref_stream)
+        assert mine == ref_stream, f"cluster {ci}: first difference at byte {next(i for i in range(len(mine)) if mine[i] != ref_stream[i])}"
+        checked += 1
+    assert checked > 0
+
+
+def test_reference_loads_device_built_index(reflib):
+    """The other direction: a stand-alone device build (its own functions and collision estimates) is exported and loaded
+    by the real reference (Index(std::istream&), collection.hpp:147-170); the reference then returns the same result sets
+    and counters as the device search for the same queries."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    data = util.planted(3000, 100, 41, n_centers=4)
+    ix = cb.init_with_config(data, cb.Config(32, 1.0, 10, 0.9, "persist"))
+    ix.set_clustering([0], np.zeros(len(data), np.uint64), [2.0])   # one cluster: local ids == point ids
+    ix.set_option("seed", 99)
+    ix.build()
+    stream = ix.export(cl.X_REFERENCE_STREAM, 0, np.uint8).tobytes()
+    ref = reflib.index_from_stream(stream)
+    assert ref.n == len(data) and ref.serialize() == stream       # the reference re-serializes it unchanged
+    q = util.planted_queries(data, 60, 42)
+    ids, dists, counts = ix.search_batch(q)
+    ctr = ix.counters(len(q))
+    for i in range(len(q)):
+        rids, met = ref.search(q[i], 10, 0.9)
+        assert sorted(rids.tolist()) == sorted(ids[i, :counts[i]].tolist())
+        assert met["distance_computations"] == int(ctr["distance_computations"][i])
+        assert met["candidates"] == int(ctr["candidates"][i])
+    ix.close()
