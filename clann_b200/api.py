@@ -13,6 +13,7 @@ C ABI in include/clann_b200.h; no arithmetic of the hot path happens in Python.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 import math
 from dataclasses import dataclass, field
@@ -320,6 +321,20 @@ class PuffinnIndex:
             return [int(ptr[i]) for i in range(k)]  # the crate reads exactly k words (puffinn.rs:108-114)
         finally:
             C.CDLL(None).free(ptr)
+
+
+    def save_to_file(self, file_path: str, index_id: int) -> None:
+        """puffinn.rs:61-75 -> CPUFFINN_save_index: appends record "index_{id}" (the bytes of puffinn::Index::serialize,
+        byte-compatible with the reference) to a flat record file; the reference uses an HDF5 dataset of the same name."""
+        _lib.load().CPUFFINN_save_index(self.raw, os.fspath(file_path).encode(), int(index_id))
+
+    @classmethod
+    def new_from_file(cls, file_path: str, index_id: int) -> "PuffinnIndex":
+        """puffinn.rs:121-141 -> CPUFFINN_load_from_file: the stored index answers queries without being rebuilt."""
+        raw = _lib.load().CPUFFINN_load_from_file(os.fspath(file_path).encode(), f"index_{int(index_id)}".encode())
+        if not raw:
+            raise SerializeError(f"could not load index_{index_id} from {file_path}: {_lib.last_error()}")
+        return cls(raw, 0)
 
 
 def get_distance_computations() -> int:

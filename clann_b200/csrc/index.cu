@@ -325,6 +325,69 @@ static std::vector<uint8_t> write_reference_stream(const HashGeom& g, const Func
     return std::move(w.out);
 }
 
+// Full reader of the same stream: everything a PUFFINN index needs to answer queries without being rebuilt.
+struct LoadedStream {
+    uint32_t d = 0, sl = 0, n = 0, L = 0;
+    std::vector<int16_t> rows;        // [n][sl]
+    std::vector<uint64_t> sketches;   // [n][32]
+    std::vector<uint32_t> hashes;     // [L][n] unpadded
+    std::vector<uint32_t> indices;    // [L][n]
+    FunctionSet fs;
+};
+
+static void read_reference_stream(const uint8_t* blob, uint64_t len, LoadedStream& out) {
+    Reader r{blob, len};
+    out.d = r.get<uint32_t>();
+    out.sl = r.get<uint32_t>();
+    out.n = r.get<uint32_t>();
+    if (out.d == 0 || out.d > 1024 || out.sl != (out.d + 15) / 16 * 16) throw StatusError(CLANN_ERR_SERIALIZE, "not a cosine PUFFINN index stream");
+    out.rows.resize((size_t)out.n * out.sl);
+    r.bytes(out.rows.data(), out.rows.size() * 2);
+    // the function set: reuse the importer on the same bytes once the number of tables is known (it sits behind the functions)
+    const HashGeom g1 = make_geom(out.d, 1);
+    {
+        Reader t{blob, len};
+        t.bytes(nullptr, 12 + out.rows.size() * 2);
+        t.bytes(nullptr, 4 + 8);                                            // sketch source type, SimHash description
+        if (t.get<uint64_t>() != (uint64_t)kNumPlanes) throw StatusError(CLANN_ERR_SERIALIZE, "expected 2048 sketch functions");
+        t.bytes(nullptr, (uint64_t)kNumPlanes * (4 + (uint64_t)out.sl * 2));
+        t.bytes(nullptr, 4 + 4 + 1 + 4 + 4);
+        const uint64_t n_sk = t.get<uint64_t>();
+        if (n_sk != (uint64_t)out.n * kNumSketches) throw StatusError(CLANN_ERR_SERIALIZE, "sketch count does not match the dataset");
+        out.sketches.resize(n_sk);
+        t.bytes(out.sketches.data(), n_sk * 8);
+        t.bytes(nullptr, 4 + 4 + 4 + 4);                                    // hash args
+        if (!t.get<uint8_t>()) throw StatusError(CLANN_ERR_SERIALIZE, "the index was never rebuilt (no hash source)");
+        t.bytes(nullptr, 8 + 12);                                           // family description + args
+        const uint64_t rows = t.get<uint64_t>();
+        for (uint64_t b = 0; b < rows; b++) t.bytes(nullptr, t.get<uint64_t>() * 4);
+        t.bytes(nullptr, 4);                                                // eps
+        const uint64_t n_fn = t.get<uint64_t>();
+        if (n_fn == 0 || n_fn % g1.fph) throw StatusError(CLANN_ERR_SERIALIZE, "unexpected number of hash functions");
+        out.L = (uint32_t)(n_fn / g1.fph);
+        t.bytes(nullptr, n_fn * (12 + (uint64_t)kRotations * g1.npts));
+        if (t.get<uint32_t>() != out.L) throw StatusError(CLANN_ERR_SERIALIZE, "table count mismatch in the hash source");
+        t.bytes(nullptr, 4 + 1 + 4 + 4);
+        if (t.get<uint64_t>() != (uint64_t)out.L) throw StatusError(CLANN_ERR_SERIALIZE, "table count mismatch");
+        if (t.get<uint8_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "chunked streams are not supported");
+        out.hashes.resize((size_t)out.L * out.n);
+        out.indices.resize((size_t)out.L * out.n);
+        std::vector<uint32_t> padded;
+        for (uint32_t tb = 0; tb < out.L; tb++) {                           // prefixmap.hpp:99-126
+            const uint64_t plen = t.get<uint64_t>();
+            if (plen != (uint64_t)out.n + 2 * kSegment) throw StatusError(CLANN_ERR_SERIALIZE, "table length does not match the dataset");
+            padded.resize(plen);
+            t.bytes(padded.data(), plen * 4);
+            memcpy(out.indices.data() + (size_t)tb * out.n, padded.data() + kSegment, (size_t)out.n * 4);
+            t.bytes(padded.data(), plen * 4);
+            memcpy(out.hashes.data() + (size_t)tb * out.n, padded.data() + kSegment, (size_t)out.n * 4);
+            if (t.get<uint64_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "the stream holds pending (unsorted) insertions");
+            t.bytes(nullptr, 4 + ((1u << 13) + 1) * 4ull);                  // hash_length, prefix_index (rebuilt here as the 8-bit directory)
+        }
+    }
+    parse_reference_stream(blob, len, make_geom(out.d, out.L), out.fs, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------------ the index
 
 }  // namespace clann
@@ -471,6 +534,55 @@ struct clann_index {
             fs->have_est = true;
         }
         built = false;
+    }
+
+    // A PUFFINN index straight from its serialized stream (collection.hpp:147-170): rows, sketches, tables and functions are
+    // taken as they are, nothing is rehashed; only the bucket directory and the host-built stop / threshold tables are derived.
+    void load_stream(const uint8_t* blob, uint64_t len) {
+        int dev_count = 0;
+        if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+            throw StatusError(CLANN_ERR_CUDA, "no CUDA device: libclann_b200 has no CPU fallback");
+        LoadedStream ls;
+        read_reference_stream(blob, len, ls);
+        cudaStream_t s = 0;
+        puffinn_mode = true;
+        cfg = clann_config{ls.L, 1.0f, 10, 0.9f};
+        n = ls.n;
+        g = make_geom(ls.d, ls.L);
+        K = 1;
+        for (auto& e : ev)
+            if (!e) CLANN_CUDA(cudaEventCreate(&e));
+        h_centers.assign(1, 0u);
+        h_radii.assign(1, 0.0f);
+        h_assign.assign(n, 0u);
+        h_sizes.assign(1, (uint32_t)n);
+        h_offsets = {0, n};
+        h_brute.assign(1, 0);
+        h_owner.assign(1, 0);
+        h_fset_of.assign(1, 0u);
+        per_cluster_functions = false;
+        fsets.clear();
+        fsets.push_back(std::move(ls.fs));
+        std::vector<uint32_t> ident(n);
+        std::iota(ident.begin(), ident.end(), 0u);
+        d_perm.upload(ident, s);
+        d_offsets.upload(h_offsets, s);
+        d_brute.upload(h_brute, s);
+        d_owner.upload(h_owner, s);
+        d_fset_of.upload(h_fset_of, s);
+        d_radii.upload(h_radii, s);
+        d_centers.upload(h_centers, s);
+        d_q15.upload(ls.rows, s);
+        d_sketches.upload(ls.sketches, s);
+        d_tbl_hash.upload(ls.hashes, s);   // one cluster: cluster-major == table-major
+        d_tbl_idx.upload(ls.indices, s);
+        d_tbl_dir.alloc((size_t)g.L * kDirEntries);
+        launch_build_dir(d_tbl_hash.p, n, d_offsets.p, d_brute.p, 1, g.L, d_tbl_dir.p, s);
+        prepare_functions(s);
+        CLANN_CUDA(cudaStreamSynchronize(s));
+        CLANN_CUDA(cudaGetLastError());
+        ws_nq = 0;
+        built = true;
     }
 
     // ---- build -----------------------------------------------------------------------------------------------
@@ -1235,6 +1347,7 @@ struct CPUFFINN {
     clann_index* ix = nullptr;
     uint32_t built_k = 0;
     unsigned num_maps = 0;
+    bool loaded = false;  // came from CPUFFINN_load_from_file: the fp32 rows are not known, so it cannot be rebuilt here
     DevBuf<float> d_query;
     DevBuf<uint32_t> d_out;  // [k] ids, then count, then distance computations
     ~CPUFFINN() { delete ix; }
@@ -1295,7 +1408,7 @@ uint64_t CPUFFINN_index_rebuild(CPUFFINN* index, unsigned int num_maps) {
     if (!index) return 0;
     try {
         if (num_maps == 0) return 0;  // collection.hpp:242-244 throws -> c_binder.cpp:57-59 returns 0
-        if (index->count == 0) return 0;
+        if (index->count == 0 || index->loaded) return 0;
         index->num_maps = num_maps;
         legacy_build(index, 10);
         const HashGeom& g = index->ix->g;
@@ -1354,19 +1467,93 @@ uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, 
 unsigned int CPUFFINN_get_distance_computations(void) { return g_legacy_distcomp.load(); }
 void CPUFFINN_clear_distance_computations(void) { g_legacy_distcomp.store(0); }
 
-// Persistence (c_binder.cpp:4-36,106-146) rides on HDF5 in the reference; this environment has none, so the two entry
-// points exist for link compatibility and report failure the way the reference does (stderr / NULL). Round-trip of the
-// Index::serialize stream is SURVEY.md section 8(f) item 1.
+// Persistence (c_binder.cpp:4-36,106-146). The reference appends the bytes of Index::serialize as dataset "index_{id}" of an
+// HDF5 file; there is no HDF5 here, so the same bytes go into a flat record file instead: a sequence of
+//   { char magic[8] = "CLB2REC"; u32 name_len; u32 reserved; u64 payload_len; name; payload }
+// records. The payload is byte-compatible with the reference (tests/test_gpu_parity.py), only the container differs.
 void CPUFFINN_save_index(CPUFFINN* index, const char* file_name, int index_number) {
-    (void)index;
-    fprintf(stderr, "Error opening HDF5 file: %s (index_%d): persistence is not available in libclann_b200\n",
-            file_name ? file_name : "(null)", index_number);
+    if (!index || !index->ix || !index->ix->built || !file_name) {
+        fprintf(stderr, "Error: CPUFFINN_save_index needs a rebuilt index and a file name\n");
+        return;
+    }
+    try {
+        clann_index* ix = index->ix;
+        const uint32_t nc = (uint32_t)ix->n, L = ix->g.L;
+        std::vector<int16_t> rows = ix->d_q15.download((size_t)nc * ix->g.sl);
+        std::vector<uint64_t> sks = ix->d_sketches.download((size_t)nc * kNumSketches);
+        std::vector<uint32_t> th = ix->d_tbl_hash.download((size_t)L * nc), ti = ix->d_tbl_idx.download((size_t)L * nc);
+        std::vector<uint8_t> blob = write_reference_stream(ix->g, ix->fsets[0], nc, rows.data(), sks.data(), th.data(), ti.data());
+        const std::string name = "index_" + std::to_string(index_number);
+        FILE* f = fopen(file_name, "ab");
+        if (!f) {
+            fprintf(stderr, "Error opening file: %s\n", file_name);
+            return;
+        }
+        const char magic[8] = {'C', 'L', 'B', '2', 'R', 'E', 'C', 0};
+        const uint32_t name_len = (uint32_t)name.size(), reserved = 0;
+        const uint64_t payload_len = blob.size();
+        bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(&name_len, 4, 1, f) == 1 && fwrite(&reserved, 4, 1, f) == 1 &&
+                  fwrite(&payload_len, 8, 1, f) == 1 && fwrite(name.data(), 1, name_len, f) == name_len &&
+                  fwrite(blob.data(), 1, blob.size(), f) == blob.size();
+        if (fclose(f) != 0 || !ok) fprintf(stderr, "Error writing %s to file: %s\n", name.c_str(), file_name);
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        fprintf(stderr, "Error saving index_%d: %s\n", index_number, e.what());
+    } catch (...) {
+        fprintf(stderr, "Error saving index_%d\n", index_number);
+    }
 }
 
+// Returns NULL on failure (the reference throws through extern "C", c_binder.cpp:8,15).
 CPUFFINN* CPUFFINN_load_from_file(const char* file_name, const char* dataset_name) {
-    fprintf(stderr, "Failed to open HDF5 file %s (%s): persistence is not available in libclann_b200\n",
-            file_name ? file_name : "(null)", dataset_name ? dataset_name : "(null)");
-    return nullptr;
+    if (!file_name || !dataset_name) return nullptr;
+    FILE* f = fopen(file_name, "rb");
+    if (!f) {
+        fprintf(stderr, "Failed to open file %s\n", file_name);
+        return nullptr;
+    }
+    CPUFFINN* h = nullptr;
+    try {
+        std::vector<uint8_t> blob;
+        bool found = false;
+        for (;;) {
+            char magic[8];
+            uint32_t name_len, reserved;
+            uint64_t payload_len;
+            if (fread(magic, 1, 8, f) != 8) break;
+            if (memcmp(magic, "CLB2REC", 8) != 0 || fread(&name_len, 4, 1, f) != 1 || fread(&reserved, 4, 1, f) != 1 ||
+                fread(&payload_len, 8, 1, f) != 1 || name_len > 4096)
+                throw StatusError(CLANN_ERR_SERIALIZE, "not a libclann_b200 record file");
+            std::string name(name_len, '\0');
+            if (fread(&name[0], 1, name_len, f) != name_len) throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
+            if (name == dataset_name) {  // the last record of that name wins (the file is append-only)
+                blob.resize(payload_len);
+                if (fread(blob.data(), 1, payload_len, f) != payload_len) throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
+                found = true;
+            } else if (fseek(f, (long)payload_len, SEEK_CUR) != 0) {
+                throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
+            }
+        }
+        if (!found) throw StatusError(CLANN_ERR_SERIALIZE, std::string("no record named ") + dataset_name);
+        h = new CPUFFINN();
+        h->ix = new clann_index();
+        h->ix->load_stream(blob.data(), blob.size());
+        h->dim = (int)h->ix->g.d;
+        h->count = (uint32_t)h->ix->n;
+        h->num_maps = h->ix->g.L;
+        h->built_k = 10;
+        h->loaded = true;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        fprintf(stderr, "Failed to load %s from %s: %s\n", dataset_name, file_name, e.what());
+        delete h;
+        h = nullptr;
+    } catch (...) {
+        delete h;
+        h = nullptr;
+    }
+    fclose(f);
+    return h;
 }
 
 }  // extern "C"

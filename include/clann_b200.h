@@ -139,6 +139,9 @@ void clann_destroy(clann_index* index);
  * (1) legacy per-cluster ABI (c_binder.h:14-26). Same signatures, same ownership, two hardening deviations:
  *     results are always max(k,1) words, 0xFFFFFFFF-padded (the reference lets Rust over-read, puffinn.rs:108-114),
  *     and no C++ exception crosses the boundary (the reference throws through extern "C", c_binder.cpp:8,15).
+ *     Persistence: save_index appends the bytes of puffinn::Index::serialize (collection.hpp:185-203, byte-compatible
+ *     with the reference) as record "index_{id}" of a flat file, load_from_file reads such a record back (NULL on failure);
+ *     the reference keeps the same bytes in an HDF5 dataset of the same name (no HDF5 in this build).
  * ------------------------------------------------------------------------------------------------------------------ */
 struct CPUFFINN;
 typedef struct CPUFFINN CPUFFINN;

@@ -324,3 +324,31 @@ def test_probe_kernel_variants_agree(tmp_path):
         for key in ("ids", "counts", "cand", "dc", "vis"):
             assert np.array_equal(ref[key], o[key]), (name, key)
         assert np.array_equal(ref["dists"].view(np.uint32), o["dists"].view(np.uint32)), name
+
+
+def test_legacy_save_and_load_round_trip(tmp_path, reflib):
+    """CPUFFINN_save_index / CPUFFINN_load_from_file (c_binder.cpp:4-36,106-146, puffinn.rs:61-75,121-141): the saved
+    record is the reference's own serialization (the real reference loads it), and an index loaded from it answers every
+    query exactly like the index that was saved — without a rebuild."""
+    import clann_b200 as cb
+    data = util.planted(1500, 25, 51, n_centers=3)
+    index, _ = cb.PuffinnIndex.new(cb.AngularData(data), 30)
+    path = str(tmp_path / "saved.clb2")
+    index.save_to_file(path, 7)
+    index.save_to_file(path, 8)  # records are appended (the reference appends datasets to one file)
+    loaded = cb.PuffinnIndex.new_from_file(path, 8)
+    with pytest.raises(cb.api.SerializeError):
+        cb.PuffinnIndex.new_from_file(path, 9)
+    queries = util.planted_queries(data, 40, 52)
+    raw = open(path, "rb").read()
+    name_len = int(np.frombuffer(raw[8:12], np.uint32)[0])
+    payload_len = int(np.frombuffer(raw[16:24], np.uint64)[0])
+    assert raw[:8] == b"CLB2REC\0" and raw[24:24 + name_len] == b"index_7"
+    ref = reflib.index_from_stream(raw[24 + name_len: 24 + name_len + payload_len])
+    for q in queries:
+        a = index.search(q, 10, float("inf"), 0.9)
+        dc = cb.api.get_distance_computations()
+        b = loaded.search(q, 10, float("inf"), 0.9)
+        assert a == b and cb.api.get_distance_computations() == dc
+        rids, met = ref.search(q, 10, 0.9)
+        assert sorted(rids.tolist()) == sorted(a) and met["distance_computations"] == dc
