@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "clann_init_with_config", "clann_set_option", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
     "clann_build", "clann_search", "clann_search_device", "clann_search_begin", "clann_search_step", "clann_state_bytes",
     "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
-    "clann_last_search_profile", "clann_last_error", "clann_destroy",
+    "clann_last_search_profile", "clann_tune", "clann_last_error", "clann_destroy",
     "CPUFFINN_load_from_file", "CPUFFINN_index_create", "CPUFFINN_index_rebuild", "CPUFFINN_index_insert_cosine",
     "CPUFFINN_search_cosine", "CPUFFINN_get_distance_computations", "CPUFFINN_clear_distance_computations",
     "CPUFFINN_save_index",
@@ -58,6 +58,7 @@ def load() -> C.CDLL:
     L.clann_init_with_config.restype = _i32
     L.clann_init_with_config.argtypes = [_vp, _u64, _u32, C.POINTER(ClannConfig), C.POINTER(_vp)]
     L.clann_set_option.restype, L.clann_set_option.argtypes = _i32, [_vp, C.c_char_p, _i64]
+    L.clann_tune.restype, L.clann_tune.argtypes = _i32, [C.c_char_p, _i64]
     L.clann_set_clustering.restype, L.clann_set_clustering.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]
     L.clann_import_reference.restype, L.clann_import_reference.argtypes = _i32, [_vp, _u64, _vp, _u64]
     L.clann_set_functions.restype, L.clann_set_functions.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]
@@ -86,6 +87,12 @@ def load() -> C.CDLL:
     L.CPUFFINN_save_index.restype, L.CPUFFINN_save_index.argtypes = None, [_vp, C.c_char_p, _i32]
     _lib = L
     return L
+
+
+def tune(key: str, value: int) -> None:
+    """Process-global launch-parameter knob of the probe kernels (clann_tune); never changes a result."""
+    if load().clann_tune(key.encode(), int(value)) != 0:
+        raise RuntimeError(last_error())
 
 
 def last_error() -> str:

@@ -879,6 +879,7 @@ struct clann_index {
         p.msd_thr = d_msd_thr.p;
         p.shard_rank = shard_rank;
         p.max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
+        p.prefetch_rows = 0;
         return p;
     }
 
@@ -1061,6 +1062,13 @@ int clann_set_option(clann_index* index, const char* key, int64_t value) {
             index->shard_count = (uint32_t)value;
         } else throw StatusError(CLANN_ERR_ARG, "unknown option '" + k + "'");
         index->built = false;
+    });
+}
+
+int clann_tune(const char* key, int64_t value) {
+    return guarded([&] {
+        if (!key) throw StatusError(CLANN_ERR_ARG, "null key");
+        clann::tune_set(key, value);
     });
 }
 

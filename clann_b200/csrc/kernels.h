@@ -77,6 +77,7 @@ struct SearchParams {
     const uint32_t* msd_thr;   // [64] msd_thr[m] = smallest v with msd[v] <= m (msd is non-increasing): msd[v] = #{m : msd_thr[m] > v}
     uint32_t shard_rank;
     uint32_t max_cluster;      // largest cluster size (sizes the per-CTA similarity memo)
+    uint32_t prefetch_rows;    // probe kernel: bulk-prefetch the Q15 rows of a batch into the L2 before gathering them
 };
 
 struct QueryBatch {
@@ -107,6 +108,11 @@ struct QueryBatch {
     uint32_t* cnt_visited;
 };
 
+// Process-global tuning knobs for A/B measurements (the defaults are the shipped configuration). The first read of a key
+// takes its value from the environment variable CLANN_TUNE_<KEY> when set; clann_tune() overrides it at any time.
+int64_t tune_get(const char* key, int64_t dflt);
+void tune_set(const char* key, int64_t value);
+
 uint64_t query_state_bytes(uint32_t k);
 void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // cdist + first (nearest cluster); the caller then sorts `first` with launch_segment_sort to obtain qperm.
@@ -116,6 +122,7 @@ void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t 
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
 void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query
 void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);   // one CTA per query
+void launch_probe_pipelined(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query, few in flight
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 uint32_t probe_memo_slots();  // upper bound on the memo regions any probe launch uses on the current device

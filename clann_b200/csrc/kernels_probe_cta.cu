@@ -712,9 +712,9 @@ __global__ void __launch_bounds__(kCtaThreads, OCC) k_probe_cta(SearchParams p, 
         if (prefetch_ahead) {
             // b.first holds the nearest cluster of every work item, in work order: whoever takes the first query of a
             // cluster prefetches it (cold start), and the cluster that comes up `prefetch_ahead` work items later
-            if (w < prefetch_ahead && (w == 0 || b.first[w] != b.first[w - 1])) l2_prefetch_cluster(p, b.first[w]);
+            if (w < prefetch_ahead && (w == 0 || b.first[w] != b.first[w - 1])) l2_prefetch_cluster(p, b.first[w] & 0xfffffu);
             const uint64_t wa = (uint64_t)w + prefetch_ahead;
-            if (wa < b.nq && b.first[wa] != b.first[wa - 1]) l2_prefetch_cluster(p, b.first[wa]);
+            if (wa < b.nq && b.first[wa] != b.first[wa - 1]) l2_prefetch_cluster(p, b.first[wa] & 0xfffffu);
         }
         QueryStateHeader* st = reinterpret_cast<QueryStateHeader*>(b.state + (uint64_t)q * state_bytes);
         if (st->done) continue;
@@ -891,24 +891,15 @@ static void launch_probe_cta_occ(const SearchParams& p, const QueryBatch& b, boo
     int ctas_per_sm = 0;
     CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe_cta<OCC>, kCtaThreads, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    static int cap = -1;
-    if (cap < 0) {
-        const char* e = getenv("CLANN_PROBE_CTAS_PER_SM");  // tuning knob: fewer resident queries = smaller L2 working set
-        cap = e ? atoi(e) : 0;
-    }
+    const int cap = (int)tune_get("probe_ctas", 0);  // knob: fewer resident queries = smaller L2 working set
     if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = cap;
     uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (b.nq < grid) grid = b.nq;
     // per-CTA similarity memo (u16 per local id of the cluster being probed), from the index workspace
     uint16_t* use = (b.memo && grid <= b.memo_slots) ? b.memo : nullptr;
     const uint64_t stride = b.memo_stride;
-    static int nosort = -1;
-    if (nosort < 0) nosort = getenv("CLANN_PROBE_NOSORT") ? 2 : 0;  // debug: measure what the nearest-cluster work order buys
-    static int pf = -1;
-    if (pf < 0) {
-        const char* e = getenv("CLANN_PROBE_PREFETCH");  // work items of lookahead for the L2 cluster prefetch; 0 = off, unset = one grid
-        pf = e ? atoi(e) : -2;
-    }
+    const int nosort = tune_get("probe_nosort", 0) ? 2 : 0;  // debug: measure what the nearest-cluster work order buys
+    const int pf = (int)tune_get("probe_prefetch", -2);  // work items of lookahead for the L2 cluster prefetch; 0 = off, -2 = one grid
     // the prefetch follows the nearest-cluster work order, which only exists for a fresh batch (not for multi-GPU re-entry)
     const uint32_t ahead = stop_at_foreign ? 0u : (pf == -2 ? (uint32_t)grid : (uint32_t)pf);
     k_probe_cta<OCC><<<(unsigned)grid, kCtaThreads, smem, s>>>(p, b, (stop_at_foreign ? 1 : 0) | nosort, use, stride, ahead);
@@ -929,12 +920,8 @@ static void launch_probe_cta_occ(const SearchParams& p, const QueryBatch& b, boo
 
 void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
     if (b.nq == 0) return;
-    static int occ = 0;
-    if (occ == 0) {
-        const char* e = getenv("CLANN_PROBE_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
-        occ = e ? atoi(e) : 4;
-        if (occ != 3 && occ != 4 && occ != 5 && occ != 6) occ = 4;
-    }
+    int occ = (int)tune_get("probe_cta_occ", 4);  // knob: resident CTAs per SM the kernel is compiled for
+    if (occ != 3 && occ != 4 && occ != 5 && occ != 6) occ = 4;
     switch (occ) {
         case 3: launch_probe_cta_occ<3>(p, b, stop_at_foreign, s); break;
         case 5: launch_probe_cta_occ<5>(p, b, stop_at_foreign, s); break;

@@ -4,11 +4,40 @@
 // the Q15 rerank gather, the 2k-slot MaxBuffer, the filter threshold update and the delta stop rule.
 // Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
 
 #include "kernels.h"
 #include "probe_common.cuh"
 
 namespace clann {
+
+static std::map<std::string, int64_t>& tune_table() {
+    static std::map<std::string, int64_t> t;
+    return t;
+}
+static std::mutex g_tune_mutex;
+
+int64_t tune_get(const char* key, int64_t dflt) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    auto& t = tune_table();
+    auto it = t.find(key);
+    if (it != t.end()) return it->second;
+    std::string env = std::string("CLANN_TUNE_") + key;
+    for (auto& ch : env) ch = (char)toupper((unsigned char)ch);
+    const char* e = getenv(env.c_str());
+    const int64_t v = e ? atoll(e) : dflt;
+    t[key] = v;
+    return v;
+}
+
+void tune_set(const char* key, int64_t value) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    tune_table()[key] = value;
+}
 
 uint64_t query_state_bytes(uint32_t k) { return sizeof(QueryStateHeader) + (uint64_t)k * 8; }
 
@@ -161,9 +190,18 @@ __global__ void __launch_bounds__(256) k_center_dist_simple(const float* __restr
     cdist[i] = distance_point(center_rows + (uint64_t)c * d, center_norms[c], queries + q * d, qnorm[q], d);
 }
 
-// Nearest centre of every query (first cluster of its visiting order); used only to schedule queries that start in
-// the same cluster next to each other so that the cluster's rows, sketches and tables are shared through L2.
-__global__ void __launch_bounds__(256) k_first_cluster(const float* __restrict__ cdist, uint64_t nq, uint32_t K, uint32_t* __restrict__ first) {
+// Work-order key of every query: its nearest centre (first cluster of its visiting order) in the low 20 bits, so that
+// queries that start in the same cluster run next to each other and share the cluster's rows, sketches and tables through
+// the L2, and above it 15 - min(15, e) where e predicts how many clusters the query will visit: the clusters whose ball
+// reaches closer than the nearest centre (distance - radius <= nearest distance; the prune test of index.rs:342-361 with the
+// nearest-centre distance standing in for the k-th neighbour distance, which is not known yet). Sorting by the key starts
+// the predicted-longest queries first. OFF by default (knob order_longest_first): measured on B200 (glove-100 shape,
+// profiles/exp/visit_stats.py) the predictor is useless — queries visit at most 6 clusters, the cost of a query is its
+// candidate count (p99 = 1.9x mean) and correlates 0.02 with e — while the coarser cluster grouping costs L2 hits (DRAM reads
+// 10.3 -> 14.0 GB for 3.08 -> 3.03 ms). The 29 % of warp slots the probe kernel leaves idle are its last wave: the queue is
+// empty after ~1.7 ms and the queries still in flight take up to one query latency more. The order never changes a result.
+__global__ void __launch_bounds__(256) k_first_cluster(const float* __restrict__ cdist, const float* __restrict__ radii, uint64_t nq, uint32_t K,
+                                                       int longest_first, uint32_t* __restrict__ first) {
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
     unsigned long long best = ~0ull;
@@ -176,7 +214,16 @@ __global__ void __launch_bounds__(256) k_first_cluster(const float* __restrict__
         unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
         best = t < best ? t : best;
     }
-    if (lane_id() == 0) first[q] = (uint32_t)best;
+    uint32_t key = (uint32_t)best;
+    if (longest_first && K <= (1u << 20)) {
+        const float nearest = float_from_order_bits((uint32_t)(best >> 32));
+        uint32_t reach = 0;
+        for (uint32_t c = lane_id(); c < K; c += 32) reach += (cdist[q * K + c] - radii[c] <= nearest) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) reach += __shfl_xor_sync(0xffffffffu, reach, o);
+        key |= (15u - (reach < 15u ? reach : 15u)) << 20;
+    }
+    if (lane_id() == 0) first[q] = key;
 }
 
 __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t state_bytes, uint32_t* work_counter) {
@@ -251,7 +298,8 @@ __device__ __forceinline__ WarpSmem carve(uint8_t* base, uint32_t L, uint32_t k)
 // math.hpp:11-44).
 template <int G>
 __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const int16_t* __restrict__ rows, uint32_t sl,
-                                       const int16_t* __restrict__ qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo) {
+                                       const int16_t* __restrict__ qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo,
+                                       bool prefetch_rows = false) {
     constexpr int CPI = 32 / G;  // candidates per warp iteration
     const uint32_t lane = lane_id();
     const uint32_t sub = lane % G;
@@ -269,6 +317,14 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
         nunk += __popc(bal);
     }
     __syncwarp();
+    if (prefetch_rows) {
+        // every row of the batch is requested into the L2 at once (TMA bulk prefetch, no destination register), so the
+        // gather below pays one DRAM latency for the batch instead of one per round of eight rows
+        for (uint32_t i = lane; i < nunk; i += 32) {
+            const int16_t* src = rows + (uint64_t)sm.pass_idx[sm.unk[i]] * sl;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(sl * 2) : "memory");
+        }
+    }
     for (uint32_t base = 0; base < nunk; base += CPI * 4) {
         int part[4];
         uint4 w[4];
@@ -444,7 +500,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             }
             __syncwarp();
             // empty the buffer (collection.hpp:909-925)
-            rerank<G>(sm, np, rows, p.g.sl, qrow_smem, qreg, qreg_valid, memo);
+            rerank<G>(sm, np, rows, p.g.sl, qrow_smem, qreg, qreg_valid, memo, p.prefetch_rows != 0);
             maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, np);
             ctr.distcomp += np;
             max_diff = p.msd[minval16 < 65536u ? minval16 : 65535u];  // filterer.hpp:108-111
@@ -771,7 +827,8 @@ void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_
         k_center_dist_simple<<<(unsigned)((b.nq * p.K + 255) / 256), 256, 0, s>>>(b.queries, b.qnorm, b.nq, p.center_rows,
                                                                                  p.center_norms, p.K, p.g.d, b.cdist);
     }
-    k_first_cluster<<<(unsigned)((b.nq * 32 + 255) / 256), 256, 0, s>>>(b.cdist, b.nq, p.K, b.first);
+    k_first_cluster<<<(unsigned)((b.nq * 32 + 255) / 256), 256, 0, s>>>(b.cdist, p.radii, b.nq, p.K,
+                                                                        tune_get("order_longest_first", 0) != 0 ? 1 : 0, b.first);
 }
 
 void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
@@ -796,8 +853,9 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     }
     const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
     const uint32_t per_warp = wb + p.g.sl * 2;
-    // warps per CTA: as many as keep OCC CTAs of shared memory on one SM, at most 8
-    uint32_t warps = 8;
+    // warps per CTA: as many as keep OCC CTAs of shared memory on one SM, at most 8 (knob: probe_warps)
+    uint32_t warps = (uint32_t)tune_get("probe_warps", 8);
+    if (warps < 1 || warps > 8) warps = 8;
     while (warps > 1 && (size_t)warps * per_warp * OCC > 200 * 1024) warps >>= 1;
     size_t smem = (size_t)warps * per_warp;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
@@ -809,38 +867,40 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     int ctas_per_sm = 0;
     CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC>, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const int cap = (int)tune_get("probe_ctas", 0);  // knob: fewer resident queries = smaller L2 working set
+    if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = cap;
     uint64_t want = (b.nq + warps - 1) / warps;
     uint64_t grid = (uint64_t)sm_count * ctas_per_sm;  // persistent: a whole number of CTAs per SM
     if (want < grid) grid = want ? want : 1;
     // per-warp similarity memo (u16 per local id of the cluster being probed), from the index workspace
-    static int no_memo = -1;
-    if (no_memo < 0) no_memo = getenv("CLANN_PROBE_NOMEMO") ? 1 : 0;  // A/B knob
+    const bool no_memo = tune_get("probe_nomemo", 0) != 0;  // A/B knob
     uint16_t* use = (!no_memo && b.memo && (uint64_t)grid * warps <= b.memo_slots) ? b.memo : nullptr;
     const uint64_t stride = b.memo_stride;
-    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(p, b, wb, stop_at_foreign ? 1 : 0, use, stride);
+    SearchParams pp = p;
+    pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
+    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride);
 }
 
 template <int G>
 static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
-    static int occ = 0;
-    if (occ == 0) {
-        const char* e = getenv("CLANN_PROBE_OCC");  // tuning knob: resident CTAs per SM the kernel is compiled for
-        occ = e ? atoi(e) : 3;
-        if (occ < 2 || occ > 4) occ = 3;
-    }
+    int occ = (int)tune_get("probe_occ", 3);  // knob: resident CTAs per SM the kernel is compiled for
+    if (occ < 2 || occ > 4) occ = 3;
     if (occ == 2) launch_probe_go<G, 2>(p, b, stop_at_foreign, s);
     else if (occ == 4) launch_probe_go<G, 4>(p, b, stop_at_foreign, s);
     else launch_probe_go<G, 3>(p, b, stop_at_foreign, s);
 }
 
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("CLANN_PROBE");  // "cta" selects the one-CTA-per-query kernel (A/B)
-        mode = (e && e[0] == 'c') ? 1 : 0;
+    const int mode = (int)tune_get("probe", 0);  // knob: 0 = one warp per query, 1 = one CTA per query, 2 = pipelined warp per query
+    static int64_t fetch_set = 0;
+    const int64_t fetch = tune_get("l2_fetch", 0);  // knob: cudaLimitMaxL2FetchGranularity in bytes (32/64/128), 0 = leave alone
+    if (fetch != fetch_set && fetch > 0) {
+        CLANN_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch));
+        fetch_set = fetch;
     }
-    if (mode == 0) launch_probe_warp(p, b, stop_at_foreign, s);
-    else launch_probe_cta(p, b, stop_at_foreign, s);
+    if (mode == 1) launch_probe_cta(p, b, stop_at_foreign, s);
+    else if (mode == 2) launch_probe_pipelined(p, b, stop_at_foreign, s);
+    else launch_probe_warp(p, b, stop_at_foreign, s);
 }
 
 void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {

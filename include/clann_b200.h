@@ -132,6 +132,11 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
  * ms[1] = probe kernel (the roofline kernel), launches = kernels launched. Measured with CUDA events on the call's stream. */
 int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches);
 
+/* Process-global launch-parameter knob for A/B measurements of the probe kernels ("probe" 0 = one warp per query,
+ * 1 = one CTA per query; "probe_occ", "probe_warps", "probe_ctas", "probe_nomemo", ...). Never changes a result. The
+ * environment variable CLANN_TUNE_<KEY> seeds a key that was not set. Not part of the reference's interface. */
+int clann_tune(const char* key, int64_t value);
+
 const char* clann_last_error(void);
 void clann_destroy(clann_index* index);
 

@@ -301,25 +301,29 @@ np.savez(sys.argv[2], ids=ids, dists=dists, counts=counts, cand=ctr["candidates"
 
 
 def test_probe_kernel_variants_agree(tmp_path):
-    """The probe kernel is selected once per process (CLANN_PROBE / CLANN_PROBE_NOMEMO): the one-warp-per-query kernel with
-    and without the similarity memo and the warp-specialised one-CTA-per-query kernel must return identical ids, distance
-    bits and reference counters (candidates, distance_computations, clusters visited) for the same index and queries —
-    planted queries plus uniform ones that walk many clusters."""
+    """Probe kernel variants (clann_tune "probe" / "probe_nomemo" / launch shapes): the one-warp-per-query kernel with and
+    without the similarity memo, with fewer resident warps, and the warp-specialised one-CTA-per-query kernel must return
+    identical ids, distance bits and reference counters (candidates, distance_computations, clusters visited) for the same
+    index and queries — planted queries plus uniform ones that walk many clusters."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for name, env in (("warp", {}), ("warp_nomemo", {"CLANN_PROBE_NOMEMO": "1"}), ("cta", {"CLANN_PROBE": "cta"})):
+    variants = (("warp", {}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}), ("cta", {"CLANN_TUNE_PROBE": "1"}),
+                ("warp_small_grid", {"CLANN_TUNE_PROBE_WARPS": "4", "CLANN_TUNE_PROBE_CTAS": "1"}),
+                ("warp_longest_first_prefetch", {"CLANN_TUNE_ORDER_LONGEST_FIRST": "1", "CLANN_TUNE_PROBE_PREFETCH_ROWS": "1"}),
+                ("pipelined", {"CLANN_TUNE_PROBE": "2"}),
+                ("pipelined_small_stage", {"CLANN_TUNE_PROBE": "2", "CLANN_TUNE_PROBE2_STAGE_ROWS": "5", "CLANN_TUNE_PROBE2_WARPS": "4"}),
+                ("pipelined_nomemo", {"CLANN_TUNE_PROBE": "2", "CLANN_TUNE_PROBE_NOMEMO": "1"}))
+    for name, env in variants:
         out = str(tmp_path / (name + ".npz"))
-        e = dict(os.environ)
-        e.pop("CLANN_PROBE", None)
-        e.pop("CLANN_PROBE_NOMEMO", None)
+        e = {k: v for k, v in os.environ.items() if not k.startswith("CLANN_TUNE_")}
         e.update(env)
         subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root, out], check=True, env=e, timeout=600)
         outs[name] = np.load(out)
     ref = outs["warp"]
     assert ref["vis"].max() > 3  # the uniform queries do walk several clusters
-    for name in ("warp_nomemo", "cta"):
+    for name, _ in variants[1:]:
         o = outs[name]
         for key in ("ids", "counts", "cand", "dc", "vis"):
             assert np.array_equal(ref[key], o[key]), (name, key)
