@@ -46,6 +46,9 @@ def workload(args):
     if args.workload == "readme":    # BASELINE.json configs[0]
         return dict(name="README example: synthetic 10,000x128 unit vectors, 10k queries, num_tables=84, k=10, delta=0.9",
                     n=10_000, d=128, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
+    if args.workload == "deep96":    # BASELINE.json configs[3] on one GPU (the index is 16 GB; sharding is optional)
+        return dict(name="deep-image-96-angular shape: synthetic 10,000,000x96 unit vectors, 10k queries, k=10, delta=0.9",
+                    n=10_000_000, d=96, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
     return dict(name="glove-100-angular shape: synthetic 1,183,514x100 unit vectors, 10k queries, k=10, delta=0.9",
                 n=1_183_514, d=100, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
 
@@ -203,9 +206,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dist", default="planted", choices=["planted", "uniform"])
     ap.add_argument("--small", action="store_true", help="reduced shape for smoke runs; NOT a valid bench number")
-    ap.add_argument("--workload", default="glove100", choices=["glove100", "glove25", "readme"],
+    ap.add_argument("--queries", type=int, default=0, help="queries per step (default: the workload's own batch, 10 000)")
+    ap.add_argument("--workload", default="glove100", choices=["glove100", "glove25", "readme", "deep96"],
                     help="glove100 (default) is the configuration the metric is quoted on; the others are BASELINE.json's parity-size configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="time `value` with stream-ordered calls (one batch at a time) instead of clann_search_device_async "
+                         "(two batches in flight); the stream-ordered figure is always reported as value_stream_ordered")
     ap.add_argument("--shard", default="queries", choices=["queries", "clusters"],
                     help="N > 1: 'queries' = the index is replicated and every rank searches its own batch (weak scaling, no "
                          "data-path collective); 'clusters' = clusters are sharded by owner and one fixed batch is stepped "
@@ -220,6 +227,9 @@ def main():
         return 0
 
     w = workload(args)
+    if args.queries > 0:
+        w["nq"] = args.queries
+        w["name"] += f" [batch overridden: {args.queries} queries per step]"
     cfg_json = {"workload": w["name"], "distribution": args.dist, "n": w["n"], "d": w["d"], "queries_per_step": w["nq"],
                 "num_tables": w["L"], "num_clusters_factor": w["factor"], "k": w["k"], "delta": w["delta"],
                 "l2": "index working set (2.4 GB: Q15 rows, sketches, tables) >> 126 MB L2; no explicit flush"}
@@ -238,7 +248,7 @@ def main():
                             np.asarray(radii, np.float32))
         line = {"impl": "reference", "metric": METRIC, "value": ref["qps_allcores"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * ref["n_sample"] / ref["qps_allcores"],
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
                 "config": cfg_json,
                 "cpu_baseline": {"value": ref["qps_allcores"], "unit": UNIT, "cores": ref["cores"], "kind": ref["kind"],
                                  "sample": ref["sample"], "qps_1thread": ref["qps_1thread"],
@@ -304,6 +314,24 @@ def main():
     def step_device():
         searcher.search_device(d_q, d_ids, d_dists, d_counts)
 
+    # batch pipelining (clann_search_device_async): consecutive steps on two internal streams, each with its own outputs
+    pipelined = single and not args.no_pipeline
+    outs = [(d_ids, d_dists, d_counts),
+            (torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts))]
+    cur_stream = torch.cuda.current_stream().cuda_stream
+
+    def run_steps(steps):
+        if not pipelined:
+            for _ in range(steps):
+                step_device()
+            return
+        for i in range(steps):
+            o = outs[i & 1]
+            if index._lib.clann_search_device_async(index.handle, d_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+                raise RuntimeError(cl.last_error())
+        if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
+            raise RuntimeError(cl.last_error())
+
     # pinned host buffers for the end-to-end arm
     h_q = torch.from_numpy(queries).pin_memory()
     h_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
@@ -349,23 +377,36 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
+    run_steps(args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # probe-kernel time, live, per step (CUDA events recorded by the library on the same stream)
+    # the timed region: exactly K steps; the stream is idle at e0 (barrier + synchronize), so e0..e1 covers every kernel of
+    # the K steps whichever internal stream ran it (clann_search_flush makes the current stream wait for all of them)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     probe_ms_sum, prep_ms_sum = 0.0, 0.0
     e0.record()
-    for _ in range(args.steps):
-        step_device()
+    run_steps(args.steps)
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
+    # the same K steps one batch at a time (stream-ordered calls), for reference
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_device()
+    f1.record()
+    barrier()
+    ordered_ms = f0.elapsed_time(f1)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+        t = torch.tensor([ordered_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ordered_ms = float(t.item())
     clocks = sampler.stop()
     launches_per_step = searcher.last_launches
     # per-kernel split from a separate pass (events inside the library); same stream, same inputs
@@ -389,7 +430,19 @@ def main():
     e2e_ms = timed(step_e2e, args.steps) / args.steps
     e2e_value = global_nq / (e2e_ms / 1000.0)
 
-    # ---- correctness of what was timed: recall@k against exact fp32 neighbours (utils/mod.rs:59-95)
+    # ---- correctness of what was timed: the pipelined batches return what the stream-ordered call returns
+    pipe_same = None
+    if pipelined:
+        run_steps(2)
+        torch.cuda.synchronize()
+        a_ids, a_dists = outs[0][0].clone(), outs[0][1].clone()
+        b_ids, b_dists = outs[1][0].clone(), outs[1][1].clone()
+        step_device()
+        torch.cuda.synchronize()
+        pipe_same = bool(torch.equal(a_ids, d_ids) and torch.equal(b_ids, d_ids) and torch.equal(a_dists, d_dists) and torch.equal(b_dists, d_dists))
+        if not pipe_same:
+            raise RuntimeError("pipelined batches returned results that differ from the stream-ordered call")
+    # ---- recall@k against exact fp32 neighbours (utils/mod.rs:59-95)
     step_device()
     torch.cuda.synchronize()
     ids = d_ids.cpu().numpy().view(np.uint32); dists = d_dists.cpu().numpy(); counts = d_counts.cpu().numpy()
@@ -397,9 +450,11 @@ def main():
     with torch.no_grad():
         dd = torch.from_numpy(data).to(dev)
         ex = torch.empty((nchk, k), device=dev)
-        for s in range(0, nchk, 250):
-            sim = d_q[s:s + 250] @ dd.T
-            ex[s:s + 250] = torch.topk(sim, k, dim=1).values
+        chunk = max(8, min(250, int(2.5e8 // w["n"])))   # keep the similarity tile under ~1 GB
+        for s in range(0, nchk, chunk):
+            e = min(s + chunk, nchk)
+            sim = d_q[s:e] @ dd.T
+            ex[s:e] = torch.topk(sim, k, dim=1).values
         kth = (1.0 - ex[:, k - 1]).cpu().numpy()
         del dd
     hit = sum(int(np.sum(dists[i, :counts[i]] <= kth[i] + 1e-3)) for i in range(nchk))
@@ -440,8 +495,11 @@ def main():
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (shard_clusters or world == 1) else "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if shard_clusters else "weak",
             "vs_baseline": None, "dtype": "i16",
+            "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
+            "pipeline": ("clann_search_device_async: two batches in flight on two internal streams; outputs identical to the "
+                         "stream-ordered call (checked)") if pipelined else "none (stream-ordered calls)",
             "data": "synthetic", "config": cfg_json, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,
                     "d2h_bytes_per_step": global_nq * k * 8 + global_nq * 4,

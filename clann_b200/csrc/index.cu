@@ -429,20 +429,31 @@ struct clann_index {
     uint32_t stop_words = 0;
     float stop_recall = -1.0f;
 
-    // search workspace
-    uint64_t ws_nq = 0;
-    DevBuf<float> w_queries, w_qnorm, w_cdist, w_out_dists;
-    DevBuf<int16_t> w_q15;
-    DevBuf<uint32_t> w_codes, w_first, w_qperm, w_out_ids, w_out_counts, w_counter, w_vis, w_sort_k, w_sort_i;
-    DevBuf<SortSegment> w_sort_seg;
-    DevBuf<uint64_t> w_sketches;
-    DevBuf<unsigned long long> w_cand, w_dc;
-    DevBuf<uint8_t> w_state;
-    DevBuf<uint16_t> w_memo;  // similarity memo scratch of the probe kernels
-    uint64_t w_memo_stride = 0;
-    uint32_t w_memo_slots = 0;
-    DevBuf<RowTile> w_tiles;
-    uint32_t w_ntiles = 0;
+    // search workspace: everything one batch of queries needs between query preparation and the result copy. Set 0 serves
+    // the stream-ordered calls; sets 1 and 2 alternate under clann_search_device_async so that consecutive batches overlap.
+    struct SearchWs {
+        uint64_t ws_nq = 0;
+        DevBuf<float> w_qnorm, w_cdist;
+        DevBuf<int16_t> w_q15;
+        DevBuf<uint32_t> w_codes, w_first, w_qperm, w_counter, w_vis, w_sort_k, w_sort_i;
+        DevBuf<SortSegment> w_sort_seg;
+        DevBuf<uint64_t> w_sketches;
+        DevBuf<unsigned long long> w_cand, w_dc;
+        DevBuf<uint8_t> w_state;
+        DevBuf<uint16_t> w_memo;  // similarity memo scratch of the probe kernels
+        uint64_t w_memo_stride = 0;
+        uint32_t w_memo_slots = 0;
+        DevBuf<RowTile> w_tiles, w_tiles_codes;
+        uint32_t w_ntiles = 0;
+        uint64_t w_tiles_codes_nq = 0;
+    };
+    SearchWs wsv[3];
+    SearchWs* W = &wsv[0];
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_done[2] = {nullptr, nullptr};
+    uint64_t pipe_calls = 0;
+    DevBuf<float> w_queries, w_out_dists;
+    DevBuf<uint32_t> w_out_ids, w_out_counts;
     uint64_t last_nq = 0;
     const float* cur_queries = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -452,6 +463,18 @@ struct clann_index {
     ~clann_index() {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : pipe_done)
+            if (e) cudaEventDestroy(e);
+        for (auto& st : pipe_stream)
+            if (st) cudaStreamDestroy(st);
+    }
+
+    void reset_workspaces() {
+        if (pipe_calls) cudaDeviceSynchronize();  // batches still in flight on the internal streams
+        for (auto& w : wsv) {
+            w.ws_nq = 0;
+            w.w_tiles_codes_nq = 0;
+        }
     }
 
     uint32_t n_fsets() const { return (uint32_t)fsets.size(); }
@@ -581,7 +604,7 @@ struct clann_index {
         prepare_functions(s);
         CLANN_CUDA(cudaStreamSynchronize(s));
         CLANN_CUDA(cudaGetLastError());
-        ws_nq = 0;
+        reset_workspaces();
         built = true;
     }
 
@@ -746,7 +769,7 @@ struct clann_index {
 
     void build() {
         cudaStream_t s = 0;
-        ws_nq = 0;  // the search workspace (memo stride, tiles) depends on the clustering
+        reset_workspaces();  // the search workspace (memo stride, tiles) depends on the clustering
         cudaEvent_t e0, e1, e2, e3;
         CLANN_CUDA(cudaEventCreate(&e0)); CLANN_CUDA(cudaEventCreate(&e1)); CLANN_CUDA(cudaEventCreate(&e2)); CLANN_CUDA(cudaEventCreate(&e3));
         CLANN_CUDA(cudaEventRecord(e0, s));
@@ -884,69 +907,69 @@ struct clann_index {
     }
 
     void ensure_workspace(uint64_t nq, cudaStream_t s) {
-        if (nq == ws_nq) return;
+        if (nq == W->ws_nq) return;
         const uint32_t F = n_fsets();
         const uint32_t k = (uint32_t)cfg.k;
-        w_qnorm.ensure(nq);
-        w_q15.ensure(nq * g.sl);
-        w_codes.ensure((size_t)F * g.L * nq);
-        w_sketches.ensure((size_t)F * nq * kNumSketches);
-        w_cdist.ensure(nq * K);
-        w_first.ensure(nq);
-        w_qperm.ensure(nq);
+        W->w_qnorm.ensure(nq);
+        W->w_q15.ensure(nq * g.sl);
+        W->w_codes.ensure((size_t)F * g.L * nq);
+        W->w_sketches.ensure((size_t)F * nq * kNumSketches);
+        W->w_cdist.ensure(nq * K);
+        W->w_first.ensure(nq);
+        W->w_qperm.ensure(nq);
         if (nq > segment_sort_smem_capacity()) {
-            w_sort_k.ensure(nq);
-            w_sort_i.ensure(nq);
+            W->w_sort_k.ensure(nq);
+            W->w_sort_i.ensure(nq);
         }
         {
             std::vector<SortSegment> seg(1, SortSegment{0, 0, (uint32_t)nq, 0});
-            w_sort_seg.upload(seg, s);
+            W->w_sort_seg.upload(seg, s);
         }
-        w_state.ensure(nq * query_state_bytes(k));
+        W->w_state.ensure(nq * query_state_bytes(k));
         {
             // one memo region (u16 per local id of the largest cluster) per resident probe warp; skipped beyond 1 GiB
             const uint32_t max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
-            w_memo_stride = ((uint64_t)max_cluster + 7) & ~7ull;
-            w_memo_slots = probe_memo_slots();
-            const uint64_t need = w_memo_stride * w_memo_slots;
-            if (need > 0 && need * sizeof(uint16_t) <= (1ull << 30)) w_memo.ensure(need);
-            else w_memo_slots = 0;
+            W->w_memo_stride = ((uint64_t)max_cluster + 7) & ~7ull;
+            W->w_memo_slots = probe_memo_slots();
+            const uint64_t need = W->w_memo_stride * W->w_memo_slots;
+            if (need > 0 && need * sizeof(uint16_t) <= (1ull << 30)) W->w_memo.ensure(need);
+            else W->w_memo_slots = 0;
         }
-        w_counter.ensure(2);
-        w_cand.ensure(nq);
-        w_dc.ensure(nq);
-        w_vis.ensure(nq);
+        W->w_counter.ensure(2);
+        W->w_cand.ensure(nq);
+        W->w_dc.ensure(nq);
+        W->w_vis.ensure(nq);
         std::vector<RowTile> tiles;
         for (uint32_t f = 0; f < F; f++)
             for (uint64_t q0 = 0; q0 < nq; q0 += 32)
                 tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
-        w_tiles.upload(tiles, s);
-        w_ntiles = (uint32_t)tiles.size();
-        ws_nq = nq;
+        W->w_tiles.upload(tiles, s);
+        W->w_ntiles = (uint32_t)tiles.size();
+        W->ws_nq = nq;
     }
 
     QueryBatch batch(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
         QueryBatch b{};
         b.nq = nq;
         b.queries = d_queries;
-        b.qnorm = w_qnorm.p;
-        b.q15 = w_q15.p;
-        b.codes = w_codes.p;
-        b.sketches = w_sketches.p;
-        b.cdist = w_cdist.p;
-        b.first = w_first.p;
-        b.qperm = w_qperm.p;
-        b.state = w_state.p;
-        b.work_counter = w_counter.p;
-        b.memo = w_memo_slots ? w_memo.p : nullptr;
-        b.memo_stride = w_memo_stride;
-        b.memo_slots = w_memo_slots;
+        b.qnorm = W->w_qnorm.p;
+        b.q15 = W->w_q15.p;
+        b.codes = W->w_codes.p;
+        b.sketches = W->w_sketches.p;
+        b.cdist = W->w_cdist.p;
+        b.first = W->w_first.p;
+        b.qperm = W->w_qperm.p;
+        b.state = W->w_state.p;
+        b.work_counter = W->w_counter.p;
+        b.memo = W->w_memo_slots ? W->w_memo.p : nullptr;
+        b.memo_stride = W->w_memo_stride;
+        b.memo_slots = W->w_memo_slots;
         b.out_ids = d_ids;
         b.out_dists = d_dists;
         b.out_counts = d_counts;
-        b.cnt_candidates = w_cand.p;
-        b.cnt_distcomp = w_dc.p;
-        b.cnt_visited = w_vis.p;
+        b.cnt_candidates = W->w_cand.p;
+        b.cnt_distcomp = W->w_dc.p;
+        b.cnt_visited = W->w_vis.p;
         return b;
     }
 
@@ -961,31 +984,29 @@ struct clann_index {
         SearchParams p = params();
         QueryBatch b = batch(d_queries, nq, nullptr, nullptr, nullptr);
         launch_prep_queries(p, b, s);
-        // sketches are indexed by out_row = fset*nq + q (w_tiles); codes by fset*L*nq + t*nq + q (w_code_tiles)
-        launch_sketch(b.q15, w_tiles.p, w_ntiles, d_planes.p, g.sl, b.sketches, s);
-        launch_codes(b.q15, w_code_tiles(nq, s), w_ntiles, d_signbits.p, g, b.codes, nq, (uint64_t)g.L * nq, s);
+        // sketches are indexed by out_row = fset*nq + q (W->w_tiles); codes by fset*L*nq + t*nq + q (w_code_tiles)
+        launch_sketch(b.q15, W->w_tiles.p, W->w_ntiles, d_planes.p, g.sl, b.sketches, s);
+        launch_codes(b.q15, w_code_tiles(nq, s), W->w_ntiles, d_signbits.p, g, b.codes, nq, (uint64_t)g.L * nq, s);
         launch_center_order(p, b, s);
         // work order: stable sort of the queries by nearest cluster (same radix sort as the tables)
-        launch_segment_sort(w_sort_seg.p, 1, (uint32_t)nq, b.first, b.qperm, w_sort_k.p, w_sort_i.p, s);
+        launch_segment_sort(W->w_sort_seg.p, 1, (uint32_t)nq, b.first, b.qperm, W->w_sort_k.p, W->w_sort_i.p, s);
         launch_init_state(p, b, s);
         cur_queries = d_queries;
         last_nq = nq;
         last_launches = 7;
     }
 
-    DevBuf<RowTile> w_tiles_codes;
-    uint64_t w_tiles_codes_nq = 0;
     const RowTile* w_code_tiles(uint64_t nq, cudaStream_t s) {
-        if (w_tiles_codes_nq != nq || !w_tiles_codes.p) {
+        if (W->w_tiles_codes_nq != nq || !W->w_tiles_codes.p) {
             std::vector<RowTile> tiles;
             for (uint32_t f = 0; f < n_fsets(); f++)
                 for (uint64_t q0 = 0; q0 < nq; q0 += 32)
                     tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)q0, (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
-            w_tiles_codes.upload(tiles, s);
+            W->w_tiles_codes.upload(tiles, s);
             CLANN_CUDA(cudaStreamSynchronize(s));
-            w_tiles_codes_nq = nq;
+            W->w_tiles_codes_nq = nq;
         }
-        return w_tiles_codes.p;
+        return W->w_tiles_codes.p;
     }
 
     void search_device(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
@@ -1002,6 +1023,41 @@ struct clann_index {
         CLANN_CUDA(cudaEventRecord(ev[3], s));
         last_launches = 9;
         profile_valid = true;
+    }
+
+    // The same search on one of two internal streams (alternating) with its own workspace set, not ordered after anything
+    // the caller has in flight: consecutive batches overlap — the next batch's hashing runs beside the probe of the current
+    // one and its probe fills the SMs the current probe's last wave leaves idle. The caller guarantees that the query buffer
+    // is complete when the call is made; results are complete once search_flush() has been waited on.
+    void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+        require_built();
+        if (nq == 0) return;
+        const int slot = (int)(pipe_calls++ & 1);
+        if (!pipe_stream[slot]) {
+            CLANN_CUDA(cudaStreamCreateWithFlags(&pipe_stream[slot], cudaStreamNonBlocking));
+            CLANN_CUDA(cudaEventCreateWithFlags(&pipe_done[slot], cudaEventDisableTiming));
+        }
+        cudaStream_t s = pipe_stream[slot];
+        SearchWs* saved = W;
+        W = &wsv[1 + slot];
+        try {
+            search_begin(d_queries, nq, s);
+            SearchParams p = params();
+            QueryBatch b = batch(d_queries, nq, d_ids, d_dists, d_counts);
+            launch_probe(p, b, false, s);
+            launch_finish(p, b, s);
+            CLANN_CUDA(cudaEventRecord(pipe_done[slot], s));
+        } catch (...) {
+            W = saved;
+            throw;
+        }
+        W = saved;
+        last_launches = 9;
+    }
+
+    void search_flush(cudaStream_t s) {
+        for (auto& e : pipe_done)
+            if (e) CLANN_CUDA(cudaStreamWaitEvent(s, e, 0));
     }
 };
 
@@ -1112,6 +1168,20 @@ int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq,
     });
 }
 
+int clann_search_device_async(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+    return guarded([&] {
+        if (!index || (nq && (!d_queries || !d_ids || !d_dists || !d_counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_device_async(d_queries, nq, d_ids, d_dists, d_counts);
+    });
+}
+
+int clann_search_flush(clann_index* index, void* stream) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->search_flush(static_cast<cudaStream_t>(stream));
+    });
+}
+
 int clann_search(clann_index* index, const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts) {
     return guarded([&] {
         if (!index || (nq && (!queries || !ids || !dists || !counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
@@ -1152,7 +1222,7 @@ int clann_search_step(clann_index* index, void* stream) {
 }
 
 uint64_t clann_state_bytes(const clann_index* index) { return index ? query_state_bytes((uint32_t)index->cfg.k) : 0; }
-void* clann_state_ptr(clann_index* index) { return index ? index->w_state.p : nullptr; }
+void* clann_state_ptr(clann_index* index) { return index ? index->W->w_state.p : nullptr; }
 
 int clann_search_merge(clann_index* index, const void* d_all_states, int world, uint64_t* active_out, void* stream) {
     return guarded([&] {
@@ -1160,11 +1230,11 @@ int clann_search_merge(clann_index* index, const void* d_all_states, int world, 
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         SearchParams p = index->params();
         QueryBatch b = index->batch(index->cur_queries, index->last_nq, nullptr, nullptr, nullptr);
-        launch_merge_states(p, b, static_cast<const uint8_t*>(d_all_states), world, index->w_counter.p + 1, s);
+        launch_merge_states(p, b, static_cast<const uint8_t*>(d_all_states), world, index->W->w_counter.p + 1, s);
         index->last_launches++;
         if (active_out) {
             uint32_t a = 0;
-            CLANN_CUDA(cudaMemcpyAsync(&a, index->w_counter.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CLANN_CUDA(cudaMemcpyAsync(&a, index->W->w_counter.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CLANN_CUDA(cudaStreamSynchronize(s));
             *active_out = a;
         }
@@ -1186,9 +1256,9 @@ int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, ui
         if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
         if (nq > index->last_nq) throw StatusError(CLANN_ERR_BOUNDS, "more counters requested than queries searched");
         CLANN_CUDA(cudaDeviceSynchronize());
-        if (candidates) CLANN_CUDA(cudaMemcpy(candidates, index->w_cand.p, nq * 8, cudaMemcpyDeviceToHost));
-        if (distance_computations) CLANN_CUDA(cudaMemcpy(distance_computations, index->w_dc.p, nq * 8, cudaMemcpyDeviceToHost));
-        if (clusters_visited) CLANN_CUDA(cudaMemcpy(clusters_visited, index->w_vis.p, nq * 4, cudaMemcpyDeviceToHost));
+        if (candidates) CLANN_CUDA(cudaMemcpy(candidates, index->W->w_cand.p, nq * 8, cudaMemcpyDeviceToHost));
+        if (distance_computations) CLANN_CUDA(cudaMemcpy(distance_computations, index->W->w_dc.p, nq * 8, cudaMemcpyDeviceToHost));
+        if (clusters_visited) CLANN_CUDA(cudaMemcpy(clusters_visited, index->W->w_vis.p, nq * 4, cudaMemcpyDeviceToHost));
     });
 }
 
@@ -1284,7 +1354,7 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 const uint64_t nq = index->last_nq, L = index->g.L;
                 const uint32_t f = index->h_fset_of[arg];
                 // device layout [L][nq] -> host layout [nq][L]
-                std::vector<uint32_t> tmp = index->w_codes.download(L * nq, (size_t)f * L * nq);
+                std::vector<uint32_t> tmp = index->W->w_codes.download(L * nq, (size_t)f * L * nq);
                 std::vector<uint32_t> outv(nq * L);
                 for (uint64_t t = 0; t < L; t++)
                     for (uint64_t q = 0; q < nq; q++) outv[q * L + t] = tmp[t * nq + q];
@@ -1295,14 +1365,14 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 need_cluster();
                 const uint64_t nq = index->last_nq;
                 const uint32_t f = index->h_fset_of[arg];
-                emit_dev(index->w_sketches.p + (size_t)f * nq * kNumSketches, nq * kNumSketches * 8);
+                emit_dev(index->W->w_sketches.p + (size_t)f * nq * kNumSketches, nq * kNumSketches * 8);
                 break;
             }
             case CLANN_X_CLUSTER_ORDER: {
                 // index.rs:592-616: stable ascending order of the centre distances, derived on the host for the tests
                 index->require_built();
                 const uint64_t nq = index->last_nq;
-                std::vector<float> cd = index->w_cdist.download(nq * K);
+                std::vector<float> cd = index->W->w_cdist.download(nq * K);
                 std::vector<uint32_t> order(nq * K);
                 for (uint64_t q = 0; q < nq; q++) {
                     uint32_t* o = order.data() + q * K;
@@ -1453,8 +1523,8 @@ uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, 
         SearchParams p = ix->params();
         QueryBatch b = ix->batch(index->d_query.p, 1, nullptr, nullptr, nullptr);
         launch_prep_queries(p, b, s);
-        launch_sketch(b.q15, ix->w_tiles.p, ix->w_ntiles, ix->d_planes.p, ix->g.sl, b.sketches, s);
-        launch_codes(b.q15, ix->w_code_tiles(1, s), ix->w_ntiles, ix->d_signbits.p, ix->g, b.codes, 1, ix->g.L, s);
+        launch_sketch(b.q15, ix->W->w_tiles.p, ix->W->w_ntiles, ix->d_planes.p, ix->g.sl, b.sketches, s);
+        launch_codes(b.q15, ix->w_code_tiles(1, s), ix->W->w_ntiles, ix->d_signbits.p, ix->g, b.codes, 1, ix->g.L, s);
         launch_puffinn_search(p, b, ix->d_stop.p, max_sim, index->d_out.p, index->d_out.p + k, index->d_out.p + k + 1, s);
         std::vector<uint32_t> out(k + 2);
         CLANN_CUDA(cudaMemcpyAsync(out.data(), index->d_out.p, sizeof(uint32_t) * (k + 2), cudaMemcpyDeviceToHost, s));

@@ -26,7 +26,6 @@ namespace clann {
 
 namespace {
 
-constexpr int kMaxAhead = 4;  // ring sweeps kept in registers ahead of the consumer (template parameter AH <= this)
 constexpr int kNT = 3;      // tables per lane evaluated in lockstep (anchors, ranges)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

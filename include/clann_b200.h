@@ -82,6 +82,15 @@ int clann_search(clann_index* index, const float* queries, uint64_t nq, uint32_t
 /* Same with DEVICE pointers (queries and outputs already resident in HBM); asynchronous on `stream` (a cudaStream_t). */
 int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
                         uint32_t* d_counts, void* stream);
+/* Batch pipelining for a stream of batches (no counterpart in the reference, which answers one query at a time): the same
+ * search, issued on one of two internal streams with its own workspace, NOT ordered after the caller's streams, so that
+ * consecutive batches overlap on the device (the next batch's hashing beside the current probe, its probe in the SMs the
+ * current probe's last wave leaves idle). The query buffer must be complete when the call is made and every batch in
+ * flight needs its own output buffers. clann_search_flush makes `stream` wait for every batch issued so far; results are
+ * complete once that stream has been synchronised. Counters and the search profile are those of the stream-ordered calls. */
+int clann_search_device_async(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
+                              uint32_t* d_counts);
+int clann_search_flush(clann_index* index, void* stream);
 
 /* Multi-GPU stepping (one process per GPU, clusters sharded by owner). clann_search_begin prepares the batch (query
  * hashing, centre ordering); each clann_search_step advances every unfinished query through the consecutive clusters

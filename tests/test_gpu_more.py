@@ -356,3 +356,33 @@ def test_legacy_save_and_load_round_trip(tmp_path, reflib):
         assert a == b and cb.api.get_distance_computations() == dc
         rids, met = ref.search(q, 10, 0.9)
         assert sorted(rids.tolist()) == sorted(a) and met["distance_computations"] == dc
+
+
+def test_async_batches_equal_stream_ordered_calls():
+    """clann_search_device_async / clann_search_flush (batch pipelining on two internal streams with their own workspaces):
+    six batches in flight back to back — different queries, one of a different size — return exactly what the
+    stream-ordered host call returns for each of them."""
+    import torch
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    data = util.planted(40_000, 64, 61)
+    ix = cb.init_with_config(data, cb.Config(40, 0.4, 10, 0.9, "async"))
+    ix.set_option("seed", 9)
+    ix.build()
+    batches = [util.planted_queries(data, 700 if i != 3 else 333, 70 + i) for i in range(6)]
+    batches[4] = util.uniform_sphere(700, 64, 99)   # walks many clusters
+    expected = [ix.search_batch(q) for q in batches]
+    dev = torch.device("cuda", 0)
+    d_q = [torch.from_numpy(q).to(dev) for q in batches]
+    outs = [(torch.empty((len(q), 10), dtype=torch.int32, device=dev), torch.empty((len(q), 10), dtype=torch.float32, device=dev),
+             torch.empty(len(q), dtype=torch.int32, device=dev)) for q in batches]
+    torch.cuda.synchronize()
+    lib = cl.load()
+    for q, o in zip(d_q, outs):
+        assert lib.clann_search_device_async(ix.handle, q.data_ptr(), q.shape[0], o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) == 0, cl.last_error()
+    assert lib.clann_search_flush(ix.handle, torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    for (ids, dists, counts), o in zip(expected, outs):
+        assert np.array_equal(ids.view(np.uint32), o[0].cpu().numpy().view(np.uint32))
+        assert np.array_equal(dists.view(np.uint32), o[1].cpu().numpy().view(np.uint32))
+        assert np.array_equal(counts.view(np.uint32), o[2].cpu().numpy().view(np.uint32))
