@@ -316,8 +316,7 @@ def main():
 
     # batch pipelining (clann_search_device_async): consecutive steps on two internal streams, each with its own outputs
     pipelined = single and not args.no_pipeline
-    outs = [(d_ids, d_dists, d_counts),
-            (torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts))]
+    outs = [(d_ids, d_dists, d_counts)] + [(torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts)) for _ in range(3)]
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def run_steps(steps):
@@ -326,7 +325,7 @@ def main():
                 step_device()
             return
         for i in range(steps):
-            o = outs[i & 1]
+            o = outs[i & 3]
             if index._lib.clann_search_device_async(index.handle, d_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
                 raise RuntimeError(cl.last_error())
         if index._lib.clann_search_flush(index.handle, cur_stream) != 0:

@@ -27,7 +27,7 @@ __all__ = [
     "Config", "MetricsOutput", "AngularData", "ClusteredIndex", "ClusteredIndexError", "ConfigError", "DataError",
     "PuffinnCreationError", "PuffinnSearchError", "IndexNotFound", "IndexOutOfBounds", "SerializeError", "MetricsError",
     "CudaError", "init", "init_with_config", "build", "search", "search_batch", "PuffinnIndex", "get_recall_values",
-    "brute_force_search", "generate_random_unit_vectors",
+    "brute_force_search", "generate_random_unit_vectors", "RunMetrics", "run_with_metrics",
 ]
 
 
@@ -357,6 +357,70 @@ def get_recall_values(dataset_distances: np.ndarray, run_distances: Sequence[Seq
     mean = float(recalls_arr.sum() / (len(recalls) * count)) if len(recalls) else 0.0
     std = float(recalls_arr.std() / count) if len(recalls) else 0.0
     return mean, std, recalls
+
+
+class RunMetrics:
+    """The run / query granularities of the reference's RunMetrics (src/utils/metrics/mod.rs:14-35,116-262) for one batch:
+    what the reference writes to sqlite (result_schema.sql: clann_results, clann_results_query) as plain rows. The
+    per-cluster granularity (cluster_n_candidates, cluster_timings, cluster_distance_computations) is summed on the device
+    into the per-query counters; per-query wall time is the batch time divided by the batch (queries run concurrently)."""
+
+    def __init__(self, config: "Config", dataset_len: int, total_search_time_s: float, counters: dict,
+                 run_distances=None, ground_truth_distances=None, indexing_duration_s: float = 0.0):
+        self.config, self.dataset_len = config, int(dataset_len)
+        self.total_search_time_s = float(total_search_time_s)
+        self.indexing_duration_s = float(indexing_duration_s)
+        self.distance_computations = np.asarray(counters["distance_computations"], np.uint64)
+        self.candidates = np.asarray(counters["candidates"], np.uint64)
+        self.clusters_visited = np.asarray(counters["clusters_visited"], np.uint32)
+        nq = len(self.distance_computations)
+        self.queries_per_second = (nq / self.total_search_time_s) if self.total_search_time_s > 0 else 0.0  # mod.rs:261
+        self.recall_mean = self.recall_std = 0.0
+        self.recalls: List[float] = []
+        if ground_truth_distances is not None and run_distances is not None:
+            self.recall_mean, self.recall_std, self.recalls = get_recall_values(ground_truth_distances, run_distances, int(config.k))
+
+    def run_row(self) -> dict:
+        c = self.config
+        return dict(num_clusters_factor=float(c.num_clusters_factor), num_tables=int(c.num_tables), k=int(c.k), delta=float(c.delta),
+                    dataset=c.dataset_name, dataset_len=self.dataset_len, indexing_duration_s=self.indexing_duration_s,
+                    total_search_time_s=self.total_search_time_s, queries_per_second=self.queries_per_second,
+                    recall_mean=self.recall_mean, recall_std=self.recall_std)
+
+    def query_rows(self) -> List[dict]:
+        nq = len(self.distance_computations)
+        per_query_s = self.total_search_time_s / nq if nq else 0.0
+        return [dict(query_idx=i, query_time_s=per_query_s, distance_computations=int(self.distance_computations[i]),
+                     n_candidates=int(self.candidates[i]), clusters_visited=int(self.clusters_visited[i]),
+                     recall=(self.recalls[i] / float(self.config.k)) if self.recalls else None) for i in range(nq)]
+
+    def to_json(self, granularity: str = "query") -> str:
+        import json
+        out = {"run": self.run_row()}
+        if granularity in ("query", "cluster"):
+            out["queries"] = self.query_rows()
+        return json.dumps(out)
+
+    def write_csv(self, path: str) -> None:
+        rows = self.query_rows()
+        with open(path, "w") as f:
+            f.write("# " + ",".join(f"{k}={v}" for k, v in self.run_row().items()) + "\n")
+            f.write("query_idx,query_time_s,distance_computations,n_candidates,clusters_visited,recall\n")
+            for r in rows:
+                f.write(",".join("" if r[k] is None else str(r[k]) for k in
+                                 ("query_idx", "query_time_s", "distance_computations", "n_candidates", "clusters_visited", "recall")) + "\n")
+
+
+def run_with_metrics(index: "ClusteredIndex", queries, ground_truth_distances=None) -> Tuple[Tuple[np.ndarray, np.ndarray, np.ndarray], RunMetrics]:
+    """One batch through clann_search with the reference's run metrics filled in (wall clock around the call, as
+    benches/distance_benches.rs:57-74 does around its query loop)."""
+    import time
+    t0 = time.perf_counter()
+    ids, dists, counts = index.search_batch(queries)
+    dt = time.perf_counter() - t0
+    ctr = index.counters(len(counts))
+    run = [dists[i, :counts[i]].tolist() for i in range(len(counts))] if ground_truth_distances is not None else None
+    return (ids, dists, counts), RunMetrics(index.config, index.data.num_points(), dt, ctr, run, ground_truth_distances)
 
 
 def generate_random_unit_vectors(n: int, dimensions: int, seed: Optional[int] = None) -> np.ndarray:

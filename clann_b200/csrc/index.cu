@@ -430,7 +430,7 @@ struct clann_index {
     float stop_recall = -1.0f;
 
     // search workspace: everything one batch of queries needs between query preparation and the result copy. Set 0 serves
-    // the stream-ordered calls; sets 1 and 2 alternate under clann_search_device_async so that consecutive batches overlap.
+    // the stream-ordered calls; the others rotate under clann_search_device_async so that consecutive batches overlap.
     struct SearchWs {
         uint64_t ws_nq = 0;
         DevBuf<float> w_qnorm, w_cdist;
@@ -447,10 +447,11 @@ struct clann_index {
         uint32_t w_ntiles = 0;
         uint64_t w_tiles_codes_nq = 0;
     };
-    SearchWs wsv[3];
+    static constexpr int kPipeMax = 4;
+    SearchWs wsv[1 + kPipeMax];
     SearchWs* W = &wsv[0];
-    cudaStream_t pipe_stream[2] = {nullptr, nullptr};
-    cudaEvent_t pipe_done[2] = {nullptr, nullptr};
+    cudaStream_t pipe_stream[kPipeMax] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[kPipeMax] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t pipe_calls = 0;
     DevBuf<float> w_queries, w_out_dists;
     DevBuf<uint32_t> w_out_ids, w_out_counts;
@@ -1032,7 +1033,9 @@ struct clann_index {
     void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
         require_built();
         if (nq == 0) return;
-        const int slot = (int)(pipe_calls++ & 1);
+        int depth = (int)tune_get("pipeline_depth", 2);  // batches in flight (knob; 2 measured best)
+        depth = depth < 1 ? 1 : (depth > kPipeMax ? kPipeMax : depth);
+        const int slot = (int)(pipe_calls++ % (uint64_t)depth);
         if (!pipe_stream[slot]) {
             CLANN_CUDA(cudaStreamCreateWithFlags(&pipe_stream[slot], cudaStreamNonBlocking));
             CLANN_CUDA(cudaEventCreateWithFlags(&pipe_done[slot], cudaEventDisableTiming));

@@ -69,3 +69,25 @@ def test_legacy_create_rejects_unknown_type(lib, capfd):
     assert lib.CPUFFINN_search_cosine(None, None, 3, 0.9, 0.0, 4) is None or not lib.CPUFFINN_search_cosine(None, None, 3, 0.9, 0.0, 4)
     lib.CPUFFINN_clear_distance_computations()
     assert lib.CPUFFINN_get_distance_computations() == 0
+
+
+def test_rust_binding_matches_header(lib):
+    """bindings/rust/src/sys.rs (the reference-side binding; not compilable here) declares only functions the header
+    declares and the library exports, with the header's status codes."""
+    header = open(os.path.join(ROOT, "include", "clann_b200.h")).read()
+    rust = open(os.path.join(ROOT, "bindings", "rust", "src", "sys.rs")).read()
+    fns = re.findall(r"pub fn ((?:clann|CPUFFINN)_[A-Za-z0-9_]+)\s*\(", rust)
+    assert len(fns) >= 18
+    declared = set(declared_functions())
+    assert not [f for f in fns if f not in declared or not hasattr(lib, f)]
+    for name, value in re.findall(r"pub const (CLANN_[A-Z_]+): i32 = (-?\d+);", rust):
+        m = re.search(r"\b" + name + r"\s*=\s*(-?\d+)", header)
+        assert m and int(m.group(1)) == int(value), name
+    # argument counts agree with the C prototypes
+    csrc = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for f in fns:
+        c_args = re.search(r"\b" + f + r"\s*\(([^)]*)\)", csrc).group(1).strip()
+        n_c = 0 if c_args in ("", "void") else c_args.count(",") + 1
+        r_args = re.search(r"pub fn " + f + r"\s*\(([^)]*)\)", rust).group(1).strip()
+        n_r = 0 if r_args == "" else r_args.count(",") + 1
+        assert n_c == n_r, (f, c_args, r_args)

@@ -44,3 +44,25 @@ def test_recall_values():  # src/utils/mod.rs:59-95
 def test_unit_vector_helper():
     v = cb.generate_random_unit_vectors(50, 16, seed=1)
     assert v.shape == (50, 16) and np.allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-5) and (v >= 0).all()
+
+
+def test_run_metrics_rows(tmp_path):
+    """RunMetrics (utils/metrics/mod.rs:14-35,254-262): queries/s = queries / total time, recall by get_recall_values."""
+    import clann_b200 as cb
+    from clann_b200 import api
+    cfg = cb.Config(84, 0.4, 2, 0.9, "unit")
+    ctr = dict(distance_computations=[5, 7, 9], candidates=[50, 70, 90], clusters_visited=[1, 2, 1])
+    gt = np.array([[0.1, 0.2, 0.3], [0.1, 0.2, 0.3], [0.5, 0.6, 0.7]], np.float32)
+    run = [[0.1, 0.2], [0.1, 0.9], [0.9, 0.95]]
+    m = api.RunMetrics(cfg, 1000, 0.5, ctr, run, gt)
+    assert m.queries_per_second == 6.0
+    assert abs(m.recall_mean - 0.5) < 1e-6 and m.recalls == [2.0, 1.0, 0.0]
+    rows = m.query_rows()
+    assert rows[1]["distance_computations"] == 7 and rows[1]["n_candidates"] == 70 and rows[1]["recall"] == 0.5
+    assert m.run_row()["num_tables"] == 84 and m.run_row()["dataset_len"] == 1000
+    p = tmp_path / "m.csv"
+    m.write_csv(str(p))
+    lines = p.read_text().splitlines()
+    assert lines[1].startswith("query_idx,") and len(lines) == 5 and lines[3].split(",")[2] == "7"
+    import json
+    assert len(json.loads(m.to_json())["queries"]) == 3
