@@ -7,8 +7,10 @@ A "step" is one search pass of the hot path over one batch of synthetic queries 
 Workload at N=1 (BASELINE.json configs[2], the one the metric is quoted on): glove-100-angular shape, synthetic
 1,183,514 x 100 unit vectors, 10,000 queries, num_tables=84, num_clusters_factor=0.4, k=10, delta=0.9.
 
-Prints ONE JSON line (rank 0). `value` = queries/s with queries and outputs resident in HBM (clann_search_device),
-`e2e` = the same through the reference-facing call clann_search with HOST buffers (H2D + D2H inside the timed region),
+Prints ONE JSON line (rank 0). `value` = queries/s with queries and outputs resident in HBM, K steps issued back to back
+through clann_search_device_async (two batches in flight; `value_stream_ordered` = one batch at a time, clann_search_device),
+`e2e` = the same with HOST buffers, H2D + D2H inside the timed region, through clann_search_async / clann_search_wait
+(`value_synchronous_call` = one blocking clann_search per step),
 `roofline` = algorithmic bytes of the probe kernel / its CUDA-event duration against the measured HBM peak,
 `cpu_baseline` = the reference's own CPU implementation (oracle/_ref, real PUFFINN headers) on a bounded query sample.
 `--impl reference` prints the reference arm's line (rank 0 only; other ranks exit 0).
@@ -32,7 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "queries/sec @ recall@10>=0.9 (glove-100 shape)"
 UNIT = "queries/s"
 # DRAM bytes of one k_probe launch from the committed ncu capture (profiles/), per workload; None = not captured
-MEASURED_TRAFFIC = {"glove100": 10.34e9}
+MEASURED_TRAFFIC = {"glove100": 10.67e9}
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -426,7 +428,48 @@ def main():
     # end to end
     for _ in range(2):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_sync_ms = timed(step_e2e, args.steps) / args.steps
+    e2e_ms, e2e_mode = e2e_sync_ms, "clann_search: one synchronous call per step (host buffers in, host buffers out)"
+    if pipelined:
+        # the same through clann_search_async: every step's H2D copy, search and D2H copies on its batch stream, two batches in
+        # flight, each with its own pinned output buffers; clann_search_wait before the clock stops
+        h_outs = [(h_ids, h_dists, h_counts)] + [(torch.empty_like(h_ids).pin_memory(), torch.empty_like(h_dists).pin_memory(),
+                                                  torch.empty_like(h_counts).pin_memory()) for _ in range(3)]
+
+        def run_e2e_async(steps):
+            for i in range(steps):
+                o = h_outs[i & 3]
+                if index._lib.clann_search_async(index.handle, h_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+                    raise RuntimeError(cl.last_error())
+            if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
+                raise RuntimeError(cl.last_error())
+
+        run_e2e_async(3)
+        if index._lib.clann_search_wait(index.handle) != 0:
+            raise RuntimeError(cl.last_error())
+        step_e2e()                                   # reference result of the synchronous call in h_outs[0]
+        want = (h_ids.clone(), h_dists.clone(), h_counts.clone())
+        run_e2e_async(4)
+        index._lib.clann_search_wait(index.handle)
+        for o in h_outs:
+            if not (torch.equal(o[0], want[0]) and torch.equal(o[1], want[1]) and torch.equal(o[2], want[2])):
+                raise RuntimeError("clann_search_async returned results that differ from clann_search")
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        run_e2e_async(args.steps)
+        g1.record()
+        index._lib.clann_search_wait(index.handle)
+        barrier()
+        e2e_ms = g0.elapsed_time(g1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e_ms /= args.steps
+        e2e_mode = ("clann_search_async + clann_search_wait: host buffers in and out, H2D / search / D2H of each step on its batch "
+                    "stream, two batches in flight; results identical to clann_search (checked)")
     e2e_value = global_nq / (e2e_ms / 1000.0)
 
     # ---- correctness of what was timed: the pipelined batches return what the stream-ordered call returns
@@ -479,7 +522,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                         "traffic": MEASURED_TRAFFIC.get(args.workload if not args.small else "small"),
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_probe launch, ncu --set full, "
-                                          "profiles/r1c_k_probe_warp_raw.csv (glove100 planted only)",
+                                          "profiles/r1d_k_probe_warp_full_raw.csv (glove100 planted only)",
                         "kernel_ms": probe_ms, "prep_ms": prep_ms,
                         "algorithmic_bytes_per_launch": rerank_bytes + filter_bytes,
                         "rerank_gbs": rerank_bytes / (probe_ms / 1000.0) / 1e9, "filter_gbs": filter_bytes / (probe_ms / 1000.0) / 1e9}
@@ -502,7 +545,8 @@ def main():
             "data": "synthetic", "config": cfg_json, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,
                     "d2h_bytes_per_step": global_nq * k * 8 + global_nq * 4,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "call": e2e_mode,
+                    "value_synchronous_call": global_nq / (e2e_sync_ms / 1000.0), "ms_per_step_synchronous_call": e2e_sync_ms},
             "gpu_launches": int(launches_per_step * args.steps * (1 if (world == 1 or shard_clusters) else world)), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "build": {"wall_s": build_wall, "gmm_ms": build_ms[0], "hash_ms": build_ms[1], "sort_ms": build_ms[2], "device_ms": build_ms[3],
                       "clusters": int(K)},

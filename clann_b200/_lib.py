@@ -29,7 +29,7 @@ OK, ERR_DATA, ERR_CONFIG, ERR_CREATION, ERR_SEARCH, ERR_NOT_BUILT, ERR_BOUNDS, E
 
 EXPORTED_SYMBOLS = [
     "clann_init_with_config", "clann_set_option", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
-    "clann_build", "clann_search", "clann_search_device", "clann_search_device_async", "clann_search_flush", "clann_search_begin", "clann_search_step", "clann_state_bytes",
+    "clann_build", "clann_search", "clann_search_device", "clann_search_device_async", "clann_search_flush", "clann_search_async", "clann_search_wait", "clann_search_begin", "clann_search_step", "clann_state_bytes",
     "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
     "clann_last_search_profile", "clann_tune", "clann_last_error", "clann_destroy",
     "CPUFFINN_load_from_file", "CPUFFINN_index_create", "CPUFFINN_index_rebuild", "CPUFFINN_index_insert_cosine",
@@ -67,6 +67,8 @@ def load() -> C.CDLL:
     L.clann_search_device.restype, L.clann_search_device.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]
     L.clann_search_device_async.restype, L.clann_search_device_async.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp]
     L.clann_search_flush.restype, L.clann_search_flush.argtypes = _i32, [_vp, _vp]
+    L.clann_search_async.restype, L.clann_search_async.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp]
+    L.clann_search_wait.restype, L.clann_search_wait.argtypes = _i32, [_vp]
     L.clann_search_begin.restype, L.clann_search_begin.argtypes = _i32, [_vp, _vp, _u64, _vp]
     L.clann_search_step.restype, L.clann_search_step.argtypes = _i32, [_vp, _vp]
     L.clann_state_bytes.restype, L.clann_state_bytes.argtypes = _u64, [_vp]

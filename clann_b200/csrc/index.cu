@@ -446,6 +446,9 @@ struct clann_index {
         DevBuf<RowTile> w_tiles, w_tiles_codes;
         uint32_t w_ntiles = 0;
         uint64_t w_tiles_codes_nq = 0;
+        // device staging of the host-buffer entry points
+        DevBuf<float> h_queries, h_dists;
+        DevBuf<uint32_t> h_ids, h_counts;
     };
     static constexpr int kPipeMax = 4;
     SearchWs wsv[1 + kPipeMax];
@@ -1030,16 +1033,18 @@ struct clann_index {
     // the caller has in flight: consecutive batches overlap — the next batch's hashing runs beside the probe of the current
     // one and its probe fills the SMs the current probe's last wave leaves idle. The caller guarantees that the query buffer
     // is complete when the call is made; results are complete once search_flush() has been waited on.
-    void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
-        require_built();
-        if (nq == 0) return;
-        int depth = (int)tune_get("pipeline_depth", 2);  // batches in flight (knob; 2 measured best)
+    int next_pipe_slot() {
+        int depth = (int)tune_get("pipeline_depth", 2);  // batches in flight (knob; 2 and 3 measured equal, 4 slower)
         depth = depth < 1 ? 1 : (depth > kPipeMax ? kPipeMax : depth);
         const int slot = (int)(pipe_calls++ % (uint64_t)depth);
         if (!pipe_stream[slot]) {
             CLANN_CUDA(cudaStreamCreateWithFlags(&pipe_stream[slot], cudaStreamNonBlocking));
             CLANN_CUDA(cudaEventCreateWithFlags(&pipe_done[slot], cudaEventDisableTiming));
         }
+        return slot;
+    }
+
+    void search_on_slot(int slot, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
         cudaStream_t s = pipe_stream[slot];
         SearchWs* saved = W;
         W = &wsv[1 + slot];
@@ -1049,13 +1054,46 @@ struct clann_index {
             QueryBatch b = batch(d_queries, nq, d_ids, d_dists, d_counts);
             launch_probe(p, b, false, s);
             launch_finish(p, b, s);
-            CLANN_CUDA(cudaEventRecord(pipe_done[slot], s));
         } catch (...) {
             W = saved;
             throw;
         }
         W = saved;
         last_launches = 9;
+    }
+
+    void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+        require_built();
+        if (nq == 0) return;
+        const int slot = next_pipe_slot();
+        search_on_slot(slot, d_queries, nq, d_ids, d_dists, d_counts);
+        CLANN_CUDA(cudaEventRecord(pipe_done[slot], pipe_stream[slot]));
+    }
+
+    // Host buffers (pinned, for the copies to be asynchronous): H2D, search and D2H of one batch on the slot's stream.
+    void search_host_async(const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts) {
+        require_built();
+        if (nq == 0) return;
+        const int slot = next_pipe_slot();
+        cudaStream_t s = pipe_stream[slot];
+        SearchWs& w = wsv[1 + slot];
+        const uint32_t k = (uint32_t)cfg.k;
+        w.h_queries.ensure(nq * g.d);
+        w.h_ids.ensure(nq * k);
+        w.h_dists.ensure(nq * k);
+        w.h_counts.ensure(nq);
+        CLANN_CUDA(cudaMemcpyAsync(w.h_queries.p, queries, nq * g.d * sizeof(float), cudaMemcpyHostToDevice, s));
+        search_on_slot(slot, w.h_queries.p, nq, w.h_ids.p, w.h_dists.p, w.h_counts.p);
+        CLANN_CUDA(cudaMemcpyAsync(ids, w.h_ids.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaMemcpyAsync(dists, w.h_dists.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaMemcpyAsync(counts, w.h_counts.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaEventRecord(pipe_done[slot], s));
+    }
+
+    void search_wait() {
+        for (auto& st : pipe_stream)
+            if (st) CLANN_CUDA(cudaStreamSynchronize(st));
+        CLANN_CUDA(cudaGetLastError());
     }
 
     void search_flush(cudaStream_t s) {
@@ -1175,6 +1213,20 @@ int clann_search_device_async(clann_index* index, const float* d_queries, uint64
     return guarded([&] {
         if (!index || (nq && (!d_queries || !d_ids || !d_dists || !d_counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
         index->search_device_async(d_queries, nq, d_ids, d_dists, d_counts);
+    });
+}
+
+int clann_search_async(clann_index* index, const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts) {
+    return guarded([&] {
+        if (!index || (nq && (!queries || !ids || !dists || !counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_host_async(queries, nq, ids, dists, counts);
+    });
+}
+
+int clann_search_wait(clann_index* index) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->search_wait();
     });
 }
 

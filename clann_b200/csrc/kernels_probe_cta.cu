@@ -177,19 +177,29 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 }
 __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory"); }
 
+// L1::no_allocate loads are EVICT_FIRST in the L2 unless told otherwise (ncu: lts__t_sectors_*_evict_first_*, see
+// kernels_probe2.cu); sketch words and rows are exactly what the other queries of the cluster re-read, so they carry an
+// explicit evict_normal policy.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ uint32_t ldg_nc_na_u32(const uint32_t* p) {
     uint32_t v;
-    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_keep_policy()));
     return v;
 }
 __device__ __forceinline__ uint64_t ldg_nc_na_u64(const uint64_t* p) {
     uint64_t v;
-    asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(l2_keep_policy()));
     return v;
 }
 __device__ __forceinline__ uint4 ldg_nc_na_v4(const uint4* p) {
     uint4 v;
-    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+        : "l"(p), "l"(l2_keep_policy()));
     return v;
 }
 

@@ -91,6 +91,11 @@ int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq,
 int clann_search_device_async(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
                               uint32_t* d_counts);
 int clann_search_flush(clann_index* index, void* stream);
+/* The same pipelining with HOST buffers (page-locked, or the copies degrade to synchronous ones): host-to-device copy,
+ * search and the three device-to-host copies of one batch are queued on the batch's internal stream and the call returns;
+ * the output buffers are complete after clann_search_wait, which blocks the host until every batch issued so far is done. */
+int clann_search_async(clann_index* index, const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts);
+int clann_search_wait(clann_index* index);
 
 /* Multi-GPU stepping (one process per GPU, clusters sharded by owner). clann_search_begin prepares the batch (query
  * hashing, centre ordering); each clann_search_step advances every unfinished query through the consecutive clusters

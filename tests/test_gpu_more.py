@@ -386,3 +386,28 @@ def test_async_batches_equal_stream_ordered_calls():
         assert np.array_equal(ids.view(np.uint32), o[0].cpu().numpy().view(np.uint32))
         assert np.array_equal(dists.view(np.uint32), o[1].cpu().numpy().view(np.uint32))
         assert np.array_equal(counts.view(np.uint32), o[2].cpu().numpy().view(np.uint32))
+
+
+def test_async_host_batches_equal_synchronous_call():
+    """clann_search_async / clann_search_wait: host buffers in and out (pinned), copies and search of every batch on its
+    internal stream; five batches back to back return what clann_search returns."""
+    import torch
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    data = util.planted(30_000, 100, 63)
+    ix = cb.init_with_config(data, cb.Config(30, 0.4, 10, 0.9, "async-host"))
+    ix.set_option("seed", 10)
+    ix.build()
+    batches = [util.planted_queries(data, 500, 80 + i) for i in range(5)]
+    expected = [ix.search_batch(q) for q in batches]
+    h_q = [torch.from_numpy(q).pin_memory() for q in batches]
+    outs = [(torch.empty((500, 10), dtype=torch.int32).pin_memory(), torch.empty((500, 10), dtype=torch.float32).pin_memory(),
+             torch.empty(500, dtype=torch.int32).pin_memory()) for _ in batches]
+    lib = cl.load()
+    for q, o in zip(h_q, outs):
+        assert lib.clann_search_async(ix.handle, q.data_ptr(), 500, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) == 0, cl.last_error()
+    assert lib.clann_search_wait(ix.handle) == 0
+    for (ids, dists, counts), o in zip(expected, outs):
+        assert np.array_equal(ids.view(np.uint32), o[0].numpy().view(np.uint32))
+        assert np.array_equal(dists.view(np.uint32), o[1].numpy().view(np.uint32))
+        assert np.array_equal(counts.view(np.uint32), o[2].numpy().view(np.uint32))
