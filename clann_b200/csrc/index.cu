@@ -443,6 +443,8 @@ struct clann_index {
         DevBuf<uint16_t> w_memo;  // similarity memo scratch of the probe kernels
         uint64_t w_memo_stride = 0;
         uint32_t w_memo_slots = 0;
+        DevBuf<uint16_t> w_dense;  // dense first-visit similarities [nq][w_dense_stride]
+        uint64_t w_dense_stride = 0;
         DevBuf<RowTile> w_tiles, w_tiles_codes;
         uint32_t w_ntiles = 0;
         uint64_t w_tiles_codes_nq = 0;
@@ -939,6 +941,14 @@ struct clann_index {
             if (need > 0 && need * sizeof(uint16_t) <= (1ull << 30)) W->w_memo.ensure(need);
             else W->w_memo_slots = 0;
         }
+        {
+            // dense first-visit similarities: one u16 per (query, row of the largest cluster); skipped beyond 2 GiB
+            const uint32_t max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
+            W->w_dense_stride = ((uint64_t)max_cluster + 63) & ~63ull;
+            const uint64_t need = W->w_dense_stride * nq;
+            if (need > 0 && need * sizeof(uint16_t) <= (2ull << 30) && !puffinn_mode) W->w_dense.ensure(need);
+            else W->w_dense_stride = 0;
+        }
         W->w_counter.ensure(2);
         W->w_cand.ensure(nq);
         W->w_dc.ensure(nq);
@@ -968,6 +978,8 @@ struct clann_index {
         b.memo = W->w_memo_slots ? W->w_memo.p : nullptr;
         b.memo_stride = W->w_memo_stride;
         b.memo_slots = W->w_memo_slots;
+        b.dense = nullptr;  // set by the single-pass search paths (use_dense_sims)
+        b.dense_stride = W->w_dense_stride;
         b.out_ids = d_ids;
         b.out_dists = d_dists;
         b.out_counts = d_counts;
@@ -1021,11 +1033,12 @@ struct clann_index {
         SearchParams p = params();
         QueryBatch b = batch(d_queries, nq, d_ids, d_dists, d_counts);
         CLANN_CUDA(cudaEventRecord(ev[1], s));
+        const bool dense = use_dense_sims(p, b, s);
         launch_probe(p, b, false, s);
         CLANN_CUDA(cudaEventRecord(ev[2], s));
         launch_finish(p, b, s);
         CLANN_CUDA(cudaEventRecord(ev[3], s));
-        last_launches = 9;
+        last_launches = dense ? 10 : 9;
         profile_valid = true;
     }
 
@@ -1033,6 +1046,17 @@ struct clann_index {
     // the caller has in flight: consecutive batches overlap — the next batch's hashing runs beside the probe of the current
     // one and its probe fills the SMs the current probe's last wave leaves idle. The caller guarantees that the query buffer
     // is complete when the call is made; results are complete once search_flush() has been waited on.
+    // Fills the memo of every query's first visit in advance (launch_dense_sims) when the default probe kernel will use it.
+    bool use_dense_sims(const SearchParams& p, QueryBatch& b, cudaStream_t s) {
+        if (!W->w_dense.p || W->w_dense_stride == 0 || tune_get("probe", 0) != 0) return false;
+        b.dense = W->w_dense.p;
+        if (!launch_dense_sims(p, b, s)) {
+            b.dense = nullptr;
+            return false;
+        }
+        return true;
+    }
+
     int next_pipe_slot() {
         int depth = (int)tune_get("pipeline_depth", 2);  // batches in flight (knob; 2 and 3 measured equal, 4 slower)
         depth = depth < 1 ? 1 : (depth > kPipeMax ? kPipeMax : depth);
@@ -1052,14 +1076,15 @@ struct clann_index {
             search_begin(d_queries, nq, s);
             SearchParams p = params();
             QueryBatch b = batch(d_queries, nq, d_ids, d_dists, d_counts);
+            const bool dense = use_dense_sims(p, b, s);
             launch_probe(p, b, false, s);
             launch_finish(p, b, s);
+            last_launches = dense ? 10 : 9;
         } catch (...) {
             W = saved;
             throw;
         }
         W = saved;
-        last_launches = 9;
     }
 
     void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
@@ -1320,8 +1345,8 @@ int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, ui
 int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches) {
     return guarded([&] {
         if (!index || !index->profile_valid) throw StatusError(CLANN_ERR_ARG, "no profiled search yet");
-        CLANN_CUDA(cudaEventSynchronize(index->ev[3]));
         if (ms) {
+            CLANN_CUDA(cudaEventSynchronize(index->ev[3]));
             CLANN_CUDA(cudaEventElapsedTime(&ms[0], index->ev[0], index->ev[1]));
             CLANN_CUDA(cudaEventElapsedTime(&ms[1], index->ev[1], index->ev[2]));
             CLANN_CUDA(cudaEventElapsedTime(&ms[2], index->ev[2], index->ev[3]));

@@ -391,7 +391,8 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
 template <int G>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
-                                  const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr) {
+                                  const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr,
+                                  bool memo_prefilled = false) {
     const uint32_t L = p.g.L, k = p.k;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -401,7 +402,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     const uint64_t* sk = p.sketches + off * kNumSketches;
 
     uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;  // maxbuffer.hpp:53-55, filterer.hpp:101
-    if (memo) {
+    if (memo && !memo_prefilled) {
         uint4* mz = reinterpret_cast<uint4*>(memo);
         for (uint32_t i = lane; i < (nc + 7) / 8; i += 32) mz[i] = make_uint4(0, 0, 0, 0);
     }
@@ -556,7 +557,7 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
 
 // src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
 // for expensive ones). Warps are persistent; grid = multiple of the SM count.
-template <int G, int OCC>
+template <int G, int OCC, bool DENSE>
 __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign,
                                                     uint16_t* memo_base, uint64_t memo_stride) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -664,7 +665,12 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 const uint64_t my_sketch = b.sketches[((uint64_t)fs * b.nq + q) * kNumSketches + lane];
                 const uint32_t* stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
                 uint16_t* use_memo = (memo && nc <= memo_stride) ? memo : nullptr;
-                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr);
+                // first visit of a fresh query: its similarities to the whole cluster were computed in advance (launch_dense_sims)
+                // (DENSE is a template parameter: the instantiation without it keeps the register allocation it had)
+                const bool prefilled = DENSE && pos == 0;
+                if (prefilled) use_memo = b.dense + (uint64_t)q * b.dense_stride;
+                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
+                                                prefilled);
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
                     uint32_t j = base + lane;
@@ -793,6 +799,116 @@ __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatc
     }
 }
 
+// ------------------------------------------------------------------------------------------------ dense first-visit similarities
+
+constexpr uint32_t kDenseRows = 128;   // rows of a cluster staged per CTA
+constexpr uint32_t kDenseQueries = 32;  // queries of the cluster staged per pass
+constexpr int kDenseNQ = 4;             // queries multiplied against one row block by a warp at a time
+
+// One CTA = (cluster c, tile of kDenseRows rows). The tile is staged in shared memory once (row pitch padded by 16 bytes:
+// conflict-free when every lane reads its own row) and the queries whose nearest cluster is c — a contiguous run of the sorted
+// work order — are staged as int32, kDenseQueries at a time. A work item = (block of 32 rows, group of kDenseNQ queries): lane =
+// row, the row's 16-byte chunk is loaded and unpacked once and multiplied against the kDenseNQ queries (broadcast reads), so
+// the multiply-round-accumulate of math.hpp:37-44 (3 instructions) is nearly all that is issued: 12.4 warp instructions per
+// (query, row) against 33 in the gather path of the probe kernel. Results go out as 64-byte stores of 32 similarities.
+__global__ void __launch_bounds__(256, 4) k_dense_sims(SearchParams p, QueryBatch b) {
+    extern __shared__ __align__(16) uint8_t s_dense[];
+    const uint32_t c = blockIdx.x, sl = p.g.sl, cpr = sl / 8, pitch = sl * 2 + 16;
+    if (p.brute[c]) return;
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t r0 = blockIdx.y * kDenseRows;
+    if (r0 >= nc || nc > b.dense_stride) return;
+    // queries whose work-order key is c: [lo, hi) in the sorted key array
+    uint32_t lo = 0, len = (uint32_t)b.nq;
+    while (len > 0) {
+        uint32_t half = len >> 1;
+        if (b.first[lo + half] < c) { lo += half + 1; len -= half + 1; } else { len = half; }
+    }
+    uint32_t hi = lo;
+    len = (uint32_t)b.nq - lo;
+    while (len > 0) {
+        uint32_t half = len >> 1;
+        if (b.first[hi + half] <= c) { hi += half + 1; len -= half + 1; } else { len = half; }
+    }
+    if (hi == lo) return;
+    uint8_t* s_tile = s_dense;                                                   // [kDenseRows][pitch]
+    int* s_q = reinterpret_cast<int*>(s_dense + (size_t)kDenseRows * pitch);     // [kDenseQueries][sl]
+    const uint32_t rows_here = nc - r0 < kDenseRows ? nc - r0 : kDenseRows;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q15 + (off + r0) * sl);
+        for (uint32_t i = threadIdx.x; i < kDenseRows * cpr; i += blockDim.x) {
+            const uint32_t r = i / cpr, ch = i % cpr;
+            const uint4 v = r < rows_here ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(s_tile + (size_t)r * pitch + ch * 16) = v;
+        }
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t nblk = (rows_here + 31) / 32;
+    for (uint32_t qbase = lo; qbase < hi; qbase += kDenseQueries) {
+        const uint32_t nqh = hi - qbase < kDenseQueries ? hi - qbase : kDenseQueries;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nqh * (sl / 2); i += blockDim.x) {
+            const uint32_t j = i / (sl / 2), e = i % (sl / 2);
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(b.q15 + (uint64_t)b.qperm[qbase + j] * sl) + e);
+            s_q[j * sl + 2 * e] = unpack_lo(w);
+            s_q[j * sl + 2 * e + 1] = unpack_hi(w);
+        }
+        __syncthreads();
+        const uint32_t ngrp = (nqh + kDenseNQ - 1) / kDenseNQ;
+        for (uint32_t item = warp; item < nblk * ngrp; item += blockDim.x >> 5) {
+            const uint32_t blk = item % nblk, qg = item / nblk;
+            const uint4* row = reinterpret_cast<const uint4*>(s_tile + (size_t)(blk * 32 + lane) * pitch);
+            const int4* qp[kDenseNQ];
+            int acc[kDenseNQ];
+#pragma unroll
+            for (int j = 0; j < kDenseNQ; j++) {
+                const uint32_t qi = qg * kDenseNQ + j < nqh ? qg * kDenseNQ + j : nqh - 1;
+                qp[j] = reinterpret_cast<const int4*>(s_q + qi * sl);
+                acc[j] = 0;
+            }
+            for (uint32_t ch = 0; ch < cpr; ch++) {
+                const uint4 v = row[ch];
+                const int a0 = unpack_lo(v.x), a1 = unpack_hi(v.x), a2 = unpack_lo(v.y), a3 = unpack_hi(v.y);
+                const int a4 = unpack_lo(v.z), a5 = unpack_hi(v.z), a6 = unpack_lo(v.w), a7 = unpack_hi(v.w);
+#pragma unroll
+                for (int j = 0; j < kDenseNQ; j++) {
+                    const int4 x = qp[j][2 * ch], y = qp[j][2 * ch + 1];
+                    int s = acc[j];
+                    s += q15_mul(a0, x.x); s += q15_mul(a1, x.y); s += q15_mul(a2, x.z); s += q15_mul(a3, x.w);
+                    s += q15_mul(a4, y.x); s += q15_mul(a5, y.y); s += q15_mul(a6, y.z); s += q15_mul(a7, y.w);
+                    acc[j] = s;
+                }
+            }
+            const uint32_t r = blk * 32 + lane;
+            if (r < rows_here) {
+#pragma unroll
+                for (int j = 0; j < kDenseNQ; j++) {
+                    const uint32_t qi = qg * kDenseNQ + j;
+                    if (qi < nqh) b.dense[(uint64_t)b.qperm[qbase + qi] * b.dense_stride + r0 + r] = (uint16_t)(acc[j] + 32768);
+                }
+            }
+        }
+    }
+}
+
+bool dense_sims_supported(const SearchParams& p) { return p.g.sl / 8 <= 32 && tune_get("dense_sims", 1) != 0; }
+
+bool launch_dense_sims(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0 || !b.dense || !dense_sims_supported(p)) return false;
+    if (tune_get("order_longest_first", 0) != 0) return false;  // the sorted keys are not plain cluster ids then
+    const size_t smem = (size_t)kDenseRows * (p.g.sl * 2 + 16) + (size_t)kDenseQueries * p.g.sl * sizeof(int);
+    dim3 grid(p.K, (p.max_cluster + kDenseRows - 1) / kDenseRows);
+    if (grid.y == 0) return false;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_dense_sims, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_dense_sims<<<grid, 256, smem, s>>>(p, b);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 
 void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
@@ -843,7 +959,7 @@ static int rerank_group(uint32_t sl) {
     return g;
 }
 
-template <int G, int OCC>
+template <int G, int OCC, bool DENSE>
 static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
     static int sm_count = 0;
     if (sm_count == 0) {
@@ -861,11 +977,11 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     int ctas_per_sm = 0;
-    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC>, warps * 32, smem));
+    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC, DENSE>, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int cap = (int)tune_get("probe_ctas", 0);  // knob: fewer resident queries = smaller L2 working set
     if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = cap;
@@ -878,16 +994,25 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     const uint64_t stride = b.memo_stride;
     SearchParams pp = p;
     pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
-    k_probe<G, OCC><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride);
+    k_probe<G, OCC, DENSE><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride);
 }
 
 template <int G>
 static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
-    int occ = (int)tune_get("probe_occ", 3);  // knob: resident CTAs per SM the kernel is compiled for
-    if (occ < 2 || occ > 4) occ = 3;
-    if (occ == 2) launch_probe_go<G, 2>(p, b, stop_at_foreign, s);
-    else if (occ == 4) launch_probe_go<G, 4>(p, b, stop_at_foreign, s);
-    else launch_probe_go<G, 3>(p, b, stop_at_foreign, s);
+    // With the first visit's similarities computed in advance (b.dense) the kernel is lighter and two CTAs per SM with 128
+    // registers beat three with 80 (measured 2.82 vs 2.94 ms including the dense kernel); without, three (3.08 vs 3.36 ms).
+    const bool dense = b.dense != nullptr && !stop_at_foreign;
+    int occ = (int)tune_get("probe_occ", 0);  // knob: resident CTAs per SM the kernel is compiled for (0 = the default above)
+    if (occ < 2 || occ > 4) occ = dense ? 2 : 3;
+    if (dense) {
+        if (occ == 2) launch_probe_go<G, 2, true>(p, b, stop_at_foreign, s);
+        else if (occ == 4) launch_probe_go<G, 4, true>(p, b, stop_at_foreign, s);
+        else launch_probe_go<G, 3, true>(p, b, stop_at_foreign, s);
+    } else {
+        if (occ == 2) launch_probe_go<G, 2, false>(p, b, stop_at_foreign, s);
+        else if (occ == 4) launch_probe_go<G, 4, false>(p, b, stop_at_foreign, s);
+        else launch_probe_go<G, 3, false>(p, b, stop_at_foreign, s);
+    }
 }
 
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {

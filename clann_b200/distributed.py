@@ -59,7 +59,9 @@ class ShardedSearcher:
         if self.world == 1:
             _check(self.lib.clann_search_device(h, d_queries.data_ptr(), nq, d_ids.data_ptr(), d_dists.data_ptr(),
                                                 d_counts.data_ptr(), stream))
-            self.last_launches, self.last_steps = 9, 1
+            launches = C.c_uint32(0)
+            _check(self.lib.clann_last_search_profile(h, None, C.byref(launches)))  # kernels the library launched for this call
+            self.last_launches, self.last_steps = int(launches.value), 1
             return
         import torch.distributed as dist
         _check(self.lib.clann_search_begin(h, d_queries.data_ptr(), nq, stream))
