@@ -1048,7 +1048,7 @@ struct clann_index {
     // is complete when the call is made; results are complete once search_flush() has been waited on.
     // Fills the memo of every query's first visit in advance (launch_dense_sims) when the default probe kernel will use it.
     bool use_dense_sims(const SearchParams& p, QueryBatch& b, cudaStream_t s) {
-        if (!W->w_dense.p || W->w_dense_stride == 0 || tune_get("probe", 0) != 0) return false;
+        if (!W->w_dense.p || W->w_dense_stride == 0 || tune_get("probe", 0) == 1) return false;  // the CTA kernel does not use it
         b.dense = W->w_dense.p;
         if (!launch_dense_sims(p, b, s)) {
             b.dense = nullptr;

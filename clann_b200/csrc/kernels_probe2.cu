@@ -26,7 +26,6 @@ namespace clann {
 
 namespace {
 
-constexpr int kNT = 3;      // tables per lane evaluated in lockstep (anchors, ranges)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -144,78 +143,6 @@ __device__ __forceinline__ W2 carve2(uint8_t* base, uint32_t L, uint32_t k, uint
 }
 
 // ------------------------------------------------------------------------------------------------ anchors and ranges
-
-// SearchBuffers ctor (collection.hpp:642-645 -> prefixmap.hpp:36-57,250-260) for kNT tables per lane in lockstep: the same
-// anchors and stride-12 common-prefix samples as table_anchor (probe_common.cuh); the searches of the kNT tables advance
-// together so that their loads overlap.
-__device__ __forceinline__ void anchors_lockstep(const SearchParams& p, const W2& sm, uint32_t c, uint64_t off, uint32_t nc,
-                                                 const uint32_t* __restrict__ codes, uint64_t code_stride) {
-    const uint32_t L = p.g.L, lane = lane_id();
-    for (uint32_t t0 = 0; t0 < L; t0 += 32 * kNT) {
-        uint32_t h[kNT], lo[kNT], len[kNT];
-        const uint32_t* H[kNT];
-        bool valid[kNT];
-#pragma unroll
-        for (int j = 0; j < kNT; j++) {
-            const uint32_t t = t0 + 32 * j + lane;
-            valid[j] = t < L;
-            const uint32_t tt = valid[j] ? t : 0;
-            h[j] = valid[j] ? __ldg(codes + (uint64_t)tt * code_stride) : 0u;
-            H[j] = p.tbl_hash + table_base(off, nc, L, tt);
-        }
-#pragma unroll
-        for (int j = 0; j < kNT; j++) {
-            const uint32_t t = valid[j] ? t0 + 32 * j + lane : 0;
-            const uint32_t* dir = p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries;
-            const uint32_t b = h[j] >> (kMaxHashBits - kDirBits);
-            lo[j] = __ldg(dir + b);
-            len[j] = valid[j] ? __ldg(dir + b + 1) - lo[j] : 0u;
-        }
-        for (;;) {
-            bool more = false;
-#pragma unroll
-            for (int j = 0; j < kNT; j++) more |= len[j] > 8;
-            if (!more) break;
-            uint32_t probe[kNT];
-#pragma unroll
-            for (int j = 0; j < kNT; j++) probe[j] = len[j] > 8 ? __ldg(H[j] + lo[j] + (len[j] >> 1)) : 0u;
-#pragma unroll
-            for (int j = 0; j < kNT; j++) {
-                if (len[j] > 8) {
-                    const uint32_t half = len[j] >> 1;
-                    if (probe[j] < h[j]) { lo[j] += half + 1; len[j] -= half + 1; } else { len[j] = half; }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kNT; j++) {
-            uint32_t below = 0;  // the codes are sorted: the lower bound is the number of entries below h
-#pragma unroll
-            for (uint32_t i = 0; i < 8; i++)
-                if (i < len[j]) below += __ldg(H[j] + lo[j] + i) < h[j] ? 1u : 0u;
-            lo[j] += below;
-        }
-#pragma unroll
-        for (int j = 0; j < kNT; j++) {
-            uint32_t up[8], dn[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t pu = lo[j] + kSegment * i;
-                up[i] = (valid[j] && pu < nc) ? lcp24(__ldg(H[j] + pu), h[j]) : 0u;
-                const int64_t pd = (int64_t)lo[j] - 1 - kSegment * i;
-                dn[i] = (valid[j] && pd >= 0) ? lcp24(__ldg(H[j] + pd), h[j]) : 0u;
-            }
-            if (valid[j]) {
-                const uint32_t t = t0 + 32 * j + lane;
-                sm.code[t] = h[j];
-                sm.anchor[t] = lo[j];
-                sm.lcp_up[t] = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
-                sm.lcp_dn[t] = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
-            }
-        }
-    }
-    __syncwarp();
-}
 
 // fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form (table_range,
 // probe_common.cuh), kNT tables per lane: start[] and the exclusive prefix of segment counts; returns the stream length.
@@ -341,7 +268,7 @@ template <int G, int kAhead>
 __device__ uint32_t probe_cluster2(const SearchParams& p, const W2& sm, const Layout2& lay, uint32_t c, const uint32_t* __restrict__ codes,
                                    uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
                                    const int (&qreg)[8], bool qreg_valid, uint16_t* gmemo, uint64_t gmemo_stride, uint32_t& phase,
-                                   ProbeCounters& ctr) {
+                                   ProbeCounters& ctr, uint16_t* prefilled) {
     const uint32_t L = p.g.L, k = p.k, sl = p.g.sl;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -355,7 +282,8 @@ __device__ uint32_t probe_cluster2(const SearchParams& p, const W2& sm, const La
     uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;  // maxbuffer.hpp:53-55, filterer.hpp:101
     // similarity memo of this visit: shared memory when the cluster fits, else the global scratch, else none
     uint16_t* memo = nc <= lay.memo_cap ? sm.memo : ((gmemo && nc <= gmemo_stride) ? gmemo : nullptr);
-    if (memo) {
+    if (prefilled) memo = prefilled;  // first visit: similarities to the whole cluster computed in advance (launch_dense_sims)
+    else if (memo) {
         uint4* mz = reinterpret_cast<uint4*>(memo);
         for (uint32_t i = lane; i < (nc + 7) / 8; i += 32) mz[i] = make_uint4(0, 0, 0, 0);
     }
@@ -630,8 +558,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_probe2(SearchParams p, QueryBatch b
                 const uint32_t* codes = b.codes + (uint64_t)fs * p.g.L * b.nq + q;
                 const uint64_t my_sketch = b.sketches[((uint64_t)fs * b.nq + q) * kNumSketches + lane];
                 const uint32_t* stop = p.stop + (uint64_t)fs * kMaxHashBits * kEstBins * p.stop_words;
+                uint16_t* prefilled = (b.dense != nullptr && pos == 0 && !stop_at_foreign) ? b.dense + (uint64_t)q * b.dense_stride : nullptr;
                 uint32_t cnt = probe_cluster2<G, AH>(p, sm, lay, c, codes, b.nq, my_sketch, stop, max_sim, qreg, qreg_valid, gmemo, gmemo_stride,
-                                                 phase, ctr);
+                                                 phase, ctr, prefilled);
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
                     uint32_t j = base + lane;

@@ -388,11 +388,13 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
 
 // One PUFFINN query against cluster c (collection.hpp:543-601 -> search_maps :768-948). On return sm.mb[0..cnt) holds the
 // best entries, best first (maxbuffer.hpp:79-96). `codes` points at this query's code of table 0 (stride code_stride).
-template <int G>
+// AHEAD (the 128-register instantiations): anchors for three tables per lane in lockstep, and the table indices of the next
+// ring sweep are requested before the sketch words of the current one, so a sweep costs one memory round trip instead of two.
+template <int G, bool AHEAD = false>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
                                   const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr,
-                                  bool memo_prefilled = false) {
+                                  bool memo_prefilled = false, unsigned long long* memo_bar = nullptr, uint32_t memo_phase = 0) {
     const uint32_t L = p.g.L, k = p.k;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -408,7 +410,8 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     }
 
     // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
-    for (uint32_t t = lane; t < L; t += 32) {
+    if constexpr (AHEAD) anchors_lockstep(p, sm, c, off, nc, codes, code_stride);
+    else for (uint32_t t = lane; t < L; t += 32) {
         const uint32_t h = codes[(uint64_t)t * code_stride];
         uint32_t A;
         uint2 up, dn;
@@ -419,6 +422,8 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         sm.lcp_dn[t] = dn;
     }
     __syncwarp();
+
+    if (memo_bar) pc_mbar_wait(memo_bar, memo_phase);  // the pre-filled memo was bulk-copied to shared memory behind the anchors
 
     bool stopped = false;
     for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
@@ -453,13 +458,27 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         };
 
         uint32_t base = 0;  // first stream segment held by the ring
+        bool have = false;  // AHEAD: n0..n3 hold this lane's segment of the full ring [base, base + 32)
+        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
         do {
             uint32_t np = 0;
             uint32_t missing = (base + kRing > S) ? (base + kRing - S > kRing ? kRing : base + kRing - S) : 0;
             while (np < kFilterBuffer && missing == 0) {  // collection.hpp:813-866: a full ring sweep, slot == lane
                 uint32_t t;
-                const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
-                uint32_t v0 = __ldg(seg), v1 = __ldg(seg + 1), v2 = __ldg(seg + 2), v3 = __ldg(seg + 3);
+                uint32_t v0, v1, v2, v3;
+                if (AHEAD && have) {
+                    v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+                } else {
+                    const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
+                    v0 = __ldg(seg); v1 = __ldg(seg + 1); v2 = __ldg(seg + 2); v3 = __ldg(seg + 3);
+                }
+                if constexpr (AHEAD) {
+                    have = base + 2 * kRing <= S;
+                    if (have) {
+                        const uint32_t* nseg = p.tbl_idx + locate(base + kRing + lane, t);
+                        n0 = __ldg(nseg); n1 = __ldg(nseg + 1); n2 = __ldg(nseg + 2); n3 = __ldg(nseg + 3);
+                    }
+                }
                 uint64_t s0 = __ldg(sk + ((uint64_t)v0 << 5 | lane)), s1 = __ldg(sk + ((uint64_t)v1 << 5 | lane));
                 uint64_t s2 = __ldg(sk + ((uint64_t)v2 << 5 | lane)), s3 = __ldg(sk + ((uint64_t)v3 << 5 | lane));
                 uint32_t p0 = (uint32_t)__popcll(s0 ^ my_sketch) <= max_diff, p1 = (uint32_t)__popcll(s1 ^ my_sketch) <= max_diff;
@@ -481,9 +500,13 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
                 const uint32_t live = kRing - missing;  // slots 0..live-1 hold real segments base+slot
                 uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0;
                 if (lane < live) {
-                    uint32_t t;
-                    const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
-                    v0 = __ldg(seg); v1 = __ldg(seg + 1); v2 = __ldg(seg + 2); v3 = __ldg(seg + 3);
+                    if (AHEAD && have) {  // a full ring whose indices are already here
+                        v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+                    } else {
+                        uint32_t t;
+                        const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
+                        v0 = __ldg(seg); v1 = __ldg(seg + 1); v2 = __ldg(seg + 2); v3 = __ldg(seg + 3);
+                    }
                     p0 = (uint32_t)__popcll((uint64_t)v0 ^ my_sketch) <= max_diff;
                     p1 = (uint32_t)__popcll((uint64_t)v1 ^ my_sketch) <= max_diff;
                     p2 = (uint32_t)__popcll((uint64_t)v2 ^ my_sketch) <= max_diff;
@@ -559,11 +582,20 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
 // for expensive ones). Warps are persistent; grid = multiple of the SM count.
 template <int G, int OCC, bool DENSE>
 __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign,
-                                                    uint16_t* memo_base, uint64_t memo_stride) {
+                                                    uint16_t* memo_base, uint64_t memo_stride, uint32_t smem_memo_cap) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    uint8_t* wbase = s_dyn + (size_t)warp * (warp_bytes + p.g.sl * 2);
+    // per warp: [query row][WarpSmem][DENSE: memo of smem_memo_cap u16 + mbarrier]
+    const uint32_t memo_extra = (DENSE && smem_memo_cap) ? smem_memo_cap * 2 + 16 : 0;
+    uint8_t* wbase = s_dyn + (size_t)warp * (warp_bytes + p.g.sl * 2 + memo_extra);
     const WarpSmem sm = carve(wbase + p.g.sl * 2, p.g.L, p.k);
+    uint16_t* memo_s = reinterpret_cast<uint16_t*>(wbase + p.g.sl * 2 + warp_bytes);
+    unsigned long long* memo_bar = reinterpret_cast<unsigned long long*>(wbase + p.g.sl * 2 + warp_bytes + smem_memo_cap * 2);
+    uint32_t memo_phase = 0;
+    if (DENSE && smem_memo_cap) {
+        if (lane == 0) pc_mbar_init(memo_bar, 1);
+        __syncwarp();
+    }
     int16_t* qrow = reinterpret_cast<int16_t*>(wbase);  // this warp's query in Q15
     const uint64_t state_bytes = sizeof(QueryStateHeader) + (uint64_t)p.k * 8;
     const uint32_t cpr = p.g.sl / 8;
@@ -669,8 +701,24 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 // (DENSE is a template parameter: the instantiation without it keeps the register allocation it had)
                 const bool prefilled = DENSE && pos == 0;
                 if (prefilled) use_memo = b.dense + (uint64_t)q * b.dense_stride;
-                uint32_t cnt = probe_cluster<G>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
-                                                prefilled);
+                unsigned long long* wait_bar = nullptr;
+                if (DENSE && smem_memo_cap && nc <= smem_memo_cap) {
+                    // the memo of this visit lives in shared memory: the pre-filled one arrives by one TMA bulk copy while the
+                    // anchors are computed; later visits zero it (probe_cluster)
+                    if (prefilled) {
+                        const uint32_t bytes = (nc * 2 + 15) & ~15u;
+                        __syncwarp();
+                        if (lane == 0) {
+                            pc_mbar_expect_tx(memo_bar, bytes);
+                            pc_bulk_g2s(memo_s, use_memo, bytes, memo_bar);
+                        }
+                        wait_bar = memo_bar;
+                    }
+                    use_memo = memo_s;
+                }
+                uint32_t cnt = probe_cluster<G, DENSE>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
+                                                       prefilled, wait_bar, memo_phase);
+                if (wait_bar) memo_phase ^= 1u;
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
                     uint32_t j = base + lane;
@@ -968,11 +1016,20 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
         CLANN_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
-    const uint32_t per_warp = wb + p.g.sl * 2;
+    uint32_t per_warp = wb + p.g.sl * 2;
     // warps per CTA: as many as keep OCC CTAs of shared memory on one SM, at most 8 (knob: probe_warps)
     uint32_t warps = (uint32_t)tune_get("probe_warps", 8);
     if (warps < 1 || warps > 8) warps = 8;
     while (warps > 1 && (size_t)warps * per_warp * OCC > 200 * 1024) warps >>= 1;
+    // DENSE: the memo of a visit in shared memory when the largest cluster fits beside the rest (knob probe_smem_memo)
+    uint32_t smem_memo_cap = 0;
+    if (DENSE && tune_get("probe_smem_memo", 1) != 0) {
+        const uint32_t cap = (p.max_cluster + 7u) & ~7u;
+        if (cap > 0 && (size_t)warps * (per_warp + cap * 2 + 16) * OCC <= 220 * 1024) {
+            smem_memo_cap = cap;
+            per_warp += cap * 2 + 16;
+        }
+    }
     size_t smem = (size_t)warps * per_warp;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
     static size_t configured = 0;
@@ -994,7 +1051,7 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     const uint64_t stride = b.memo_stride;
     SearchParams pp = p;
     pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
-    k_probe<G, OCC, DENSE><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride);
+    k_probe<G, OCC, DENSE><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride, smem_memo_cap);
 }
 
 template <int G>

@@ -328,4 +328,109 @@ __device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, 
     return (uint32_t)start;
 }
 
+// ------------------------------------------------------------------------------------------------ TMA bulk copy + mbarrier
+
+__device__ __forceinline__ uint32_t pc_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pc_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pc_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pc_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pc_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pc_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(pc_smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();  // a copy that never lands must fail loudly, not hang the GPU
+    } while (!ok);
+}
+// global -> shared bulk copy (SASS: UBLKCP), bytes a multiple of 16, both addresses 16-byte aligned. The destination may have
+// been written through the generic proxy before (zeroing, memo updates): the proxy fence orders those writes before the copy.
+__device__ __forceinline__ void pc_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pc_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(pc_smem_addr(bar))
+                 : "memory");
+}
+
+constexpr int kNT = 3;  // tables per lane evaluated in lockstep (anchors, ranges)
+
+// SearchBuffers ctor (collection.hpp:642-645 -> prefixmap.hpp:36-57,250-260) for kNT tables per lane in lockstep: the same
+// anchors and stride-12 common-prefix samples as table_anchor (probe_common.cuh); the searches of the kNT tables advance
+// together so that their loads overlap.
+template <typename Smem>
+__device__ __forceinline__ void anchors_lockstep(const SearchParams& p, const Smem& sm, uint32_t c, uint64_t off, uint32_t nc,
+                                                 const uint32_t* __restrict__ codes, uint64_t code_stride) {
+    const uint32_t L = p.g.L, lane = lane_id();
+    for (uint32_t t0 = 0; t0 < L; t0 += 32 * kNT) {
+        uint32_t h[kNT], lo[kNT], len[kNT];
+        const uint32_t* H[kNT];
+        bool valid[kNT];
+#pragma unroll
+        for (int j = 0; j < kNT; j++) {
+            const uint32_t t = t0 + 32 * j + lane;
+            valid[j] = t < L;
+            const uint32_t tt = valid[j] ? t : 0;
+            h[j] = valid[j] ? __ldg(codes + (uint64_t)tt * code_stride) : 0u;
+            H[j] = p.tbl_hash + table_base(off, nc, L, tt);
+        }
+#pragma unroll
+        for (int j = 0; j < kNT; j++) {
+            const uint32_t t = valid[j] ? t0 + 32 * j + lane : 0;
+            const uint32_t* dir = p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries;
+            const uint32_t b = h[j] >> (kMaxHashBits - kDirBits);
+            lo[j] = __ldg(dir + b);
+            len[j] = valid[j] ? __ldg(dir + b + 1) - lo[j] : 0u;
+        }
+        for (;;) {
+            bool more = false;
+#pragma unroll
+            for (int j = 0; j < kNT; j++) more |= len[j] > 8;
+            if (!more) break;
+            uint32_t probe[kNT];
+#pragma unroll
+            for (int j = 0; j < kNT; j++) probe[j] = len[j] > 8 ? __ldg(H[j] + lo[j] + (len[j] >> 1)) : 0u;
+#pragma unroll
+            for (int j = 0; j < kNT; j++) {
+                if (len[j] > 8) {
+                    const uint32_t half = len[j] >> 1;
+                    if (probe[j] < h[j]) { lo[j] += half + 1; len[j] -= half + 1; } else { len[j] = half; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kNT; j++) {
+            uint32_t below = 0;  // the codes are sorted: the lower bound is the number of entries below h
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++)
+                if (i < len[j]) below += __ldg(H[j] + lo[j] + i) < h[j] ? 1u : 0u;
+            lo[j] += below;
+        }
+#pragma unroll
+        for (int j = 0; j < kNT; j++) {
+            uint32_t up[8], dn[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t pu = lo[j] + kSegment * i;
+                up[i] = (valid[j] && pu < nc) ? lcp24(__ldg(H[j] + pu), h[j]) : 0u;
+                const int64_t pd = (int64_t)lo[j] - 1 - kSegment * i;
+                dn[i] = (valid[j] && pd >= 0) ? lcp24(__ldg(H[j] + pd), h[j]) : 0u;
+            }
+            if (valid[j]) {
+                const uint32_t t = t0 + 32 * j + lane;
+                sm.code[t] = h[j];
+                sm.anchor[t] = lo[j];
+                sm.lcp_up[t] = make_uint2(up[0] | up[1] << 8 | up[2] << 16 | up[3] << 24, up[4] | up[5] << 8 | up[6] << 16 | up[7] << 24);
+                sm.lcp_dn[t] = make_uint2(dn[0] | dn[1] << 8 | dn[2] << 16 | dn[3] << 24, dn[4] | dn[5] << 8 | dn[6] << 16 | dn[7] << 24);
+            }
+        }
+    }
+    __syncwarp();
+}
+
 }  // namespace clann
