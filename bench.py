@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "queries/sec @ recall@10>=0.9 (glove-100 shape)"
 UNIT = "queries/s"
 # DRAM bytes of one k_probe launch from the committed ncu capture (profiles/), per workload; None = not captured
-MEASURED_TRAFFIC = {"glove100": 10.67e9}
+MEASURED_TRAFFIC = {"glove100": 3.46e9}
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -522,7 +522,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                         "traffic": MEASURED_TRAFFIC.get(args.workload if not args.small else "small"),
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_probe launch, ncu --set full, "
-                                          "profiles/r1d_k_probe_warp_full_raw.csv (glove100 planted only)",
+                                          "k_dense_sims + k_probe, profiles/r1e_k_dense_sims_k_probe_full_raw.csv (glove100 planted only)",
                         "kernel_ms": probe_ms, "prep_ms": prep_ms,
                         "kernel_ms_note": "k_dense_sims (the rerank arithmetic of every query's first visit, streamed) + k_probe: the "
                                           "two kernels between the library's events; both are counted against the same algorithmic bytes",
