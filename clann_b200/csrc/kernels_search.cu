@@ -1060,14 +1060,12 @@ static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop
     // registers beat three with 80 (measured 2.82 vs 2.94 ms including the dense kernel); without, three (3.08 vs 3.36 ms).
     const bool dense = b.dense != nullptr && !stop_at_foreign;
     int occ = (int)tune_get("probe_occ", 0);  // knob: resident CTAs per SM the kernel is compiled for (0 = the default above)
-    if (occ < 2 || occ > 4) occ = dense ? 2 : 3;
+    if (occ < 2 || occ > 3) occ = dense ? 2 : 3;  // (four CTAs of 64 registers spill: 5.5 ms, instantiation dropped)
     if (dense) {
         if (occ == 2) launch_probe_go<G, 2, true>(p, b, stop_at_foreign, s);
-        else if (occ == 4) launch_probe_go<G, 4, true>(p, b, stop_at_foreign, s);
         else launch_probe_go<G, 3, true>(p, b, stop_at_foreign, s);
     } else {
         if (occ == 2) launch_probe_go<G, 2, false>(p, b, stop_at_foreign, s);
-        else if (occ == 4) launch_probe_go<G, 4, false>(p, b, stop_at_foreign, s);
         else launch_probe_go<G, 3, false>(p, b, stop_at_foreign, s);
     }
 }

@@ -411,3 +411,53 @@ def test_async_host_batches_equal_synchronous_call():
         assert np.array_equal(ids.view(np.uint32), o[0].numpy().view(np.uint32))
         assert np.array_equal(dists.view(np.uint32), o[1].numpy().view(np.uint32))
         assert np.array_equal(counts.view(np.uint32), o[2].numpy().view(np.uint32))
+
+
+def test_properties_at_full_glove100_shape():
+    """BASELINE.json configs[2] at full size (1 183 514 x 100, L = 84, K = 435): size-independent properties — perm is a
+    permutation, sampled tables are sorted by (hash, id) and hold every local id once, recall@10 >= 0.9 against exact fp32
+    neighbours (utils/mod.rs:59-95), the dense first-visit path and the gather path agree, two batches in flight agree with
+    the blocking call, determinism."""
+    import torch
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    n, d = 1_183_514, 100
+    data = util.planted(n, d, 42)
+    ix = cb.init_with_config(data, cb.Config(84, 0.4, 10, 0.9, "glove-100-shape"))
+    ix.set_option("seed", 1234)
+    ix.build()
+    assert ix.num_clusters == 435
+    perm = ix.export(cl.X_PERM, 0, np.uint32)
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+    off = ix.export(cl.X_OFFSETS, 0, np.uint64)
+    brute = ix.export(cl.X_BRUTE, 0, np.uint8)
+    for ci in np.flatnonzero(brute == 0)[[0, 200, -1]]:
+        nc = int(off[ci + 1] - off[ci])
+        th = ix.export(cl.X_TABLE_HASHES, int(ci), np.uint32).reshape(84, nc)
+        ti = ix.export(cl.X_TABLE_INDICES, int(ci), np.uint32).reshape(84, nc)
+        key = (th.astype(np.uint64) << np.uint64(32)) | ti
+        assert np.all(np.diff(key.astype(np.int64), axis=1) > 0) and th.max() < (1 << 24)
+        assert np.array_equal(np.sort(ti, axis=1), np.broadcast_to(np.arange(nc, dtype=np.uint32), (84, nc)))
+    q = util.planted_queries(data, 2000, 43)
+    ids, dists, counts = ix.search_batch(q)
+    ctr = ix.counters(len(q))
+    # recall against exact neighbours computed on the device (torch is test plumbing here)
+    dd = torch.from_numpy(data).cuda()
+    qq = torch.from_numpy(q).cuda()
+    kth = torch.cat([torch.topk(qq[s:s + 200] @ dd.T, 10, dim=1).values[:, 9] for s in range(0, len(q), 200)])
+    kth = (1.0 - kth).cpu().numpy()
+    hit = sum(int(np.sum(dists[i, :counts[i]] <= kth[i] + 1e-3)) for i in range(len(q)))
+    assert hit / (len(q) * 10) >= 0.9
+    del dd, qq
+    # the gather path (no dense similarities) returns the same ids, distances and counters
+    cl.tune("dense_sims", 0)
+    try:
+        ids2, dists2, counts2 = ix.search_batch(q)
+        ctr2 = ix.counters(len(q))
+    finally:
+        cl.tune("dense_sims", 1)
+    assert np.array_equal(ids, ids2) and np.array_equal(dists.view(np.uint32), dists2.view(np.uint32)) and np.array_equal(counts, counts2)
+    for key in ("candidates", "distance_computations", "clusters_visited"):
+        assert np.array_equal(ctr[key], ctr2[key]), key
+    ids3, dists3, _ = ix.search_batch(q)
+    assert np.array_equal(ids, ids3) and np.array_equal(dists.view(np.uint32), dists3.view(np.uint32))
