@@ -102,6 +102,13 @@ struct QueryBatch {
     // query q to every row of its nearest cluster, i.e. the memo of its first visit filled in advance; null = not computed
     uint16_t* dense;
     uint64_t dense_stride;
+    // first-visit anchors and ranges (launch_first_ranges): pre_anchor[q * L + t] = anchor of query q in table t of its nearest
+    // cluster; pre_range[(q * 24 + depth - 1) * L + t] = segments of the range at `depth` | upward << 31; null = not computed
+    uint32_t* pre_anchor;
+    uint32_t* pre_range;
+    // pre_lcp[q * L + t] = the stride-12 common-prefix samples of table_anchor (up.x, up.y, dn.x, dn.y); with pre_range null
+    // the probe takes anchors and samples from here and evaluates the ranges itself, depth by depth, as far as it gets
+    uint4* pre_lcp;
     // outputs
     uint32_t* out_ids;      // [nq][k]
     float* out_dists;       // [nq][k]
@@ -127,6 +134,9 @@ void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t 
 // glove-100 shape — then only looks similarities up instead of gathering rows. Returns false when the geometry is unsupported.
 bool launch_dense_sims(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 bool dense_sims_supported(const SearchParams& p);
+// Anchors (prefixmap.hpp:36-57) and the ranges of all 24 depths (prefixmap.hpp:267-304) of every query in its nearest cluster,
+// one thread per (query, table) instead of a dependent chain inside the probe; needs b.codes, sorted b.first and b.qperm.
+void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
 void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query

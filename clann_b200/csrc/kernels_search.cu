@@ -394,7 +394,9 @@ template <int G, bool AHEAD = false>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
                                   const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr,
-                                  bool memo_prefilled = false, unsigned long long* memo_bar = nullptr, uint32_t memo_phase = 0) {
+                                  bool memo_prefilled = false, unsigned long long* memo_bar = nullptr, uint32_t memo_phase = 0,
+                                  const uint32_t* __restrict__ pre_anchor = nullptr, const uint32_t* __restrict__ pre_range = nullptr,
+                                  const uint4* __restrict__ pre_lcp = nullptr) {
     const uint32_t L = p.g.L, k = p.k;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -410,7 +412,17 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     }
 
     // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
-    if constexpr (AHEAD) anchors_lockstep(p, sm, c, off, nc, codes, code_stride);
+    if (AHEAD && pre_range) {  // anchors and every depth's range computed in advance by k_first_ranges
+        for (uint32_t t = lane; t < L; t += 32) sm.anchor[t] = __ldg(pre_anchor + t);
+    } else if (AHEAD && pre_lcp) {  // anchors and samples computed in advance; ranges evaluated here as far as the visit gets
+        for (uint32_t t = lane; t < L; t += 32) {
+            const uint4 l = __ldg(pre_lcp + t);
+            sm.code[t] = codes[(uint64_t)t * code_stride];
+            sm.anchor[t] = __ldg(pre_anchor + t);
+            sm.lcp_up[t] = make_uint2(l.x, l.y);
+            sm.lcp_dn[t] = make_uint2(l.z, l.w);
+        }
+    } else if constexpr (AHEAD) anchors_lockstep(p, sm, c, off, nc, codes, code_stride);
     else for (uint32_t t = lane; t < L; t += 32) {
         const uint32_t h = codes[(uint64_t)t * code_stride];
         uint32_t A;
@@ -432,7 +444,13 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         for (uint32_t t0 = 0; t0 < L; t0 += 32) {
             const uint32_t t = t0 + lane;
             uint32_t nseg = 0;
-            if (t < L)
+            if (AHEAD && pre_range) {
+                if (t < L) {
+                    const uint32_t w = __ldg(pre_range + (size_t)(depth - 1) * L + t);
+                    nseg = w & 0x7fffffffu;
+                    sm.start[t] = (w >> 31) ? sm.anchor[t] : sm.anchor[t] - 4u * nseg;  // downward ranges end at the anchor
+                }
+            } else if (t < L)
                 sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc,
                                           sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
             uint32_t total;
@@ -716,8 +734,11 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                     }
                     use_memo = memo_s;
                 }
+                const uint32_t* pre_a = (prefilled && b.pre_anchor) ? b.pre_anchor + (uint64_t)q * p.g.L : nullptr;
+                const uint32_t* pre_r = (prefilled && b.pre_range) ? b.pre_range + (uint64_t)q * kMaxHashBits * p.g.L : nullptr;
+                const uint4* pre_l = (prefilled && b.pre_lcp && !b.pre_range) ? b.pre_lcp + (uint64_t)q * p.g.L : nullptr;
                 uint32_t cnt = probe_cluster<G, DENSE>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
-                                                       prefilled, wait_bar, memo_phase);
+                                                       prefilled, wait_bar, memo_phase, pre_a, pre_r, pre_l);
                 if (wait_bar) memo_phase ^= 1u;
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
@@ -845,6 +866,44 @@ __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatc
         *out_count = cnt;
         *out_distcomp = (uint32_t)ctr.distcomp;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ first-visit anchors and ranges
+
+// One thread per (work item w, table t): the anchor of query qperm[w] in table t of its nearest cluster first[w] and the range of
+// every depth, exactly as the probe kernel derives them (table_anchor / table_range, probe_common.cuh) — but as 840 000
+// independent threads instead of three dependent rounds per warp at the head of every visit and a round of directory reads or
+// binary searches at every depth.
+__global__ void __launch_bounds__(256) k_first_ranges(SearchParams p, QueryBatch b) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = p.g.L;
+    if (i >= b.nq * L) return;
+    const uint32_t w = (uint32_t)(i / L), t = (uint32_t)(i % L);
+    const uint32_t q = b.qperm[w], c = b.first[w];
+    if (p.brute[c]) return;
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t h = b.codes[((uint64_t)p.fset_of[c] * L + t) * b.nq + q];
+    const uint32_t* H = p.tbl_hash + table_base(off, nc, L, t);
+    const uint32_t* dir = p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries;
+    uint32_t A;
+    uint2 up, dn;
+    table_anchor(H, dir, nc, h, A, up, dn);
+    b.pre_anchor[(uint64_t)q * L + t] = A;
+    if (b.pre_lcp) b.pre_lcp[(uint64_t)q * L + t] = make_uint4(up.x, up.y, dn.x, dn.y);
+    if (!b.pre_range) return;
+    uint32_t* out = b.pre_range + (uint64_t)q * kMaxHashBits * L + t;
+    for (uint32_t depth = kMaxHashBits; depth > 0; depth--) {
+        uint32_t nseg;
+        const uint32_t start = table_range(H, dir, nc, h, A, up, dn, depth, nseg);
+        out[(size_t)(depth - 1) * L] = nseg | (start == A ? 0x80000000u : 0u);  // start == A: upward (or empty: nseg == 0)
+    }
+}
+
+void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0 || !b.pre_anchor || (!b.pre_range && !b.pre_lcp)) return;
+    const uint64_t threads = b.nq * p.g.L;
+    k_first_ranges<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p, b);
 }
 
 // ------------------------------------------------------------------------------------------------ dense first-visit similarities

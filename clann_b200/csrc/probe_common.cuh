@@ -280,52 +280,45 @@ __device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, 
     const uint32_t dir_bit = 1u << (it >= 2 ? it - 2 : 0);     // removed bit (prefixmap.hpp:268-274)
     const bool upward = (h & dir_bit) == 0;
     const uint32_t b = h >> (kMaxHashBits - kDirBits);
+    // j = 12-entry strides covered by the matching block on the probed side of the anchor. The common cases are written
+    // without a branch on the direction (the tables of one query split about evenly between the two): one directory word for
+    // depth <= 8 bits, the stride-12 samples otherwise.
     uint32_t j;
     if (depth <= kDirBits) {
         const uint32_t sh = kDirBits - depth, pb = b >> sh;
-        if (upward) {
-            const uint32_t hi = __ldg(dir + ((pb + 1) << sh));
-            j = hi > A ? (hi - A + kSegment - 1) / kSegment : 0u;
-        } else {
-            const uint32_t lo = __ldg(dir + (pb << sh));
-            j = A > lo ? (A - lo + kSegment - 1) / kSegment : 0u;
-        }
-    } else if (upward) {
-        j = lead_count(lcp_up, depth);
-        if (j == 8) {  // first position >= A + 96 whose prefix differs; it cannot lie beyond the bucket of the top byte
-            uint32_t lo = A + 8 * kSegment, end = __ldg(dir + b + 1);
-            uint32_t len = end > lo ? end - lo : 0;
-            while (len > 0) {
-                uint32_t half = len >> 1, mid = lo + half;
-                if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
-            }
-            j = (lo - A + kSegment - 1) / kSegment;
-        }
+        const uint32_t edge = __ldg(dir + ((upward ? pb + 1 : pb) << sh));  // end of the block above / start of the block below
+        const uint32_t gap = upward ? (edge > A ? edge - A : 0u) : (A > edge ? A - edge : 0u);
+        j = (gap + kSegment - 1) / kSegment;
     } else {
-        j = lead_count(lcp_dn, depth);
-        if (j == 8) {  // first position of the matching block below A - 96, not before the bucket start
-            const uint32_t beg = __ldg(dir + b);
-            const uint32_t top = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [beg, top) undecided
-            uint32_t lo = beg, len = top > beg ? top - beg : 0;
-            while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
-                uint32_t half = len >> 1, mid = lo + half;
-                if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+        j = lead_count(upward ? lcp_up : lcp_dn, depth);
+        if (j == 8) {
+            if (upward) {  // first position >= A + 96 whose prefix differs; it cannot lie beyond the bucket of the top byte
+                uint32_t lo = A + 8 * kSegment, end = __ldg(dir + b + 1);
+                uint32_t len = end > lo ? end - lo : 0;
+                while (len > 0) {
+                    uint32_t half = len >> 1, mid = lo + half;
+                    if (lcp24(__ldg(H + mid), h) >= depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                }
+                j = (lo - A + kSegment - 1) / kSegment;
+            } else {       // first position of the matching block below A - 96, not before the bucket start
+                const uint32_t beg = __ldg(dir + b);
+                const uint32_t top = A >= 8 * kSegment ? A - 8 * kSegment : 0;  // positions [beg, top) undecided
+                uint32_t lo = beg, len = top > beg ? top - beg : 0;
+                while (len > 0) {  // lower_bound of "prefix matches" (monotone: false ... false true ... true)
+                    uint32_t half = len >> 1, mid = lo + half;
+                    if (lcp24(__ldg(H + mid), h) < depth) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                }
+                j = (A - lo + kSegment - 1) / kSegment;
             }
-            j = (A - lo + kSegment - 1) / kSegment;
         }
     }
-    int64_t start, end;
-    if (upward) {  // prefixmap.hpp:277-290
-        start = A;
-        end = (int64_t)A + (int64_t)kSegment * j;
-        if (end >= (int64_t)nc) end = (end - kSegment) > start ? (end - kSegment) : start;
-    } else {       // prefixmap.hpp:291-303
-        end = A;
-        start = (int64_t)A - (int64_t)kSegment * j;
-        if (start < 0) start = (start + kSegment) < end ? (start + kSegment) : end;
-    }
-    nseg = (uint32_t)(end - start) >> 2;
-    return (uint32_t)start;
+    // prefixmap.hpp:277-290 (upward: start = A, end = A + 12 j, `end >= len - 12` clamp) and :291-303 (downward: end = A,
+    // start = A - 12 j, `start < 12` clamp): either clamp takes one stride off the far end, never past the anchor.
+    uint64_t span = (uint64_t)kSegment * j;
+    const bool over = upward ? ((uint64_t)A + span >= (uint64_t)nc) : (span > (uint64_t)A);
+    if (over) span = span > kSegment ? span - kSegment : 0;
+    nseg = (uint32_t)(span >> 2);
+    return upward ? A : (uint32_t)((uint64_t)A - span);
 }
 
 // ------------------------------------------------------------------------------------------------ TMA bulk copy + mbarrier

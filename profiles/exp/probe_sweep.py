@@ -83,7 +83,7 @@ def main():
 
 
 DEFAULTS = {"probe": 0, "probe_occ": 0, "probe_warps": 8, "probe_ctas": 0, "probe_nomemo": 0, "probe_cta_occ": 4,
-            "probe_nosort": 0, "probe_prefetch": -2, "probe2_warps": 8, "probe2_ctas": 1, "probe2_stage_rows": 64, "l2_fetch": 64, "dense_sims": 1, "order_longest_first": 0, "probe_prefetch_rows": 0, "probe2_l2": 1, "probe2_l2rows": 1, "probe2_l2idx": 1}
+            "probe_nosort": 0, "probe_prefetch": -2, "probe2_warps": 8, "probe2_ctas": 1, "probe2_stage_rows": 64, "l2_fetch": 64, "dense_sims": 1, "first_ranges": 2, "probe_smem_memo": 1, "order_longest_first": 0, "probe_prefetch_rows": 0, "probe2_l2": 1, "probe2_l2rows": 1, "probe2_l2idx": 1}
 
 if __name__ == "__main__":
     main()
