@@ -283,6 +283,109 @@ __global__ void __launch_bounds__(256) k_codes(const int16_t* __restrict__ q15, 
     }
 }
 
+// The same codes for 2^M = 32..128 points with the per-function overheads taken out of the instruction stream (the FHT itself
+// is 3 x N log2 N / ... adds and cannot shrink): the 32 rows of the tile are converted to float ONCE per CTA (the plain
+// kernel re-reads and converts the int16 row for each of the L*fph functions), the +-1 diagonals of a table are expanded to
+// sign-bit masks in shared memory once per warp (one XOR per element instead of shift + and + xor), and the signed arg-max
+// (crosspolytope.hpp:131-144: strict comparisons, the first maximum of |v| wins, code = index + N for a negative winner) is a
+// left-biased tournament on (value, index) — 3 instructions per comparison instead of 6 per element.
+template <int M>
+__global__ void __launch_bounds__(256) k_codes_fast(const int16_t* __restrict__ q15, const RowTile* __restrict__ tiles,
+                                                    const uint32_t* __restrict__ signbits, HashGeom g, uint32_t* __restrict__ codes,
+                                                    uint64_t code_stride, uint64_t fset_stride) {
+    constexpr int N = 1 << M;
+    constexpr int W = (N + 31) / 32;
+    constexpr int PITCH = N + 4;  // words per row: 16-byte aligned, conflict-free LDS.128 with lane = row
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    float* s_f = reinterpret_cast<float*>(s_raw);                                      // [32][PITCH]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_raw + (size_t)32 * PITCH * 4);     // [8 warps][fph][3][N]
+    const RowTile tile = tiles[blockIdx.x];
+    for (uint32_t e = threadIdx.x; e < 32 * N; e += blockDim.x) {
+        const uint32_t r = e / N, i = e % N;
+        const float v = (r < tile.count && i < g.d) ? __fmul_rn((float)q15[(uint64_t)(tile.in_row0 + r) * g.sl + i], 1.0f / 32768.0f) : 0.0f;
+        s_f[r * PITCH + i] = v;
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t t = blockIdx.y * (blockDim.x >> 5) + warp;
+    uint32_t* mymask = s_mask + (size_t)warp * g.fph * kRotations * N;
+    if (t < g.L) {
+        const uint32_t* sb = signbits + ((uint64_t)tile.fset * (g.L * g.fph) + (uint64_t)t * g.fph) * (kRotations * W);
+        for (uint32_t e = lane; e < g.fph * kRotations * N; e += 32) {
+            const uint32_t fr = e / N, i = e % N;  // fr = function * 3 + rotation
+            mymask[e] = ((__ldg(sb + fr * W + (i >> 5)) >> (i & 31)) & 1u) << 31;
+        }
+    }
+    __syncthreads();
+    if (t >= g.L) return;
+    const float4* row4 = reinterpret_cast<const float4*>(s_f + lane * PITCH);
+    uint64_t code = 0;
+    for (uint32_t f = 0; f < g.fph; f++) {
+        float x[N];
+        const uint4* mk = reinterpret_cast<const uint4*>(mymask + (size_t)f * kRotations * N);
+#pragma unroll
+        for (int i = 0; i < N / 4; i++) {
+            if ((i & 3) == 0) asm volatile("" ::: "memory");  // keep the loads from being hoisted en bloc (255 registers + spills)
+            const float4 v = row4[i];
+            const uint4 m = mk[i];
+            x[4 * i + 0] = __uint_as_float(__float_as_uint(v.x) ^ m.x);
+            x[4 * i + 1] = __uint_as_float(__float_as_uint(v.y) ^ m.y);
+            x[4 * i + 2] = __uint_as_float(__float_as_uint(v.z) ^ m.z);
+            x[4 * i + 3] = __uint_as_float(__float_as_uint(v.w) ^ m.w);
+        }
+        fht_inplace<N, true>(x);
+#pragma unroll 1
+        for (int r = 1; r < kRotations; r++) {
+            const uint4* mr = mk + r * (N / 4);
+#pragma unroll
+            for (int i = 0; i < N / 4; i++) {
+                if ((i & 3) == 0) asm volatile("" ::: "memory");
+                const uint4 m = mr[i];
+                x[4 * i + 0] = __uint_as_float(__float_as_uint(x[4 * i + 0]) ^ m.x);
+                x[4 * i + 1] = __uint_as_float(__float_as_uint(x[4 * i + 1]) ^ m.y);
+                x[4 * i + 2] = __uint_as_float(__float_as_uint(x[4 * i + 2]) ^ m.z);
+                x[4 * i + 3] = __uint_as_float(__float_as_uint(x[4 * i + 3]) ^ m.w);
+            }
+            fht_inplace<N, true>(x);
+        }
+        // tournament in blocks of 16 (keeps the index registers few): the left entry wins ties, so the lowest index among equal
+        // |v| survives, as in the sequential scan
+        float bv = 0.0f;
+        int bi = 0;
+#pragma unroll
+        for (int c = 0; c < N / 16; c++) {
+            float v[8];
+            int id[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const bool right = fabsf(x[16 * c + 2 * i + 1]) > fabsf(x[16 * c + 2 * i]);
+                v[i] = right ? x[16 * c + 2 * i + 1] : x[16 * c + 2 * i];
+                id[i] = 16 * c + 2 * i + (right ? 1 : 0);
+            }
+#pragma unroll
+            for (int len = 4; len >= 1; len >>= 1) {
+#pragma unroll
+                for (int i = 0; i < len; i++) {
+                    const bool right = fabsf(v[2 * i + 1]) > fabsf(v[2 * i]);
+                    v[i] = right ? v[2 * i + 1] : v[2 * i];
+                    id[i] = right ? id[2 * i + 1] : id[2 * i];
+                }
+            }
+            const bool right = c > 0 && fabsf(v[0]) > fabsf(bv);
+            if (c == 0 || right) {
+                bv = v[0];
+                bi = id[0];
+            }
+        }
+        const uint32_t hval = (uint32_t)bi + (bv < 0.0f ? (uint32_t)N : 0u);
+        code = (code << g.bpf) | hval;
+    }
+    code >>= g.cut;
+    if (lane < tile.count) {
+        if (tile.code_stride) codes[tile.code_base + (uint64_t)t * tile.code_stride + lane] = (uint32_t)code;
+        else codes[(uint64_t)tile.fset * fset_stride + (uint64_t)t * code_stride + tile.out_row0 + lane] = (uint32_t)code;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ segmented radix sort
 
 constexpr uint32_t kSortThreads = 512;
@@ -496,9 +599,22 @@ void launch_sketch(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, c
 template <int M>
 static void launch_codes_m(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const uint32_t* signbits, HashGeom g,
                            uint32_t* codes, uint64_t code_stride, uint64_t fset_stride, cudaStream_t s) {
+    dim3 grid(n_tiles, (g.L + 7) / 8);
+    if constexpr (M >= 5 && M <= 7) {
+        if (tune_get("codes_fast", 1) != 0) {  // knob: 0 = the plain kernel (A/B)
+            constexpr int N = 1 << M;
+            const size_t fsmem = (size_t)32 * (N + 4) * 4 + (size_t)8 * g.fph * kRotations * N * 4;
+            static size_t configured = 0;
+            if (fsmem > 48 * 1024 && fsmem > configured) {
+                CLANN_CUDA(cudaFuncSetAttribute(k_codes_fast<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                configured = fsmem;
+            }
+            k_codes_fast<M><<<grid, 256, fsmem, s>>>(q15, tiles, signbits, g, codes, code_stride, fset_stride);
+            return;
+        }
+    }
     size_t smem = (size_t)32 * (g.sl + 2) * sizeof(int16_t);
     if (smem > 48 * 1024) CLANN_CUDA(cudaFuncSetAttribute(k_codes<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(n_tiles, (g.L + 7) / 8);
     k_codes<M><<<grid, 256, smem, s>>>(q15, tiles, signbits, g, codes, code_stride, fset_stride);
 }
 
