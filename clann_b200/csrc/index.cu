@@ -857,7 +857,7 @@ struct clann_index {
         }
         launch_segment_sort(d_segs.p, (uint32_t)segs.size(), max_len, d_tbl_hash.p, d_tbl_idx.p, scratch_k.p, scratch_i.p, s);
         {
-            // bucket directory over the top 8 code bits of every table this rank built
+            // bucket directory over the top 12 code bits of every table this rank built
             std::vector<uint8_t> skip(K);
             for (uint32_t c = 0; c < K; c++)
                 skip[c] = h_brute[c] || h_sizes[c] == 0 || (shard_count > 1 && h_owner[c] != shard_rank);

@@ -38,10 +38,10 @@ void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_
                          uint32_t* scratch_keys, uint32_t* scratch_idx, cudaStream_t s);
 uint32_t segment_sort_smem_capacity();  // segments up to this length are sorted entirely in shared memory
 
-// Bucket directory over the top 8 bits of the sorted codes (the role of PrefixMap::prefix_index, prefixmap.hpp:86,231-240,
-// at 8 instead of 13 bits): dir[(c*L + t)*kDirEntries + b] = first position, inside cluster c of table t, whose code has a
-// top byte >= b (b = 0..256; entry 256 = cluster size). Built after the sort; brute-force / foreign clusters are skipped.
-constexpr uint32_t kDirBits = 8;
+// Bucket directory over the top 12 bits of the sorted codes (the role of PrefixMap::prefix_index, prefixmap.hpp:86,231-240,
+// at 12 instead of 13 bits): dir[(c*L + t)*kDirEntries + b] = first position, inside cluster c of table t, whose code has a
+// top 12 bits >= b (b = 0..4096; entry 4096 = cluster size). Built after the sort; brute-force / foreign clusters are skipped.
+constexpr uint32_t kDirBits = 12;
 constexpr uint32_t kDirEntries = (1u << kDirBits) + 1;
 void launch_build_dir(const uint32_t* tbl_hash, uint64_t n, const uint64_t* offsets, const uint8_t* skip, uint32_t K, uint32_t L,
                       uint32_t* dir, cudaStream_t s);
@@ -65,7 +65,7 @@ struct SearchParams {
     const uint64_t* sketches;  // [n][32]
     const uint32_t* tbl_hash;  // cluster-major: table t of cluster c at table_base(offsets[c], nc, L, t) (common.cuh)
     const uint32_t* tbl_idx;   // same layout
-    const uint32_t* tbl_dir;   // [K][L][kDirEntries] bucket directory over the top 8 code bits
+    const uint32_t* tbl_dir;   // [K][L][kDirEntries] bucket directory over the top 12 code bits
     const float* center_rows;  // [K][d]
     const float* center_norms; // [K]
     const float* radii;        // [K]

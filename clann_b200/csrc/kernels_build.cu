@@ -650,28 +650,30 @@ void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_
     k_segment_sort<<<n_segs, kSortThreads, smem, s>>>(segs, cap, keys, idx, scratch_keys, scratch_idx);
 }
 
-// One CTA per (table, cluster): thread b finds the lower bound of (b << 16) in the sorted 24-bit codes of the segment.
-__global__ void __launch_bounds__(320) k_build_dir(const uint32_t* __restrict__ tbl_hash, uint64_t n, const uint64_t* __restrict__ offsets,
+// One CTA per (table, cluster): one pass over the sorted 24-bit codes; wherever the top kDirBits bits step from `lo` to `hi`
+// at position i, entries lo+1 .. hi of the directory are i (the lower bound of b << 12 for each of those b); position nc closes
+// the directory. O(nc + 2^kDirBits) per table instead of 2^kDirBits binary searches.
+__global__ void __launch_bounds__(256) k_build_dir(const uint32_t* __restrict__ tbl_hash, uint64_t n, const uint64_t* __restrict__ offsets,
                                                    const uint8_t* __restrict__ skip, uint32_t K, uint32_t* __restrict__ dir) {
-    const uint32_t c = blockIdx.x, t = blockIdx.y, b = threadIdx.x;
-    if (b >= kDirEntries || skip[c]) return;
+    const uint32_t c = blockIdx.x, t = blockIdx.y;
+    if (skip[c]) return;
     const uint64_t off = offsets[c];
     const uint32_t nc = (uint32_t)(offsets[c + 1] - off);
     const uint32_t* H = tbl_hash + table_base(off, nc, gridDim.y, t);
-    const uint32_t key = b << (kMaxHashBits - kDirBits);
-    uint32_t lo = 0, len = nc;
-    while (len > 0) {
-        uint32_t half = len >> 1, mid = lo + half;
-        if (__ldg(H + mid) < key) { lo = mid + 1; len -= half + 1; } else { len = half; }
+    uint32_t* out = dir + ((uint64_t)c * gridDim.y + t) * kDirEntries;
+    constexpr uint32_t shift = kMaxHashBits - kDirBits;
+    for (uint32_t i = threadIdx.x; i <= nc; i += blockDim.x) {
+        const int hi = i < nc ? (int)(__ldg(H + i) >> shift) : (int)(1u << kDirBits);
+        const int lo = i > 0 ? (int)(__ldg(H + i - 1) >> shift) : -1;
+        for (int b = lo + 1; b <= hi; b++) out[b] = i;
     }
-    dir[((uint64_t)c * gridDim.y + t) * kDirEntries + b] = lo;
 }
 
 void launch_build_dir(const uint32_t* tbl_hash, uint64_t n, const uint64_t* offsets, const uint8_t* skip, uint32_t K, uint32_t L,
                       uint32_t* dir, cudaStream_t s) {
     if (K == 0 || L == 0) return;
     dim3 grid(K, L);
-    k_build_dir<<<grid, 320, 0, s>>>(tbl_hash, n, offsets, skip, K, dir);
+    k_build_dir<<<grid, 256, 0, s>>>(tbl_hash, n, offsets, skip, K, dir);
 }
 
 void launch_cp_estimates(uint32_t m, uint32_t reps, uint64_t seed, float* est, uint32_t* scratch_counts, cudaStream_t s) {

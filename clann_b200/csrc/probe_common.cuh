@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t lead_count(uint2 packed, uint32_t depth) {
 // ------------------------------------------------------------------------------------------------ per-table probe state
 
 // SearchBuffers ctor for one table (collection.hpp:642-645 -> prefixmap.hpp:36-57,250-260): the anchor A = lower bound of
-// the query code h in the cluster's sorted codes H[0..nc), found inside bucket [dir[b], dir[b+1]) of its top byte b
+// the query code h in the cluster's sorted codes H[0..nc), found inside bucket [dir[b], dir[b+1]) of its top 12 bits b
 // (lower_bound == the reference's hinted halving search), plus the common-prefix length with the codes at
 // A + 12 j and A - 1 - 12 j, j = 0..7, packed one byte each (beyond the data lie the 0xffffffff sentinels,
 // prefixmap.hpp:215-226, which match nothing).
@@ -272,7 +272,7 @@ __device__ __forceinline__ void table_anchor(const uint32_t* __restrict__ H, con
 // PrefixMap::get_next_range (prefixmap.hpp:267-304) in closed form for one table at `depth`: with [lo, hi)
 // the block of codes sharing the query's `depth`-bit prefix, upward [A, A + 12 ceil((hi - A)/12)) then the `>= len-12`
 // clamp, downward [A - 12 ceil((A - lo)/12), A) then the `< 12` clamp; the anchors are never advanced (:278,292).
-// The block comes from the directory when depth <= 8 bits, from the stride-12 samples otherwise (a block longer than the
+// The block comes from the directory when depth <= 12 bits (kDirBits), from the stride-12 samples otherwise (a block longer than the
 // samples is resolved by a binary search confined to the code's bucket). Returns the range start; nseg = 4-entry segments.
 __device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, const uint32_t* __restrict__ dir, uint32_t nc, uint32_t h,
                                                 uint32_t A, uint2 lcp_up, uint2 lcp_dn, uint32_t depth, uint32_t& nseg) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, 
     const uint32_t b = h >> (kMaxHashBits - kDirBits);
     // j = 12-entry strides covered by the matching block on the probed side of the anchor. The common cases are written
     // without a branch on the direction (the tables of one query split about evenly between the two): one directory word for
-    // depth <= 8 bits, the stride-12 samples otherwise.
+    // depth <= kDirBits, the stride-12 samples otherwise.
     uint32_t j;
     if (depth <= kDirBits) {
         const uint32_t sh = kDirBits - depth, pb = b >> sh;
@@ -292,7 +292,7 @@ __device__ __forceinline__ uint32_t table_range(const uint32_t* __restrict__ H, 
     } else {
         j = lead_count(upward ? lcp_up : lcp_dn, depth);
         if (j == 8) {
-            if (upward) {  // first position >= A + 96 whose prefix differs; it cannot lie beyond the bucket of the top byte
+            if (upward) {  // first position >= A + 96 whose prefix differs; it cannot lie beyond the bucket of the top 12 bits
                 uint32_t lo = A + 8 * kSegment, end = __ldg(dir + b + 1);
                 uint32_t len = end > lo ? end - lo : 0;
                 while (len > 0) {

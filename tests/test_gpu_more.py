@@ -268,17 +268,17 @@ def test_sharded_search_equals_single_gpu(big):
 
 
 def test_bucket_directory_matches_tables(big):
-    """The bucket directory (role of PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 8 bits): entry b of table t is the
-    lower bound of (b << 16) in that table's sorted codes; entry 256 is the cluster size."""
+    """The bucket directory (role of PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 12 bits): entry b of table t is the
+    lower bound of (b << 12) in that table's sorted codes; entry 4096 is the cluster size."""
     from clann_b200 import _lib as cl
     _, ix = big
     off = ix.export(cl.X_OFFSETS, 0, np.uint64)
     brute = ix.export(cl.X_BRUTE, 0, np.uint8)
-    keys = (np.arange(257, dtype=np.uint32) << np.uint32(16))
+    keys = (np.arange(4097, dtype=np.uint32) << np.uint32(12))
     for ci in np.flatnonzero(brute == 0)[:4]:
         nc = int(off[ci + 1] - off[ci])
         th = ix.export(cl.X_TABLE_HASHES, int(ci), np.uint32).reshape(84, nc)
-        dr = ix.export(cl.X_TABLE_DIR, int(ci), np.uint32).reshape(84, 257)
+        dr = ix.export(cl.X_TABLE_DIR, int(ci), np.uint32).reshape(84, 4097)
         for t in range(84):
             assert np.array_equal(dr[t], np.searchsorted(th[t], keys, side="left").astype(np.uint32))
 
