@@ -27,7 +27,7 @@ __all__ = [
     "Config", "MetricsOutput", "AngularData", "ClusteredIndex", "ClusteredIndexError", "ConfigError", "DataError",
     "PuffinnCreationError", "PuffinnSearchError", "IndexNotFound", "IndexOutOfBounds", "SerializeError", "MetricsError",
     "CudaError", "init", "init_with_config", "build", "search", "search_batch", "PuffinnIndex", "get_recall_values",
-    "brute_force_search", "generate_random_unit_vectors", "RunMetrics", "run_with_metrics",
+    "brute_force_search", "generate_random_unit_vectors", "RunMetrics", "run_with_metrics", "serialize", "init_from_file",
 ]
 
 
@@ -280,6 +280,99 @@ def search(index: ClusteredIndex, query) -> List[Tuple[float, int]]:
 
 def search_batch(index: ClusteredIndex, queries):
     return index.search_batch(queries)
+
+
+# ------------------------------------------------------------------------------------------------ persistence (index.rs:107-162,511-557)
+
+_REC_MAGIC = b"CLB2REC\0"
+
+
+def _write_record(f, name: str, payload: bytes) -> None:
+    """One record of the flat container CPUFFINN_save_index writes (index.cu): magic, name length, reserved, payload length."""
+    nb = name.encode()
+    f.write(_REC_MAGIC + np.uint32(len(nb)).tobytes() + np.uint32(0).tobytes() + np.uint64(len(payload)).tobytes() + nb + payload)
+
+
+def _read_records(path: str) -> dict:
+    out = {}
+    with open(path, "rb") as f:
+        raw = f.read()
+    pos = 0
+    while pos < len(raw):
+        if raw[pos:pos + 8] != _REC_MAGIC:
+            raise SerializeError(f"{path} is not a libclann_b200 record file")
+        name_len = int(np.frombuffer(raw[pos + 8:pos + 12], np.uint32)[0])
+        payload_len = int(np.frombuffer(raw[pos + 16:pos + 24], np.uint64)[0])
+        name = raw[pos + 24:pos + 24 + name_len].decode()
+        start = pos + 24 + name_len
+        if start + payload_len > len(raw):
+            raise SerializeError(f"{path}: truncated record {name}")
+        out[name] = raw[start:start + payload_len]   # the last record of a name wins (append-only file)
+        pos = start + payload_len
+    return out
+
+
+def serialize(index: ClusteredIndex, directory_path: str) -> str:
+    """lib.rs:255-264 -> ClusteredIndex::serialize (index.rs:511-557): the records the reference writes as HDF5 datasets —
+    `config` (serde JSON of Config), `clusters` (serde JSON of Vec<ClusterCenter>: idx, center_idx, radius, assignment,
+    brute_force, memory_used) and `index_{i}` = the bytes of puffinn::Index::serialize for every cluster that has a PUFFINN
+    index — in the flat record container of CPUFFINN_save_index (there is no HDF5 here; only the container differs).
+    Returns the file path (index_{dataset}_k{factor:.2}_L{tables}.clb2; the reference's name ends in .h5)."""
+    import json
+    if not os.path.isdir(directory_path):
+        raise SerializeError(f"directory {directory_path} doesn't exist")   # index.rs:512-517
+    if not index.built:
+        raise SerializeError("index has not been built")
+    cfg = index.config
+    path = os.path.join(directory_path, "index_%s_k%.2f_L%d.clb2" % (cfg.dataset_name, cfg.num_clusters_factor, cfg.num_tables))
+    K = index.num_clusters
+    centers = index.export(_lib.X_CENTERS, 0, np.uint64)
+    radii = index.export(_lib.X_RADII, 0, np.float32)
+    offsets = index.export(_lib.X_OFFSETS, 0, np.uint64)
+    perm = index.export(_lib.X_PERM, 0, np.uint32)
+    brute = index.export(_lib.X_BRUTE, 0, np.uint8)
+    clusters = [dict(idx=c, center_idx=int(centers[c]), radius=float(radii[c]),
+                     assignment=perm[int(offsets[c]):int(offsets[c + 1])].tolist(), brute_force=bool(brute[c]), memory_used=0)
+                for c in range(K)]
+    config_json = json.dumps(dict(num_tables=int(cfg.num_tables), num_clusters_factor=float(cfg.num_clusters_factor), k=int(cfg.k),
+                                  delta=float(cfg.delta), dataset_name=cfg.dataset_name, metrics_output="None"))
+    with open(path, "wb") as f:
+        _write_record(f, "config", config_json.encode())
+        _write_record(f, "clusters", json.dumps(clusters).encode())
+        for c in range(K):
+            if not brute[c]:
+                _write_record(f, f"index_{c}", index.export(_lib.X_REFERENCE_STREAM, c, np.uint8).tobytes())
+    return path
+
+
+def init_from_file(data, file_path: str) -> ClusteredIndex:
+    """lib.rs:41-47 -> ClusteredIndex::new_from_file (index.rs:107-162): config and clusters from their JSON records, the hash
+    functions of every cluster from its `index_{i}` stream; the device tables are rebuilt from them (0.3 s at the glove-100
+    shape) instead of being copied — same functions, same rows, hence the same tables and the same answers."""
+    import json
+    if not os.path.exists(file_path):
+        raise ConfigError(f"file {file_path} not found")   # index.rs:108-113
+    rec = _read_records(file_path)
+    try:
+        c = json.loads(rec["config"].decode())
+        clusters = json.loads(rec["clusters"].decode())
+    except KeyError as e:
+        raise ConfigError(f"record {e} missing in {file_path}")
+    cfg = Config(int(c["num_tables"]), float(c["num_clusters_factor"]), int(c["k"]), float(c["delta"]), c.get("dataset_name", ""))
+    index = init_with_config(data, cfg)
+    n = index.data.num_points()
+    assignment = np.zeros(n, np.uint64)
+    for cl_ in clusters:
+        assignment[np.asarray(cl_["assignment"], np.int64)] = cl_["idx"]
+    index.set_clustering([cl_["center_idx"] for cl_ in clusters], assignment, [cl_["radius"] for cl_ in clusters])
+    for cl_ in clusters:
+        if not cl_["brute_force"]:
+            name = f"index_{cl_['idx']}"
+            if name not in rec:
+                raise IndexNotFound()
+            index.import_reference(cl_["idx"], rec[name])
+    index.build()
+    return index
 
 
 # ------------------------------------------------------------------------------------------------ PuffinnIndex (legacy ABI)

@@ -691,6 +691,24 @@ struct clann_index {
         }
     }
 
+    // Per-cluster sets that were all imported and turn out identical (an index this library saved with its shared set and
+    // loads again through clann_import_reference) collapse into one shared set: a query is then hashed once, not per cluster.
+    void collapse_identical_function_sets() {
+        if (!per_cluster_functions || fsets.size() <= 1 || fsets.size() != K) return;
+        const FunctionSet* first = nullptr;
+        for (size_t f = 0; f < fsets.size(); f++) {
+            if (h_brute[f]) continue;
+            const FunctionSet& fs = fsets[f];
+            if (!fs.have_fn || !fs.have_est) return;
+            if (!first) first = &fs;
+            else if (fs.planes != first->planes || fs.signbits != first->signbits || fs.est != first->est) return;
+        }
+        if (!first) return;
+        FunctionSet keep = *first;
+        fsets.assign(1, keep);
+        per_cluster_functions = false;
+    }
+
     void prepare_functions(cudaStream_t s) {
         ensure_fsets();
         // collision estimates: one Monte-Carlo table per dimension, shared by every set that did not import its own
@@ -787,6 +805,7 @@ struct clann_index {
         h_brute.resize(K);
         for (uint32_t c = 0; c < K; c++)
             h_brute[c] = puffinn_mode ? 0 : (h_sizes[c] < 100 || h_sizes[c] < cfg.k);  // index.rs:204-205
+        collapse_identical_function_sets();
         h_fset_of.resize(K);
         for (uint32_t c = 0; c < K; c++) h_fset_of[c] = per_cluster_functions ? c : 0;
         assign_owners();

@@ -462,3 +462,39 @@ def test_properties_at_full_glove100_shape():
         assert np.array_equal(ctr[key], ctr2[key]), key
     ids3, dists3, _ = ix.search_batch(q)
     assert np.array_equal(ids, ids3) and np.array_equal(dists.view(np.uint32), dists3.view(np.uint32))
+
+
+def test_serialize_and_init_from_file_round_trip(tmp_path):
+    """lib.rs:41-47,255-264 (index.rs:107-162,511-557): serialize writes `config`, `clusters` and one `index_{i}` record per
+    PUFFINN cluster; init_from_file(data, path) answers every query exactly like the index that was saved — ids, distance
+    bits, counters — and the per-cluster streams are the reference's bytes (the real reference loads one of them)."""
+    import json
+    import clann_b200 as cb
+    from clann_b200 import api
+    data = util.planted(20_000, 48, 71)
+    ix = cb.init_with_config(data, cb.Config(24, 0.4, 10, 0.9, "roundtrip"))
+    ix.set_option("seed", 5)
+    ix.build()
+    q = np.concatenate([util.planted_queries(data, 300, 72), util.uniform_sphere(20, 48, 73)])
+    ids, dists, counts = ix.search_batch(q)
+    ctr = ix.counters(len(q))
+    with pytest.raises(cb.api.SerializeError):
+        cb.serialize(ix, str(tmp_path / "no_such_dir"))
+    path = cb.serialize(ix, str(tmp_path))
+    assert os.path.basename(path) == "index_roundtrip_k0.40_L24.clb2"
+    rec = api._read_records(path)
+    cfg = json.loads(rec["config"])
+    clusters = json.loads(rec["clusters"])
+    assert cfg["num_tables"] == 24 and cfg["k"] == 10 and len(clusters) == ix.num_clusters
+    assert sorted(sum((c["assignment"] for c in clusters), [])) == list(range(len(data)))
+    assert all((f"index_{c['idx']}" in rec) == (not c["brute_force"]) for c in clusters)
+    loaded = cb.init_from_file(data, path)
+    ids2, dists2, counts2 = loaded.search_batch(q)
+    ctr2 = loaded.counters(len(q))
+    assert np.array_equal(ids, ids2) and np.array_equal(dists.view(np.uint32), dists2.view(np.uint32)) and np.array_equal(counts, counts2)
+    for key in ("candidates", "distance_computations", "clusters_visited"):
+        assert np.array_equal(ctr[key], ctr2[key]), key
+    # a second save of the loaded index writes the same records
+    os.makedirs(tmp_path / "again")
+    rec2 = api._read_records(cb.serialize(loaded, str(tmp_path / "again")))
+    assert rec2.keys() == rec.keys() and all(rec2[k] == rec[k] for k in rec if k != "config") and json.loads(rec2["config"]) == cfg

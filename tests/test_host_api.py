@@ -66,3 +66,26 @@ def test_run_metrics_rows(tmp_path):
     assert lines[1].startswith("query_idx,") and len(lines) == 5 and lines[3].split(",")[2] == "7"
     import json
     assert len(json.loads(m.to_json())["queries"]) == 3
+
+
+def test_record_container_round_trip(tmp_path):
+    """The flat record container of serialize / CPUFFINN_save_index: append-only, the last record of a name wins, foreign
+    files and truncated records are SerializeError; a missing file is ConfigError (index.rs:108-113)."""
+    import clann_b200 as cb
+    from clann_b200 import api
+    p = tmp_path / "f.clb2"
+    with open(p, "wb") as f:
+        api._write_record(f, "config", b'{"a": 1}')
+        api._write_record(f, "index_3", bytes(range(200)))
+        api._write_record(f, "config", b'{"a": 2}')
+    rec = api._read_records(str(p))
+    assert rec["config"] == b'{"a": 2}' and rec["index_3"] == bytes(range(200)) and set(rec) == {"config", "index_3"}
+    raw = p.read_bytes()
+    (tmp_path / "t.clb2").write_bytes(raw[:-10])
+    with pytest.raises(cb.api.SerializeError):
+        api._read_records(str(tmp_path / "t.clb2"))
+    (tmp_path / "x.clb2").write_bytes(b"not a record file at all")
+    with pytest.raises(cb.api.SerializeError):
+        api._read_records(str(tmp_path / "x.clb2"))
+    with pytest.raises(cb.api.ConfigError):
+        api.init_from_file(np.zeros((4, 4), np.float32), str(tmp_path / "missing.clb2"))
