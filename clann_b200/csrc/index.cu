@@ -445,6 +445,7 @@ struct clann_index {
         uint32_t w_memo_slots = 0;
         DevBuf<uint16_t> w_dense;  // dense first-visit similarities [nq][w_dense_stride]
         uint64_t w_dense_stride = 0;
+        DevBuf<unsigned long long> w_stats;           // {running sum of clusters visited, finished-block ticket} of k_finish
         DevBuf<uint32_t> w_pre_anchor, w_pre_range;  // first-visit anchors [nq][L] and ranges [nq][24][L]
         DevBuf<uint4> w_pre_lcp;                     // first-visit common-prefix samples [nq][L]
         DevBuf<RowTile> w_tiles, w_tiles_codes;
@@ -457,6 +458,11 @@ struct clann_index {
     static constexpr int kPipeMax = 4;
     SearchWs wsv[1 + kPipeMax];
     SearchWs* W = &wsv[0];
+    // {clusters visited, queries} of the last finished batch, written by k_finish into mapped host memory and read without any
+    // synchronisation: when queries walk many clusters (avg > 3: overlapping or unclustered data) the dense first-visit
+    // precompute buys nothing and the 24-warp schedule of the gather path is the faster one
+    unsigned long long* h_stats = nullptr;
+    unsigned long long* h_stats_dev = nullptr;
     cudaStream_t pipe_stream[kPipeMax] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done[kPipeMax] = {nullptr, nullptr, nullptr, nullptr};
     uint64_t pipe_calls = 0;
@@ -475,6 +481,7 @@ struct clann_index {
             if (e) cudaEventDestroy(e);
         for (auto& st : pipe_stream)
             if (st) cudaStreamDestroy(st);
+        if (h_stats) cudaFreeHost(h_stats);
     }
 
     void reset_workspaces() {
@@ -483,6 +490,7 @@ struct clann_index {
             w.ws_nq = 0;
             w.w_tiles_codes_nq = 0;
         }
+        if (h_stats) h_stats[0] = h_stats[1] = 0;
     }
 
     uint32_t n_fsets() const { return (uint32_t)fsets.size(); }
@@ -977,6 +985,15 @@ struct clann_index {
             }
         }
         W->w_counter.ensure(2);
+        if (!W->w_stats.p) {
+            W->w_stats.ensure(2);
+            CLANN_CUDA(cudaMemsetAsync(W->w_stats.p, 0, 2 * sizeof(unsigned long long), s));
+        }
+        if (!h_stats) {
+            CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_stats), 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+            h_stats[0] = h_stats[1] = 0;
+            CLANN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_stats_dev), h_stats, 0));
+        }
         W->w_cand.ensure(nq);
         W->w_dc.ensure(nq);
         W->w_vis.ensure(nq);
@@ -1010,6 +1027,8 @@ struct clann_index {
         b.pre_anchor = nullptr;
         b.pre_range = nullptr;
         b.pre_lcp = nullptr;
+        b.stats_dev = (d_ids && h_stats_dev) ? W->w_stats.p : nullptr;
+        b.stats_host = h_stats_dev;
         b.out_ids = d_ids;
         b.out_dists = d_dists;
         b.out_counts = d_counts;
@@ -1079,6 +1098,11 @@ struct clann_index {
     // Fills the memo of every query's first visit in advance (launch_dense_sims) when the default probe kernel will use it.
     bool use_dense_sims(const SearchParams& p, QueryBatch& b, cudaStream_t s) {
         if (!W->w_dense.p || W->w_dense_stride == 0 || tune_get("probe", 0) == 1) return false;  // the CTA kernel does not use it
+        if (h_stats && tune_get("dense_adaptive", 1) != 0) {
+            const unsigned long long visited = reinterpret_cast<volatile unsigned long long*>(h_stats)[0];
+            const unsigned long long queries = reinterpret_cast<volatile unsigned long long*>(h_stats)[1];
+            if (queries > 0 && visited > 3 * queries) return false;  // the last finished batch walked > 3 clusters per query
+        }
         b.dense = W->w_dense.p;
         if (!launch_dense_sims(p, b, s)) {
             b.dense = nullptr;

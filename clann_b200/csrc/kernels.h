@@ -104,6 +104,11 @@ struct QueryBatch {
     uint64_t dense_stride;
     // first-visit anchors and ranges (launch_first_ranges): pre_anchor[q * L + t] = anchor of query q in table t of its nearest
     // cluster; pre_range[(q * 24 + depth - 1) * L + t] = segments of the range at `depth` | upward << 31; null = not computed
+    // batch statistics for the host's choice of schedule (no synchronisation: the host reads the page-locked words whenever it
+    // next looks): stats_dev[0] = running sum of clusters visited, [1] = finished-block ticket; the last block of k_finish
+    // publishes {sum of clusters visited, queries} of the batch to stats_host (mapped host memory); null = not collected
+    unsigned long long* stats_dev;
+    volatile unsigned long long* stats_host;
     uint32_t* pre_anchor;
     uint32_t* pre_range;
     // pre_lcp[q * L + t] = the stride-12 common-prefix samples of table_anchor (up.x, up.y, dn.x, dn.y); with pre_range null

@@ -802,10 +802,12 @@ __global__ void k_merge_states(uint8_t* __restrict__ mine, const uint8_t* __rest
 __global__ void __launch_bounds__(128) k_finish(const uint8_t* __restrict__ state, uint64_t nq, uint32_t k, uint64_t state_bytes,
                                                 uint32_t* __restrict__ out_ids, float* __restrict__ out_dists,
                                                 uint32_t* __restrict__ out_counts, unsigned long long* __restrict__ cnt_cand,
-                                                unsigned long long* __restrict__ cnt_dc, uint32_t* __restrict__ cnt_vis) {
+                                                unsigned long long* __restrict__ cnt_dc, uint32_t* __restrict__ cnt_vis,
+                                                unsigned long long* stats_dev, volatile unsigned long long* stats_host) {
     // one warp per query; selection sort by repeated minimum is fine for small k, bitonic otherwise is unnecessary here
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= nq) return;
+    uint32_t my_visited = 0;
+    if (q < nq) {
     const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(state + q * state_bytes);
     const unsigned long long* heap = reinterpret_cast<const unsigned long long*>(h + 1);
     const uint32_t len = h->heap_len;
@@ -830,6 +832,27 @@ __global__ void __launch_bounds__(128) k_finish(const uint8_t* __restrict__ stat
         if (cnt_cand) cnt_cand[q] = h->candidates;
         if (cnt_dc) cnt_dc[q] = h->distcomp;
         if (cnt_vis) cnt_vis[q] = h->visited;
+        my_visited = h->visited;
+    }
+    }
+    // batch statistics: clusters visited summed per block, the last block to finish publishes the batch total to the host
+    if (stats_dev) {
+        __shared__ uint32_t s_vis;
+        if (threadIdx.x == 0) s_vis = 0;
+        __syncthreads();
+        if (my_visited) atomicAdd(&s_vis, my_visited);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&stats_dev[0], (unsigned long long)s_vis);
+            __threadfence();
+            const unsigned long long ticket = atomicAdd(&stats_dev[1], 1ull);
+            if (ticket == gridDim.x - 1) {
+                stats_host[0] = atomicExch(&stats_dev[0], 0ull);
+                stats_host[1] = nq;
+                stats_dev[1] = 0;
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -1172,7 +1195,8 @@ void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
     if (b.nq == 0) return;
     uint64_t threads = b.nq * 32;
     k_finish<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(b.state, b.nq, p.k, query_state_bytes(p.k), b.out_ids, b.out_dists,
-                                                               b.out_counts, b.cnt_candidates, b.cnt_distcomp, b.cnt_visited);
+                                                               b.out_counts, b.cnt_candidates, b.cnt_distcomp, b.cnt_visited, b.stats_dev,
+                                                               b.stats_host);
 }
 
 template <int G>
