@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_store_q15(const float* __restrict__ dat
 // filterer.hpp:76-102 + simhash.hpp:41-44 + independent.hpp:70-86 (function 64*s+b -> bit 63-b of sketch s).
 // One CTA = one tile of <=32 rows x 256 hyperplanes (4 sketches). Thread = hyperplane; rows live in shared memory as
 // int32 so that each 16-element unit costs 4 broadcast LDS.128 + 48 integer ops per row.
-__global__ void __launch_bounds__(256) k_sketch(const int16_t* __restrict__ q15, const RowTile* __restrict__ tiles,
+__global__ void __launch_bounds__(256, 3) k_sketch(const int16_t* __restrict__ q15, const RowTile* __restrict__ tiles,
                                                 const int16_t* __restrict__ planes, uint32_t sl, uint64_t* __restrict__ sketches) {
     extern __shared__ int s_rows[];  // [32][sl]
     const RowTile tile = tiles[blockIdx.x];
