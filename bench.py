@@ -8,7 +8,7 @@ Workload at N=1 (BASELINE.json configs[2], the one the metric is quoted on): glo
 1,183,514 x 100 unit vectors, 10,000 queries, num_tables=84, num_clusters_factor=0.4, k=10, delta=0.9.
 
 Prints ONE JSON line (rank 0). `value` = queries/s with queries and outputs resident in HBM, K steps issued back to back
-through clann_search_device_async (two batches in flight; `value_stream_ordered` = one batch at a time, clann_search_device),
+through clann_search_device_async (three batches in flight; `value_stream_ordered` = one batch at a time, clann_search_device),
 `e2e` = the same with HOST buffers, H2D + D2H inside the timed region, through clann_search_async / clann_search_wait
 (`value_synchronous_call` = one blocking clann_search per step),
 `roofline` = algorithmic bytes of the probe kernel / its CUDA-event duration against the measured HBM peak,
@@ -214,7 +214,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="time `value` with stream-ordered calls (one batch at a time) instead of clann_search_device_async "
-                         "(two batches in flight); the stream-ordered figure is always reported as value_stream_ordered")
+                         "(three batches in flight); the stream-ordered figure is always reported as value_stream_ordered")
     ap.add_argument("--shard", default="queries", choices=["queries", "clusters"],
                     help="N > 1: 'queries' = the index is replicated and every rank searches its own batch (weak scaling, no "
                          "data-path collective); 'clusters' = clusters are sharded by owner and one fixed batch is stepped "
@@ -316,9 +316,12 @@ def main():
     def step_device():
         searcher.search_device(d_q, d_ids, d_dists, d_counts)
 
-    # batch pipelining (clann_search_device_async): consecutive steps on two internal streams, each with its own outputs
+    # batch pipelining (clann_search_device_async): consecutive steps on the internal streams (three batches in flight), each with its own outputs
     pipelined = single and not args.no_pipeline
-    outs = [(d_ids, d_dists, d_counts)] + [(torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts)) for _ in range(3)]
+    # 12 output sets: calls i and i + 12 land on the same internal stream for every pipeline depth (2, 3 or 4), so a set is never
+    # written by two batches that could be in flight together
+    NSETS = 12
+    outs = [(d_ids, d_dists, d_counts)] + [(torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts)) for _ in range(NSETS - 1)]
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def run_steps(steps):
@@ -327,7 +330,7 @@ def main():
                 step_device()
             return
         for i in range(steps):
-            o = outs[i & 3]
+            o = outs[i % NSETS]
             if index._lib.clann_search_device_async(index.handle, d_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
                 raise RuntimeError(cl.last_error())
         if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
@@ -434,11 +437,11 @@ def main():
         # the same through clann_search_async: every step's H2D copy, search and D2H copies on its batch stream, two batches in
         # flight, each with its own pinned output buffers; clann_search_wait before the clock stops
         h_outs = [(h_ids, h_dists, h_counts)] + [(torch.empty_like(h_ids).pin_memory(), torch.empty_like(h_dists).pin_memory(),
-                                                  torch.empty_like(h_counts).pin_memory()) for _ in range(3)]
+                                                  torch.empty_like(h_counts).pin_memory()) for _ in range(NSETS - 1)]
 
         def run_e2e_async(steps):
             for i in range(steps):
-                o = h_outs[i & 3]
+                o = h_outs[i % NSETS]
                 if index._lib.clann_search_async(index.handle, h_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
                     raise RuntimeError(cl.last_error())
             if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
@@ -449,7 +452,7 @@ def main():
             raise RuntimeError(cl.last_error())
         step_e2e()                                   # reference result of the synchronous call in h_outs[0]
         want = (h_ids.clone(), h_dists.clone(), h_counts.clone())
-        run_e2e_async(4)
+        run_e2e_async(NSETS)
         index._lib.clann_search_wait(index.handle)
         for o in h_outs:
             if not (torch.equal(o[0], want[0]) and torch.equal(o[1], want[1]) and torch.equal(o[2], want[2])):
@@ -469,16 +472,16 @@ def main():
             e2e_ms = float(t.item())
         e2e_ms /= args.steps
         e2e_mode = ("clann_search_async + clann_search_wait: host buffers in and out, H2D / search / D2H of each step on its batch "
-                    "stream, two batches in flight; results identical to clann_search (checked)")
+                    "stream, three batches in flight; results identical to clann_search (checked)")
     e2e_value = global_nq / (e2e_ms / 1000.0)
 
     # ---- correctness of what was timed: the pipelined batches return what the stream-ordered call returns
     pipe_same = None
     if pipelined:
-        run_steps(2)
+        run_steps(3)
         torch.cuda.synchronize()
-        a_ids, a_dists = outs[0][0].clone(), outs[0][1].clone()
-        b_ids, b_dists = outs[1][0].clone(), outs[1][1].clone()
+        a_ids, a_dists = outs[1][0].clone(), outs[1][1].clone()
+        b_ids, b_dists = outs[2][0].clone(), outs[2][1].clone()
         step_device()
         torch.cuda.synchronize()
         pipe_same = bool(torch.equal(a_ids, d_ids) and torch.equal(b_ids, d_ids) and torch.equal(a_dists, d_dists) and torch.equal(b_dists, d_dists))
@@ -543,7 +546,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if shard_clusters else "weak",
             "vs_baseline": None, "dtype": "i16",
             "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
-            "pipeline": ("clann_search_device_async: two batches in flight on two internal streams; outputs identical to the "
+            "pipeline": ("clann_search_device_async: three batches in flight on three internal streams; outputs identical to the "
                          "stream-ordered call (checked)") if pipelined else "none (stream-ordered calls)",
             "data": "synthetic", "config": cfg_json, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,

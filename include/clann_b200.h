@@ -83,7 +83,7 @@ int clann_search(clann_index* index, const float* queries, uint64_t nq, uint32_t
 int clann_search_device(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
                         uint32_t* d_counts, void* stream);
 /* Batch pipelining for a stream of batches (no counterpart in the reference, which answers one query at a time): the same
- * search, issued on one of two internal streams with its own workspace, NOT ordered after the caller's streams, so that
+ * search, issued on one of three internal streams (knob pipeline_depth) with its own workspace, NOT ordered after the caller's streams, so that
  * consecutive batches overlap on the device (the next batch's hashing beside the current probe, its probe in the SMs the
  * current probe's last wave leaves idle). The query buffer must be complete when the call is made and every batch in
  * flight needs its own output buffers. clann_search_flush makes `stream` wait for every batch issued so far; results are
