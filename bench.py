@@ -434,7 +434,7 @@ def main():
     e2e_sync_ms = timed(step_e2e, args.steps) / args.steps
     e2e_ms, e2e_mode = e2e_sync_ms, "clann_search: one synchronous call per step (host buffers in, host buffers out)"
     if pipelined:
-        # the same through clann_search_async: every step's H2D copy, search and D2H copies on its batch stream, two batches in
+        # the same through clann_search_async: every step's H2D copy, search and D2H copies on its batch stream, three batches in
         # flight, each with its own pinned output buffers; clann_search_wait before the clock stops
         h_outs = [(h_ids, h_dists, h_counts)] + [(torch.empty_like(h_ids).pin_memory(), torch.empty_like(h_dists).pin_memory(),
                                                   torch.empty_like(h_counts).pin_memory()) for _ in range(NSETS - 1)]

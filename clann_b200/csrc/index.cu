@@ -1091,7 +1091,7 @@ struct clann_index {
         profile_valid = true;
     }
 
-    // The same search on one of two internal streams (alternating) with its own workspace set, not ordered after anything
+    // The same search on one of the internal streams (rotating, pipeline_depth of them) with its own workspace set, not ordered after anything
     // the caller has in flight: consecutive batches overlap — the next batch's hashing runs beside the probe of the current
     // one and its probe fills the SMs the current probe's last wave leaves idle. The caller guarantees that the query buffer
     // is complete when the call is made; results are complete once search_flush() has been waited on.
