@@ -498,3 +498,21 @@ def test_serialize_and_init_from_file_round_trip(tmp_path):
     os.makedirs(tmp_path / "again")
     rec2 = api._read_records(cb.serialize(loaded, str(tmp_path / "again")))
     assert rec2.keys() == rec.keys() and all(rec2[k] == rec[k] for k in rec if k != "config") and json.loads(rec2["config"]) == cfg
+
+
+def test_run_with_metrics_on_device():
+    """run_with_metrics (the run / query rows of the reference's RunMetrics): counters per query come from the device, recall
+    from get_recall_values against exact distances, queries/s from the wall clock around the batched call."""
+    import clann_b200 as cb
+    data = util.planted(15_000, 32, 81)
+    ix = cb.init_with_config(data, cb.Config(30, 0.4, 10, 0.9, "metrics"))
+    ix.build()
+    q = util.planted_queries(data, 200, 82)
+    gt = np.sort(util.exact_distances(data, q), axis=1)[:, :10]
+    (ids, dists, counts), m = cb.run_with_metrics(ix, q, gt)
+    assert m.queries_per_second > 0 and m.recall_mean >= 0.9 and len(m.query_rows()) == 200
+    ctr = ix.counters(200)
+    rows = m.query_rows()
+    assert [r["distance_computations"] for r in rows] == ctr["distance_computations"].tolist()
+    assert [r["n_candidates"] for r in rows] == ctr["candidates"].tolist()
+    assert m.run_row()["dataset_len"] == 15_000 and m.run_row()["dataset"] == "metrics"
