@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "probe_common.cuh"
 
 namespace clann {
 
@@ -178,7 +179,7 @@ struct Reader {
     const uint8_t* p;
     uint64_t len, off = 0;
     void bytes(void* dst, uint64_t n) {
-        if (off + n > len) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");
+        if (n > len - off) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");  // overflow-safe: off <= len always
         if (dst) memcpy(dst, p + off, n);
         off += n;
     }
@@ -205,6 +206,7 @@ static void parse_reference_stream(const uint8_t* blob, uint64_t len, const Hash
     }
     r.get<uint32_t>(); r.get<uint32_t>(); r.get<uint8_t>(); r.get<uint32_t>(); r.get<uint32_t>();  // independent.hpp:64-68
     uint64_t n_sk = r.get<uint64_t>();
+    if (n_sk > len / 8) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");
     r.bytes(nullptr, n_sk * 8);                                // stored sketches (filterer.hpp:62-68)
     if (r.get<int32_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "hash source is not IndependentHashSource");
     uint32_t rot = r.get<uint32_t>();
@@ -220,6 +222,8 @@ static void parse_reference_stream(const uint8_t* blob, uint64_t len, const Hash
         if (r.get<uint64_t>() != (uint64_t)kEstBins) throw StatusError(CLANN_ERR_SERIALIZE, "collision estimate table has the wrong width");
         r.bytes(fs.est.data() + b * kEstBins, sizeof(float) * kEstBins);
     }
+    for (float v : fs.est)
+        if (!(v >= 0.0f && v <= 1.0f)) throw StatusError(CLANN_ERR_SERIALIZE, "collision estimate outside [0, 1]");
     r.get<float>();                                            // eps
     uint64_t n_fn = r.get<uint64_t>();
     if (n_fn != (uint64_t)g.L * g.fph) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream has a different number of tables");
@@ -341,6 +345,7 @@ static void read_reference_stream(const uint8_t* blob, uint64_t len, LoadedStrea
     out.sl = r.get<uint32_t>();
     out.n = r.get<uint32_t>();
     if (out.d == 0 || out.d > 1024 || out.sl != (out.d + 15) / 16 * 16) throw StatusError(CLANN_ERR_SERIALIZE, "not a cosine PUFFINN index stream");
+    if ((uint64_t)out.n * out.sl * 2 > len) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");
     out.rows.resize((size_t)out.n * out.sl);
     r.bytes(out.rows.data(), out.rows.size() * 2);
     // the function set: reuse the importer on the same bytes once the number of tables is known (it sits behind the functions)
@@ -360,10 +365,15 @@ static void read_reference_stream(const uint8_t* blob, uint64_t len, LoadedStrea
         if (!t.get<uint8_t>()) throw StatusError(CLANN_ERR_SERIALIZE, "the index was never rebuilt (no hash source)");
         t.bytes(nullptr, 8 + 12);                                           // family description + args
         const uint64_t rows = t.get<uint64_t>();
-        for (uint64_t b = 0; b < rows; b++) t.bytes(nullptr, t.get<uint64_t>() * 4);
+        if (rows > 64) throw StatusError(CLANN_ERR_SERIALIZE, "collision estimate table has the wrong height");
+        for (uint64_t b = 0; b < rows; b++) {
+            const uint64_t w = t.get<uint64_t>();
+            if (w > len / 4) throw StatusError(CLANN_ERR_SERIALIZE, "reference stream truncated");
+            t.bytes(nullptr, w * 4);
+        }
         t.bytes(nullptr, 4);                                                // eps
         const uint64_t n_fn = t.get<uint64_t>();
-        if (n_fn == 0 || n_fn % g1.fph) throw StatusError(CLANN_ERR_SERIALIZE, "unexpected number of hash functions");
+        if (n_fn == 0 || n_fn % g1.fph || n_fn > len / 12) throw StatusError(CLANN_ERR_SERIALIZE, "unexpected number of hash functions");
         out.L = (uint32_t)(n_fn / g1.fph);
         t.bytes(nullptr, n_fn * (12 + (uint64_t)kRotations * g1.npts));
         if (t.get<uint32_t>() != out.L) throw StatusError(CLANN_ERR_SERIALIZE, "table count mismatch in the hash source");
@@ -381,8 +391,17 @@ static void read_reference_stream(const uint8_t* blob, uint64_t len, LoadedStrea
             memcpy(out.indices.data() + (size_t)tb * out.n, padded.data() + kSegment, (size_t)out.n * 4);
             t.bytes(padded.data(), plen * 4);
             memcpy(out.hashes.data() + (size_t)tb * out.n, padded.data() + kSegment, (size_t)out.n * 4);
+            {
+                // the probe trusts the tables: every index must name a row, the codes must be 24-bit and sorted
+                const uint32_t* I = out.indices.data() + (size_t)tb * out.n;
+                const uint32_t* H = out.hashes.data() + (size_t)tb * out.n;
+                for (uint32_t i = 0; i < out.n; i++) {
+                    if (I[i] >= out.n) throw StatusError(CLANN_ERR_SERIALIZE, "table index out of range in the stream");
+                    if (H[i] >> kMaxHashBits || (i && H[i] < H[i - 1])) throw StatusError(CLANN_ERR_SERIALIZE, "table codes are not sorted 24-bit values");
+                }
+            }
             if (t.get<uint64_t>() != 0) throw StatusError(CLANN_ERR_SERIALIZE, "the stream holds pending (unsorted) insertions");
-            t.bytes(nullptr, 4 + ((1u << 13) + 1) * 4ull);                  // hash_length, prefix_index (rebuilt here as the 8-bit directory)
+            t.bytes(nullptr, 4 + ((1u << 13) + 1) * 4ull);                  // hash_length, prefix_index (rebuilt here as the 12-bit bucket directory)
         }
     }
     parse_reference_stream(blob, len, make_geom(out.d, out.L), out.fs, nullptr);
@@ -803,6 +822,7 @@ struct clann_index {
 
     void build() {
         cudaStream_t s = 0;
+        if (shard_rank >= shard_count) throw StatusError(CLANN_ERR_CONFIG, "shard_rank must be below shard_count");
         reset_workspaces();  // the search workspace (memo stride, tiles) depends on the clustering
         cudaEvent_t e0, e1, e2, e3;
         CLANN_CUDA(cudaEventCreate(&e0)); CLANN_CUDA(cudaEventCreate(&e1)); CLANN_CUDA(cudaEventCreate(&e2)); CLANN_CUDA(cudaEventCreate(&e3));
@@ -1041,6 +1061,17 @@ struct clann_index {
     void require_built() const {
         if (!built) throw StatusError(CLANN_ERR_NOT_BUILT, "index has not been built");
     }
+    // A cluster-sharded index holds tables for its own clusters only: the single-pass entry points would walk foreign clusters
+    // through tables that were never built. Only the stepping / sharded calls may search it.
+    void require_unsharded(const char* what) const {
+        if (shard_count > 1)
+            throw StatusError(CLANN_ERR_CONFIG, std::string(what) + " needs the whole index on this GPU; a cluster-sharded index "
+                                                "(shard_count > 1) is searched with clann_search_begin/step/merge/end or clann_search_sharded");
+    }
+    void require_owned(uint64_t cluster) const {
+        if (shard_count > 1 && h_owner[cluster] != shard_rank)
+            throw StatusError(CLANN_ERR_CONFIG, "cluster is owned by another shard: its rows and tables are not on this rank");
+    }
 
     // hashing of the query batch with every function set in use, centre ordering, state reset
     void search_begin(const float* d_queries, uint64_t nq, cudaStream_t s) {
@@ -1076,6 +1107,7 @@ struct clann_index {
 
     void search_device(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
         require_built();
+        require_unsharded("clann_search / clann_search_device");
         if (nq == 0) return;
         CLANN_CUDA(cudaEventRecord(ev[0], s));
         search_begin(d_queries, nq, s);
@@ -1097,7 +1129,7 @@ struct clann_index {
     // is complete when the call is made; results are complete once search_flush() has been waited on.
     // Fills the memo of every query's first visit in advance (launch_dense_sims) when the default probe kernel will use it.
     bool use_dense_sims(const SearchParams& p, QueryBatch& b, cudaStream_t s) {
-        if (!W->w_dense.p || W->w_dense_stride == 0 || tune_get("probe", 0) == 1) return false;  // the CTA kernel does not use it
+        if (!W->w_dense.p || W->w_dense_stride == 0) return false;
         if (h_stats && tune_get("dense_adaptive", 1) != 0) {
             const unsigned long long visited = reinterpret_cast<volatile unsigned long long*>(h_stats)[0];
             const unsigned long long queries = reinterpret_cast<volatile unsigned long long*>(h_stats)[1];
@@ -1111,7 +1143,7 @@ struct clann_index {
         // knob: 0 off, 1 anchors + every depth's range, 2 anchors + samples only (default: same total time as 1 on the glove-100
         // shape — 0.10 + 1.94 ms against 0.32 + 1.72 ms — with 13 MB instead of 94 MB of workspace per 10 000 queries)
         const int64_t fr = tune_get("first_ranges", 2);
-        if (W->w_pre_range.p && fr != 0 && tune_get("probe", 0) == 0) {
+        if (W->w_pre_range.p && fr != 0) {
             b.pre_anchor = W->w_pre_anchor.p;
             if (fr == 2) b.pre_lcp = W->w_pre_lcp.p;
             else b.pre_range = W->w_pre_range.p;
@@ -1153,6 +1185,7 @@ struct clann_index {
 
     void search_device_async(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
         require_built();
+        require_unsharded("clann_search_device_async");
         if (nq == 0) return;
         const int slot = next_pipe_slot();
         search_on_slot(slot, d_queries, nq, d_ids, d_dists, d_counts);
@@ -1162,6 +1195,7 @@ struct clann_index {
     // Host buffers (pinned, for the copies to be asynchronous): H2D, search and D2H of one batch on the slot's stream.
     void search_host_async(const float* queries, uint64_t nq, uint32_t* ids, float* dists, uint32_t* counts) {
         require_built();
+        require_unsharded("clann_search_async");
         if (nq == 0) return;
         const int slot = next_pipe_slot();
         cudaStream_t s = pipe_stream[slot];
@@ -1242,8 +1276,10 @@ int clann_set_option(clann_index* index, const char* key, int64_t value) {
         if (k == "seed") index->seed = (uint64_t)value;
         else if (k == "function_sets") index->per_cluster_functions = value != 0;
         else if (k == "strict") { if (value != 1) throw StatusError(CLANN_ERR_ARG, "only strict mode is implemented"); }
-        else if (k == "shard_rank") index->shard_rank = (uint32_t)value;
-        else if (k == "shard_count") {
+        else if (k == "shard_rank") {
+            if (value < 0 || value > 254) throw StatusError(CLANN_ERR_ARG, "shard_rank must be in 0..254");
+            index->shard_rank = (uint32_t)value;
+        } else if (k == "shard_count") {
             if (value < 1 || value > 255) throw StatusError(CLANN_ERR_ARG, "shard_count must be in 1..255");
             index->shard_count = (uint32_t)value;
         } else throw StatusError(CLANN_ERR_ARG, "unknown option '" + k + "'");
@@ -1442,6 +1478,10 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
             index->require_built();
             if (arg >= K) throw StatusError(CLANN_ERR_BOUNDS, "cluster out of range");
         };
+        auto need_owned_cluster = [&]() {  // per-cluster arrays that only the owning shard builds
+            need_cluster();
+            index->require_owned(arg);
+        };
         switch (what) {
             case CLANN_X_NUM_CLUSTERS: {
                 uint64_t k64 = K;
@@ -1468,12 +1508,12 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 emit_dev(index->d_q15.p + index->h_offsets[arg] * index->g.sl, (uint64_t)index->h_sizes[arg] * index->g.sl * 2);
                 break;
             case CLANN_X_SKETCHES:
-                need_cluster();
+                need_owned_cluster();
                 emit_dev(index->d_sketches.p + index->h_offsets[arg] * kNumSketches, (uint64_t)index->h_sizes[arg] * kNumSketches * 8);
                 break;
             case CLANN_X_TABLE_HASHES:
             case CLANN_X_TABLE_INDICES: {
-                need_cluster();
+                need_owned_cluster();
                 const uint32_t nc = index->h_sizes[arg], L = index->g.L;
                 const uint64_t bytes = (uint64_t)L * nc * 4;
                 if (size) *size = bytes;
@@ -1529,7 +1569,7 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
             }
             case CLANN_X_BUILD_MS: emit(index->build_ms, sizeof(index->build_ms)); break;
             case CLANN_X_REFERENCE_STREAM: {
-                need_cluster();
+                need_owned_cluster();
                 if (index->h_brute[arg] || index->h_sizes[arg] == 0)
                     throw StatusError(CLANN_ERR_SERIALIZE, "brute-force clusters have no PUFFINN index (index.rs:204-205)");
                 const uint32_t nc = index->h_sizes[arg], L = index->g.L;
@@ -1544,9 +1584,45 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 break;
             }
             case CLANN_X_TABLE_DIR: {
-                need_cluster();
+                need_owned_cluster();
                 const uint64_t L = index->g.L;
                 emit_dev(index->d_tbl_dir.p + (uint64_t)arg * L * kDirEntries, L * kDirEntries * 4);
+                break;
+            }
+            case CLANN_X_QUERY_ANCHORS:
+            case CLANN_X_QUERY_RANGES: {
+                need_cluster();
+                if (index->last_nq == 0 || !index->W->w_codes.p) throw StatusError(CLANN_ERR_NOT_BUILT, "no search batch to trace yet");
+                if (index->h_brute[arg] || index->h_sizes[arg] == 0 || (index->shard_count > 1 && index->h_owner[arg] != index->shard_rank))
+                    throw StatusError(CLANN_ERR_ARG, "cluster has no tables on this rank (brute-force, empty or foreign)");
+                const uint64_t nq = index->last_nq, L = index->g.L;
+                const uint64_t na = nq * L, nr = nq * kMaxHashBits * L * 2;
+                const uint64_t bytes = (what == CLANN_X_QUERY_ANCHORS ? na : nr) * 4;
+                if (size) *size = bytes;
+                if (dst) {
+                    if (cap < bytes) throw StatusError(CLANN_ERR_BOUNDS, "export buffer too small");
+                    DevBuf<uint32_t> d_a, d_r;
+                    d_a.alloc(na);
+                    d_r.alloc(nr);
+                    SearchParams p = index->params();
+                    QueryBatch b = index->batch(index->cur_queries, nq, nullptr, nullptr, nullptr);
+                    launch_export_ranges(p, b, (uint32_t)arg, d_a.p, d_r.p, 0);
+                    CLANN_CUDA(cudaMemcpy(dst, what == CLANN_X_QUERY_ANCHORS ? d_a.p : d_r.p, bytes, cudaMemcpyDeviceToHost));
+                }
+                break;
+            }
+            case CLANN_X_STOP_POINTS: {
+                index->require_built();
+                const uint64_t nq = index->last_nq;
+                const uint64_t sb = query_state_bytes((uint32_t)index->cfg.k);
+                std::vector<uint8_t> st = index->W->w_state.download(nq * sb);
+                std::vector<uint32_t> outv(nq * 2);
+                for (uint64_t q = 0; q < nq; q++) {
+                    const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(st.data() + q * sb);
+                    outv[2 * q] = (uint32_t)(h->stop_point >> 32);
+                    outv[2 * q + 1] = (uint32_t)h->stop_point;
+                }
+                emit(outv.data(), outv.size() * 4);
                 break;
             }
             default: throw StatusError(CLANN_ERR_ARG, "unknown export selector");
@@ -1706,6 +1782,23 @@ void CPUFFINN_save_index(CPUFFINN* index, const char* file_name, int index_numbe
         std::vector<uint32_t> th = ix->d_tbl_hash.download((size_t)L * nc), ti = ix->d_tbl_idx.download((size_t)L * nc);
         std::vector<uint8_t> blob = write_reference_stream(ix->g, ix->fsets[0], nc, rows.data(), sks.data(), th.data(), ti.data());
         const std::string name = "index_" + std::to_string(index_number);
+        {
+            // The reference appends an HDF5 dataset to the file ClusteredIndex::serialize has just created (index.rs:526-552,
+            // c_binder.cpp:106-146). There is no HDF5 here: appending records to such a file would produce a container neither
+            // side can read, so anything that is not empty and does not start with a CLB2REC record is refused, loudly.
+            FILE* probe = fopen(file_name, "rb");
+            if (probe) {
+                char head[8];
+                const size_t got = fread(head, 1, 8, probe);
+                fclose(probe);
+                if (got > 0 && (got < 8 || memcmp(head, "CLB2REC", 8) != 0)) {
+                    g_last_error = std::string("CPUFFINN_save_index: ") + file_name + " is not a libclann_b200 record file (an HDF5 "
+                                   "container written by the unmodified crate?); persistence through HDF5 is not supported, nothing written";
+                    fprintf(stderr, "Error: %s\n", g_last_error.c_str());
+                    return;
+                }
+            }
+        }
         FILE* f = fopen(file_name, "ab");
         if (!f) {
             fprintf(stderr, "Error opening file: %s\n", file_name);
@@ -1738,6 +1831,12 @@ CPUFFINN* CPUFFINN_load_from_file(const char* file_name, const char* dataset_nam
     try {
         std::vector<uint8_t> blob;
         bool found = false;
+        uint64_t file_size = 0;
+        if (fseek(f, 0, SEEK_END) == 0) {
+            const long e = ftell(f);
+            file_size = e > 0 ? (uint64_t)e : 0;
+        }
+        rewind(f);
         for (;;) {
             char magic[8];
             uint32_t name_len, reserved;
@@ -1749,10 +1848,11 @@ CPUFFINN* CPUFFINN_load_from_file(const char* file_name, const char* dataset_nam
             std::string name(name_len, '\0');
             if (fread(&name[0], 1, name_len, f) != name_len) throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
             if (name == dataset_name) {  // the last record of that name wins (the file is append-only)
+                if (payload_len > file_size) throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
                 blob.resize(payload_len);
                 if (fread(blob.data(), 1, payload_len, f) != payload_len) throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
                 found = true;
-            } else if (fseek(f, (long)payload_len, SEEK_CUR) != 0) {
+            } else if (payload_len > (uint64_t)0x7fffffffffffll || fseek(f, (long)payload_len, SEEK_CUR) != 0) {
                 throw StatusError(CLANN_ERR_SERIALIZE, "truncated record file");
             }
         }

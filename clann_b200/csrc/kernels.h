@@ -142,11 +142,13 @@ bool dense_sims_supported(const SearchParams& p);
 // Anchors (prefixmap.hpp:36-57) and the ranges of all 24 depths (prefixmap.hpp:267-304) of every query in its nearest cluster,
 // one thread per (query, table) instead of a dependent chain inside the probe; needs b.codes, sorted b.first and b.qperm.
 void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+// Trace export for the parity tests: anchors[nq*L] and ranges[nq*24*L*2] of the batch's queries in `cluster`, in the
+// reference's padded table coordinates (needs b.codes of the last search_begin).
+void launch_export_ranges(const SearchParams& p, const QueryBatch& b, uint32_t cluster, uint32_t* anchors, uint32_t* ranges,
+                          cudaStream_t s);
 // Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
 void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query
-void launch_probe_cta(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);   // one CTA per query
-void launch_probe_pipelined(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query, few in flight
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 uint32_t probe_memo_slots();  // upper bound on the memo regions any probe launch uses on the current device

@@ -238,7 +238,7 @@ __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t 
     h->candidates = 0;
     h->distcomp = 0;
     h->last_key = 0;
-    h->pad = 0;
+    h->stop_point = 0;
 }
 
 // Per-warp scratch carved out of dynamic shared memory.
@@ -438,6 +438,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     if (memo_bar) pc_mbar_wait(memo_bar, memo_phase);  // the pre-filled memo was bulk-copied to shared memory behind the anchors
 
     bool stopped = false;
+    ctr.stop_point = 0;
     for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
         // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
         uint32_t running = 0;
@@ -564,6 +565,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (table_idx >> 5));
             if ((word >> (table_idx & 31)) & 1u) {
                 stopped = true;
+                ctr.stop_point = ((unsigned long long)depth << 32) | table_idx;
                 break;
             }
         } while (base + kRing < S);
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
         uint32_t pos = st->next_pos;
         unsigned long long last_key = st->last_key;
         uint32_t visited = st->visited;
-        ProbeCounters ctr{st->candidates, st->distcomp};
+        ProbeCounters ctr{st->candidates, st->distcomp, st->stop_point};
         for (uint32_t i = lane; i < heap_len; i += 32) sm.heap[i] = st_heap[i];
         // query row -> shared memory and this lane's 16-byte chunk -> registers
         for (uint32_t i = lane; i < p.g.sl / 2; i += 32)
@@ -770,6 +772,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
             st->done = done ? 1u : 0u;
             st->candidates = ctr.candidates;
             st->distcomp = ctr.distcomp;
+            st->stop_point = ctr.stop_point;
         }
         __syncwarp();
     }
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatc
         qreg[0] = unpack_lo(w.x); qreg[1] = unpack_hi(w.x); qreg[2] = unpack_lo(w.y); qreg[3] = unpack_hi(w.y);
         qreg[4] = unpack_lo(w.z); qreg[5] = unpack_hi(w.z); qreg[6] = unpack_lo(w.w); qreg[7] = unpack_hi(w.w);
     }
-    ProbeCounters ctr{0, 0};
+    ProbeCounters ctr{0, 0, 0};
     uint32_t cnt;
     if (p.n < 100) {  // collection.hpp:550-555
         cnt = probe_bruteforce_q15<G>(p, sm, 0, qrow, qreg, qreg_valid);
@@ -921,6 +924,42 @@ __global__ void __launch_bounds__(256) k_first_ranges(SearchParams p, QueryBatch
         const uint32_t start = table_range(H, dir, nc, h, A, up, dn, depth, nseg);
         out[(size_t)(depth - 1) * L] = nseg | (start == A ? 0x80000000u : 0u);  // start == A: upward (or empty: nseg == 0)
     }
+}
+
+// Order-free trace of the probe (SURVEY.md 8b clann_export_trace): the anchor of every query of the batch in every table of
+// cluster c (prefixmap.hpp:36-57,250-260) and the range get_next_range returns at each of its 24 calls (prefixmap.hpp:267-304),
+// in the reference's own coordinates (positions in the table padded by 12 sentinels each side): anchors[q*L + t],
+// ranges[((q*24 + it)*L + t)*2 + {0,1}] = {start, end} of call it = 0..23 (depth 24 - it). The same table_anchor /
+// table_range the probe kernel uses, so the parity tests pin them directly against the reference's golden arrays.
+__global__ void __launch_bounds__(256) k_export_ranges(SearchParams p, QueryBatch b, uint32_t c, uint32_t* __restrict__ anchors,
+                                                       uint32_t* __restrict__ ranges) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = p.g.L;
+    if (i >= b.nq * L) return;
+    const uint32_t q = (uint32_t)(i / L), t = (uint32_t)(i % L);
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t h = b.codes[((uint64_t)p.fset_of[c] * L + t) * b.nq + q];
+    const uint32_t* H = p.tbl_hash + table_base(off, nc, L, t);
+    const uint32_t* dir = p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries;
+    uint32_t A;
+    uint2 up, dn;
+    table_anchor(H, dir, nc, h, A, up, dn);
+    anchors[(uint64_t)q * L + t] = A + kSegment;
+    for (uint32_t it = 0; it < (uint32_t)kMaxHashBits; it++) {
+        uint32_t nseg;
+        const uint32_t start = table_range(H, dir, nc, h, A, up, dn, kMaxHashBits - it, nseg);
+        uint32_t* out = ranges + (((uint64_t)q * kMaxHashBits + it) * L + t) * 2;
+        out[0] = start + kSegment;
+        out[1] = start + kSegment + 4 * nseg;
+    }
+}
+
+void launch_export_ranges(const SearchParams& p, const QueryBatch& b, uint32_t cluster, uint32_t* anchors, uint32_t* ranges,
+                          cudaStream_t s) {
+    if (b.nq == 0) return;
+    const uint64_t threads = b.nq * p.g.L;
+    k_export_ranges<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p, b, cluster, anchors, ranges);
 }
 
 void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
@@ -1153,16 +1192,13 @@ static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop
 }
 
 void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
-    const int mode = (int)tune_get("probe", 0);  // knob: 0 = one warp per query, 1 = one CTA per query, 2 = pipelined warp per query
     static int64_t fetch_set = 0;
     const int64_t fetch = tune_get("l2_fetch", 0);  // knob: cudaLimitMaxL2FetchGranularity in bytes (32/64/128), 0 = leave alone
     if (fetch != fetch_set && fetch > 0) {
         CLANN_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch));
         fetch_set = fetch;
     }
-    if (mode == 1) launch_probe_cta(p, b, stop_at_foreign, s);
-    else if (mode == 2) launch_probe_pipelined(p, b, stop_at_foreign, s);
-    else launch_probe_warp(p, b, stop_at_foreign, s);
+    launch_probe_warp(p, b, stop_at_foreign, s);
 }
 
 void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {

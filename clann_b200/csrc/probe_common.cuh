@@ -1,5 +1,4 @@
-// Device helpers shared by the probe kernels (kernels_search.cu: one warp per query; kernels_probe_cta.cu: one CTA per
-// query): per-query state, fp32 distance, warp primitives, TopKClosestHeap and MaxBuffer emulation, range helpers.
+// Device helpers of the probe kernel (kernels_search.cu: one warp per query): per-query state, fp32 distance, warp primitives, TopKClosestHeap and MaxBuffer emulation, range helpers.
 // Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
 #pragma once
 
@@ -18,7 +17,7 @@ struct QueryStateHeader {
     unsigned long long candidates;  // performance.hpp:82-86 summed over visits
     unsigned long long distcomp;    // performance.hpp:72-76 summed over visits
     unsigned long long last_key;    // (order_bits(centre distance) << 32 | cluster) of the last consumed cluster, 0 = none
-    unsigned long long pad;
+    unsigned long long stop_point;  // last PUFFINN visit: (stop depth << 32) | table index at the stop (collection.hpp:927-943), 0 = no stop
     // followed by k x u64 heap keys: (order_bits(distance) << 32) | point id
 };
 
@@ -220,6 +219,7 @@ __device__ __forceinline__ void maxbuffer_insert_list(unsigned long long* mb, ui
 
 struct ProbeCounters {
     unsigned long long candidates, distcomp;
+    unsigned long long stop_point;  // of the last visit: (depth << 32) | table_idx where the stop rule fired, 0 = ran out of depths
 };
 
 __device__ __forceinline__ uint32_t lcp24(uint32_t a, uint32_t b) {

@@ -134,11 +134,19 @@ typedef enum {
     CLANN_X_QUERY_SKETCHES = 14, /* u64[nq*32] likewise */
     CLANN_X_CLUSTER_ORDER = 15,  /* u32[nq*K] visiting order of the last search batch (index.rs:592-616) */
     CLANN_X_BUILD_MS = 16,    /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
-    CLANN_X_TABLE_DIR = 17,   /* u32[L*257] bucket directory of cluster `arg`: first position per top code byte (the role of
-                                 PrefixMap::prefix_index, prefixmap.hpp:86,231-240, at 8 bits), table-major */
-    CLANN_X_REFERENCE_STREAM = 18 /* bytes of puffinn::Index::serialize (collection.hpp:185-203) for cluster `arg`: what the CPU
+    CLANN_X_TABLE_DIR = 17,   /* u32[L*4097] bucket directory of cluster `arg`: entry b of table t = first position whose top 12
+                                 code bits are >= b, entry 4096 = cluster size (the role of PrefixMap::prefix_index,
+                                 prefixmap.hpp:86,231-240, at 12 instead of 13 bits), table-major */
+    CLANN_X_REFERENCE_STREAM = 18, /* bytes of puffinn::Index::serialize (collection.hpp:185-203) for cluster `arg`: what the CPU
                                  reference would write for the same rows and functions, loadable by Index(std::istream&) —
                                  persistence compatible with the reference without HDF5 (CPUFFINN_save_index's payload) */
+    /* order-free probe traces of the last search batch against cluster `arg` (SURVEY.md 8b clann_export_trace), in the
+       reference's coordinates: positions in the table padded by 12 sentinels each side (prefixmap.hpp:215-226) */
+    CLANN_X_QUERY_ANCHORS = 19, /* u32[nq*L]       PrefixMapQuery anchors (prefixmap.hpp:36-57,250-260) */
+    CLANN_X_QUERY_RANGES = 20,  /* u32[nq*24*L*2]  {start, end} returned by call it = 0..23 of get_next_range
+                                   (prefixmap.hpp:267-304; depth 24 - it), layout [query][it][table][2] */
+    CLANN_X_STOP_POINTS = 21    /* u32[nq*2]       {depth, table index} at which the stop rule (collection.hpp:927-943) ended the
+                                   last PUFFINN visit of each query of the last batch; {0, 0} = the visit ran out of depths */
 } clann_export_what;
 int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size);
 

@@ -33,7 +33,7 @@ def test_gpu_matches_golden_fixture(name):
     n = len(data)
     for si, (k, rec, ms) in enumerate(g["searches"]):
         if not np.isinf(ms):
-            continue  # max_sim is internal to the CLANN loop; the first cluster always sees -inf (index.rs:329)
+            continue  # an explicit max_sim only exists in the legacy call: test_gpu_matches_golden_fixture_with_max_sim
         ix = _single_cluster_index(cb, data, L, int(k), float(rec), g["stream"].tobytes())
         ids, dists, counts = ix.search_batch(queries)
         ctr = ix.counters(len(queries))
@@ -51,6 +51,68 @@ def test_gpu_matches_golden_fixture(name):
         key = th.astype(np.int64)
         assert np.all(np.diff(key, axis=1) >= 0)
         ix.close()
+
+
+def _write_record_file(path, name, payload):
+    """One CLB2REC record (the flat container CPUFFINN_save_index writes; layout in index.cu)."""
+    with open(path, "wb") as f:
+        f.write(b"CLB2REC\0")
+        f.write(np.array([len(name), 0], np.uint32).tobytes())
+        f.write(np.array([len(payload)], np.uint64).tobytes())
+        f.write(name.encode())
+        f.write(payload)
+
+
+@pytest.mark.parametrize("name", ["puffinn_d25", "puffinn_d100"])
+def test_gpu_matches_golden_fixture_with_max_sim(name, tmp_path):
+    """Every golden search, including those with an explicit max_sim (CLANN's addition to the stop rule, collection.hpp:324-330,
+    927-943), through the legacy symbol that takes it: CPUFFINN_load_from_file on the reference's own stream, then
+    CPUFFINN_search_cosine(query, k, recall, max_sim). Ids (as sets; the golden order is the reference's tie order) and
+    the distance-computation counter must equal the real reference's."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    path = str(tmp_path / "golden.clb2")
+    _write_record_file(path, "index_0", g["stream"].tobytes())
+    L = cl.load()
+    handle = L.CPUFFINN_load_from_file(path.encode(), b"index_0")
+    assert handle, cl.last_error()
+    d = g["queries"].shape[1]
+    checked_ms = 0
+    for si, (k, rec, ms) in enumerate(g["searches"]):
+        k = int(k)
+        for qi, q in enumerate(g["queries"]):
+            q = np.ascontiguousarray(q, np.float32)
+            ptr = L.CPUFFINN_search_cosine(handle, q.ctypes.data, k, float(rec), float(ms), d)
+            assert ptr
+            got = [ptr[i] for i in range(max(k, 1))]
+            C.CDLL(None).free(ptr)
+            cnt = int(g["res_cnt"][si, qi])
+            assert sorted(got[:cnt]) == sorted(g["res_ids"][si, qi, :cnt].tolist()), (si, qi)
+            assert all(v == 0xFFFFFFFF for v in got[cnt:])
+            assert L.CPUFFINN_get_distance_computations() == int(g["res_met"][si, qi, 0]), (si, qi)
+        checked_ms += int(not np.isinf(ms))
+    assert checked_ms > 0  # the fixture does hold searches with a finite max_sim
+
+
+def test_legacy_save_refuses_foreign_container(tmp_path):
+    """ClusteredIndex::serialize in the unmodified crate creates an HDF5 file and hands the same path to CPUFFINN_save_index
+    (index.rs:526-552). Without HDF5 here the call must not append records to such a file: it refuses and leaves the file
+    untouched; a fresh or CLB2REC file is appended to as before."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    data = util.planted(400, 16, 55, n_centers=2)
+    index, _ = cb.PuffinnIndex.new(cb.AngularData(data), 6)
+    foreign = tmp_path / "index_x.h5"
+    foreign.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    before = foreign.read_bytes()
+    cl.load().CPUFFINN_save_index(index.raw, str(foreign).encode(), 3)
+    assert foreign.read_bytes() == before
+    assert "not a libclann_b200 record file" in cl.last_error()
+    assert not cl.load().CPUFFINN_load_from_file(str(foreign).encode(), b"index_3")
+    ok = tmp_path / "fresh.clb2"
+    index.save_to_file(str(ok), 3)
+    assert ok.read_bytes()[:8] == b"CLB2REC\0"
 
 
 def test_legacy_abi_recall():
@@ -130,16 +192,17 @@ def test_edge_cases_against_oracle(oracle):
     assert np.array_equal(cen, oc) and np.array_equal(asg, oa)
     brute = ix.export(cl.X_BRUTE, 0, np.uint8)
     orc = oracle.clann(data, 4, 0.9, cen, asg, rad)
-    est = None
-    for ci in range(K):
+    assert brute.any()                     # the shape does produce brute-force clusters (index.rs:204-205)
+    for ci in range(K):                    # ... and whatever is not brute force is searched by the oracle over the same tables
         if not brute[ci]:
-            est = ix.export(cl.X_EST, ci, np.float32)
-    qs = np.concatenate([util.planted_queries(data, 20, 6), data[20:22]])
-    if brute.all():
-        ids, dists, counts = ix.search_batch(qs)
-        for i, q in enumerate(qs):
-            o_ids, o_d, _, _ = orc.search(q)
-            assert util.same_ids_up_to_ties(ids[i, : counts[i]], dists[i, : counts[i]], o_ids.astype(np.uint32), o_d)
+            orc.set_cluster_stream(ci, ix.export(cl.X_REFERENCE_STREAM, ci, np.uint8).tobytes())
+    qs = np.concatenate([util.planted_queries(data, 20, 6), data[20:22], data[10:11] + 1e-3])
+    ids, dists, counts = ix.search_batch(qs)
+    ctr = ix.counters(len(qs))
+    for i, q in enumerate(qs):
+        o_ids, o_d, _, o_ctr = orc.search(q)
+        assert util.same_ids_up_to_ties(ids[i, : counts[i]], dists[i, : counts[i]], o_ids.astype(np.uint32), o_d), i
+        assert int(ctr["clusters_visited"][i]) == o_ctr["visited"] and int(ctr["distance_computations"][i]) == o_ctr["distance_computations"]
     ix.close(); orc.free()
     # (c) k larger than every cluster -> every cluster is brute force (index.rs:204-205), results exact
     data = util.planted(1200, 10, 7)
@@ -301,21 +364,17 @@ np.savez(sys.argv[2], ids=ids, dists=dists, counts=counts, cand=ctr["candidates"
 
 
 def test_probe_kernel_variants_agree(tmp_path):
-    """Probe kernel variants (clann_tune "probe" / "probe_nomemo" / launch shapes): the one-warp-per-query kernel with and
-    without the similarity memo, with fewer resident warps, and the warp-specialised one-CTA-per-query kernel must return
-    identical ids, distance bits and reference counters (candidates, distance_computations, clusters visited) for the same
+    """Probe schedule variants (clann_tune knobs: dense first-visit similarities on / off, first-visit anchors / ranges /
+    stream on / off, memo in shared or global memory or absent, launch shapes): every variant must return identical ids, distance bits and reference counters (candidates, distance_computations, clusters visited) for the same
     index and queries — planted queries plus uniform ones that walk many clusters."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     variants = (("warp", {}), ("warp_no_dense_sims", {"CLANN_TUNE_DENSE_SIMS": "0"}),
-                ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "0"}), ("warp_all_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "1"}), ("warp_no_smem_memo", {"CLANN_TUNE_PROBE_SMEM_MEMO": "0"}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}), ("cta", {"CLANN_TUNE_PROBE": "1"}),
+                ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "0"}), ("warp_all_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "1"}), ("warp_no_smem_memo", {"CLANN_TUNE_PROBE_SMEM_MEMO": "0"}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}),
                 ("warp_small_grid", {"CLANN_TUNE_PROBE_WARPS": "4", "CLANN_TUNE_PROBE_CTAS": "1"}),
-                ("warp_longest_first_prefetch", {"CLANN_TUNE_ORDER_LONGEST_FIRST": "1", "CLANN_TUNE_PROBE_PREFETCH_ROWS": "1"}),
-                ("pipelined", {"CLANN_TUNE_PROBE": "2"}),
-                ("pipelined_small_stage", {"CLANN_TUNE_PROBE": "2", "CLANN_TUNE_PROBE2_STAGE_ROWS": "5", "CLANN_TUNE_PROBE2_WARPS": "4"}),
-                ("pipelined_nomemo", {"CLANN_TUNE_PROBE": "2", "CLANN_TUNE_PROBE_NOMEMO": "1"}))
+                ("warp_longest_first_prefetch", {"CLANN_TUNE_ORDER_LONGEST_FIRST": "1", "CLANN_TUNE_PROBE_PREFETCH_ROWS": "1"}))
     for name, env in variants:
         out = str(tmp_path / (name + ".npz"))
         e = {k: v for k, v in os.environ.items() if not k.startswith("CLANN_TUNE_")}
