@@ -467,6 +467,11 @@ struct clann_index {
         DevBuf<unsigned long long> w_stats;           // {running sum of clusters visited, finished-block ticket} of k_finish
         DevBuf<uint32_t> w_pre_anchor, w_pre_range;  // first-visit anchors [nq][L] and ranges [nq][24][L]
         DevBuf<uint4> w_pre_lcp;                     // first-visit common-prefix samples [nq][L]
+        // first-visit candidate stream (QueryBatch::fs_*): [nq][w_fs_cap] segments
+        DevBuf<uint16_t> w_fs_idx;
+        DevBuf<uint32_t> w_fs_hd, w_fs_meta;
+        DevBuf<uint8_t> w_fs_tab;
+        uint32_t w_fs_cap = 0;
         DevBuf<RowTile> w_tiles, w_tiles_codes;
         uint32_t w_ntiles = 0;
         uint64_t w_tiles_codes_nq = 0;
@@ -1003,6 +1008,22 @@ struct clann_index {
                 W->w_pre_range.ensure(words);
                 W->w_pre_lcp.ensure(nq * g.L);
             }
+            // first-visit candidate stream: room for 2 x the largest cluster in segments per query (a visit scans ~4 candidates
+            // per cluster row on the planted shapes, p99 ~2x that), 12 bytes per segment; only what a visit needs is written
+            W->w_fs_cap = 0;
+            if (W->w_dense_stride && max_cluster <= 65536u && g.L <= 255) {
+                uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(2ull * max_cluster, 1024), 16384);
+                const int64_t knob = tune_get("first_stream_cap", 0);
+                if (knob > 0) cap = (uint64_t)knob;
+                cap = (cap + 31) & ~31ull;
+                if (nq * cap * 12 <= (6ull << 30)) {
+                    W->w_fs_idx.ensure(nq * cap * 4);
+                    W->w_fs_hd.ensure(nq * cap);
+                    W->w_fs_tab.ensure(nq * cap / 32);
+                    W->w_fs_meta.ensure(nq * kFsMeta);
+                    W->w_fs_cap = (uint32_t)cap;
+                }
+            }
         }
         W->w_counter.ensure(2);
         if (!W->w_stats.p) {
@@ -1047,6 +1068,11 @@ struct clann_index {
         b.pre_anchor = nullptr;
         b.pre_range = nullptr;
         b.pre_lcp = nullptr;
+        b.fs_idx = nullptr;
+        b.fs_hd = nullptr;
+        b.fs_tab = nullptr;
+        b.fs_meta = nullptr;
+        b.fs_cap = W->w_fs_cap;
         b.stats_dev = (d_ids && h_stats_dev) ? W->w_stats.p : nullptr;
         b.stats_host = h_stats_dev;
         b.out_ids = d_ids;
@@ -1142,6 +1168,19 @@ struct clann_index {
         }
         // knob: 0 off, 1 anchors + every depth's range, 2 anchors + samples only (default: same total time as 1 on the glove-100
         // shape — 0.10 + 1.94 ms against 0.32 + 1.72 ms — with 13 MB instead of 94 MB of workspace per 10 000 queries)
+        // knob first_stream (default 1): the whole first visit's candidate stream ahead of the probe (launch_first_stream); it
+        // includes the anchors, so first_ranges is not launched then
+        if (W->w_fs_cap && tune_get("first_stream", 1) != 0) {
+            b.fs_idx = W->w_fs_idx.p;
+            b.fs_hd = W->w_fs_hd.p;
+            b.fs_tab = W->w_fs_tab.p;
+            b.fs_meta = W->w_fs_meta.p;
+            if (launch_first_stream(p, b, s)) {
+                last_pre_launches = 2;
+                return true;
+            }
+            b.fs_idx = nullptr; b.fs_hd = nullptr; b.fs_tab = nullptr; b.fs_meta = nullptr;
+        }
         const int64_t fr = tune_get("first_ranges", 2);
         if (W->w_pre_range.p && fr != 0) {
             b.pre_anchor = W->w_pre_anchor.p;

@@ -80,6 +80,8 @@ struct SearchParams {
     uint32_t prefetch_rows;    // probe kernel: bulk-prefetch the Q15 rows of a batch into the L2 before gathering them
 };
 
+constexpr uint32_t kFsMeta = 52;  // u32 words of stream metadata per query (QueryBatch::fs_meta)
+
 struct QueryBatch {
     uint64_t nq;
     const float* queries;   // [nq][d]
@@ -114,6 +116,22 @@ struct QueryBatch {
     // pre_lcp[q * L + t] = the stride-12 common-prefix samples of table_anchor (up.x, up.y, dn.x, dn.y); with pre_range null
     // the probe takes anchors and samples from here and evaluates the ranges itself, depth by depth, as far as it gets
     uint4* pre_lcp;
+    // First-visit candidate stream (launch_first_stream): the candidates of every query's first visit laid out in the order
+    // search_maps consumes them — depth by depth, ring sweep by ring sweep — with the sketch test already evaluated as a
+    // Hamming distance. Per query q (stride fs_cap segments; a segment = 4 candidates = one ring slot, collection.hpp:802-808):
+    //   fs_idx[(q*fs_cap + s)*4 + j]  local id of candidate j of stream segment s (u16: clusters up to 65 536 rows)
+    //   fs_hd[q*fs_cap + s]           byte j = popcount(sketch[id_j][slot] ^ query_sketch[slot]), slot = s mod 32 (filterer.hpp:28-31)
+    //   fs_tab[(q*fs_cap + s) / 32]   table of the first segment of the ring sweep that starts at s (stop rule, collection.hpp:927-943)
+    //   fs_meta[q*kFsMeta + ..]       [depth-1] = segments of the depth's stream, [24 + depth-1] = its first segment in the
+    //                                 stream, [48] = lowest depth present (25 = none): deeper levels are evaluated by the probe
+    // The block of a depth starts at a multiple of 32 segments. How deep the stream goes is a prediction (the first depth at
+    // whose end the stop rule fires for the cluster's true k-th similarity); it never changes a result: the probe takes what
+    // is there and evaluates the rest itself. null = not computed.
+    uint16_t* fs_idx;
+    uint32_t* fs_hd;
+    uint8_t* fs_tab;
+    uint32_t* fs_meta;
+    uint32_t fs_cap;
     // outputs
     uint32_t* out_ids;      // [nq][k]
     float* out_dists;       // [nq][k]
@@ -142,6 +160,11 @@ bool dense_sims_supported(const SearchParams& p);
 // Anchors (prefixmap.hpp:36-57) and the ranges of all 24 depths (prefixmap.hpp:267-304) of every query in its nearest cluster,
 // one thread per (query, table) instead of a dependent chain inside the probe; needs b.codes, sorted b.first and b.qperm.
 void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+// The first-visit candidate stream of every query (QueryBatch::fs_*): anchors, per-depth ranges, table indices and the sketch
+// test of every candidate of the first visit, as one warp per query with every load independent of the search state — the
+// probe kernel then replays the sequential decisions from a linear stream. Needs b.dense (launch_dense_sims) for the depth
+// prediction, sorted b.first and b.qperm. Returns false when the geometry is unsupported (then nothing was written).
+bool launch_first_stream(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // Trace export for the parity tests: anchors[nq*L] and ranges[nq*24*L*2] of the batch's queries in `cluster`, in the
 // reference's padded table coordinates (needs b.codes of the last search_begin).
 void launch_export_ranges(const SearchParams& p, const QueryBatch& b, uint32_t cluster, uint32_t* anchors, uint32_t* ranges,

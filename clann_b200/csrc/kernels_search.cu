@@ -390,13 +390,21 @@ __device__ __forceinline__ void rerank(const WarpSmem& sm, uint32_t count, const
 // best entries, best first (maxbuffer.hpp:79-96). `codes` points at this query's code of table 0 (stride code_stride).
 // AHEAD (the 128-register instantiations): anchors for three tables per lane in lockstep, and the table indices of the next
 // ring sweep are requested before the sketch words of the current one, so a sweep costs one memory round trip instead of two.
+// This query's slice of the first-visit candidate stream (QueryBatch::fs_*); meta == nullptr = no stream.
+struct FsView {
+    const uint2* idx;      // 4 x u16 local ids per segment
+    const uint32_t* hd;    // 4 x u8 Hamming distances per segment
+    const uint8_t* tab;    // table of the first segment of every ring sweep
+    const uint32_t* meta;  // kFsMeta words
+};
+
 template <int G, bool AHEAD = false>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
                                   const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr,
                                   bool memo_prefilled = false, unsigned long long* memo_bar = nullptr, uint32_t memo_phase = 0,
                                   const uint32_t* __restrict__ pre_anchor = nullptr, const uint32_t* __restrict__ pre_range = nullptr,
-                                  const uint4* __restrict__ pre_lcp = nullptr) {
+                                  const uint4* __restrict__ pre_lcp = nullptr, FsView fs = FsView{nullptr, nullptr, nullptr, nullptr}) {
     const uint32_t L = p.g.L, k = p.k;
     const uint32_t lane = lane_id();
     const uint64_t off = p.offsets[c];
@@ -411,8 +419,13 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         for (uint32_t i = lane; i < (nc + 7) / 8; i += 32) mz[i] = make_uint4(0, 0, 0, 0);
     }
 
+    // --- first-visit candidate stream: the depths down to fs_lo are replayed from it; anchors and ranges are only computed if
+    // the visit goes deeper than the stream (or there is none)
+    const uint32_t fs_lo = (AHEAD && fs.meta) ? __ldg(fs.meta + 48) : (uint32_t)kMaxHashBits + 1;
+    bool anchors_ready = fs_lo > (uint32_t)kMaxHashBits;
     // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
-    if (AHEAD && pre_range) {  // anchors and every depth's range computed in advance by k_first_ranges
+    if (!anchors_ready) {
+    } else if (AHEAD && pre_range) {  // anchors and every depth's range computed in advance by k_first_ranges
         for (uint32_t t = lane; t < L; t += 32) sm.anchor[t] = __ldg(pre_anchor + t);
     } else if (AHEAD && pre_lcp) {  // anchors and samples computed in advance; ranges evaluated here as far as the visit gets
         for (uint32_t t = lane; t < L; t += 32) {
@@ -440,9 +453,18 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     bool stopped = false;
     ctr.stop_point = 0;
     for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
+        const bool streamed = AHEAD && depth >= fs_lo;
+        uint32_t soff = 0;  // first segment of this depth's block in the stream
         // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
         uint32_t running = 0;
-        for (uint32_t t0 = 0; t0 < L; t0 += 32) {
+        if (streamed) {
+            running = __ldg(fs.meta + depth - 1);
+            soff = __ldg(fs.meta + kMaxHashBits + depth - 1);
+        } else if (!anchors_ready) {  // the visit outlived the stream: from here on it is probed the ordinary way
+            if constexpr (AHEAD) anchors_lockstep(p, sm, c, off, nc, codes, code_stride);
+            anchors_ready = true;
+        }
+        for (uint32_t t0 = 0; t0 < L && !streamed; t0 += 32) {
             const uint32_t t = t0 + lane;
             uint32_t nseg = 0;
             if (AHEAD && pre_range) {
@@ -459,7 +481,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             if (t < L) sm.segbase[t] = running + ex;
             running += total;
         }
-        if (lane == 0) sm.segbase[L] = running;
+        if (lane == 0 && !streamed) sm.segbase[L] = running;
         __syncwarp();
         const uint32_t S = running;
         if (S <= kRing) continue;  // the initial ring fill swallows the whole stream (collection.hpp:802-810)
@@ -477,16 +499,24 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         };
 
         uint32_t base = 0;  // first stream segment held by the ring
-        bool have = false;  // AHEAD: n0..n3 hold this lane's segment of the full ring [base, base + 32)
-        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        bool have = false;  // AHEAD: n0..n3 (and nh) hold this lane's segment of the full ring [base, base + 32)
+        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0, nh = 0;
+        // one lane's segment of the stream: ids as 4 x u16, Hamming distances as 4 x u8
+        auto stream_load = [&](uint32_t s, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3, uint32_t& h4) {
+            const uint2 iv = __ldg(fs.idx + soff + s);
+            h4 = __ldg(fs.hd + soff + s);
+            a0 = iv.x & 0xffffu; a1 = iv.x >> 16; a2 = iv.y & 0xffffu; a3 = iv.y >> 16;
+        };
         do {
             uint32_t np = 0;
             uint32_t missing = (base + kRing > S) ? (base + kRing - S > kRing ? kRing : base + kRing - S) : 0;
             while (np < kFilterBuffer && missing == 0) {  // collection.hpp:813-866: a full ring sweep, slot == lane
                 uint32_t t;
-                uint32_t v0, v1, v2, v3;
+                uint32_t v0, v1, v2, v3, h4 = 0;
                 if (AHEAD && have) {
-                    v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+                    v0 = n0; v1 = n1; v2 = n2; v3 = n3; h4 = nh;
+                } else if (streamed) {
+                    stream_load(base + lane, v0, v1, v2, v3, h4);
                 } else {
                     const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
                     v0 = __ldg(seg); v1 = __ldg(seg + 1); v2 = __ldg(seg + 2); v3 = __ldg(seg + 3);
@@ -494,14 +524,24 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
                 if constexpr (AHEAD) {
                     have = base + 2 * kRing <= S;
                     if (have) {
-                        const uint32_t* nseg = p.tbl_idx + locate(base + kRing + lane, t);
-                        n0 = __ldg(nseg); n1 = __ldg(nseg + 1); n2 = __ldg(nseg + 2); n3 = __ldg(nseg + 3);
+                        if (streamed) {
+                            stream_load(base + kRing + lane, n0, n1, n2, n3, nh);
+                        } else {
+                            const uint32_t* nseg = p.tbl_idx + locate(base + kRing + lane, t);
+                            n0 = __ldg(nseg); n1 = __ldg(nseg + 1); n2 = __ldg(nseg + 2); n3 = __ldg(nseg + 3);
+                        }
                     }
                 }
-                uint64_t s0 = __ldg(sk + ((uint64_t)v0 << 5 | lane)), s1 = __ldg(sk + ((uint64_t)v1 << 5 | lane));
-                uint64_t s2 = __ldg(sk + ((uint64_t)v2 << 5 | lane)), s3 = __ldg(sk + ((uint64_t)v3 << 5 | lane));
-                uint32_t p0 = (uint32_t)__popcll(s0 ^ my_sketch) <= max_diff, p1 = (uint32_t)__popcll(s1 ^ my_sketch) <= max_diff;
-                uint32_t p2 = (uint32_t)__popcll(s2 ^ my_sketch) <= max_diff, p3 = (uint32_t)__popcll(s3 ^ my_sketch) <= max_diff;
+                uint32_t p0, p1, p2, p3;
+                if (streamed) {  // the sketch test was evaluated ahead of time; only the threshold is applied here
+                    p0 = (h4 & 0xffu) <= max_diff; p1 = ((h4 >> 8) & 0xffu) <= max_diff;
+                    p2 = ((h4 >> 16) & 0xffu) <= max_diff; p3 = (h4 >> 24) <= max_diff;
+                } else {
+                    uint64_t s0 = __ldg(sk + ((uint64_t)v0 << 5 | lane)), s1 = __ldg(sk + ((uint64_t)v1 << 5 | lane));
+                    uint64_t s2 = __ldg(sk + ((uint64_t)v2 << 5 | lane)), s3 = __ldg(sk + ((uint64_t)v3 << 5 | lane));
+                    p0 = (uint32_t)__popcll(s0 ^ my_sketch) <= max_diff; p1 = (uint32_t)__popcll(s1 ^ my_sketch) <= max_diff;
+                    p2 = (uint32_t)__popcll(s2 ^ my_sketch) <= max_diff; p3 = (uint32_t)__popcll(s3 ^ my_sketch) <= max_diff;
+                }
                 uint32_t cnt = p0 + p1 + p2 + p3, total;
                 uint32_t pos = np + warp_excl_scan(cnt, total);
                 if (p0) sm.pass_idx[pos++] = v0;
@@ -521,6 +561,9 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
                 if (lane < live) {
                     if (AHEAD && have) {  // a full ring whose indices are already here
                         v0 = n0; v1 = n1; v2 = n2; v3 = n3;
+                    } else if (streamed) {
+                        uint32_t h4;
+                        stream_load(base + lane, v0, v1, v2, v3, h4);
                     } else {
                         uint32_t t;
                         const uint32_t* seg = p.tbl_idx + locate(base + lane, t);
@@ -550,7 +593,9 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             // stop rule (collection.hpp:927-943)
             uint32_t pulled = base + kRing;
             uint32_t table_idx = L;
-            if (pulled < S) {
+            if (streamed) {
+                if (pulled < S) table_idx = __ldg(fs.tab + ((soff + pulled) >> 5));
+            } else if (pulled < S) {
                 uint32_t lo = 0, len = L;
                 while (len > 0) {
                     uint32_t half = len >> 1, mid = lo + half;
@@ -739,8 +784,16 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 const uint32_t* pre_a = (prefilled && b.pre_anchor) ? b.pre_anchor + (uint64_t)q * p.g.L : nullptr;
                 const uint32_t* pre_r = (prefilled && b.pre_range) ? b.pre_range + (uint64_t)q * kMaxHashBits * p.g.L : nullptr;
                 const uint4* pre_l = (prefilled && b.pre_lcp && !b.pre_range) ? b.pre_lcp + (uint64_t)q * p.g.L : nullptr;
+                FsView fsv{nullptr, nullptr, nullptr, nullptr};
+                if (prefilled && b.fs_meta) {
+                    const uint64_t sbase = (uint64_t)q * b.fs_cap;
+                    fsv.idx = reinterpret_cast<const uint2*>(b.fs_idx) + sbase;
+                    fsv.hd = b.fs_hd + sbase;
+                    fsv.tab = b.fs_tab + (sbase >> 5);
+                    fsv.meta = b.fs_meta + (uint64_t)q * kFsMeta;
+                }
                 uint32_t cnt = probe_cluster<G, DENSE>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
-                                                       prefilled, wait_bar, memo_phase, pre_a, pre_r, pre_l);
+                                                       prefilled, wait_bar, memo_phase, pre_a, pre_r, pre_l, fsv);
                 if (wait_bar) memo_phase ^= 1u;
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
                 for (uint32_t base = 0; base < cnt; base += 32) {
@@ -966,6 +1019,224 @@ void launch_first_ranges(const SearchParams& p, const QueryBatch& b, cudaStream_
     if (b.nq == 0 || !b.pre_anchor || (!b.pre_range && !b.pre_lcp)) return;
     const uint64_t threads = b.nq * p.g.L;
     k_first_ranges<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p, b);
+}
+
+// ------------------------------------------------------------------------------------------------ first-visit candidate stream
+
+// Per-warp scratch of k_first_stream (the fields anchors_lockstep fills, plus range starts, segment prefix and a histogram).
+struct StreamSmem {
+    uint2* lcp_up;
+    uint2* lcp_dn;
+    uint32_t* anchor;
+    uint32_t* code;
+    uint32_t* start;
+    uint32_t* segbase;
+    uint32_t* hist;  // [256]
+};
+
+__host__ __device__ inline uint32_t stream_smem_bytes(uint32_t L) {
+    uint32_t b = L * (8 + 8 + 4 + 4 + 4) + (L + 1) * 4;
+    b = (b + 15) & ~15u;
+    return b + 256 * 4;
+}
+
+// k-th largest of n u16 values (n < 65 536 * 2) by a two-pass byte radix select over a warp-private histogram; 0 when n < k.
+// `v` is 4-byte aligned. This is the largest value MaxBuffer's k-th entry can ever take in this cluster (maxbuffer.hpp:25-46).
+__device__ __forceinline__ uint32_t warp_kth_largest_u16(const uint16_t* __restrict__ v, uint32_t n, uint32_t k, uint32_t* hist) {
+    if (k == 0 || n < k) return 0;
+    const uint32_t lane = lane_id();
+    const uint32_t* v32 = reinterpret_cast<const uint32_t*>(v);
+    uint32_t prefix = 0, want = k;  // rank (from the top) still to be located inside the current prefix class
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < (n + 1) / 2; i += 32) {
+            const uint32_t w = __ldg(v32 + i);
+            const uint32_t a = w & 0xffffu, bb = w >> 16;
+            if (pass == 0) {
+                atomicAdd(&hist[a >> 8], 1u);
+                if (2 * i + 1 < n) atomicAdd(&hist[bb >> 8], 1u);
+            } else {
+                if ((a >> 8) == prefix) atomicAdd(&hist[a & 0xffu], 1u);
+                if (2 * i + 1 < n && (bb >> 8) == prefix) atomicAdd(&hist[bb & 0xffu], 1u);
+            }
+        }
+        __syncwarp();
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mine += hist[8 * lane + j];
+        uint32_t suf = mine;  // entries in the bins of this lane and of every higher lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+            if (lane + o < 32) suf += t;
+        }
+        const uint32_t above = suf - mine;
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, above < want && want <= suf)) - 1;
+        uint32_t bin = 0, rem = 0;
+        if (lane == owner) {
+            uint32_t acc = above;
+            for (int j = 7; j >= 0; j--) {
+                const uint32_t h = hist[8 * lane + j];
+                if (acc + h >= want) {
+                    bin = 8 * lane + j;
+                    rem = want - acc;
+                    break;
+                }
+                acc += h;
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, owner);
+        rem = __shfl_sync(0xffffffffu, rem, owner);
+        __syncwarp();
+        if (pass == 0) {
+            prefix = bin;
+            want = rem;
+        } else {
+            return (prefix << 8) | bin;
+        }
+    }
+    return 0;
+}
+
+// One warp per work item (query qperm[w], its nearest cluster first[w]): everything of the query's first visit that does not
+// depend on the search state, written out in the order search_maps consumes it (QueryBatch::fs_*). Per depth 24, 23, ...:
+// the ranges of all tables (fill_ranges, collection.hpp:650-667 — the same table_anchor / table_range as the probe), then
+// for every 4-entry segment of the concatenated ranges its table indices and, for ring slot = segment mod 32 (= lane), the
+// Hamming distance of each candidate's sketch word to the query's (filterer.hpp:28-31). All loads are independent of one
+// another across segments, so they overlap freely — inside the probe the same loads form a chain of two dependent round trips per
+// ring sweep. The stream stops after the first depth at whose end the stop rule (collection.hpp:927-943) fires for the
+// cluster's true k-th similarity: the lagging k-th value of MaxBuffer can only be lower, so the visit cannot end earlier.
+__global__ void __launch_bounds__(256, 3) k_first_stream(SearchParams p, QueryBatch b, uint32_t warp_bytes) {
+    extern __shared__ __align__(16) uint8_t s_stream[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (w >= b.nq) return;
+    const uint32_t q = b.qperm[w], c = b.first[w];
+    uint32_t* meta = b.fs_meta + (uint64_t)q * kFsMeta;
+    const uint32_t L = p.g.L;
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    if (p.brute[c] || nc > 65536u || nc > b.dense_stride) {
+        if (lane == 0) meta[48] = kMaxHashBits + 1;  // nothing streamed: the probe does it all
+        return;
+    }
+    StreamSmem sm;
+    {
+        uint8_t* ptr = s_stream + (size_t)warp * warp_bytes;
+        sm.lcp_up = reinterpret_cast<uint2*>(ptr); ptr += L * 8;
+        sm.lcp_dn = reinterpret_cast<uint2*>(ptr); ptr += L * 8;
+        sm.anchor = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.code = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.start = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.segbase = reinterpret_cast<uint32_t*>(ptr);
+        sm.hist = reinterpret_cast<uint32_t*>(s_stream + (size_t)warp * warp_bytes + (((L * 28 + (L + 1) * 4) + 15) & ~15u));
+    }
+    const uint32_t fsid = p.fset_of[c];
+    const uint32_t* codes = b.codes + (uint64_t)fsid * L * b.nq + q;
+    const uint64_t my_sketch = b.sketches[((uint64_t)fsid * b.nq + q) * kNumSketches + lane];
+    const uint32_t* stop = p.stop + (uint64_t)fsid * kMaxHashBits * kEstBins * p.stop_words;
+    const uint64_t* sk = p.sketches + off * kNumSketches;
+    anchors_lockstep(p, sm, c, off, nc, codes, b.nq);
+    // the similarity bin the stop rule will look at once MaxBuffer holds the cluster's true top k
+    const uint32_t kth16 = warp_kth_largest_u16(b.dense + (uint64_t)q * b.dense_stride, nc, p.k, sm.hist);
+    uint32_t bin = (uint32_t)__fdiv_rn(__fdiv_rn((float)kth16, 65536.0f), 0.005f);
+    bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
+
+    const uint64_t sbase = (uint64_t)q * b.fs_cap;
+    uint2* out_idx = reinterpret_cast<uint2*>(b.fs_idx) + sbase;
+    uint32_t* out_hd = b.fs_hd + sbase;
+    uint8_t* out_tab = b.fs_tab + (sbase >> 5);
+    uint32_t cum = 0, lowest = kMaxHashBits + 1;
+    uint32_t my_S = 0, my_off = 0;  // lane d-1 keeps the record of depth d
+    for (uint32_t depth = kMaxHashBits; depth > 0; depth--) {
+        uint32_t running = 0;
+        for (uint32_t t0 = 0; t0 < L; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            uint32_t nseg = 0;
+            if (t < L)
+                sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc,
+                                          sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
+            uint32_t total;
+            const uint32_t ex = warp_excl_scan(nseg, total);
+            if (t < L) sm.segbase[t] = running + ex;
+            running += total;
+        }
+        if (lane == 0) sm.segbase[L] = running;
+        __syncwarp();
+        const uint32_t S = running;
+        const uint32_t S32 = (S + 31u) & ~31u;
+        if (S > (uint32_t)kRing && cum + S32 > b.fs_cap) break;  // no room: the probe evaluates this depth and the deeper ones
+        if (lane == depth - 1) {
+            my_S = S;
+            my_off = cum;
+        }
+        lowest = depth;
+        if (S <= (uint32_t)kRing) continue;  // skipped by search_maps (collection.hpp:802-810): nothing to stream, no stop check
+        for (uint32_t s0 = 0; s0 < S; s0 += 2 * kRing) {
+            uint32_t v[2][4], tb[2];
+            bool valid[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t s = s0 + u * kRing + lane;
+                valid[u] = s < S;
+                tb[u] = 0;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0;
+                if (valid[u]) {
+                    uint32_t lo = 0, len = L;  // upper_bound(segbase, s) - 1 over segbase[0..L)
+                    while (len > 0) {
+                        const uint32_t half = len >> 1, mid = lo + half;
+                        if (sm.segbase[mid] <= s) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                    }
+                    const uint32_t t = lo - 1;
+                    tb[u] = t;
+                    const uint32_t* seg = p.tbl_idx + table_base(off, nc, L, t) + sm.start[t] + 4 * (s - sm.segbase[t]);
+                    v[u][0] = __ldg(seg); v[u][1] = __ldg(seg + 1); v[u][2] = __ldg(seg + 2); v[u][3] = __ldg(seg + 3);
+                }
+            }
+            uint64_t sw[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) sw[u][j] = valid[u] ? __ldg(sk + ((uint64_t)v[u][j] << 5 | lane)) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!valid[u]) continue;
+                const uint32_t s = s0 + u * kRing + lane;
+                const uint32_t h4 = (uint32_t)__popcll(sw[u][0] ^ my_sketch) | (uint32_t)__popcll(sw[u][1] ^ my_sketch) << 8 |
+                                    (uint32_t)__popcll(sw[u][2] ^ my_sketch) << 16 | (uint32_t)__popcll(sw[u][3] ^ my_sketch) << 24;
+                out_idx[cum + s] = make_uint2(v[u][0] | v[u][1] << 16, v[u][2] | v[u][3] << 16);
+                out_hd[cum + s] = h4;
+                if (lane == 0) out_tab[(cum + s) >> 5] = (uint8_t)tb[u];
+            }
+        }
+        cum += S32;
+        // would the stop rule fire at the end of this depth (table index L, every table consumed) for the cluster's true k-th value?
+        const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (L >> 5));
+        if ((word >> (L & 31)) & 1u) break;
+    }
+    if (lane < (uint32_t)kMaxHashBits) {
+        meta[lane] = my_S;
+        meta[kMaxHashBits + lane] = my_off;
+    }
+    if (lane == 0) meta[48] = lowest;
+}
+
+bool launch_first_stream(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
+    if (b.nq == 0 || !b.fs_meta || !b.fs_idx || !b.fs_hd || !b.fs_tab || !b.dense || b.fs_cap < 64) return false;
+    if (p.g.L > 255) return false;  // fs_tab holds the table index in a byte
+    const uint32_t wb = stream_smem_bytes(p.g.L);
+    const uint32_t warps = 8;
+    const size_t smem = (size_t)warps * wb;
+    if (smem > 200 * 1024) return false;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_first_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_first_stream<<<(unsigned)((b.nq + warps - 1) / warps), warps * 32, smem, s>>>(p, b, wb);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------ dense first-visit similarities

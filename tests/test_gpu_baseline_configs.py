@@ -141,15 +141,16 @@ def _standalone_index(oracle, data, L, k, delta, fn_seed, name):
 
 
 def _both_schedules(ix, data, q, k, delta, oracle, **kw):
-    """The default schedule (dense first-visit similarities + first-visit anchors) and the gather schedule."""
+    """The default schedule (dense first-visit similarities + first-visit candidate stream) and the two older ones."""
     from clann_b200 import _lib as cl
     stats = compare_with_oracle(ix, data, q, k, delta, oracle, **kw)
-    cl.tune("dense_sims", 0)
-    try:
-        stats_gather = compare_with_oracle(ix, data, q, k, delta, oracle, independent_builds=0, trace_queries=0)
-    finally:
-        cl.tune("dense_sims", 1)
-    assert stats_gather["candidates_mean"] == stats["candidates_mean"] and stats_gather["dc_mean"] == stats["dc_mean"]
+    for knob in ("dense_sims", "first_stream"):   # the gather schedule; dense similarities + first-visit anchors without the stream
+        cl.tune(knob, 0)
+        try:
+            other = compare_with_oracle(ix, data, q, k, delta, oracle, independent_builds=0, trace_queries=0)
+        finally:
+            cl.tune(knob, 1)
+        assert other["candidates_mean"] == stats["candidates_mean"] and other["dc_mean"] == stats["dc_mean"], knob
     return stats
 
 

