@@ -452,6 +452,7 @@ struct clann_index {
     // the stream-ordered calls; the others rotate under clann_search_device_async so that consecutive batches overlap.
     struct SearchWs {
         uint64_t ws_nq = 0;
+        bool ws_fs = false;  // the workspace was sized with the first-visit stream buffers (knob first_stream)
         DevBuf<float> w_qnorm, w_cdist;
         DevBuf<int16_t> w_q15;
         DevBuf<uint32_t> w_codes, w_first, w_qperm, w_counter, w_vis, w_sort_k, w_sort_i;
@@ -967,7 +968,9 @@ struct clann_index {
     }
 
     void ensure_workspace(uint64_t nq, cudaStream_t s) {
-        if (nq == W->ws_nq) return;
+        const bool want_fs = tune_get("first_stream", 0) != 0;
+        if (nq == W->ws_nq && want_fs == W->ws_fs) return;
+        W->ws_fs = want_fs;
         const uint32_t F = n_fsets();
         const uint32_t k = (uint32_t)cfg.k;
         W->w_qnorm.ensure(nq);
@@ -1011,7 +1014,7 @@ struct clann_index {
             // first-visit candidate stream: room for 2 x the largest cluster in segments per query (a visit scans ~4 candidates
             // per cluster row on the planted shapes, p99 ~2x that), 12 bytes per segment; only what a visit needs is written
             W->w_fs_cap = 0;
-            if (W->w_dense_stride && max_cluster <= 65536u && g.L <= 255) {
+            if (W->w_dense_stride && max_cluster <= 65536u && g.L <= 255 && want_fs) {
                 uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(2ull * max_cluster, 1024), 16384);
                 const int64_t knob = tune_get("first_stream_cap", 0);
                 if (knob > 0) cap = (uint64_t)knob;
@@ -1168,9 +1171,12 @@ struct clann_index {
         }
         // knob: 0 off, 1 anchors + every depth's range, 2 anchors + samples only (default: same total time as 1 on the glove-100
         // shape — 0.10 + 1.94 ms against 0.32 + 1.72 ms — with 13 MB instead of 94 MB of workspace per 10 000 queries)
-        // knob first_stream (default 1): the whole first visit's candidate stream ahead of the probe (launch_first_stream); it
-        // includes the anchors, so first_ranges is not launched then
-        if (W->w_fs_cap && tune_get("first_stream", 1) != 0) {
+        // knob first_stream (default 0): the whole first visit's candidate stream ahead of the probe (launch_first_stream); it
+        // includes the anchors, so first_ranges is not launched then. Measured on B200 (glove-100 shape, 10 000 queries,
+        // profiles/r2d_*): the probe falls from 1.89 to 1.35 ms (DRAM reads 2.85 -> 0.81 GB) but k_first_stream itself takes
+        // 1.22 ms at 24 warps per SM (latency-bound: 310 M L2 sectors, L2 hit rate 37 %), so the step is slower (3.04 vs
+        // 2.43 ms) and the stream stays opt-in until that kernel is restructured.
+        if (W->w_fs_cap && tune_get("first_stream", 0) != 0) {
             b.fs_idx = W->w_fs_idx.p;
             b.fs_hd = W->w_fs_hd.p;
             b.fs_tab = W->w_fs_tab.p;

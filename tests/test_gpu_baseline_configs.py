@@ -141,15 +141,16 @@ def _standalone_index(oracle, data, L, k, delta, fn_seed, name):
 
 
 def _both_schedules(ix, data, q, k, delta, oracle, **kw):
-    """The default schedule (dense first-visit similarities + first-visit candidate stream) and the two older ones."""
+    """The default schedule (dense first-visit similarities + first-visit anchors) and the two alternatives."""
     from clann_b200 import _lib as cl
     stats = compare_with_oracle(ix, data, q, k, delta, oracle, **kw)
-    for knob in ("dense_sims", "first_stream"):   # the gather schedule; dense similarities + first-visit anchors without the stream
-        cl.tune(knob, 0)
+    # the gather schedule (no precompute at all), and the opt-in first-visit candidate stream
+    for knob, value, restore in (("dense_sims", 0, 1), ("first_stream", 1, 0)):
+        cl.tune(knob, value)
         try:
             other = compare_with_oracle(ix, data, q, k, delta, oracle, independent_builds=0, trace_queries=0)
         finally:
-            cl.tune(knob, 1)
+            cl.tune(knob, restore)
         assert other["candidates_mean"] == stats["candidates_mean"] and other["dc_mean"] == stats["dc_mean"], knob
     return stats
 

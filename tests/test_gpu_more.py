@@ -372,11 +372,11 @@ def test_probe_kernel_variants_agree(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     variants = (("warp", {}), ("warp_no_dense_sims", {"CLANN_TUNE_DENSE_SIMS": "0"}),
-                ("no_first_stream", {"CLANN_TUNE_FIRST_STREAM": "0"}),
-                ("first_stream_cut_short", {"CLANN_TUNE_FIRST_STREAM_CAP": "256"}),   # most visits outlive a 256-segment stream
-                ("first_stream_tiny", {"CLANN_TUNE_FIRST_STREAM_CAP": "64"}),
-                ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_STREAM": "0", "CLANN_TUNE_FIRST_RANGES": "0"}),
-                ("warp_all_first_ranges", {"CLANN_TUNE_FIRST_STREAM": "0", "CLANN_TUNE_FIRST_RANGES": "1"}), ("warp_no_smem_memo", {"CLANN_TUNE_PROBE_SMEM_MEMO": "0"}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}),
+                ("first_stream", {"CLANN_TUNE_FIRST_STREAM": "1"}),
+                ("first_stream_cut_short", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "256"}),   # most visits outlive it
+                ("first_stream_tiny", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "64"}),
+                ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "0"}),
+                ("warp_all_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "1"}), ("warp_no_smem_memo", {"CLANN_TUNE_PROBE_SMEM_MEMO": "0"}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}),
                 ("warp_small_grid", {"CLANN_TUNE_PROBE_WARPS": "4", "CLANN_TUNE_PROBE_CTAS": "1"}),
                 ("warp_longest_first_prefetch", {"CLANN_TUNE_ORDER_LONGEST_FIRST": "1", "CLANN_TUNE_PROBE_PREFETCH_ROWS": "1"}))
     for name, env in variants:
