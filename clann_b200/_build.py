@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libclann_b200.so")
-SOURCES = ["index.cu", "kernels_build.cu", "kernels_search.cu"]
+SOURCES = ["index.cu", "kernels_build.cu", "kernels_search.cu", "kernels_tc.cu"]
 HEADERS = ["common.cuh", "kernels.h", "probe_common.cuh", os.path.join("..", "..", "include", "clann_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -443,6 +443,7 @@ struct clann_index {
     DevBuf<uint32_t> d_msd_thr;
     // device: PUFFINN layer
     DevBuf<int16_t> d_q15, d_planes;
+    DevBuf<uint8_t> d_plane_slices;  // int8 slices of the hyperplanes for the tensor-pipe sketch projection (kernels_tc.cu)
     DevBuf<uint64_t> d_sketches;
     DevBuf<uint32_t> d_tbl_hash, d_tbl_idx, d_tbl_dir, d_signbits, d_stop;
     uint32_t stop_words = 0;
@@ -474,6 +475,9 @@ struct clann_index {
         DevBuf<uint8_t> w_fs_tab;
         uint32_t w_fs_cap = 0;
         DevBuf<RowTile> w_tiles, w_tiles_codes;
+        DevBuf<uint8_t> w_qslices;        // int8 slices of the query batch (tensor-pipe sketches)
+        DevBuf<SketchTcTile> w_tc_tiles;  // 128-query tiles per function set
+        uint32_t w_n_tc_tiles = 0;
         uint32_t w_ntiles = 0;
         uint64_t w_tiles_codes_nq = 0;
         // device staging of the host-buffer entry points
@@ -786,6 +790,10 @@ struct clann_index {
         }
         d_planes.upload(all_planes, s);
         d_signbits.upload(all_signs, s);
+        if (sketch_tc_supported(g.sl)) {
+            d_plane_slices.alloc((size_t)fsets.size() * kNumPlanes * 2 * sketch_tc_kp(g.sl));
+            launch_q15_slices(d_planes.p, (uint64_t)fsets.size() * kNumPlanes, g.sl, d_plane_slices.p, s);
+        }
         build_msd_table(h_msd);
         d_msd.upload(h_msd, s);
         {
@@ -824,6 +832,43 @@ struct clann_index {
         d_stop.upload(all, s);
         CLANN_CUDA(cudaStreamSynchronize(s));
         stop_recall = recall;
+    }
+
+    // knob tc_sketch (default 1): the sketch projection on the tensor pipe (k_sketch_tc) instead of the CUDA-core kernel
+    bool use_tc_sketch() const { return sketch_tc_supported(g.sl) && d_plane_slices.p && tune_get("tc_sketch", 1) != 0; }
+
+    // filterer.hpp:76-97 for every PUFFINN cluster this rank builds, on the tensor pipe: tiles of up to 128 consecutive rows of
+    // one cluster; the int8 slices of the rows go through a bounded scratch buffer (at most ~4 M rows at a time).
+    void build_sketches_tc(cudaStream_t s) {
+        const uint32_t kp = sketch_tc_kp(g.sl);
+        const uint64_t cap_rows = (uint64_t)std::max<int64_t>(1 << 16, tune_get("tc_sketch_chunk_rows", 4 << 20));
+        DevBuf<uint8_t> slices;
+        DevBuf<SketchTcTile> d_tc;
+        std::vector<SketchTcTile> tc_tiles;
+        uint64_t lo = 0, hi = 0;  // row span [lo, hi) covered by the pending tiles
+        auto flush = [&]() {
+            if (tc_tiles.empty()) return;
+            slices.ensure((hi - lo) * 2 * kp);
+            launch_q15_slices(d_q15.p + lo * g.sl, hi - lo, g.sl, slices.p, s);
+            d_tc.upload(tc_tiles, s);
+            launch_sketch_tc(d_tc.p, (uint32_t)tc_tiles.size(), slices.p, (uint32_t)lo, hi - lo, d_plane_slices.p, n_fsets(), d_q15.p,
+                             d_planes.p, g.sl, d_sketches.p, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));  // the host vectors and the scratch are reused by the next chunk
+            tc_tiles.clear();
+        };
+        for (uint32_t c = 0; c < K; c++) {
+            if (h_brute[c] || h_sizes[c] == 0) continue;
+            if (shard_count > 1 && h_owner[c] != shard_rank) continue;
+            const uint64_t c_lo = h_offsets[c], c_hi = h_offsets[c] + h_sizes[c];
+            if (!tc_tiles.empty() && c_hi - lo > cap_rows) flush();
+            if (tc_tiles.empty()) lo = c_lo;
+            hi = c_hi;
+            for (uint32_t r = 0; r < h_sizes[c]; r += 128) {
+                const uint32_t row0 = (uint32_t)c_lo + r;
+                tc_tiles.push_back(SketchTcTile{row0, row0, std::min<uint32_t>(128, h_sizes[c] - r), h_fset_of[c]});
+            }
+        }
+        flush();
     }
 
     void build() {
@@ -883,7 +928,8 @@ struct clann_index {
         DevBuf<RowTile> d_tiles;
         d_tiles.upload(tiles, s);
         d_sketches.alloc((size_t)n * kNumSketches);
-        launch_sketch(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_planes.p, g.sl, d_sketches.p, s);
+        if (use_tc_sketch()) build_sketches_tc(s);
+        else launch_sketch(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_planes.p, g.sl, d_sketches.p, s);
         d_tbl_hash.alloc((size_t)g.L * n);
         d_tbl_idx.alloc((size_t)g.L * n);
         launch_codes(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_signbits.p, g, d_tbl_hash.p, n, 0, s);
@@ -1047,6 +1093,17 @@ struct clann_index {
                 tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
         W->w_tiles.upload(tiles, s);
         W->w_ntiles = (uint32_t)tiles.size();
+        W->w_n_tc_tiles = 0;
+        if (sketch_tc_supported(g.sl) && nq < (1ull << 31)) {
+            std::vector<SketchTcTile> tct;
+            for (uint32_t f = 0; f < F; f++)
+                for (uint64_t q0 = 0; q0 < nq; q0 += 128)
+                    tct.push_back(SketchTcTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(128, nq - q0), f});
+            W->w_tc_tiles.upload(tct, s);
+            W->w_n_tc_tiles = (uint32_t)tct.size();
+            W->w_qslices.ensure(nq * 2 * sketch_tc_kp(g.sl));
+            CLANN_CUDA(cudaStreamSynchronize(s));  // the host vector goes out of scope
+        }
         W->ws_nq = nq;
     }
 
@@ -1110,7 +1167,13 @@ struct clann_index {
         QueryBatch b = batch(d_queries, nq, nullptr, nullptr, nullptr);
         launch_prep_queries(p, b, s);
         // sketches are indexed by out_row = fset*nq + q (W->w_tiles); codes by fset*L*nq + t*nq + q (w_code_tiles)
-        launch_sketch(b.q15, W->w_tiles.p, W->w_ntiles, d_planes.p, g.sl, b.sketches, s);
+        if (use_tc_sketch() && W->w_n_tc_tiles && nq >= 64) {
+            launch_q15_slices(b.q15, nq, g.sl, W->w_qslices.p, s);
+            launch_sketch_tc(W->w_tc_tiles.p, W->w_n_tc_tiles, W->w_qslices.p, 0, nq, d_plane_slices.p, n_fsets(), b.q15, d_planes.p, g.sl,
+                             b.sketches, s);
+        } else {
+            launch_sketch(b.q15, W->w_tiles.p, W->w_ntiles, d_planes.p, g.sl, b.sketches, s);
+        }
         launch_codes(b.q15, w_code_tiles(nq, s), W->w_ntiles, d_signbits.p, g, b.codes, nq, (uint64_t)g.L * nq, s);
         launch_center_order(p, b, s);
         // work order: stable sort of the queries by nearest cluster (same radix sort as the tables)
@@ -1118,7 +1181,7 @@ struct clann_index {
         launch_init_state(p, b, s);
         cur_queries = d_queries;
         last_nq = nq;
-        last_launches = 7;
+        last_launches = (use_tc_sketch() && W->w_n_tc_tiles && nq >= 64) ? 8 : 7;
     }
 
     const RowTile* w_code_tiles(uint64_t nq, cudaStream_t s) {

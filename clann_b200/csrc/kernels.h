@@ -26,6 +26,19 @@ void launch_sketch(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, c
 void launch_codes(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, const uint32_t* signbits, HashGeom g,
                   uint32_t* codes, uint64_t code_stride, uint64_t fset_stride, cudaStream_t s);
 
+// The same projection on the tensor pipe (kernels_tc.cu): exact integer dot products from int8 slices by tcgen05.mma.kind::i8
+// into TMEM, the sign decided wherever the rounding slack cannot change it, the remaining ~1.4 % of the pairs evaluated the
+// reference's way. Bit-identical to launch_sketch. Tiles hold up to 128 consecutive rows of one function set.
+struct SketchTcTile {
+    uint32_t in_row0, out_row0, count, fset;
+};
+bool sketch_tc_supported(uint32_t sl);
+uint32_t sketch_tc_kp(uint32_t sl);  // slice row length: SL rounded up to 128; a slice row is 2 * kp bytes (high bytes, low bytes)
+void launch_q15_slices(const int16_t* q15, uint64_t rows, uint32_t sl, uint8_t* out, cudaStream_t s);
+void launch_sketch_tc(const void* tiles, uint32_t n_tiles, const uint8_t* row_slices, uint32_t slice_row_base, uint64_t slice_rows,
+                      const uint8_t* plane_slices, uint32_t n_fsets, const int16_t* q15, const int16_t* planes, uint32_t sl,
+                      uint64_t* sketches, cudaStream_t s);
+
 struct SortSegment {
     uint64_t base;          // offset of the segment in keys / idx arrays
     uint64_t scratch_base;  // offset in the scratch arrays (only used when len > smem capacity)
