@@ -673,7 +673,9 @@ struct clann_index {
         d_assign.alloc(n);
         d_keys.alloc(K);
         d_keys.zero(s);
-        for (uint32_t c = 0; c < K; c++) launch_gmm_pass(d_data.p, d_norms.p, n, g.d, c, d_keys.p, d_dist.p, d_assign.p, s);
+        DevBuf<float> d_cc;
+        d_cc.alloc(K);
+        for (uint32_t c = 0; c < K; c++) launch_gmm_pass(d_data.p, d_norms.p, n, g.d, c, d_keys.p, d_dist.p, d_assign.p, d_cc.p, s);
         d_centers.alloc(K);
         d_radii.alloc(K);
         d_radii.zero(s);

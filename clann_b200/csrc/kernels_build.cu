@@ -67,6 +67,97 @@ __global__ void __launch_bounds__(256) k_gmm_pass(const float* __restrict__ data
     }
 }
 
+// Distances from the centre chosen for pass c to every earlier centre j < c (angulardata.rs:25-27), for the triangle-inequality
+// filter of k_gmm_pass_v. One thread per earlier centre.
+__global__ void __launch_bounds__(128) k_gmm_centre_dists(const float* __restrict__ data, const float* __restrict__ norms, uint32_t d,
+                                                          uint32_t c, const uint64_t* __restrict__ keys, float* __restrict__ cc) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c) return;
+    const uint32_t ci = gmm_key_index(keys[c - 1]);
+    const uint32_t cj = j == 0 ? 0u : gmm_key_index(keys[j - 1]);
+    const float dot = ndarray_dot_thread(data + (uint64_t)cj * d, data + (uint64_t)ci * d, d);
+    cc[j] = __fsub_rn(1.0f, __fdiv_rn(dot, __fmul_rn(norms[cj], norms[ci])));
+}
+
+// gmm.rs:40-53, vectorised (d % 4 == 0): two lanes per row, each streaming its half of every 8-element chunk as one 128-bit load
+// (a full 32-byte sector per row and load instruction, 16 rows per warp in flight), the centre row in shared memory. The
+// arithmetic is ndarray's unrolled_dot exactly: lane s owns the partial sums p[4s .. 4s+3], the fold (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7)
+// and the tail run on the even lane.
+// PRUNE: a row is not read at all when the triangle inequality already rules out a reassignment. With chord lengths
+// e(x,y) = sqrt(2 dist(x,y)) (a metric on directions), e(row, new) >= e(centre_of_row, new) - e(row, centre_of_row); if
+// e(centre_of_row, new) >= 2 e(row, centre_of_row) + 0.03 the new distance exceeds the current one by more than any rounding of the
+// fp32 evaluations involved (each within ~1e-5 of the exact value, i.e. within 4.5e-3 in chord length), so the reference's
+// strict `new < old` (gmm.rs:49) is false and nothing changes for that row. Every comparison with a NaN (zero vectors) is
+// false, which keeps such rows on the evaluated path.
+template <bool PRUNE>
+__global__ void __launch_bounds__(256) k_gmm_pass_v(const float* __restrict__ data, const float* __restrict__ norms, uint64_t n,
+                                                    uint32_t d, uint32_t c, uint64_t* __restrict__ keys, float* __restrict__ dist,
+                                                    uint32_t* __restrict__ assign, const float* __restrict__ cc) {
+    extern __shared__ __align__(16) float s_y[];  // centre row
+    __shared__ uint64_t s_key[8];
+    const uint32_t ci = (c == 0) ? 0u : gmm_key_index(keys[c - 1]);
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) s_y[i] = data[(uint64_t)ci * d + i];
+    __syncthreads();
+    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t s = threadIdx.x & 1u;
+    const bool valid = row < n;
+    const uint64_t r = valid ? row : n - 1;
+    float cur = INFINITY;
+    bool need = valid;
+    if (c > 0 && valid) {
+        cur = dist[r];
+        if (PRUNE) {
+            const float dcc = cc[assign[r]];
+            const bool skip = sqrtf(2.0f * dcc) >= 2.0f * sqrtf(2.0f * fmaxf(cur, 0.0f)) + 0.03f;
+            need = !skip;
+        }
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, need);
+    if (need) {
+        const float4* x = reinterpret_cast<const float4*>(data + r * d) + s;
+        const float4* y = reinterpret_cast<const float4*>(s_y) + s;
+        float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+        const uint32_t chunks = d / 8;
+#pragma unroll 4
+        for (uint32_t j = 0; j < chunks; j++) {
+            const float4 a = __ldg(x + 2 * j), b = y[2 * j];
+            p0 = __fadd_rn(p0, __fmul_rn(a.x, b.x));
+            p1 = __fadd_rn(p1, __fmul_rn(a.y, b.y));
+            p2 = __fadd_rn(p2, __fmul_rn(a.z, b.z));
+            p3 = __fadd_rn(p3, __fmul_rn(a.w, b.w));
+        }
+        const float q0 = __shfl_xor_sync(mask, p0, 1), q1 = __shfl_xor_sync(mask, p1, 1);
+        const float q2 = __shfl_xor_sync(mask, p2, 1), q3 = __shfl_xor_sync(mask, p3, 1);
+        if (s == 0) {
+            float sum = 0.0f;
+            sum = __fadd_rn(sum, __fadd_rn(p0, q0));
+            sum = __fadd_rn(sum, __fadd_rn(p1, q1));
+            sum = __fadd_rn(sum, __fadd_rn(p2, q2));
+            sum = __fadd_rn(sum, __fadd_rn(p3, q3));
+            const float* xs = data + r * d;
+            for (uint32_t i = chunks * 8; i < d; i++) sum = __fadd_rn(sum, __fmul_rn(xs[i], s_y[i]));
+            const float nd = __fsub_rn(1.0f, __fdiv_rn(sum, __fmul_rn(norms[r], norms[ci])));  // angulardata.rs:25-27
+            if (c == 0 || nd < cur) {  // gmm.rs:49
+                cur = nd;
+                dist[r] = nd;
+                assign[r] = c;
+            }
+        }
+    }
+    uint64_t key = (valid && s == 0) ? gmm_key(cur, row) : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if (lane_id() == 0) s_key[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t best = s_key[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) best = s_key[w] > best ? s_key[w] : best;
+        atomicMax((unsigned long long*)&keys[c], (unsigned long long)best);
+    }
+}
+
 // gmm.rs:56-60 radii, cluster sizes, and decoding of the centre list.
 __global__ void k_gmm_finish(const uint64_t* __restrict__ keys, uint32_t K, uint64_t n, const float* __restrict__ dist,
                              const uint32_t* __restrict__ assign, uint32_t* __restrict__ centers, float* __restrict__ radii,
@@ -561,7 +652,20 @@ void launch_row_norms(const float* data, uint64_t n, uint32_t d, float* norms, c
 }
 
 void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t d, uint32_t c, uint64_t* keys, float* dist,
-                     uint32_t* assign, cudaStream_t s) {
+                     uint32_t* assign, float* cc, cudaStream_t s) {
+    // knobs (never change a result): gmm_vec 0 = the 8-lanes-per-row kernel; gmm_prune 0 = evaluate every row in every pass
+    if (d % 4 == 0 && d * sizeof(float) <= 40 * 1024 && tune_get("gmm_vec", 1) != 0) {
+        const uint64_t threads = n * 2;
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        const size_t smem = d * sizeof(float);
+        if (c > 0 && cc && tune_get("gmm_prune", 1) != 0) {
+            k_gmm_centre_dists<<<(c + 127) / 128, 128, 0, s>>>(data, norms, d, c, keys, cc);
+            k_gmm_pass_v<true><<<grid, 256, smem, s>>>(data, norms, n, d, c, keys, dist, assign, cc);
+        } else {
+            k_gmm_pass_v<false><<<grid, 256, smem, s>>>(data, norms, n, d, c, keys, dist, assign, cc);
+        }
+        return;
+    }
     uint64_t threads = n * 8;
     k_gmm_pass<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, norms, n, d, c, keys, dist, assign);
 }

@@ -34,7 +34,7 @@ constexpr uint32_t kSliceBytes = kTileM * kKBlock;     // 16 KiB: one int8 slice
 constexpr uint32_t kStages = 2;
 constexpr uint32_t kEpiWarps = 8;
 constexpr uint32_t kThreads = (2 + kEpiWarps) * 32;
-constexpr uint32_t kListCap = 2048;     // undecided (vector, hyperplane) pairs queued per tile; beyond that a thread resolves its own
+constexpr uint32_t kListCap = 6144;     // undecided (vector, hyperplane) pairs queued per CTA (~3 700 expected at d = 100); beyond that a thread resolves its own
 constexpr uint32_t kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,6 +170,8 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SketchTcTile tile = tiles[blockIdx.x];
     constexpr uint32_t kTilesN = kNumPlanes / kTileN;  // 16
+    // blockIdx.y splits the 16 plane tiles between CTAs (small batches: more CTAs than row tiles, shorter per-CTA latency)
+    const uint32_t j_begin = blockIdx.y * (kTilesN / gridDim.y), j_end = j_begin + kTilesN / gridDim.y;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -199,7 +201,7 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
             }
             // hyperplanes: ring over (tile of 128 planes, K block)
             uint32_t it = 0;
-            for (uint32_t j = 0; j < kTilesN; j++) {
+            for (uint32_t j = j_begin; j < j_end; j++) {
                 for (uint32_t kb = 0; kb < KB; kb++, it++) {
                     const uint32_t s = it % kStages;
                     mbar_wait(b_empty + s, ((it / kStages) & 1u) ^ 1u);
@@ -215,8 +217,8 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
             const uint32_t id_ss = idesc_i8(1, 1), id_su = idesc_i8(1, 0), id_us = idesc_i8(0, 1), id_uu = idesc_i8(0, 0);
             mbar_wait(a_full, 0);
             uint32_t it = 0;
-            for (uint32_t j = 0; j < kTilesN; j++) {
-                mbar_wait(t_empty, (j & 1u) ^ 1u);  // the epilogue has drained the accumulators of tile j - 1
+            for (uint32_t j = j_begin; j < j_end; j++) {
+                mbar_wait(t_empty, ((j - j_begin) & 1u) ^ 1u);  // the epilogue has drained the accumulators of the previous tile
                 fence_after_sync();
                 for (uint32_t kb = 0; kb < KB; kb++, it++) {
                     const uint32_t s = it % kStages;
@@ -251,8 +253,8 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
         const int wrap_guard = (1 << 22) - T - 1;
         const uint32_t cpr = sl / 8;
         const uint32_t et = threadIdx.x - 64;                 // 0..255 among the epilogue threads
-        for (uint32_t j = 0; j < kTilesN; j++) {
-            mbar_wait(t_full, j & 1u);
+        for (uint32_t j = j_begin; j < j_end; j++) {
+            mbar_wait(t_full, (j - j_begin) & 1u);
             fence_after_sync();
             unsigned long long word = 0, undecided = 0;
 #pragma unroll
@@ -264,6 +266,11 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
                 tmem_ld32(taddr + 1 * kTileN, p2);
                 tmem_ld32(taddr + 2 * kTileN, p0);
                 tmem_ld_wait();
+                if (c0 == 32) {
+                    // the accumulators are in registers: hand TMEM back to the MMA warp for the next tile
+                    fence_before_sync();
+                    mbar_arrive(t_empty);
+                }
 #pragma unroll
                 for (int c = 0; c < 32; c++) {
                     // Z = floor(S / 256): S = 2^16 P1 + 2^8 P2 + P0 lies in [256 Z, 256 Z + 255]
@@ -275,9 +282,6 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
                     if (!one && !zero) undecided |= bit;
                 }
             }
-            // the accumulators are in registers: hand TMEM back to the MMA warp for the next tile
-            fence_before_sync();
-            mbar_arrive(t_empty);
             const uint32_t sk = j * 2 + half;  // sketch word of this half tile: planes 64 sk .. 64 sk + 63
             if (!live) undecided = 0;
             // queue the undecided pairs; when the list is full the thread evaluates its own (any input stays correct)
@@ -296,23 +300,27 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
                 }
             }
             s_out[r * kNumSketches + sk] = word;
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            // ---- resolve the queued pairs exactly (math.hpp:37-44 on the Q15 originals), 16 lanes per pair, two pairs in flight
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        // ---- resolve the queued pairs exactly (math.hpp:37-44 on the Q15 originals): 8 lanes per pair, four pairs in flight per
+        // group, so that the L2 round trips of 128 pairs overlap
+        {
             const uint32_t npairs = min(*s_count, kListCap);
-            const uint32_t sub = lane & 15u, grp = et >> 4;   // 16 groups of 16 lanes
-            for (uint32_t base0 = 0; base0 < npairs; base0 += 32) {  // trip count uniform over the warp: the loop shuffles
-                const uint32_t i0 = base0 + grp * 2;
-                int part[2] = {0, 0};
-                uint32_t ent[2];
+            const uint32_t sub = lane & 7u, grp = et >> 3;   // 32 groups of 8 lanes
+            for (uint32_t base0 = 0; base0 < npairs; base0 += 128) {  // trip count uniform over the warp: the loop shuffles
+                int part[4];
+                uint32_t ent[4];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    ent[u] = i0 + u < npairs ? s_list[i0 + u] : 0xffffffffu;
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = base0 + grp * 4 + u;
+                    ent[u] = i < npairs ? s_list[i] : 0xffffffffu;
+                    part[u] = 0;
                     if (ent[u] == 0xffffffffu) continue;
                     const uint32_t rr = ent[u] >> 16, f = ent[u] & 0xffffu;
                     const uint4* x = reinterpret_cast<const uint4*>(q15 + (uint64_t)(tile.in_row0 + rr) * sl);
                     const uint4* y = reinterpret_cast<const uint4*>(planes + ((uint64_t)tile.fset * kNumPlanes + f) * sl);
                     int s = 0;
-                    for (uint32_t ch = sub; ch < cpr; ch += 16) {
+                    for (uint32_t ch = sub; ch < cpr; ch += 8) {
                         const uint4 a = __ldg(x + ch), bq = __ldg(y + ch);
                         s += q15_mul(unpack_lo(a.x), unpack_lo(bq.x)); s += q15_mul(unpack_hi(a.x), unpack_hi(bq.x));
                         s += q15_mul(unpack_lo(a.y), unpack_lo(bq.y)); s += q15_mul(unpack_hi(a.y), unpack_hi(bq.y));
@@ -322,23 +330,24 @@ k_sketch_tc(const __grid_constant__ CUtensorMap rows_map, const __grid_constant_
                     part[u] = s;
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < 4; u++) {
                     int s = part[u];
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                     if (sub == 0 && ent[u] != 0xffffffffu && (int16_t)s >= 0) {
                         const uint32_t rr = ent[u] >> 16, f = ent[u] & 0xffffu;
                         atomicOr(&s_out[rr * kNumSketches + (f >> 6)], 1ull << (63 - (f & 63u)));
                     }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            if (et == 0) *s_count = 0;
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
-        // ---- the 32 words of every live vector, coalesced
-        for (uint32_t i = et; i < tile.count * kNumSketches; i += kEpiWarps * 32)
-            sketches[(uint64_t)tile.out_row0 * kNumSketches + i] = s_out[i];
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        // ---- this CTA's words of every live vector
+        const uint32_t w0 = j_begin * 2, nw = (j_end - j_begin) * 2;
+        for (uint32_t i = et; i < tile.count * nw; i += kEpiWarps * 32) {
+            const uint32_t rr = i / nw, wq = w0 + i % nw;
+            sketches[((uint64_t)tile.out_row0 + rr) * kNumSketches + wq] = s_out[rr * kNumSketches + wq];
+        }
     }
     fence_before_sync();
     __syncthreads();
@@ -408,7 +417,13 @@ void launch_sketch_tc(const void* tiles, uint32_t n_tiles, const uint8_t* row_sl
         CLANN_CUDA(cudaFuncSetAttribute(k_sketch_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_sketch_tc<<<n_tiles, tc::kThreads, smem, s>>>(rows_map, planes_map, static_cast<const SketchTcTile*>(tiles), slice_row_base, q15,
+    // few row tiles (a query batch): split the plane tiles over blockIdx.y until the grid covers the GPU about twice
+    int sms = 0, dev = 0;
+    CLANN_CUDA(cudaGetDevice(&dev));
+    CLANN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t split = 1;
+    while (split < 4 && (uint64_t)n_tiles * split < 2ull * (uint32_t)sms) split *= 2;
+    k_sketch_tc<<<dim3(n_tiles, split), tc::kThreads, smem, s>>>(rows_map, planes_map, static_cast<const SketchTcTile*>(tiles), slice_row_base, q15,
                                                     planes, sl, kp, sketches);
 }
 

@@ -579,3 +579,34 @@ def test_run_with_metrics_on_device():
     assert [r["distance_computations"] for r in rows] == ctr["distance_computations"].tolist()
     assert [r["n_candidates"] for r in rows] == ctr["candidates"].tolist()
     assert m.run_row()["dataset_len"] == 15_000 and m.run_row()["dataset"] == "metrics"
+
+
+@pytest.mark.parametrize("shape", [(30_000, 64, "planted"), (12_000, 100, "uniform"), (9_000, 36, "planted")])
+def test_gmm_kernel_variants_match_oracle(oracle, shape):
+    """greedy_minimum_maximum (gmm.rs:21-62) on the device in its three forms — 8 lanes per row, vectorised two lanes per row,
+    vectorised with the triangle-inequality filter that skips rows — against the oracle's restatement: centres, assignment and
+    radii bit for bit (the filter must never change a decision, on clustered and on unclustered data)."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    n, d, kind = shape
+    data = util.planted(n, d, 91) if kind == "planted" else util.uniform_sphere(n, d, 92)
+    data[17] = 0.0                      # a zero vector: NaN distances must stay on the evaluated path
+    data[40] = data[41]                 # duplicates: zero residual distance
+    K = oracle.num_clusters(0.4, n)
+    oc, oa, orad = oracle.gmm(data, K)
+    for knobs in ({"gmm_vec": 0}, {"gmm_prune": 0}, {}):
+        for k_, v in knobs.items():
+            cl.tune(k_, v)
+        try:
+            ix = cb.init_with_config(data, cb.Config(4, 0.4, 5, 0.9, "gmm"))
+            ix.build()
+            cen = ix.export(cl.X_CENTERS, 0, np.uint64)
+            asg = ix.export(cl.X_ASSIGNMENT, 0, np.uint64)
+            rad = ix.export(cl.X_RADII, 0, np.float32)
+            ix.close()
+        finally:
+            for k_ in knobs:
+                cl.tune(k_, 1)
+        assert np.array_equal(cen, oc), knobs
+        assert np.array_equal(asg, oa), knobs
+        assert np.array_equal(rad.view(np.uint32), orad.view(np.uint32)), knobs
