@@ -453,8 +453,9 @@ struct clann_index {
     // the stream-ordered calls; the others rotate under clann_search_device_async so that consecutive batches overlap.
     struct SearchWs {
         uint64_t ws_nq = 0;
+        bool ws_tc_center = false;  // the batch in this workspace was scored by the tensor-pipe screen (cdist exact only below exact_limit)
         bool ws_fs = false;  // the workspace was sized with the first-visit stream buffers (knob first_stream)
-        DevBuf<float> w_qnorm, w_cdist;
+        DevBuf<float> w_qnorm, w_cdist, w_exact_limit;
         DevBuf<int16_t> w_q15;
         DevBuf<uint32_t> w_codes, w_first, w_qperm, w_counter, w_vis, w_sort_k, w_sort_i;
         DevBuf<SortSegment> w_sort_seg;
@@ -836,6 +837,20 @@ struct clann_index {
         stop_recall = recall;
     }
 
+    // knob tc_center (default 1): query x centre scoring as a tf32 tensor-core GEMM screen + exact evaluation of each query's 32
+    // nearest candidates (k_center_gemm_tc, k_center_refine) instead of the all-exact CUDA-core kernel. Queries that walk past
+    // their 32 candidates re-evaluate their row inside the probe, so when the last finished batch averaged more than 8 clusters
+    // per query (overlapping or unclustered data) the all-exact kernel is used from the start. Never changes a result.
+    bool use_tc_center() const {
+        if (!center_gemm_tc_supported(g.d) || puffinn_mode || tune_get("tc_center", 1) == 0) return false;
+        if (h_stats && tune_get("dense_adaptive", 1) != 0) {
+            const unsigned long long visited = reinterpret_cast<volatile unsigned long long*>(h_stats)[0];
+            const unsigned long long queries = reinterpret_cast<volatile unsigned long long*>(h_stats)[1];
+            if (queries > 0 && visited > 8 * queries) return false;
+        }
+        return true;
+    }
+
     // knob tc_sketch (default 1): the sketch projection on the tensor pipe (k_sketch_tc) instead of the CUDA-core kernel
     bool use_tc_sketch() const { return sketch_tc_supported(g.sl) && d_plane_slices.p && tune_get("tc_sketch", 1) != 0; }
 
@@ -1026,6 +1041,7 @@ struct clann_index {
         W->w_codes.ensure((size_t)F * g.L * nq);
         W->w_sketches.ensure((size_t)F * nq * kNumSketches);
         W->w_cdist.ensure(nq * K);
+        W->w_exact_limit.ensure(nq);
         W->w_first.ensure(nq);
         W->w_qperm.ensure(nq);
         if (nq > segment_sort_smem_capacity()) {
@@ -1118,6 +1134,7 @@ struct clann_index {
         b.codes = W->w_codes.p;
         b.sketches = W->w_sketches.p;
         b.cdist = W->w_cdist.p;
+        b.exact_limit = W->ws_tc_center ? W->w_exact_limit.p : nullptr;
         b.first = W->w_first.p;
         b.qperm = W->w_qperm.p;
         b.state = W->w_state.p;
@@ -1165,6 +1182,7 @@ struct clann_index {
     void search_begin(const float* d_queries, uint64_t nq, cudaStream_t s) {
         require_built();
         ensure_workspace(nq, s);
+        W->ws_tc_center = use_tc_center();  // decided once per batch: every later view of this workspace must agree with it
         SearchParams p = params();
         QueryBatch b = batch(d_queries, nq, nullptr, nullptr, nullptr);
         launch_prep_queries(p, b, s);
@@ -1666,7 +1684,22 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                 // index.rs:592-616: stable ascending order of the centre distances, derived on the host for the tests
                 index->require_built();
                 const uint64_t nq = index->last_nq;
-                std::vector<float> cd = index->W->w_cdist.download(nq * K);
+                // the workspace may hold the tensor-pipe screen (exact only below each query's limit): evaluate every distance
+                // exactly into a scratch copy. Needs the query buffer of the last search to be still alive.
+                DevBuf<float> d_cd;
+                DevBuf<uint32_t> d_first;
+                d_cd.alloc(nq * K);
+                d_first.alloc(nq);
+                {
+                    SearchParams p = index->params();
+                    QueryBatch b = index->batch(index->cur_queries, nq, nullptr, nullptr, nullptr);
+                    b.cdist = d_cd.p;
+                    b.first = d_first.p;
+                    b.exact_limit = nullptr;
+                    launch_center_order(p, b, 0);
+                    CLANN_CUDA(cudaDeviceSynchronize());
+                }
+                std::vector<float> cd = d_cd.download(nq * K);
                 std::vector<uint32_t> order(nq * K);
                 for (uint64_t q = 0; q < nq; q++) {
                     uint32_t* o = order.data() + q * K;

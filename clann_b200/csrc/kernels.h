@@ -104,6 +104,10 @@ struct QueryBatch {
     uint32_t* codes;        // [n_fsets][L][nq]   (table-major per function set)
     uint64_t* sketches;     // [n_fsets][nq][32]
     float* cdist;           // [nq][K] distance to every centre (unsorted; the probe kernel walks it in key order)
+    // Tensor-pipe screen (launch_center_order with the tf32 GEMM): cdist[q][c] is the reference's exact fp32 value wherever it is
+    // below exact_limit[q]; every other entry is a lower bound of the exact value that is itself >= exact_limit[q]. The probe
+    // re-evaluates the whole row exactly when its walk reaches the limit (and sets it to +inf). null = every entry is exact.
+    float* exact_limit;     // [nq]
     uint32_t* first;        // [nq] nearest cluster (scratch: sorted in place to derive qperm)
     uint32_t* qperm;        // [nq] work order: queries sorted by nearest cluster
     // per-query running state (also the multi-GPU exchange unit): see kernels_search.cu
@@ -163,6 +167,12 @@ void tune_set(const char* key, int64_t value);
 
 uint64_t query_state_bytes(uint32_t k);
 void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
+// Tensor-pipe centre scoring (kernels_tc.cu): approx[q*K + c] = 1 - dot_tf32(q, c) / (|q| |c|), within kCentreEps of the exact value.
+constexpr float kCentreEps = 0.004f;   // tf32 operands: |error| <= 2^-9 |q||c| on the dot, i.e. 0.00195 on the cosine; doubled
+constexpr uint32_t kCentreExact = 32;  // candidates per query evaluated exactly by launch_center_refine
+bool center_gemm_tc_supported(uint32_t d);
+void launch_center_gemm_tc(const float* queries, const float* qnorm, uint64_t nq, const float* center_rows, const float* center_norms,
+                           uint32_t K, uint32_t d, float* approx, cudaStream_t s);
 // cdist + first (nearest cluster); the caller then sorts `first` with launch_segment_sort to obtain qperm.
 void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 void launch_init_state(const SearchParams& p, const QueryBatch& b, cudaStream_t s);

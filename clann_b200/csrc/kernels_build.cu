@@ -167,7 +167,9 @@ __global__ void k_gmm_finish(const uint64_t* __restrict__ keys, uint32_t K, uint
     if (i < n) {
         uint32_t a = assign[i];
         // radii start at 0.0 and take f32::max: as signed ints, negative floats order below 0 and positives order naturally.
-        atomicMax((int*)&radii[a], __float_as_int(dist[i]));
+        // f32::max ignores a NaN operand (gmm.rs:58-60; the distance of a zero vector is NaN)
+        const float di = dist[i];
+        if (di == di) atomicMax((int*)&radii[a], __float_as_int(di));
         atomicAdd(&sizes[a], 1u);
     }
 }

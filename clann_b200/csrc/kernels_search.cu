@@ -226,6 +226,128 @@ __global__ void __launch_bounds__(256) k_first_cluster(const float* __restrict__
     if (lane_id() == 0) first[q] = key;
 }
 
+// k-th smallest (k >= 1) of n u32 keys read through `key(i)`, by a four-pass byte radix select over a warp-private histogram.
+template <typename KeyFn>
+__device__ __forceinline__ uint32_t warp_kth_smallest_u32(KeyFn key, uint32_t n, uint32_t k, uint32_t* hist) {
+    const uint32_t lane = lane_id();
+    uint32_t prefix = 0, want = k;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+        const uint32_t shift = 24 - 8 * pass;
+        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t v = key(i);
+            if (pass == 0 || (v >> (shift + 8)) == prefix) atomicAdd(&hist[(v >> shift) & 0xffu], 1u);
+        }
+        __syncwarp();
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) mine += hist[8 * lane + j];
+        uint32_t pre = mine;  // entries in the bins of this lane and of every lower lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+            if ((int)lane >= o) pre += t;
+        }
+        const uint32_t below = pre - mine;
+        const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, below < want && want <= pre)) - 1;
+        uint32_t bin = 0, rem = 0;
+        if (lane == owner) {
+            uint32_t acc = below;
+            for (int j = 0; j < 8; j++) {
+                const uint32_t h = hist[8 * lane + j];
+                if (acc + h >= want) {
+                    bin = 8 * lane + j;
+                    rem = want - acc;
+                    break;
+                }
+                acc += h;
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, owner);
+        rem = __shfl_sync(0xffffffffu, rem, owner);
+        __syncwarp();
+        prefix = (prefix << 8) | bin;
+        want = rem;
+    }
+    return prefix;
+}
+
+// After the tensor-pipe screen: one warp per query. The kCentreExact centres with the smallest approximate distance are
+// evaluated exactly (distance_point: the reference's fp32 arithmetic, index.rs:592-600 over angulardata.rs:29-35) and stored;
+// every other entry becomes approx - kCentreEps, a lower bound of its exact value; exact_limit[q] = (the smallest
+// approximate distance that was not selected) - kCentreEps, so that every stored value below the limit is exact and every
+// value at or above it belongs to a centre whose exact distance is at or above it too. first[q] = the nearest centre (exact;
+// if the best exact value does not beat the limit the whole row is evaluated exactly here).
+__global__ void __launch_bounds__(256) k_center_refine(const float* __restrict__ queries, const float* __restrict__ qnorm, uint64_t nq,
+                                                       const float* __restrict__ center_rows, const float* __restrict__ center_norms,
+                                                       uint32_t K, uint32_t d, float* __restrict__ cdist, float* __restrict__ exact_limit,
+                                                       uint32_t* __restrict__ first) {
+    __shared__ uint32_t s_hist[8][256];
+    __shared__ uint32_t s_sel[8][kCentreExact];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    float* cd = cdist + q * K;
+    const float* qv = queries + q * d;
+    const float qn = qnorm[q];
+    float limit = INFINITY;
+    if (K > kCentreExact) {
+        // tau = the (kCentreExact + 1)-th smallest approximate distance; selected = entries strictly below it (at most kCentreExact)
+        const uint32_t tau_bits = warp_kth_smallest_u32([&](uint32_t i) { return float_order_bits(cd[i]); }, K, kCentreExact + 1, s_hist[warp]);
+        const float tau = float_from_order_bits(tau_bits);
+        uint32_t nsel = 0;
+        for (uint32_t c0 = 0; c0 < K; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const float a = c < K ? cd[c] : INFINITY;
+            const bool sel = c < K && float_order_bits(a) < tau_bits;
+            const uint32_t bal = __ballot_sync(0xffffffffu, sel);
+            if (sel) s_sel[warp][nsel + __popc(bal & ((1u << lane) - 1u))] = c;
+            if (c < K && !sel) cd[c] = a - kCentreEps;
+            nsel += __popc(bal);
+        }
+        __syncwarp();
+        unsigned long long best = ~0ull;
+        if (lane < nsel) {
+            const uint32_t c = s_sel[warp][lane];
+            const float e = distance_point(center_rows + (uint64_t)c * d, center_norms[c], qv, qn, d);
+            cd[c] = e;
+            best = ((unsigned long long)float_order_bits(e) << 32) | c;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t < best ? t : best;
+        }
+        limit = tau - kCentreEps;
+        if (nsel > 0 && float_from_order_bits((uint32_t)(best >> 32)) < limit) {
+            if (lane == 0) {
+                first[q] = (uint32_t)best;
+                exact_limit[q] = limit;
+            }
+            return;
+        }
+    }
+    // small K, NaN rows (zero query) or a nearest centre that does not clear the limit: the whole row, exactly
+    unsigned long long best = ~0ull;
+    for (uint32_t c = lane; c < K; c += 32) {
+        const float e = distance_point(center_rows + (uint64_t)c * d, center_norms[c], qv, qn, d);
+        cd[c] = e;
+        const unsigned long long key = ((unsigned long long)float_order_bits(e) << 32) | c;
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+        best = t < best ? t : best;
+    }
+    if (lane == 0) {
+        first[q] = (uint32_t)best;
+        exact_limit[q] = INFINITY;
+    }
+}
+
 __global__ void k_init_state(uint8_t* __restrict__ state, uint64_t nq, uint64_t state_bytes, uint32_t* work_counter) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q == 0) *work_counter = 0;
@@ -696,18 +818,30 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
         const float qn = b.qnorm[q];
         bool done = false, foreign = false;
 
-        const float* cd = b.cdist + (uint64_t)q * p.K;
+        float* cd = b.cdist + (uint64_t)q * p.K;
+        float exact_limit = b.exact_limit ? b.exact_limit[q] : INFINITY;
         for (; pos < p.K; pos++) {
             // next cluster of the stable ascending centre-distance order (index.rs:592-616): smallest key above last_key
-            unsigned long long nk = ~0ull;
-            for (uint32_t cc = lane; cc < p.K; cc += 32) {
-                unsigned long long key = ((unsigned long long)float_order_bits(cd[cc]) << 32) | cc;
-                if ((pos == 0 || key > last_key) && key < nk) nk = key;
-            }
+            unsigned long long nk;
+            for (;;) {
+                nk = ~0ull;
+                for (uint32_t cc = lane; cc < p.K; cc += 32) {
+                    unsigned long long key = ((unsigned long long)float_order_bits(cd[cc]) << 32) | cc;
+                    if ((pos == 0 || key > last_key) && key < nk) nk = key;
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long t = __shfl_xor_sync(0xffffffffu, nk, o);
-                nk = t < nk ? t : nk;
+                for (int o = 16; o > 0; o >>= 1) {
+                    unsigned long long t = __shfl_xor_sync(0xffffffffu, nk, o);
+                    nk = t < nk ? t : nk;
+                }
+                // tensor-pipe screen: values below exact_limit are exact and precede everything else; once the walk reaches the
+                // limit the row is re-evaluated with the reference's arithmetic (the keys consumed so far were exact and stay)
+                if (!(float_from_order_bits((uint32_t)(nk >> 32)) >= exact_limit)) break;
+                for (uint32_t cc = lane; cc < p.K; cc += 32)
+                    cd[cc] = distance_point(p.center_rows + (uint64_t)cc * p.g.d, p.center_norms[cc], qv, qn, p.g.d);
+                exact_limit = INFINITY;
+                if (lane == 0) b.exact_limit[q] = INFINITY;
+                __syncwarp();
             }
             const uint32_t c = (uint32_t)nk;
             float max_dist = INFINITY;
@@ -1358,6 +1492,13 @@ void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_
 
 void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
     if (b.nq == 0) return;
+    if (b.exact_limit && center_gemm_tc_supported(p.g.d) && tune_get("order_longest_first", 0) == 0) {
+        // nq x K x d on the tensor pipe as a screen, then the exact evaluation of each query's nearest candidates
+        launch_center_gemm_tc(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms, p.K, p.g.d, b.cdist, s);
+        k_center_refine<<<(unsigned)((b.nq + 7) / 8), 256, 0, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms, p.K, p.g.d,
+                                                                    b.cdist, b.exact_limit, b.first);
+        return;
+    }
     const uint32_t stride = p.g.d | 1;
     size_t smem = (size_t)96 * stride * sizeof(float);
     if (p.g.d <= 256) {

@@ -427,4 +427,156 @@ void launch_sketch_tc(const void* tiles, uint32_t n_tiles, const uint8_t* row_sl
                                                     planes, sl, kp, sketches);
 }
 
+
+// ================================================================================================ centre scoring GEMM
+//
+// src/core/index.rs:592-600 scores a query against every centre: K dot products of length d. For a batch that is the
+// nq x K x d GEMM north_star asks to put on the tensor cores. The reference's values are fp32 in ndarray's summation order,
+// and they decide the visiting order and the prune test bit for bit, so the tensor pipe cannot simply replace them. It
+// produces a SCREEN instead: tf32 products (kind::tf32, fp32 accumulate in TMEM) give every distance to within
+// kCentreEps; k_center_refine then evaluates exactly (the reference's arithmetic) the 32 nearest candidates of each query —
+// the only ones a search ever touches unless it walks more than 32 clusters — and publishes, per query, the bound below which
+// every stored value is exact. The probe kernel re-evaluates a query's whole row exactly the moment its walk reaches that bound.
+
+namespace tc {
+constexpr uint32_t kGemmKBlock = 32;                    // fp32 elements per 128-byte swizzle row
+constexpr uint32_t kGemmTile = kTileM * 128;            // bytes of one 128 x 32 fp32 tile
+constexpr uint32_t kGemmMaxKB = 4;                      // K blocks resident at once: d <= 128 in one pass, more in rounds
+
+// D[tmem] (+)= A[smem] * B[smem]^T with tf32 operands (SASS: UTCHMMA.tf32 family), M = 128, N = 128, K = 8 per instruction.
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::tf32: D = f32 (bits 4-5 = 1), A and B formats = 2 (TF32), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t idesc_tf32() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((kTileN >> 3) << 17) | ((kTileM >> 4) << 24);
+}
+}  // namespace tc
+
+// One CTA = 128 queries x 128 centres: approx[q * K + c] = 1 - dot_tf32(query q, centre c) / (|q| |c|).
+// q_map: 2-D fp32 tensor [nq][d], c_map: [K][d]; box = 32 floats x 128 rows, 128B swizzle; out-of-range rows and columns read 0.
+__global__ void __launch_bounds__(192, 1)
+k_center_gemm_tc(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap c_map, uint64_t nq, uint32_t K,
+                 uint32_t d, const float* __restrict__ qnorm, const float* __restrict__ cnorm, float* __restrict__ approx) {
+    using namespace tc;
+    extern __shared__ uint8_t s_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = base;                                   // [kGemmMaxKB] query tiles
+    uint8_t* s_b = base + (size_t)kGemmMaxKB * kGemmTile;  // [kGemmMaxKB] centre tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + (size_t)kGemmMaxKB * kGemmTile);
+    uint64_t* full = bars;       // operands of the current round landed
+    uint64_t* drained = bars + 1;  // the MMAs of the current round have read them
+    uint64_t* done = bars + 2;   // accumulator complete
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t q0 = blockIdx.x * kTileM, c0 = blockIdx.y * kTileN;
+    const uint32_t nkb = (d + kGemmKBlock - 1) / kGemmKBlock;
+    const uint32_t rounds = (nkb + kGemmMaxKB - 1) / kGemmMaxKB;
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        mbar_init(drained, 1);
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        // 128 columns of TMEM for the fp32 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (uint32_t r = 0; r < rounds; r++) {
+                if (r > 0) mbar_wait(drained, (r - 1) & 1u);
+                const uint32_t kb0 = r * kGemmMaxKB, kbn = min(kGemmMaxKB, nkb - kb0);
+                mbar_expect_tx(full, kbn * 2 * kGemmTile);
+                for (uint32_t i = 0; i < kbn; i++) {
+                    tma_load_2d(s_a + (size_t)i * kGemmTile, &q_map, full, (int32_t)((kb0 + i) * kGemmKBlock), (int32_t)q0);
+                    tma_load_2d(s_b + (size_t)i * kGemmTile, &c_map, full, (int32_t)((kb0 + i) * kGemmKBlock), (int32_t)c0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id = idesc_tf32();
+            for (uint32_t r = 0; r < rounds; r++) {
+                mbar_wait(full, r & 1u);
+                fence_after_sync();
+                const uint32_t kb0 = r * kGemmMaxKB, kbn = min(kGemmMaxKB, nkb - kb0);
+                for (uint32_t i = 0; i < kbn; i++) {
+#pragma unroll
+                    for (uint32_t k = 0; k < kGemmKBlock / 8; k++)
+                        mma_tf32(tmem, smem_desc(s_a + (size_t)i * kGemmTile, k * 32), smem_desc(s_b + (size_t)i * kGemmTile, k * 32), id,
+                                 (r | i | k) == 0 ? 0u : 1u);
+                }
+                mma_commit(drained);
+            }
+            mma_commit(done);
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4, thread = query row
+        const uint32_t quarter = warp & 3u;
+        const uint32_t q = q0 + quarter * 32 + lane;
+        mbar_wait(done, 0);
+        fence_after_sync();
+        const float qn = q < nq ? qnorm[q] : 1.0f;
+#pragma unroll 1
+        for (uint32_t cc = 0; cc < kTileN; cc += 32) {
+            int v[32];
+            tmem_ld32(tmem + ((quarter * 32u) << 16) + cc, v);
+            tmem_ld_wait();
+            if (q < nq) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t c = c0 + cc + j;
+                    if (c < K) approx[(uint64_t)q * K + c] = __fsub_rn(1.0f, __fdiv_rn(__int_as_float(v[j]), __fmul_rn(cnorm[c], qn)));
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        fence_after_sync();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128) : "memory");
+    }
+}
+
+// [rows][d] fp32, box = 32 floats x 128 rows, 128B swizzle
+static CUtensorMap f32_map(const float* base, uint64_t rows, uint32_t d) {
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
+    const cuuint32_t box[2] = {tc::kGemmKBlock, tc::kTileM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (fp32) failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+bool center_gemm_tc_supported(uint32_t d) { return d % 4 == 0 && d >= 4; }
+
+void launch_center_gemm_tc(const float* queries, const float* qnorm, uint64_t nq, const float* center_rows, const float* center_norms,
+                           uint32_t K, uint32_t d, float* approx, cudaStream_t s) {
+    if (nq == 0 || K == 0) return;
+    const CUtensorMap qm = f32_map(queries, nq, d), cm = f32_map(center_rows, K, d);
+    const size_t smem = 1024 + (size_t)2 * tc::kGemmMaxKB * tc::kGemmTile + 64;
+    static bool configured = false;
+    if (!configured) {
+        CLANN_CUDA(cudaFuncSetAttribute(k_center_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)((nq + tc::kTileM - 1) / tc::kTileM), (K + tc::kTileN - 1) / tc::kTileN);
+    k_center_gemm_tc<<<grid, 192, smem, s>>>(qm, cm, nq, K, d, qnorm, center_norms, approx);
+}
+
 }  // namespace clann

@@ -783,7 +783,7 @@ uint64_t orc_gmm(const float* data, uint64_t n, uint32_t d, uint64_t K, uint64_t
     for (uint64_t c = 0; c < K; c++) radii[c] = 0;
     for (uint64_t i = 0; i < n; i++) {
         float r = radii[assignment[i]];
-        radii[assignment[i]] = r > dist[i] ? r : dist[i]; /* f32::max */
+        radii[assignment[i]] = dist[i] > r ? dist[i] : r; /* f32::max: a NaN distance (zero vector) is ignored, r is never NaN */
     }
     free(norms); free(dist); free(nd);
     return K;

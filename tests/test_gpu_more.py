@@ -372,6 +372,8 @@ def test_probe_kernel_variants_agree(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
     variants = (("warp", {}), ("warp_no_dense_sims", {"CLANN_TUNE_DENSE_SIMS": "0"}),
+                ("no_tensor_centre_scoring", {"CLANN_TUNE_TC_CENTER": "0"}), ("no_tensor_sketches", {"CLANN_TUNE_TC_SKETCH": "0"}),
+                ("no_tensor_at_all", {"CLANN_TUNE_TC_CENTER": "0", "CLANN_TUNE_TC_SKETCH": "0"}),
                 ("first_stream", {"CLANN_TUNE_FIRST_STREAM": "1"}),
                 ("first_stream_cut_short", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "256"}),   # most visits outlive it
                 ("first_stream_tiny", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "64"}),

@@ -71,3 +71,37 @@ def test_tensor_sketches_equal_cuda_core_and_oracle(oracle, d):
     for i in range(len(queries)):
         assert np.array_equal(got[1][1][i], oi.sketch(q15[i])), f"query {i}"
     oi.free()
+
+
+@pytest.mark.parametrize("shape", [(40_000, 100, 10), (25_000, 64, 10), (20_000, 200, 5)])
+def test_tensor_centre_scoring_changes_nothing(shape):
+    """Query x centre scoring as a tf32 tensor-core GEMM screen + exact evaluation of the 32 nearest candidates
+    (k_center_gemm_tc, k_center_refine; index.rs:592-600) against the all-exact CUDA-core kernel: identical visiting order,
+    ids, distance bits and counters — for planted queries (one or two clusters), for uniform ones that walk far beyond the 32
+    exact candidates (the probe re-evaluates their row), and for a zero query (NaN distances)."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    n, d, k = shape
+    data = util.planted(n, d, 300 + d)
+    q = np.concatenate([util.planted_queries(data, 300, 301), util.uniform_sphere(60, d, 302), np.zeros((1, d), np.float32)])
+    ix = cb.init_with_config(data, cb.Config(20, 0.4, k, 0.9, "centre"))
+    ix.set_option("seed", 3)
+    ix.build()
+    K = ix.num_clusters
+    assert K > 40   # more centres than exact candidates per query
+    res = {}
+    for tc in (1, 0):
+        cl.tune("tc_center", tc)
+        cl.tune("dense_adaptive", 0)   # keep the screen on whatever the previous batch did
+        try:
+            ids, dists, counts = ix.search_batch(q)
+            ctr = ix.counters(len(q))
+            order = ix.export(cl.X_CLUSTER_ORDER, 0, np.uint32).reshape(len(q), K).copy()
+            res[tc] = (ids, dists.view(np.uint32), counts, ctr["candidates"], ctr["distance_computations"], ctr["clusters_visited"], order)
+        finally:
+            cl.tune("tc_center", 1)
+            cl.tune("dense_adaptive", 1)
+    assert res[0][5].max() > 32    # some query does walk past the exact candidates
+    for a, b in zip(res[1], res[0]):
+        assert np.array_equal(a, b)
+    ix.close()
