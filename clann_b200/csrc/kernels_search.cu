@@ -520,7 +520,7 @@ struct FsView {
     const uint32_t* meta;  // kFsMeta words
 };
 
-template <int G, bool AHEAD = false>
+template <int G, bool AHEAD = false, bool STREAM = false>
 __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
                                   uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop, float max_sim,
                                   const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, uint16_t* memo, ProbeCounters& ctr,
@@ -543,7 +543,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
 
     // --- first-visit candidate stream: the depths down to fs_lo are replayed from it; anchors and ranges are only computed if
     // the visit goes deeper than the stream (or there is none)
-    const uint32_t fs_lo = (AHEAD && fs.meta) ? __ldg(fs.meta + 48) : (uint32_t)kMaxHashBits + 1;
+    const uint32_t fs_lo = (STREAM && fs.meta) ? __ldg(fs.meta + 48) : (uint32_t)kMaxHashBits + 1;
     bool anchors_ready = fs_lo > (uint32_t)kMaxHashBits;
     // --- SearchBuffers ctor (collection.hpp:642-645): anchor per table + 8 stride-12 samples each way
     if (!anchors_ready) {
@@ -575,7 +575,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
     bool stopped = false;
     ctr.stop_point = 0;
     for (uint32_t depth = kMaxHashBits; depth > 0 && !stopped; depth--) {
-        const bool streamed = AHEAD && depth >= fs_lo;
+        const bool streamed = STREAM && depth >= fs_lo;
         uint32_t soff = 0;  // first segment of this depth's block in the stream
         // --- fill_ranges (collection.hpp:650-667) with get_next_range (prefixmap.hpp:267-304) in closed form
         uint32_t running = 0;
@@ -732,7 +732,7 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (table_idx >> 5));
             if ((word >> (table_idx & 31)) & 1u) {
                 stopped = true;
-                ctr.stop_point = ((unsigned long long)depth << 32) | table_idx;
+                ctr.stop_point = depth << 16 | table_idx;
                 break;
             }
         } while (base + kRing < S);
@@ -767,7 +767,13 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
 
 // src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
 // for expensive ones). Warps are persistent; grid = multiple of the SM count.
-template <int G, int OCC, bool DENSE>
+// Cold path of the tensor-pipe centre screen: every distance of one query's row with the reference's arithmetic (one warp).
+__device__ __noinline__ void exact_center_row(const float* __restrict__ center_rows, const float* __restrict__ center_norms, uint32_t K,
+                                              uint32_t d, const float* __restrict__ qv, float qn, float* __restrict__ cd) {
+    for (uint32_t cc = lane_id(); cc < K; cc += 32) cd[cc] = distance_point(center_rows + (uint64_t)cc * d, center_norms[cc], qv, qn, d);
+}
+
+template <int G, int OCC, bool DENSE, bool STREAM>
 __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign,
                                                     uint16_t* memo_base, uint64_t memo_stride, uint32_t smem_memo_cap) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -802,7 +808,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
         uint32_t pos = st->next_pos;
         unsigned long long last_key = st->last_key;
         uint32_t visited = st->visited;
-        ProbeCounters ctr{st->candidates, st->distcomp, st->stop_point};
+        ProbeCounters ctr{st->candidates, st->distcomp, (uint32_t)((st->stop_point >> 32) << 16 | (st->stop_point & 0xffffu))};
         for (uint32_t i = lane; i < heap_len; i += 32) sm.heap[i] = st_heap[i];
         // query row -> shared memory and this lane's 16-byte chunk -> registers
         for (uint32_t i = lane; i < p.g.sl / 2; i += 32)
@@ -837,8 +843,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 // tensor-pipe screen: values below exact_limit are exact and precede everything else; once the walk reaches the
                 // limit the row is re-evaluated with the reference's arithmetic (the keys consumed so far were exact and stay)
                 if (!(float_from_order_bits((uint32_t)(nk >> 32)) >= exact_limit)) break;
-                for (uint32_t cc = lane; cc < p.K; cc += 32)
-                    cd[cc] = distance_point(p.center_rows + (uint64_t)cc * p.g.d, p.center_norms[cc], qv, qn, p.g.d);
+                exact_center_row(p.center_rows, p.center_norms, p.K, p.g.d, qv, qn, cd);
                 exact_limit = INFINITY;
                 if (lane == 0) b.exact_limit[q] = INFINITY;
                 __syncwarp();
@@ -919,14 +924,14 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 const uint32_t* pre_r = (prefilled && b.pre_range) ? b.pre_range + (uint64_t)q * kMaxHashBits * p.g.L : nullptr;
                 const uint4* pre_l = (prefilled && b.pre_lcp && !b.pre_range) ? b.pre_lcp + (uint64_t)q * p.g.L : nullptr;
                 FsView fsv{nullptr, nullptr, nullptr, nullptr};
-                if (prefilled && b.fs_meta) {
+                if (STREAM && prefilled && b.fs_meta) {
                     const uint64_t sbase = (uint64_t)q * b.fs_cap;
                     fsv.idx = reinterpret_cast<const uint2*>(b.fs_idx) + sbase;
                     fsv.hd = b.fs_hd + sbase;
                     fsv.tab = b.fs_tab + (sbase >> 5);
                     fsv.meta = b.fs_meta + (uint64_t)q * kFsMeta;
                 }
-                uint32_t cnt = probe_cluster<G, DENSE>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
+                uint32_t cnt = probe_cluster<G, DENSE, STREAM>(p, sm, c, codes, b.nq, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, use_memo, ctr,
                                                        prefilled, wait_bar, memo_phase, pre_a, pre_r, pre_l, fsv);
                 if (wait_bar) memo_phase ^= 1u;
                 // map_candidates + fp32 distance + heap (index.rs:392-416); results are visited best-first
@@ -959,7 +964,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
             st->done = done ? 1u : 0u;
             st->candidates = ctr.candidates;
             st->distcomp = ctr.distcomp;
-            st->stop_point = ctr.stop_point;
+            st->stop_point = ((unsigned long long)(ctr.stop_point >> 16) << 32) | (ctr.stop_point & 0xffffu);
         }
         __syncwarp();
     }
@@ -1540,7 +1545,7 @@ static int rerank_group(uint32_t sl) {
     return g;
 }
 
-template <int G, int OCC, bool DENSE>
+template <int G, int OCC, bool DENSE, bool STREAM = false>
 static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
     static int sm_count = 0;
     if (sm_count == 0) {
@@ -1567,11 +1572,11 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC, DENSE, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     int ctas_per_sm = 0;
-    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC, DENSE>, warps * 32, smem));
+    CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC, DENSE, STREAM>, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const int cap = (int)tune_get("probe_ctas", 0);  // knob: fewer resident queries = smaller L2 working set
     if (cap > 0 && cap < ctas_per_sm) ctas_per_sm = cap;
@@ -1584,7 +1589,7 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     const uint64_t stride = b.memo_stride;
     SearchParams pp = p;
     pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
-    k_probe<G, OCC, DENSE><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride, smem_memo_cap);
+    k_probe<G, OCC, DENSE, STREAM><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride, smem_memo_cap);
 }
 
 template <int G>
@@ -1594,7 +1599,9 @@ static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop
     const bool dense = b.dense != nullptr && !stop_at_foreign;
     int occ = (int)tune_get("probe_occ", 0);  // knob: resident CTAs per SM the kernel is compiled for (0 = the default above)
     if (occ < 2 || occ > 3) occ = dense ? 2 : 3;  // (four CTAs of 64 registers spill: 5.5 ms, instantiation dropped)
-    if (dense) {
+    if (dense && b.fs_meta) {  // the opt-in first-visit candidate stream has its own instantiation (it costs registers)
+        launch_probe_go<G, 2, true, true>(p, b, stop_at_foreign, s);
+    } else if (dense) {
         if (occ == 2) launch_probe_go<G, 2, true>(p, b, stop_at_foreign, s);
         else launch_probe_go<G, 3, true>(p, b, stop_at_foreign, s);
     } else {

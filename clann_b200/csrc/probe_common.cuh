@@ -219,7 +219,7 @@ __device__ __forceinline__ void maxbuffer_insert_list(unsigned long long* mb, ui
 
 struct ProbeCounters {
     unsigned long long candidates, distcomp;
-    unsigned long long stop_point;  // of the last visit: (depth << 32) | table_idx where the stop rule fired, 0 = ran out of depths
+    uint32_t stop_point;  // of the last visit: (depth << 16) | table_idx where the stop rule fired, 0 = ran out of depths
 };
 
 __device__ __forceinline__ uint32_t lcp24(uint32_t a, uint32_t b) {
