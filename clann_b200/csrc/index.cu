@@ -2,7 +2,9 @@
 // declared in include/clann_b200.h. Citations are file:line into /root/reference.
 #include "../../include/clann_b200.h"
 
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -413,6 +415,49 @@ static void read_reference_stream(const uint8_t* blob, uint64_t len, LoadedStrea
 
 using namespace clann;
 
+// ------------------------------------------------------------------------------------------------ collectives
+
+// NCCL is resolved at run time (dlopen): the library has no link-time dependency on it, a single-GPU user never loads it, and
+// inside a process that already holds a copy (torch's bundled libnccl) that copy is the one found.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool loaded = false;
+    if (!loaded) {
+        void* h = nullptr;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) throw StatusError(CLANN_ERR_CONFIG, "NCCL (libnccl.so.2) not found: clann_comm_init needs it; use clann_set_collectives for another transport");
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.AllReduce)
+            throw StatusError(CLANN_ERR_CONFIG, "libnccl.so.2 lacks the expected entry points");
+        loaded = true;
+    }
+    return api;
+}
+
+#define CLANN_NCCL(expr)                                                                                                  \
+    do {                                                                                                                  \
+        ncclResult_t _r = (expr);                                                                                         \
+        if (_r != ncclSuccess)                                                                                            \
+            throw CudaError(std::string(#expr) + ": " + (nccl_api().GetErrorString ? nccl_api().GetErrorString(_r) : "NCCL error")); \
+    } while (0)
+
 struct clann_index {
     // configuration
     clann_config cfg{};
@@ -424,6 +469,22 @@ struct clann_index {
     bool puffinn_mode = false;  // legacy single-index handle: one cluster, no CLANN layer
     uint32_t shard_rank = 0, shard_count = 1;
     bool clustering_imposed = false, built = false;
+
+    // cluster-sharded search (search_sharded): the transport — NCCL (clann_comm_init) or caller-supplied collectives
+    // (clann_set_collectives) — and its buffers, all sized for the global batch
+    ncclComm_t comm = nullptr;
+    clann_allgather_fn user_allgather = nullptr;
+    clann_allreduce_min_u64_fn user_allreduce_min = nullptr;
+    void* user_ctx = nullptr;
+    struct ShardBufs {
+        DevBuf<uint32_t> first_all, list0, list1, counts;
+        DevBuf<unsigned long long> packed, packed1, top_local, top_all, counters;
+        DevBuf<float> q0, q1;
+        uint32_t* h_counts = nullptr;  // pinned: {queries routed to this rank in round one, queries still open in round two}
+        uint64_t nq = 0;
+        uint32_t n0 = 0, n1 = 0;
+        bool last_was_sharded = false;
+    } sh;
 
     // host mirrors
     std::vector<uint32_t> h_centers, h_sizes, h_assign;
@@ -512,6 +573,8 @@ struct clann_index {
         for (auto& st : pipe_stream)
             if (st) cudaStreamDestroy(st);
         if (h_stats) cudaFreeHost(h_stats);
+        if (sh.h_counts) cudaFreeHost(sh.h_counts);
+        if (comm) nccl_api().CommDestroy(comm);
     }
 
     void reset_workspaces() {
@@ -1152,6 +1215,8 @@ struct clann_index {
         b.fs_tab = nullptr;
         b.fs_meta = nullptr;
         b.fs_cap = W->w_fs_cap;
+        b.first_is_own = false;
+        b.shard_packed = nullptr;
         b.stats_dev = (d_ids && h_stats_dev) ? W->w_stats.p : nullptr;
         b.stats_host = h_stats_dev;
         b.out_ids = d_ids;
@@ -1183,6 +1248,7 @@ struct clann_index {
         require_built();
         ensure_workspace(nq, s);
         W->ws_tc_center = use_tc_center();  // decided once per batch: every later view of this workspace must agree with it
+        sh.last_was_sharded = false;
         SearchParams p = params();
         QueryBatch b = batch(d_queries, nq, nullptr, nullptr, nullptr);
         launch_prep_queries(p, b, s);
@@ -1279,6 +1345,125 @@ struct clann_index {
             last_pre_launches = 2;
         } else last_pre_launches = 1;
         return true;
+    }
+
+    // ---- cluster-sharded search: one process per GPU, every rank calls this with the same global batch ------------
+    void all_gather(const void* send, void* recv, uint64_t bytes, cudaStream_t s) {
+        if (user_allgather) {
+            if (user_allgather(user_ctx, send, recv, bytes, s) != 0) throw StatusError(CLANN_ERR_SEARCH, "the caller's all-gather failed");
+        } else if (comm) {
+            CLANN_NCCL(nccl_api().AllGather(send, recv, bytes, ncclUint8, comm, s));
+        } else throw StatusError(CLANN_ERR_CONFIG, "no transport: call clann_comm_init or clann_set_collectives first");
+    }
+    void all_reduce_min_u64(void* buf, uint64_t count, cudaStream_t s) {
+        if (user_allreduce_min) {
+            if (user_allreduce_min(user_ctx, buf, count, s) != 0) throw StatusError(CLANN_ERR_SEARCH, "the caller's all-reduce failed");
+        } else if (comm) {
+            CLANN_NCCL(nccl_api().AllReduce(buf, buf, count, ncclUint64, ncclMin, comm, s));
+        } else throw StatusError(CLANN_ERR_CONFIG, "no transport: call clann_comm_init or clann_set_collectives first");
+    }
+
+    // Each rank owns the clusters assign_owners gave it and holds tables for those only. Per batch:
+    //   route   every rank scores its 1/world slice of the queries against the (replicated) centres; one all-gather of the nearest
+    //           cluster ids tells every rank which queries start in its own clusters
+    //   round 1 a rank runs the reference's loop (index.rs:311-439) on those queries, unchanged, for as long as the visiting order
+    //           stays inside its own clusters: prune test, radius early exit, max_sim, heap — first visits are 83 % of all visits
+    //           on the planted shape and 4 of 5 queries end here
+    //   bound   one all-reduce(min) of 8 bytes per query: finished, or the k-th distance reached and the clusters consumed
+    //   round 2 every rank walks the order of the queries still open, prunes with the agreed bound (tightened by its own k-th
+    //           distance once its heap is full) and visits its own clusters among those — a superset of the reference's visits
+    //   merge   one all-gather of nq x k x (distance, id) and a k-way merge
+    // No step moves more than a few megabytes; results have recall >= the single-GPU search (identical whenever the walk of a query
+    // stays on one rank).
+    void search_sharded(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
+        require_built();
+        if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded needs an index built with shard_count > 1");
+        if (nq == 0) return;
+        if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
+        const uint32_t world = shard_count, rank = shard_rank, k = (uint32_t)cfg.k, d = g.d;
+        const uint64_t chunk = (nq + world - 1) / world;
+        if (sh.nq != nq) {
+            sh.first_all.ensure(chunk * world);
+            sh.list0.ensure(nq);
+            sh.list1.ensure(nq);
+            sh.counts.ensure(2);
+            sh.packed.ensure(nq);
+            sh.packed1.ensure(nq);
+            sh.top_local.ensure(nq * k);
+            sh.top_all.ensure(nq * k * world);
+            sh.counters.ensure(nq * 3);
+            sh.q0.ensure(nq * d);
+            sh.q1.ensure(nq * d);
+            if (!sh.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&sh.h_counts), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            sh.nq = nq;
+        }
+        SearchWs* saved = W;
+        try {
+            CLANN_CUDA(cudaMemsetAsync(sh.counts.p, 0, 2 * sizeof(uint32_t), s));
+            // ---- route: nearest centre of this rank's slice of the batch
+            const uint64_t lo = std::min<uint64_t>(nq, rank * chunk), hi = std::min<uint64_t>(nq, lo + chunk);
+            W = &wsv[2];
+            if (hi > lo) {
+                ensure_workspace(hi - lo, s);
+                W->ws_tc_center = use_tc_center();
+                SearchParams p = params();
+                QueryBatch b = batch(d_queries + lo * d, hi - lo, nullptr, nullptr, nullptr);
+                launch_prep_queries(p, b, s);
+                launch_center_order(p, b, s);
+                CLANN_CUDA(cudaMemcpyAsync(sh.first_all.p + lo, b.first, (hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            }
+            // in-place all-gather: every rank's slice sits at rank * chunk of the same buffer
+            all_gather(sh.first_all.p + rank * chunk, sh.first_all.p, chunk * sizeof(uint32_t), s);
+            launch_shard_select_owned(sh.first_all.p, d_owner.p, rank, nq, sh.list0.p, sh.counts.p, s);
+            CLANN_CUDA(cudaMemcpyAsync(sh.h_counts, sh.counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CLANN_CUDA(cudaStreamSynchronize(s));
+            const uint32_t n0 = sh.h_counts[0];
+            sh.n0 = n0;
+            // ---- round one
+            launch_fill_u64(sh.packed.p, nq, 0xff800000ffffffffull, s);  // {+inf, nothing consumed}
+            launch_fill_u64(sh.top_local.p, nq * k, ~0ull, s);
+            CLANN_CUDA(cudaMemsetAsync(sh.counters.p, 0, nq * 3 * sizeof(unsigned long long), s));
+            W = &wsv[0];
+            if (n0) {
+                launch_shard_gather_rows(d_queries, sh.list0.p, n0, d, sh.q0.p, s);
+                search_begin(sh.q0.p, n0, s);
+                SearchParams p = params();
+                QueryBatch b = batch(sh.q0.p, n0, nullptr, nullptr, nullptr);
+                b.first_is_own = true;  // by construction of list0
+                use_dense_sims(p, b, s);
+                launch_probe(p, b, 1, s);
+                launch_shard_pack_bounds(W->w_state.p, k, sh.list0.p, n0, sh.packed.p, s);
+                launch_shard_collect(W->w_state.p, k, sh.list0.p, n0, sh.top_local.p, false, sh.counters.p, s);
+            }
+            // ---- agree on the bounds, select what is still open
+            all_reduce_min_u64(sh.packed.p, nq, s);
+            launch_shard_select_open(sh.packed.p, nq, sh.list1.p, sh.packed1.p, sh.counts.p + 1, s);
+            CLANN_CUDA(cudaMemcpyAsync(sh.h_counts + 1, sh.counts.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CLANN_CUDA(cudaStreamSynchronize(s));
+            const uint32_t n1 = sh.h_counts[1];
+            sh.n1 = n1;
+            // ---- round two
+            W = &wsv[1];
+            if (n1) {
+                launch_shard_gather_rows(d_queries, sh.list1.p, n1, d, sh.q1.p, s);
+                search_begin(sh.q1.p, n1, s);
+                SearchParams p = params();
+                QueryBatch b = batch(sh.q1.p, n1, nullptr, nullptr, nullptr);
+                b.shard_packed = sh.packed1.p;
+                launch_probe(p, b, 2, s);
+                launch_shard_collect(W->w_state.p, k, sh.list1.p, n1, sh.top_local.p, true, sh.counters.p, s);
+            }
+            // ---- merge
+            all_gather(sh.top_local.p, sh.top_all.p, nq * k * sizeof(unsigned long long), s);
+            launch_shard_final_merge(sh.top_all.p, world, nq, k, d_ids, d_dists, d_counts, s);
+            sh.last_was_sharded = true;
+            last_nq = nq;
+            last_launches = 0;
+        } catch (...) {
+            W = saved;
+            throw;
+        }
+        W = saved;
     }
 
     int next_pipe_slot() {
@@ -1559,11 +1744,70 @@ int clann_search_end(clann_index* index, uint32_t* d_ids, float* d_dists, uint32
     });
 }
 
+int clann_comm_unique_id(uint8_t* out, uint64_t cap) {
+    return guarded([&] {
+        if (!out || cap < sizeof(ncclUniqueId)) throw StatusError(CLANN_ERR_ARG, "unique id buffer must hold 128 bytes");
+        ncclUniqueId id;
+        CLANN_NCCL(nccl_api().GetUniqueId(&id));
+        memcpy(out, &id, sizeof(id));
+    });
+}
+
+int clann_comm_init(clann_index* index, int rank, int world, const uint8_t* unique_id) {
+    return guarded([&] {
+        if (!index || !unique_id || world < 1 || rank < 0 || rank >= world) throw StatusError(CLANN_ERR_ARG, "bad communicator arguments");
+        if ((uint32_t)world != index->shard_count || (uint32_t)rank != index->shard_rank)
+            throw StatusError(CLANN_ERR_CONFIG, "rank / world must equal the index's shard_rank / shard_count options");
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof(id));
+        if (index->comm) {
+            nccl_api().CommDestroy(index->comm);
+            index->comm = nullptr;
+        }
+        CLANN_NCCL(nccl_api().CommInitRank(&index->comm, world, id, rank));
+    });
+}
+
+int clann_set_collectives(clann_index* index, clann_allgather_fn allgather, clann_allreduce_min_u64_fn allreduce_min, void* ctx) {
+    return guarded([&] {
+        if (!index || !allgather || !allreduce_min) throw StatusError(CLANN_ERR_ARG, "null index or collective");
+        index->user_allgather = allgather;
+        index->user_allreduce_min = allreduce_min;
+        index->user_ctx = ctx;
+    });
+}
+
+int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts,
+                         void* stream) {
+    return guarded([&] {
+        if (!index || (nq && (!d_queries || !d_ids || !d_dists || !d_counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_sharded(d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        if (routed_round_one) *routed_round_one = index->sh.n0;
+        if (open_round_two) *open_round_two = index->sh.n1;
+    });
+}
+
 int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, uint64_t* distance_computations, uint32_t* clusters_visited) {
     return guarded([&] {
         if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
         if (nq > index->last_nq) throw StatusError(CLANN_ERR_BOUNDS, "more counters requested than queries searched");
         CLANN_CUDA(cudaDeviceSynchronize());
+        if (index->sh.last_was_sharded) {
+            // this rank's share of every query's counters (sum them over the ranks for the totals)
+            std::vector<unsigned long long> c = index->sh.counters.download(nq * 3);
+            for (uint64_t q = 0; q < nq; q++) {
+                if (candidates) candidates[q] = c[q * 3];
+                if (distance_computations) distance_computations[q] = c[q * 3 + 1];
+                if (clusters_visited) clusters_visited[q] = (uint32_t)c[q * 3 + 2];
+            }
+            return;
+        }
         if (candidates) CLANN_CUDA(cudaMemcpy(candidates, index->W->w_cand.p, nq * 8, cudaMemcpyDeviceToHost));
         if (distance_computations) CLANN_CUDA(cudaMemcpy(distance_computations, index->W->w_dc.p, nq * 8, cudaMemcpyDeviceToHost));
         if (clusters_visited) CLANN_CUDA(cudaMemcpy(clusters_visited, index->W->w_vis.p, nq * 4, cudaMemcpyDeviceToHost));

@@ -150,6 +150,10 @@ struct QueryBatch {
     uint8_t* fs_tab;
     uint32_t* fs_meta;
     uint32_t fs_cap;
+    // cluster-sharded search (index.cu search_sharded): first_is_own = every query's nearest cluster is owned by this rank (round one);
+    // shard_packed[q] = (order_bits(bound) << 32) | (0xffffffff - clusters consumed in round one), the input of round two
+    bool first_is_own;
+    const unsigned long long* shard_packed;
     // outputs
     uint32_t* out_ids;      // [nq][k]
     float* out_dists;       // [nq][k]
@@ -193,9 +197,25 @@ bool launch_first_stream(const SearchParams& p, const QueryBatch& b, cudaStream_
 // reference's padded table coordinates (needs b.codes of the last search_begin).
 void launch_export_ranges(const SearchParams& p, const QueryBatch& b, uint32_t cluster, uint32_t* anchors, uint32_t* ranges,
                           cudaStream_t s);
-// Advances every unfinished query through the clusters owned by this shard (all of them when single_pass).
-void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);
-void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s);  // one warp per query
+// stop_at_foreign: 0 = walk every cluster (one GPU holds the whole index); 1 = advance every unfinished query through the consecutive
+// clusters this shard owns and stop at the first foreign one (stepping protocol; round one of the sharded search); 2 = round two of
+// the sharded search: walk the whole order from the start, skip what round one consumed and what other shards own, prune with the
+// agreed bound (QueryBatch::shard_packed).
+void launch_probe(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s);
+void launch_probe_warp(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s);  // one warp per query
+// Cluster-sharded search (index.cu search_sharded): routing, bound exchange and result merge helpers.
+void launch_shard_select_owned(const uint32_t* first_all, const uint8_t* owner, uint32_t rank, uint64_t nq, uint32_t* list, uint32_t* count,
+                               cudaStream_t s);
+void launch_shard_select_open(const unsigned long long* packed, uint64_t nq, uint32_t* list, unsigned long long* packed_local,
+                              uint32_t* count, cudaStream_t s);
+void launch_shard_gather_rows(const float* all, const uint32_t* list, uint32_t count, uint32_t d, float* out, cudaStream_t s);
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);
+void launch_shard_pack_bounds(const uint8_t* state, uint32_t k, const uint32_t* list, uint32_t count, unsigned long long* packed,
+                              cudaStream_t s);
+void launch_shard_collect(const uint8_t* state, uint32_t k, const uint32_t* list, uint32_t count, unsigned long long* top, bool merge,
+                          unsigned long long* counters, cudaStream_t s);
+void launch_shard_final_merge(const unsigned long long* all, uint32_t world, uint64_t nq, uint32_t k, uint32_t* out_ids, float* out_dists,
+                              uint32_t* out_counts, cudaStream_t s);
 void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8_t* all_states, int world, uint32_t* active, cudaStream_t s);
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 uint32_t probe_memo_slots();  // upper bound on the memo regions any probe launch uses on the current device

@@ -826,6 +826,15 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
 
         float* cd = b.cdist + (uint64_t)q * p.K;
         float exact_limit = b.exact_limit ? b.exact_limit[q] : INFINITY;
+        // cluster-sharded second round (stop_at_foreign == 2): the bound every rank agreed on after the first round and the number
+        // of clusters the first round consumed (all on the rank that owns the query's nearest cluster)
+        float ext_bound = INFINITY;
+        uint32_t pos0 = 0;
+        if (stop_at_foreign == 2) {
+            const unsigned long long pk = b.shard_packed[q];
+            ext_bound = float_from_order_bits((uint32_t)(pk >> 32));
+            pos0 = 0xffffffffu - (uint32_t)pk;
+        }
         for (; pos < p.K; pos++) {
             // next cluster of the stable ascending centre-distance order (index.rs:592-616): smallest key above last_key
             unsigned long long nk;
@@ -850,7 +859,26 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
             }
             const uint32_t c = (uint32_t)nk;
             float max_dist = INFINITY;
-            if (heap_len > 0) {  // index.rs:342-361
+            if (stop_at_foreign == 2) {
+                // The prune test of index.rs:342-361 against a bound that is never below the reference's running k-th distance:
+                // the agreed bound of round one, tightened by this rank's own k-th distance once its local heap is full. The walk
+                // therefore ends no earlier than the reference's, and visits this rank's clusters among the ones the reference
+                // would visit (a superset: recall >= the reference's).
+                if (heap_len >= p.k) {
+                    unsigned long long top = topk_peek(sm.heap, heap_len);
+                    max_dist = float_from_order_bits((uint32_t)(top >> 32));
+                }
+                max_dist = fminf(max_dist, ext_bound);
+                float cmin = __fsub_rn(float_from_order_bits((uint32_t)(nk >> 32)), p.radii[c]);
+                if (cmin > max_dist) {
+                    done = true;
+                    break;
+                }
+                if (pos < pos0 || p.owner[c] != p.shard_rank) {  // consumed in round one, or another rank's cluster
+                    last_key = nk;
+                    continue;
+                }
+            } else if (heap_len > 0) {  // index.rs:342-361
                 unsigned long long top = topk_peek(sm.heap, heap_len);
                 max_dist = float_from_order_bits((uint32_t)(top >> 32));
                 float cmin = __fsub_rn(float_from_order_bits((uint32_t)(nk >> 32)), p.radii[c]);
@@ -859,7 +887,7 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                     break;
                 }
             }
-            if (stop_at_foreign && p.owner[c] != p.shard_rank) {
+            if (stop_at_foreign == 1 && p.owner[c] != p.shard_rank) {
                 foreign = true;
                 break;
             }
@@ -991,6 +1019,170 @@ __global__ void k_merge_states(uint8_t* __restrict__ mine, const uint8_t* __rest
     uint64_t* dst = reinterpret_cast<uint64_t*>(mine + q * state_bytes);
     for (uint64_t i = 0; i < state_bytes / 8; i++) dst[i] = src[i];
     if (!best_done) atomicAdd(active, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------ cluster-sharded search
+
+// Round-one routing: the global ids of the queries whose nearest cluster this rank owns.
+__global__ void __launch_bounds__(256) k_shard_select_owned(const uint32_t* __restrict__ first_all, const uint8_t* __restrict__ owner,
+                                                            uint32_t rank, uint64_t nq, uint32_t* __restrict__ list, uint32_t* count) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = gid < nq && owner[first_all[gid]] == rank;
+    const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+    uint32_t base = 0;
+    if (lane_id() == 0 && bal) base = atomicAdd(count, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (mine) list[base + __popc(bal & ((1u << lane_id()) - 1u))] = (uint32_t)gid;
+}
+
+// Round-two routing: the queries no rank has finished (agreed bound >= 0), with their packed (bound, consumed) word.
+__global__ void __launch_bounds__(256) k_shard_select_open(const unsigned long long* __restrict__ packed, uint64_t nq,
+                                                           uint32_t* __restrict__ list, unsigned long long* __restrict__ packed_local,
+                                                           uint32_t* count) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long pk = gid < nq ? packed[gid] : 0ull;
+    const bool open = gid < nq && (uint32_t)(pk >> 32) >= 0x80000000u;  // order bits of a non-negative float
+    const uint32_t bal = __ballot_sync(0xffffffffu, open);
+    uint32_t base = 0;
+    if (lane_id() == 0 && bal) base = atomicAdd(count, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (open) {
+        const uint32_t slot = base + __popc(bal & ((1u << lane_id()) - 1u));
+        list[slot] = (uint32_t)gid;
+        packed_local[slot] = pk;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_shard_gather_rows(const float* __restrict__ all, const uint32_t* __restrict__ list, uint32_t count,
+                                                           uint32_t d, float* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint64_t)count * d) out[i] = all[(uint64_t)list[i / d] * d + i % d];
+}
+
+__global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* __restrict__ p, uint64_t n, unsigned long long v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// What a rank tells the others about the queries it advanced in round one: a bound on the k-th distance that holds whatever the
+// other ranks find — the heap top once the heap is full (index.rs:342-361 peeks earlier; an unfilled heap bounds nothing), -1 for
+// a finished query — and how many clusters of the visiting order it consumed. min over ranks of
+// (order_bits(bound) << 32) | (0xffffffff - consumed) picks the advancing rank's word (the others hold +inf / 0).
+__global__ void __launch_bounds__(256) k_shard_pack_bounds(const uint8_t* __restrict__ state, uint64_t state_bytes, uint32_t k,
+                                                           const uint32_t* __restrict__ list, uint32_t count,
+                                                           unsigned long long* __restrict__ packed) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(state + (uint64_t)i * state_bytes);
+    const unsigned long long* heap = reinterpret_cast<const unsigned long long*>(h + 1);
+    uint32_t bits = float_order_bits(INFINITY);
+    if (h->done) bits = float_order_bits(-1.0f);
+    else if (h->heap_len >= k) {
+        uint32_t top = 0;
+        for (uint32_t j = 0; j < h->heap_len; j++) top = max(top, (uint32_t)(heap[j] >> 32));
+        bits = top;
+    }
+    packed[list[i]] = ((unsigned long long)bits << 32) | (0xffffffffu - h->next_pos);
+}
+
+// This rank's candidates of every query it touched, ascending, into top[gid * k .. + k) (~0 = empty); one warp per local query.
+// merge != 0: the row already holds the sorted candidates of an earlier round. Counters are accumulated per global query.
+__global__ void __launch_bounds__(256) k_shard_collect(const uint8_t* __restrict__ state, uint64_t state_bytes, uint32_t k,
+                                                       const uint32_t* __restrict__ list, uint32_t count, unsigned long long* __restrict__ top,
+                                                       int merge, unsigned long long* __restrict__ counters) {
+    extern __shared__ unsigned long long s_cand[];  // [warps][2k]
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (i >= count) return;
+    const uint32_t gid = list[i];
+    const QueryStateHeader* h = reinterpret_cast<const QueryStateHeader*>(state + (uint64_t)i * state_bytes);
+    const unsigned long long* heap = reinterpret_cast<const unsigned long long*>(h + 1);
+    unsigned long long* cand = s_cand + (size_t)warp * 2 * k;
+    unsigned long long* row = top + (uint64_t)gid * k;
+    for (uint32_t j = lane; j < k; j += 32) {
+        cand[j] = j < h->heap_len ? heap[j] : ~0ull;
+        cand[k + j] = merge ? row[j] : ~0ull;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < 2 * k; j += 32) {
+        const unsigned long long key = cand[j];
+        if (key == ~0ull) continue;
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < 2 * k; o++) rank += (cand[o] < key) || (cand[o] == key && o < j);
+        if (rank < k) row[rank] = key;
+    }
+    if (!merge) {
+        uint32_t valid = h->heap_len < k ? h->heap_len : k;
+        for (uint32_t j = valid + lane; j < k; j += 32) row[j] = ~0ull;
+    }
+    if (lane == 0 && counters) {
+        counters[(uint64_t)gid * 3 + 0] += h->candidates;
+        counters[(uint64_t)gid * 3 + 1] += h->distcomp;
+        counters[(uint64_t)gid * 3 + 2] += h->visited;
+    }
+}
+
+// k-way merge of the ranks' candidate lists (all[r * nq * k + q * k ..]) into the final results (heap.rs:42-48 order); one warp per query.
+__global__ void __launch_bounds__(256) k_shard_final_merge(const unsigned long long* __restrict__ all, uint32_t world, uint64_t nq, uint32_t k,
+                                                           uint32_t* __restrict__ out_ids, float* __restrict__ out_dists,
+                                                           uint32_t* __restrict__ out_counts) {
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const uint32_t lane = lane_id();
+    const uint32_t total = world * k;
+    uint32_t valid = 0;
+    for (uint32_t j = lane; j < total; j += 32) {
+        const unsigned long long key = all[(uint64_t)(j / k) * nq * k + q * k + j % k];
+        if (key == ~0ull) continue;
+        valid++;
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < total; o++) {
+            const unsigned long long other = all[(uint64_t)(o / k) * nq * k + q * k + o % k];
+            rank += (other < key) || (other == key && o < j);
+        }
+        if (rank < k) {
+            out_ids[q * k + rank] = (uint32_t)key;
+            out_dists[q * k + rank] = float_from_order_bits((uint32_t)(key >> 32));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+    const uint32_t cnt = valid < k ? valid : k;
+    for (uint32_t j = cnt + lane; j < k; j += 32) {
+        out_ids[q * k + j] = 0xffffffffu;
+        out_dists[q * k + j] = INFINITY;
+    }
+    if (lane == 0) out_counts[q] = cnt;
+}
+
+void launch_shard_select_owned(const uint32_t* first_all, const uint8_t* owner, uint32_t rank, uint64_t nq, uint32_t* list, uint32_t* count,
+                               cudaStream_t s) {
+    if (nq) k_shard_select_owned<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(first_all, owner, rank, nq, list, count);
+}
+void launch_shard_select_open(const unsigned long long* packed, uint64_t nq, uint32_t* list, unsigned long long* packed_local,
+                              uint32_t* count, cudaStream_t s) {
+    if (nq) k_shard_select_open<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(packed, nq, list, packed_local, count);
+}
+void launch_shard_gather_rows(const float* all, const uint32_t* list, uint32_t count, uint32_t d, float* out, cudaStream_t s) {
+    const uint64_t n = (uint64_t)count * d;
+    if (n) k_shard_gather_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(all, list, count, d, out);
+}
+void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s) {
+    if (n) k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
+}
+void launch_shard_pack_bounds(const uint8_t* state, uint32_t k, const uint32_t* list, uint32_t count, unsigned long long* packed,
+                              cudaStream_t s) {
+    if (count) k_shard_pack_bounds<<<(count + 255) / 256, 256, 0, s>>>(state, query_state_bytes(k), k, list, count, packed);
+}
+void launch_shard_collect(const uint8_t* state, uint32_t k, const uint32_t* list, uint32_t count, unsigned long long* top, bool merge,
+                          unsigned long long* counters, cudaStream_t s) {
+    if (!count) return;
+    const size_t smem = (size_t)8 * 2 * k * sizeof(unsigned long long);
+    k_shard_collect<<<(count + 7) / 8, 256, smem, s>>>(state, query_state_bytes(k), k, list, count, top, merge ? 1 : 0, counters);
+}
+void launch_shard_final_merge(const unsigned long long* all, uint32_t world, uint64_t nq, uint32_t k, uint32_t* out_ids, float* out_dists,
+                              uint32_t* out_counts, cudaStream_t s) {
+    if (nq) k_shard_final_merge<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(all, world, nq, k, out_ids, out_dists, out_counts);
 }
 
 // heap.rs:42-48 — results ascending by distance; pads with 0xFFFFFFFF / +inf.
@@ -1546,7 +1738,7 @@ static int rerank_group(uint32_t sl) {
 }
 
 template <int G, int OCC, bool DENSE, bool STREAM = false>
-static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+static void launch_probe_go(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s) {
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev;
@@ -1589,14 +1781,16 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, bool sto
     const uint64_t stride = b.memo_stride;
     SearchParams pp = p;
     pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
-    k_probe<G, OCC, DENSE, STREAM><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign ? 1 : 0, use, stride, smem_memo_cap);
+    k_probe<G, OCC, DENSE, STREAM><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign, use, stride, smem_memo_cap);
 }
 
 template <int G>
-static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+static void launch_probe_g(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s) {
     // With the first visit's similarities computed in advance (b.dense) the kernel is lighter and two CTAs per SM with 128
     // registers beat three with 80 (measured 2.82 vs 2.94 ms including the dense kernel); without, three (3.08 vs 3.36 ms).
-    const bool dense = b.dense != nullptr && !stop_at_foreign;
+    // dense first-visit similarities need the query's nearest cluster on this rank: always true unsharded, and in the first round of
+    // the sharded search (queries are routed to the owner of their nearest cluster); the stepping protocol gives no such guarantee
+    const bool dense = b.dense != nullptr && (!stop_at_foreign || (stop_at_foreign == 1 && b.first_is_own));
     int occ = (int)tune_get("probe_occ", 0);  // knob: resident CTAs per SM the kernel is compiled for (0 = the default above)
     if (occ < 2 || occ > 3) occ = dense ? 2 : 3;  // (four CTAs of 64 registers spill: 5.5 ms, instantiation dropped)
     if (dense && b.fs_meta) {  // the opt-in first-visit candidate stream has its own instantiation (it costs registers)
@@ -1610,7 +1804,7 @@ static void launch_probe_g(const SearchParams& p, const QueryBatch& b, bool stop
     }
 }
 
-void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+void launch_probe(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s) {
     static int64_t fetch_set = 0;
     const int64_t fetch = tune_get("l2_fetch", 0);  // knob: cudaLimitMaxL2FetchGranularity in bytes (32/64/128), 0 = leave alone
     if (fetch != fetch_set && fetch > 0) {
@@ -1620,7 +1814,7 @@ void launch_probe(const SearchParams& p, const QueryBatch& b, bool stop_at_forei
     launch_probe_warp(p, b, stop_at_foreign, s);
 }
 
-void launch_probe_warp(const SearchParams& p, const QueryBatch& b, bool stop_at_foreign, cudaStream_t s) {
+void launch_probe_warp(const SearchParams& p, const QueryBatch& b, int stop_at_foreign, cudaStream_t s) {
     if (b.nq == 0) return;
     switch (rerank_group(p.g.sl)) {
         case 2: launch_probe_g<2>(p, b, stop_at_foreign, s); break;

@@ -88,3 +88,138 @@ class ShardedSearcher:
 
     def counters(self, nq: int):
         return self.index.counters(nq)
+
+
+# ------------------------------------------------------------------------------------------------ cluster-sharded search (fast mode)
+
+INF_BITS = 0xFF800000          # order bits of +inf (clann_b200/csrc/common.cuh float_order_bits)
+NOTHING = (INF_BITS << 32) | 0xFFFFFFFF
+
+
+def order_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> uint32 preserving order (float_order_bits in common.cuh)."""
+    b = np.asarray(x, np.float32).view(np.uint32)
+    return np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+
+
+def pack_bound(bound: np.ndarray, consumed: np.ndarray) -> np.ndarray:
+    """(bound on the k-th distance, clusters consumed in round one) -> the u64 word the ranks min-reduce (k_shard_pack_bounds):
+    the smaller bound wins, at equal bounds the rank that consumed more."""
+    return (order_bits(bound).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.asarray(consumed, np.uint64))
+
+
+def u64_min_key(x):
+    """torch has no unsigned 64-bit min: flip the top bit and compare as int64 (order preserving)."""
+    import torch
+    return torch.bitwise_xor(x.view(torch.int64), torch.tensor(-2 ** 63, dtype=torch.int64, device=x.device))
+
+
+def merge_topk(lists: np.ndarray, k: int) -> np.ndarray:
+    """k-way merge of per-rank candidate keys ((order_bits(dist) << 32) | id, ~0 = empty), as k_shard_final_merge does:
+    lists [world, nq, k] -> [nq, k] ascending."""
+    world, nq, kk = lists.shape
+    flat = np.transpose(lists, (1, 0, 2)).reshape(nq, world * kk)
+    return np.sort(flat, axis=1)[:, :k]
+
+
+class ClusterShardedSearcher:
+    """bench.py / user-facing driver of clann_search_sharded with the NCCL transport: the 128-byte NCCL unique id is created on
+    rank 0 and broadcast with torch.distributed (any channel would do), then every rank creates its communicator inside the
+    library. All ranks must build the index with shard_count = world, shard_rank = rank over the same data."""
+
+    def __init__(self, index: ClusteredIndex, world: int, rank: int):
+        import torch
+        import torch.distributed as dist
+        self.index, self.world, self.rank = index, world, rank
+        self.lib = _lib.load()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _check(self.lib.clann_comm_unique_id(buf, 128))
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        uid_dev = uid.to(dev)
+        dist.broadcast(uid_dev, src=0)
+        host = uid_dev.cpu().numpy()
+        _check(self.lib.clann_comm_init(index.handle, rank, world, host.ctypes.data))
+
+    def search_device(self, d_queries, d_ids, d_dists, d_counts) -> None:
+        import torch
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _check(self.lib.clann_search_sharded(self.index.handle, d_queries.data_ptr(), d_queries.shape[0], d_ids.data_ptr(),
+                                             d_dists.data_ptr(), d_counts.data_ptr(), stream))
+
+    def stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self.lib.clann_shard_stats(self.index.handle, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+
+class InProcessTransport:
+    """Collectives for `world` indices living in ONE process (one thread per rank, any number of GPUs including one): the
+    clann_set_collectives callbacks copy through a shared staging tensor between two thread barriers. Kernels of different ranks
+    never wait on each other on the device — only the host threads meet — so this is safe on a single GPU. Used by the tests."""
+
+    def __init__(self, world: int, device):
+        import threading
+        import torch
+        self.world, self.device = world, device
+        self.barrier = threading.Barrier(world)
+        self.stage = None
+        self.lock = threading.Lock()
+        self.torch = torch
+        self._keep = []
+
+    def _ensure(self, nbytes):
+        with self.lock:
+            if self.stage is None or self.stage.shape[1] < nbytes:
+                self.stage = self.torch.empty((self.world, nbytes), dtype=self.torch.uint8, device=self.device)
+
+    def _view(self, ptr, nbytes):
+        return self.torch.as_tensor(_DeviceBytes(ptr, nbytes), device=self.device)
+
+    def callbacks(self, rank: int):
+        t = self.torch
+
+        def allgather(ctx, send, recv, nbytes, stream):
+            try:
+                t.cuda.synchronize()
+                self.barrier.wait()
+                if rank == 0:
+                    self._ensure(nbytes)
+                self.barrier.wait()
+                self.stage[rank, :nbytes].copy_(self._view(send, nbytes))
+                t.cuda.synchronize()
+                self.barrier.wait()
+                self._view(recv, nbytes * self.world).copy_(self.stage[:, :nbytes].reshape(-1))
+                t.cuda.synchronize()
+                self.barrier.wait()
+                return 0
+            except Exception:  # a broken barrier / CUDA error must surface as a failed collective, not a hang
+                self.barrier.abort()
+                return 1
+
+        def allreduce_min(ctx, buf, count, stream):
+            try:
+                nbytes = count * 8
+                t.cuda.synchronize()
+                self.barrier.wait()
+                if rank == 0:
+                    self._ensure(nbytes)
+                self.barrier.wait()
+                self.stage[rank, :nbytes].copy_(self._view(buf, nbytes))
+                t.cuda.synchronize()
+                self.barrier.wait()
+                keys = u64_min_key(self.stage[:, :nbytes].contiguous().view(t.int64).reshape(self.world, count))
+                best = t.bitwise_xor(keys.min(dim=0).values, t.tensor(-2 ** 63, dtype=t.int64, device=self.device))
+                self._view(buf, nbytes).copy_(best.view(t.uint8))
+                t.cuda.synchronize()
+                self.barrier.wait()
+                return 0
+            except Exception:
+                self.barrier.abort()
+                return 1
+
+        ag, ar = _lib.ALLGATHER_FN(allgather), _lib.ALLREDUCE_MIN_FN(allreduce_min)
+        self._keep += [ag, ar]  # ctypes callbacks must outlive the calls
+        return ag, ar

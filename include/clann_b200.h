@@ -110,6 +110,27 @@ void* clann_state_ptr(clann_index* index);
 int clann_search_merge(clann_index* index, const void* d_all_states, int world, uint64_t* active_out, void* stream);
 int clann_search_end(clann_index* index, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, void* stream);
 
+/* Cluster-sharded search, the multi-GPU mode BASELINE.json's north_star names: one process per GPU, each index built
+ * with options shard_count = world and shard_rank = rank over the SAME data (every rank derives the same clustering and the same
+ * longest-processing-time ownership of clusters, and builds tables for its own clusters only). Every rank then calls
+ * clann_search_sharded with the same global batch (device pointers) and receives the complete results. Inside: each rank scores its
+ * slice of the queries against the replicated centres, one all-gather routes every query to the owner of its nearest cluster, that
+ * rank runs the reference's loop for as long as the walk stays in its own clusters, one all-reduce(min) of 8 bytes per query
+ * publishes the bound reached, every rank visits its own clusters among those the bound does not prune for the queries still open,
+ * and one all-gather of nq x k x (distance, id) feeds a k-way merge. Visits are a superset of the single-GPU search's (recall >=).
+ * The transport is NCCL over NVLink (clann_comm_unique_id on one rank, broadcast the 128 bytes by any means, clann_comm_init on
+ * all — libnccl.so.2 is resolved at run time), or any two collectives the caller supplies (clann_set_collectives; e.g. MPI, or the
+ * in-process transport of the tests). The exact stepping protocol above remains available. */
+typedef int (*clann_allgather_fn)(void* ctx, const void* d_send, void* d_recv, uint64_t bytes_per_rank, void* stream);
+typedef int (*clann_allreduce_min_u64_fn)(void* ctx, void* d_buf, uint64_t count, void* stream);
+int clann_comm_unique_id(uint8_t* out, uint64_t cap /* >= 128 */);
+int clann_comm_init(clann_index* index, int rank, int world, const uint8_t* unique_id);
+int clann_set_collectives(clann_index* index, clann_allgather_fn allgather, clann_allreduce_min_u64_fn allreduce_min, void* ctx);
+int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts,
+                         void* stream);
+/* queries routed to this rank in round one / still open in round two of the last clann_search_sharded */
+int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two);
+
 /* Per-query counters of the last search, the same quantities the reference keeps (performance.hpp:72-86 plus the
  * cluster count): any pointer may be NULL. Arrays of nq. */
 int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, uint64_t* distance_computations,

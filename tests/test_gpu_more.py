@@ -612,3 +612,83 @@ def test_gmm_kernel_variants_match_oracle(oracle, shape):
         assert np.array_equal(cen, oc), knobs
         assert np.array_equal(asg, oa), knobs
         assert np.array_equal(rad.view(np.uint32), orad.view(np.uint32)), knobs
+
+
+def test_cluster_sharded_search_two_ranks_in_process(big):
+    """clann_search_sharded (the multi-GPU mode of SURVEY.md 8e: route by nearest cluster, reference loop on the owner, one
+    all-reduce(min) of bounds, pruned second round on every rank, one all-gather + k-way merge) with two ranks as two threads
+    of this process on one GPU, talking through clann_set_collectives. Against the single-GPU search of the same index:
+    identical results whenever the walk of a query stayed inside one cluster, every rank gets the same answer, every visit of
+    the single-GPU search is also made here (visits are a superset), recall is at least the single-GPU recall."""
+    import threading
+    import torch
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    from clann_b200.distributed import InProcessTransport
+    data, full = big
+    L = cl.load()
+    q = np.concatenate([util.planted_queries(data, 1200, 123), util.uniform_sphere(12, 96, 124)])
+    nq, k = len(q), 10
+    ids0, d0, c0 = full.search_batch(q)
+    ctr0 = full.counters(nq)
+    shards = []
+    for r in range(2):
+        ix = cb.init_with_config(data, cb.Config(84, 0.4, 10, 0.9, "big"))
+        ix.set_option("seed", 5)
+        ix.set_option("shard_count", 2)
+        ix.set_option("shard_rank", r)
+        ix.build()
+        shards.append(ix)
+    # the single-pass entry points refuse a sharded index (it holds tables for its own clusters only)
+    with pytest.raises(cb.ConfigError):
+        shards[0].search_batch(q[:4])
+    dev = torch.device("cuda", 0)
+    dq = torch.from_numpy(q).to(dev)
+    transport = InProcessTransport(2, dev)
+    outs, errors, per_rank = [None, None], [], [None, None]
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            ix = shards[rank]
+            ag, ar = transport.callbacks(rank)
+            assert L.clann_set_collectives(ix.handle, ag, ar, None) == 0
+            ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+            dd = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            cc = torch.empty(nq, dtype=torch.int32, device=dev)
+            for _ in range(2):  # twice: buffers are reused, results must not change
+                rc = L.clann_search_sharded(ix.handle, dq.data_ptr(), nq, ids.data_ptr(), dd.data_ptr(), cc.data_ptr(), None)
+                assert rc == 0, cl.last_error()
+                torch.cuda.synchronize()
+            outs[rank] = (ids.cpu().numpy().view(np.uint32), dd.cpu().numpy(), cc.cpu().numpy().view(np.uint32))
+            per_rank[rank] = ix.counters(nq)
+        except Exception as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+            transport.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    assert all(o is not None for o in outs)
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))          # every rank holds the same merged result
+    ids, dd, cc = outs[0]
+    vis0 = ctr0["clusters_visited"]
+    one = vis0 == 1
+    assert one.sum() > 800
+    assert np.array_equal(ids[one], ids0[one]) and np.array_equal(dd[one].view(np.uint32), d0[one].view(np.uint32)) and np.array_equal(cc[one], c0[one])
+    vis = per_rank[0]["clusters_visited"].astype(np.int64) + per_rank[1]["clusters_visited"].astype(np.int64)
+    assert np.all(vis >= vis0)                                               # superset of the reference's visits
+    assert np.all(np.diff(dd, axis=1)[np.isfinite(dd[:, 1:])] >= 0)          # ascending
+    sample = np.arange(0, nq, 4)
+    rec_sharded = util.recall_at_k(data, q[sample], dd[sample], cc[sample], k)
+    rec_single = util.recall_at_k(data, q[sample], d0[sample], c0[sample], k)
+    assert rec_sharded >= rec_single >= 0.9, (rec_sharded, rec_single)
+    # the k-th distance never gets worse for the planted queries (same functions, same or more visits)
+    worse = np.sum(dd[:1200, k - 1] > d0[:1200, k - 1] + 1e-6)
+    assert worse <= 12, worse
+    for ix in shards:
+        ix.close()
