@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """bench.py — the headline benchmark of the CLANN hot path on B200 ("Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dist planted|uniform] [--small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...] [--dist planted|uniform]
 
 A "step" is one search pass of the hot path over one batch of synthetic queries against a built index.
 Workload at N=1 (BASELINE.json configs[2], the one the metric is quoted on): glove-100-angular shape, synthetic
 1,183,514 x 100 unit vectors, 10,000 queries, num_tables=84, num_clusters_factor=0.4, k=10, delta=0.9.
 
-Prints ONE JSON line (rank 0). `value` = queries/s with queries and outputs resident in HBM, K steps issued back to back
-through clann_search_device_async (three batches in flight; `value_stream_ordered` = one batch at a time, clann_search_device),
-`e2e` = the same with HOST buffers, H2D + D2H inside the timed region, through clann_search_async / clann_search_wait
-(`value_synchronous_call` = one blocking clann_search per step),
-`roofline` = algorithmic bytes of the probe kernel / its CUDA-event duration against the measured HBM peak,
-`cpu_baseline` = the reference's own CPU implementation (oracle/_ref, real PUFFINN headers) on a bounded query sample.
+Prints ONE JSON line (rank 0).
+  N = 1   `value` = queries/s with queries and outputs resident in HBM, K steps issued back to back through
+          clann_search_device_async (three batches in flight, four distinct query batches in rotation);
+          `value_stream_ordered` = one batch at a time (clann_search_device).
+  N > 1   `value` = the cluster-sharded search north_star names (clann_search_sharded: every GPU owns a share of the clusters
+          and builds only those; the global batch of N x 10,000 queries is routed by nearest cluster; one all-reduce of bounds
+          and one all-gather of top-k lists over NCCL) — weak scaling, the index shrinks per GPU as N grows. `replicas` = the
+          other way to use N GPUs when the index fits one (index replicated, queries sharded, no collective), for comparison.
+  `e2e`   the same with HOST buffers: H2D of the step's queries and D2H of its results inside the timed region.
+  `roofline` = algorithmic bytes of the rerank / filter kernels over their CUDA-event duration against the measured HBM peak.
+  `cpu_baseline` = the reference's own CPU implementation (oracle/_ref, real PUFFINN headers) on a bounded query sample.
 `--impl reference` prints the reference arm's line (rank 0 only; other ranks exit 0).
 """
 from __future__ import annotations
@@ -33,8 +38,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "queries/sec @ recall@10>=0.9 (glove-100 shape)"
 UNIT = "queries/s"
-# DRAM bytes of one k_probe launch from the committed ncu capture (profiles/), per workload; None = not captured
-MEASURED_TRAFFIC = {"glove100": 3.57e9}
+# DRAM bytes (read + write) of the roofline kernels of one step from the committed ncu capture (profiles/), per workload
+MEASURED_TRAFFIC = {"glove100": None}
+TRAFFIC_SOURCE = "profiles/README.md"
+try:
+    _t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    MEASURED_TRAFFIC.update(_t.get("bytes", {}))
+    TRAFFIC_SOURCE = _t.get("source", TRAFFIC_SOURCE)
+except Exception:
+    pass
+N_QUERY_BATCHES = 4   # distinct query batches rotated through the timed loops (do not resubmit one buffer)
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -48,11 +61,28 @@ def workload(args):
     if args.workload == "readme":    # BASELINE.json configs[0]
         return dict(name="README example: synthetic 10,000x128 unit vectors, 10k queries, num_tables=84, k=10, delta=0.9",
                     n=10_000, d=128, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
-    if args.workload == "deep96":    # BASELINE.json configs[3] on one GPU (the index is 16 GB; sharding is optional)
+    if args.workload == "deep96":    # BASELINE.json configs[3]
         return dict(name="deep-image-96-angular shape: synthetic 10,000,000x96 unit vectors, 10k queries, k=10, delta=0.9",
                     n=10_000_000, d=96, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
+    if args.workload == "sweep100m":  # BASELINE.json configs[4]: fp16 rows, 100k-query batches, k=100, delta from --delta
+        return dict(name=f"large-scale sweep: synthetic {args.rows or 100_000_000:,}x96 fp16 unit vectors, 100k-query batches, k=100, "
+                         f"delta={args.delta or 0.9}",
+                    n=args.rows or 100_000_000, d=96, nq=100_000, L=84, factor=0.4, k=100, delta=args.delta or 0.9, fp16=True)
     return dict(name="glove-100-angular shape: synthetic 1,183,514x100 unit vectors, 10k queries, k=10, delta=0.9",
                 n=1_183_514, d=100, nq=10_000, L=84, factor=0.4, k=10, delta=0.9)
+
+
+def make_queries(data, nq, d, dist, seed):
+    rq = np.random.default_rng(seed)
+    n = data.shape[0]
+    if dist == "planted":
+        src = rq.integers(0, n, nq)
+        q = data[src].astype(np.float32) + np.float32(0.05) * rq.standard_normal((nq, d), dtype=np.float32)
+    else:
+        src = np.full(nq, -1)
+        q = rq.standard_normal((nq, d), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.ascontiguousarray(q, np.float32), src
 
 
 def make_data(w, dist):
@@ -69,15 +99,9 @@ def make_data(w, dist):
     else:
         data = rng.standard_normal((n, d), dtype=np.float32)
     data /= np.linalg.norm(data, axis=1, keepdims=True)
-    rq = np.random.default_rng(43)
-    if dist == "planted":
-        src = rq.integers(0, n, nq)
-        q = data[src] + np.float32(0.05) * rq.standard_normal((nq, d), dtype=np.float32)
-    else:
-        src = np.full(nq, -1)
-        q = rq.standard_normal((nq, d), dtype=np.float32)
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    return np.ascontiguousarray(data, np.float32), np.ascontiguousarray(q, np.float32), src
+    data = np.ascontiguousarray(data, np.float32)
+    q, src = make_queries(data, nq, d, dist, 43)
+    return data, q, src
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -129,73 +153,95 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm
 
-def reference_sample(w, data, queries, src, centers, assignment, radii, n_clusters=6, per_cluster=12):
-    """Bounded sample for the CPU arms: queries grouped by the cluster of their source point, a few clusters, a dozen
-    queries each, so that the reference (2.2-2.5 s of Monte-Carlo per PUFFINN index) only builds what the sample visits."""
+def reference_sample(queries, src, assignment, n_centers, n_clusters, per_cluster):
+    """Bounded sample for the CPU arms: queries grouped by the cluster of their source point — `n_clusters` home clusters,
+    up to `per_cluster` distinct queries each — so that the reference (2.2-2.5 s of single-threaded Monte-Carlo per PUFFINN
+    index) only builds what the sample visits."""
     rng = np.random.default_rng(7)
     if src[0] >= 0:
         home = assignment[src]
-        sizes = np.bincount(assignment.astype(np.int64), minlength=len(centers))
-        eligible = [c for c in np.unique(home) if sizes[c] >= 100]
+        sizes = np.bincount(assignment.astype(np.int64), minlength=n_centers)
+        counts = np.bincount(home.astype(np.int64), minlength=n_centers)
+        eligible = [c for c in np.unique(home) if sizes[c] >= 100 and counts[c] >= min(per_cluster, 8)]
         chosen = rng.permutation(eligible)[:n_clusters]
-        idx = np.concatenate([np.nonzero(home == c)[0][:per_cluster] for c in chosen])
-        desc = f"{len(idx)} of {len(queries)} queries: {per_cluster} per home cluster for {len(chosen)} random clusters"
+        groups = [np.nonzero(home == c)[0][:per_cluster] for c in chosen]
+        desc = (f"{sum(len(g) for g in groups)} distinct queries of the step's {len(queries)}: up to {per_cluster} per home cluster "
+                f"for {len(chosen)} random clusters, one pass each")
     else:
-        idx = np.arange(min(2, len(queries)))
-        desc = f"{len(idx)} of {len(queries)} queries (uniform data visits every cluster)"
-    return idx, desc
+        groups = [np.arange(min(2, len(queries)))]
+        desc = f"{len(groups[0])} of {len(queries)} queries (uniform data visits every cluster)"
+    return groups, desc
 
 
-def run_reference(w, data, queries, src, centers, assignment, radii, threads=None):
-    """The reference's own CPU implementation of the path (oracle/_ref: the real PUFFINN headers + the CLANN loop) on a
-    bounded sample. Index builds are lazy and excluded from the search time. Search is one query at a time per worker, as
-    in the reference (collection.hpp:104-113); `threads` forked workers each own a copy-on-write view of the indices."""
-    from oracle.pyoracle import RefLib, OracleLib
-    idx, desc = reference_sample(w, data, queries, src, centers, assignment, radii)
-    sample = queries[idx]
-    kind = "reference" if RefLib.available() else "port"
-    if kind == "reference":
-        eng = RefLib().clann(data, w["L"], w["k"], w["delta"], centers, assignment, radii, seed_base=1234)
-    else:
+def run_reference(w, data, queries, src, centers, assignment, radii, workers=None, n_clusters=50, per_cluster=24):
+    """The reference's own CPU implementation of the path (oracle/_ref: the real PUFFINN headers under the CLANN loop of
+    index.rs:311-439) on a bounded sample. The sample's home clusters are dealt to `workers` forked processes; each builds the
+    PUFFINN indices its queries visit (lazily, in an untimed first pass — in the reference this is `build`), then answers its
+    queries ONE pass, one query at a time (collection.hpp:104-113 allows nothing else per index). Reported: q/s of one core
+    (queries / sum of the workers' search times) and of the whole host (queries / slowest worker), recall of the sample."""
+    from oracle.pyoracle import RefLib
+    if not RefLib.available():
         raise RuntimeError("oracle/_ref/libpuffinn_ref.so is missing; build it with `make -C oracle` where /root/reference exists")
-    t0 = time.time()
-    results = [eng.search(q) for q in sample]          # first pass builds the visited clusters (lazy), untimed
-    build_s = eng.build_seconds
+    groups, desc = reference_sample(queries, src, assignment, len(centers), n_clusters, per_cluster)
     ncores = os.cpu_count() or 1
-    P = threads or max(1, min(ncores, len(sample)))
-    # timed pass: P forked workers, each its slice, sequential queries inside a worker
-    eng.search_seconds.value = 0.0
-    t1 = time.time()
-    for q in sample:
-        eng.search(q)
-    single_s = time.time() - t1
-    pids, slices = [], np.array_split(np.arange(len(sample)), P)
-    reps = 20
-    r, wfd = os.pipe()
-    t2 = time.time()
-    for sl in slices:
+    P = max(1, min(workers or ncores, len(groups)))
+    eng = RefLib().clann(data, w["L"], w["k"], w["delta"], centers, assignment, radii, seed_base=1234)
+    k = w["k"]
+    t0 = time.time()
+    deals = [np.concatenate(groups[i::P]) if len(groups[i::P]) else np.zeros(0, np.int64) for i in range(P)]
+    pipes, pids = [], []
+    for wi in range(P):
+        r, wfd = os.pipe()
         pid = os.fork()
         if pid == 0:
             try:
+                os.close(r)
+                idx = deals[wi]
+                for i in idx:                       # pass 1: builds what the queries visit (untimed)
+                    eng.search(queries[i])
+                build_s = eng.build_seconds
                 ts = time.time()
-                for _ in range(reps):
-                    for i in sl:
-                        eng.search(sample[i])
-                os.write(wfd, (f"{time.time() - ts:.6f}\n").encode())
+                out = []
+                for i in idx:                       # pass 2: the timed pass, every query once
+                    ids, dd, _, ctr = eng.search(queries[i])
+                    out.append((int(i), dd.tolist(), ctr["visited"], ctr["distance_computations"]))
+                search_s = time.time() - ts
+                os.write(wfd, json.dumps({"search_s": search_s, "build_s": build_s, "res": out}).encode())
             finally:
                 os._exit(0)
+        os.close(wfd)
+        pipes.append(r)
         pids.append(pid)
-    for pid in pids:
+    results = []
+    for r, pid in zip(pipes, pids):
+        buf = b""
+        while True:
+            chunk = os.read(r, 1 << 20)
+            if not chunk:
+                break
+            buf += chunk
+        os.close(r)
         os.waitpid(pid, 0)
-    os.close(wfd)
-    times = [float(x) for x in os.read(r, 1 << 16).decode().split()]
-    os.close(r)
-    multi_s = max(times) / reps if times else float("inf")
-    visited = float(np.mean([res[3]["visited"] for res in results]))
-    dc = float(np.mean([res[3]["distance_computations"] for res in results]))
-    return dict(kind=kind, sample=desc, n_sample=len(sample), build_s=build_s, qps_1thread=len(sample) / single_s,
-                qps_allcores=len(sample) / multi_s, cores=P, visited=visited, distcomp=dc, results=results, idx=idx,
-                wall_s=time.time() - t0)
+        if buf:
+            results.append(json.loads(buf.decode()))
+    n_sample = sum(len(x["res"]) for x in results)
+    if n_sample == 0:
+        raise RuntimeError("the reference workers returned nothing")
+    sum_s = sum(x["search_s"] for x in results)
+    max_s = max(x["search_s"] for x in results)
+    # recall of the sample against exact fp32 neighbours (utils/mod.rs:59-95)
+    rows = [r for x in results for r in x["res"]]
+    idx = np.array([r[0] for r in rows])
+    hit = 0
+    for s0 in range(0, len(idx), 64):
+        sel = idx[s0:s0 + 64]
+        ex = 1.0 - queries[sel] @ data.T
+        kth = np.partition(ex, k - 1, axis=1)[:, k - 1]
+        for j, gi in enumerate(range(s0, min(s0 + 64, len(idx)))):
+            hit += int(np.sum(np.asarray(rows[gi][1], np.float32) <= kth[j] + 1e-3))
+    return dict(kind="reference", sample=desc, n_sample=n_sample, build_s=max(x["build_s"] for x in results),
+                qps_1thread=n_sample / sum_s, qps_allcores=n_sample / max_s, cores=P, recall=hit / (n_sample * k),
+                visited=float(np.mean([r[2] for r in rows])), distcomp=float(np.mean([r[3] for r in rows])), wall_s=time.time() - t0)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -208,17 +254,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dist", default="planted", choices=["planted", "uniform"])
     ap.add_argument("--small", action="store_true", help="reduced shape for smoke runs; NOT a valid bench number")
-    ap.add_argument("--queries", type=int, default=0, help="queries per step (default: the workload's own batch, 10 000)")
-    ap.add_argument("--workload", default="glove100", choices=["glove100", "glove25", "readme", "deep96"],
-                    help="glove100 (default) is the configuration the metric is quoted on; the others are BASELINE.json's parity-size configs")
+    ap.add_argument("--queries", type=int, default=0, help="queries per step and GPU (default: the workload's own batch)")
+    ap.add_argument("--workload", default="glove100", choices=["glove100", "glove25", "readme", "deep96", "sweep100m"],
+                    help="glove100 (default) is the configuration the metric is quoted on; the others are BASELINE.json's other configs")
+    ap.add_argument("--rows", type=int, default=0, help="sweep100m: number of rows (default 100 000 000)")
+    ap.add_argument("--delta", type=float, default=0.0, help="sweep100m: target recall (0.8 / 0.9 / 0.95)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="time `value` with stream-ordered calls (one batch at a time) instead of clann_search_device_async "
-                         "(three batches in flight); the stream-ordered figure is always reported as value_stream_ordered")
-    ap.add_argument("--shard", default="queries", choices=["queries", "clusters"],
-                    help="N > 1: 'queries' = the index is replicated and every rank searches its own batch (weak scaling, no "
-                         "data-path collective); 'clusters' = clusters are sharded by owner and one fixed batch is stepped "
-                         "through the ranks with an all-gather per step (strong scaling; for indices beyond one GPU)")
+    ap.add_argument("--no-pipeline", action="store_true", help="N = 1: time `value` with stream-ordered calls")
+    ap.add_argument("--shard", default="clusters", choices=["clusters", "replicas", "stepping"],
+                    help="N > 1: clusters (default) = clann_search_sharded; replicas = index replicated, queries sharded, no "
+                         "collective; stepping = the exact hand-over protocol (clann_search_begin/step/merge/end)")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the replica comparison run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -234,7 +280,7 @@ def main():
         w["name"] += f" [batch overridden: {args.queries} queries per step]"
     cfg_json = {"workload": w["name"], "distribution": args.dist, "n": w["n"], "d": w["d"], "queries_per_step": w["nq"],
                 "num_tables": w["L"], "num_clusters_factor": w["factor"], "k": w["k"], "delta": w["delta"],
-                "l2": "index working set (2.4 GB: Q15 rows, sketches, tables) >> 126 MB L2; no explicit flush"}
+                "l2": "index working set (2.4 GB: Q15 rows, sketches, tables) >> 126 MB L2; four distinct query batches in rotation; no explicit flush"}
 
     if args.impl == "reference":
         # The reference arm never touches the GPU or libclann_b200: data and clustering on the host (the clustering is the
@@ -249,11 +295,13 @@ def main():
         ref = run_reference(w, data, queries, src, np.asarray(centers, np.uint64), np.asarray(assignment, np.uint64),
                             np.asarray(radii, np.float32))
         line = {"impl": "reference", "metric": METRIC, "value": ref["qps_allcores"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * ref["n_sample"] / ref["qps_allcores"],
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * w["nq"] / ref["qps_allcores"],
+                "ms_per_step_note": "time the host would need for one step of queries_per_step queries at the sampled rate",
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16", "data": "synthetic",
-                "config": cfg_json,
+                "config": cfg_json, "recall_at_k": ref["recall"], "recall_queries_checked": ref["n_sample"],
                 "cpu_baseline": {"value": ref["qps_allcores"], "unit": UNIT, "cores": ref["cores"], "kind": ref["kind"],
-                                 "sample": ref["sample"], "qps_1thread": ref["qps_1thread"],
+                                 "sample": ref["sample"], "qps_1thread": ref["qps_1thread"], "recall_at_k": ref["recall"],
+                                 "clusters_visited_per_query": ref["visited"], "distance_computations_per_query": ref["distcomp"],
                                  "index_build_s_for_sample": ref["build_s"], "clustering_s": gmm_s,
                                  "clustering": "oracle C restatement of gmm.rs on the host (no Rust toolchain), untimed setup"},
                 "e2e": {"value": ref["qps_allcores"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -269,90 +317,86 @@ def main():
 
     import clann_b200 as cb
     from clann_b200 import _lib as cl
-    from clann_b200.distributed import ShardedSearcher
+    from clann_b200.distributed import ClusterShardedSearcher, ShardedSearcher
 
+    dev = torch.device("cuda", local_rank)
     data, queries, src = make_data(w, args.dist)
     nq, k, d = w["nq"], w["k"], w["d"]
-    shard_clusters = world > 1 and args.shard == "clusters"
-    if world > 1 and not shard_clusters:
-        # weak scaling: every rank owns a full replica and its own batch of nq queries (same distribution, its own seed)
-        rq = np.random.default_rng(43 + 1000 * rank)
-        if args.dist == "planted":
-            src = rq.integers(0, w["n"], nq)
-            queries = data[src] + np.float32(0.05) * rq.standard_normal((nq, d), dtype=np.float32)
+    mode = "single" if world == 1 else args.shard
+    gnq = nq * world if mode in ("clusters", "stepping") else nq      # queries every rank holds per step
+    global_nq = nq * world if world > 1 else nq                        # queries the whole job answers per step
+    # distinct query batches (host): batch j of the job; in replica mode every rank draws its own
+    seed0 = 43 + (1000 * rank if mode == "replicas" else 0)
+    batches = []
+    for j in range(N_QUERY_BATCHES):
+        if j == 0 and gnq == nq and mode != "replicas":
+            batches.append(queries)
         else:
-            queries = rq.standard_normal((nq, d), dtype=np.float32)
-        queries /= np.linalg.norm(queries, axis=1, keepdims=True)
-        queries = np.ascontiguousarray(queries, np.float32)
-    cfg_json["parallelism"] = ("single GPU" if world == 1 else
-                               f"clusters sharded over {world} GPUs, one batch stepped with an all-gather of query states per step"
-                               if shard_clusters else
-                               f"index replicated on {world} GPUs, {nq} queries per GPU per step (global batch {nq * world}), no data-path collective")
+            batches.append(make_queries(data, gnq, d, args.dist, seed0 + 17 * j)[0])
+    parallelism = ("single GPU" if world == 1 else
+                   f"clusters sharded over {world} GPUs (each builds and holds its own clusters only); global batch {global_nq} queries per step "
+                   f"routed by nearest cluster; all-gather of nearest-cluster ids, all-reduce(min) of bounds, all-gather of top-k lists (NCCL)"
+                   if mode == "clusters" else
+                   f"clusters sharded over {world} GPUs, exact stepping: all-gather of the per-query states per step" if mode == "stepping" else
+                   f"index replicated on {world} GPUs, {nq} queries per GPU per step (global batch {global_nq}), no data-path collective")
 
     # ---- build (untimed setup of the search benchmark; reported on its own)
-    t0 = time.time()
-    index = cb.init_with_config(data, cb.Config(w["L"], w["factor"], w["k"], w["delta"], "bench"))
-    index.set_option("seed", 1234)
-    if shard_clusters:
-        index.set_option("shard_count", world)
-        index.set_option("shard_rank", rank)
-    index.build()
-    torch.cuda.synchronize()
-    build_wall = time.time() - t0
-    build_ms = index.export(cl.X_BUILD_MS, 0, np.float64)
+    def build_index(sharded):
+        t0 = time.time()
+        ix = cb.init_with_config(data, cb.Config(w["L"], w["factor"], w["k"], w["delta"], "bench"))
+        ix.set_option("seed", 1234)
+        if sharded:
+            ix.set_option("shard_count", world)
+            ix.set_option("shard_rank", rank)
+        ix.build()
+        torch.cuda.synchronize()
+        return ix, time.time() - t0, ix.export(cl.X_BUILD_MS, 0, np.float64).copy()
+
+    index, build_wall, build_ms = build_index(mode in ("clusters", "stepping"))
+    if world == 1:   # a second, warm build: the first one pays module loading and the first cudaMallocs
+        index.close()
+        index, build_wall2, build_ms2 = build_index(False)
+    else:
+        build_wall2, build_ms2 = build_wall, build_ms
     K = index.num_clusters
     centers = index.export(cl.X_CENTERS, 0, np.uint64).copy()
     assignment = index.export(cl.X_ASSIGNMENT, 0, np.uint64).copy()
     radii = index.export(cl.X_RADII, 0, np.float32).copy()
 
-    dev = torch.device("cuda", local_rank)
-    d_q = torch.from_numpy(queries).to(dev)
-    d_ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    d_dists = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    d_counts = torch.empty(nq, dtype=torch.int32, device=dev)
-    searcher = ShardedSearcher(index, world, rank) if shard_clusters else ShardedSearcher(index, 1, 0)
-    single = not shard_clusters  # this rank runs the whole single-GPU path on its own batch
+    d_batches = [torch.from_numpy(b).to(dev) for b in batches]
+    d_q = d_batches[0]
+    d_ids = torch.empty((gnq, k), dtype=torch.int32, device=dev)
+    d_dists = torch.empty((gnq, k), dtype=torch.float32, device=dev)
+    d_counts = torch.empty(gnq, dtype=torch.int32, device=dev)
+    if mode == "clusters":
+        searcher = ClusterShardedSearcher(index, world, rank)
+    elif mode == "stepping":
+        searcher = ShardedSearcher(index, world, rank)
+    else:
+        searcher = ShardedSearcher(index, 1, 0)
+    single = mode in ("single", "replicas")  # this rank runs the whole single-GPU path on its own batch
 
-    def step_device():
-        searcher.search_device(d_q, d_ids, d_dists, d_counts)
+    def step_device(i=0):
+        searcher.search_device(d_batches[i % N_QUERY_BATCHES], d_ids, d_dists, d_counts)
 
-    # batch pipelining (clann_search_device_async): consecutive steps on the internal streams (three batches in flight), each with its own outputs
     pipelined = single and not args.no_pipeline
-    # 12 output sets: calls i and i + 12 land on the same internal stream for every pipeline depth (2, 3 or 4), so a set is never
-    # written by two batches that could be in flight together
+    # 12 output sets: calls i and i + 12 land on the same internal stream for every pipeline depth (2, 3 or 4)
     NSETS = 12
     outs = [(d_ids, d_dists, d_counts)] + [(torch.empty_like(d_ids), torch.empty_like(d_dists), torch.empty_like(d_counts)) for _ in range(NSETS - 1)]
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def run_steps(steps):
         if not pipelined:
-            for _ in range(steps):
-                step_device()
+            for i in range(steps):
+                step_device(i)
             return
         for i in range(steps):
             o = outs[i % NSETS]
-            if index._lib.clann_search_device_async(index.handle, d_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+            q = d_batches[i % N_QUERY_BATCHES]
+            if index._lib.clann_search_device_async(index.handle, q.data_ptr(), gnq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
                 raise RuntimeError(cl.last_error())
         if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
             raise RuntimeError(cl.last_error())
-
-    # pinned host buffers for the end-to-end arm
-    h_q = torch.from_numpy(queries).pin_memory()
-    h_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
-    h_dists = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    h_counts = torch.empty(nq, dtype=torch.int32).pin_memory()
-
-    def step_e2e():
-        if single:
-            # the reference-facing call: host pointers in, host pointers out (copies inside clann_search)
-            st = index._lib.clann_search(index.handle, h_q.data_ptr(), nq, h_ids.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr())
-            if st != 0:
-                raise RuntimeError(cl.last_error())
-        else:
-            d_q.copy_(h_q, non_blocking=True)
-            searcher.search_device(d_q, d_ids, d_dists, d_counts)
-            h_ids.copy_(d_ids, non_blocking=True); h_dists.copy_(d_dists, non_blocking=True); h_counts.copy_(d_counts, non_blocking=True)
-            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -360,155 +404,183 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        probe_ms = 0.0
-        for _ in range(steps):
-            fn()
-            if world == 1:
-                pass
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            return float(t.item())
         return ms
 
-    for _ in range(args.warmup):
-        step_device()
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    for i in range(args.warmup):
+        step_device(i)
     run_steps(args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
     # the timed region: exactly K steps; the stream is idle at e0 (barrier + synchronize), so e0..e1 covers every kernel of
     # the K steps whichever internal stream ran it (clann_search_flush makes the current stream wait for all of them)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    probe_ms_sum, prep_ms_sum = 0.0, 0.0
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    # the same K steps one batch at a time (stream-ordered calls), for reference
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        step_device()
-    f1.record()
-    barrier()
-    ordered_ms = f0.elapsed_time(f1)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([total_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        t = torch.tensor([ordered_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ordered_ms = float(t.item())
+    total_ms = timed(run_steps, args.steps)
+    ordered_ms = timed(lambda steps: [step_device(i) for i in range(steps)], args.steps)
     clocks = sampler.stop()
-    launches_per_step = searcher.last_launches
-    # per-kernel split from a separate pass (events inside the library); same stream, same inputs
-    if single:
-        for _ in range(args.steps):
-            step_device()
+    # kernels per step: counted by the library on the single-GPU path; the sharded search launches 3 (route) + 4 (select, fills) +
+    # 14 (round one: gather, 8 prep, 2 precompute, probe, pack, collect) + 1 + 11 (round two) + 1 (merge) of its own kernels
+    launches_per_step = 34 if mode == "clusters" else getattr(searcher, "last_launches", 0)
+    probe_ms = prep_ms = None
+    if single:  # per-kernel split from a separate pass (events inside the library); same stream, same inputs
+        ps, pr = 0.0, 0.0
+        for i in range(args.steps):
+            step_device(i)
             prof = index.search_profile()
-            probe_ms_sum += prof["probe_ms"]; prep_ms_sum += prof["prep_ms"]
-        probe_ms = probe_ms_sum / args.steps
-        prep_ms = prep_ms_sum / args.steps
-    else:
-        probe_ms = prep_ms = None
+            ps += prof["probe_ms"]; pr += prof["prep_ms"]
+        probe_ms, prep_ms = ps / args.steps, pr / args.steps
 
     ms_per_step = total_ms / args.steps
-    global_nq = nq if (world == 1 or shard_clusters) else nq * world   # queries the whole job answers per step
     value = global_nq / (ms_per_step / 1000.0)
 
-    # end to end
-    for _ in range(2):
-        step_e2e()
-    e2e_sync_ms = timed(step_e2e, args.steps) / args.steps
-    e2e_ms, e2e_mode = e2e_sync_ms, "clann_search: one synchronous call per step (host buffers in, host buffers out)"
+    # ---- end to end: host buffers in and out, copies inside the timed region
+    h_batches = [torch.from_numpy(b).pin_memory() for b in batches]
+    h_ids = torch.empty((gnq, k), dtype=torch.int32).pin_memory()
+    h_dists = torch.empty((gnq, k), dtype=torch.float32).pin_memory()
+    h_counts = torch.empty(gnq, dtype=torch.int32).pin_memory()
+    lo_q, hi_q = (rank * nq, (rank + 1) * nq) if mode in ("clusters", "stepping") else (0, nq)
+
+    def e2e_sync(steps):
+        for i in range(steps):
+            hq = h_batches[i % N_QUERY_BATCHES]
+            if single:
+                # the reference-facing call: host pointers in, host pointers out (copies inside clann_search)
+                if index._lib.clann_search(index.handle, hq.data_ptr(), nq, h_ids.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr()) != 0:
+                    raise RuntimeError(cl.last_error())
+            else:
+                # every rank uploads ITS slice of the step's queries and the slices are all-gathered over NVLink (queries are
+                # broadcast); after the search every rank downloads the results of its slice
+                import torch.distributed as dist
+                d_slice.copy_(hq[lo_q:hi_q], non_blocking=True)
+                dist.all_gather_into_tensor(d_q, d_slice)
+                searcher.search_device(d_q, d_ids, d_dists, d_counts)
+                h_ids[lo_q:hi_q].copy_(d_ids[lo_q:hi_q], non_blocking=True)
+                h_dists[lo_q:hi_q].copy_(d_dists[lo_q:hi_q], non_blocking=True)
+                h_counts[lo_q:hi_q].copy_(d_counts[lo_q:hi_q], non_blocking=True)
+                torch.cuda.synchronize()
+
+    if not single:
+        d_q = torch.empty_like(d_batches[0])
+        d_slice = torch.empty((nq, d), dtype=torch.float32, device=dev)
+    e2e_sync(2)
+    e2e_sync_ms = timed(e2e_sync, args.steps) / args.steps
+    e2e_ms = e2e_sync_ms
+    e2e_mode = ("clann_search: one synchronous call per step (host buffers in, host buffers out)" if single else
+                "per step: H2D of this rank's slice of the queries, NCCL all-gather of the slices, clann_search_sharded, D2H of the "
+                "slice's results; blocking")
     if pipelined:
         # the same through clann_search_async: every step's H2D copy, search and D2H copies on its batch stream, three batches in
         # flight, each with its own pinned output buffers; clann_search_wait before the clock stops
         h_outs = [(h_ids, h_dists, h_counts)] + [(torch.empty_like(h_ids).pin_memory(), torch.empty_like(h_dists).pin_memory(),
                                                   torch.empty_like(h_counts).pin_memory()) for _ in range(NSETS - 1)]
 
-        def run_e2e_async(steps):
+        def run_e2e_async(steps, batch_of=lambda i: i % N_QUERY_BATCHES):
             for i in range(steps):
                 o = h_outs[i % NSETS]
-                if index._lib.clann_search_async(index.handle, h_q.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+                hq = h_batches[batch_of(i)]
+                if index._lib.clann_search_async(index.handle, hq.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
                     raise RuntimeError(cl.last_error())
-            if index._lib.clann_search_flush(index.handle, cur_stream) != 0:
+            if index._lib.clann_search_wait(index.handle) != 0:
                 raise RuntimeError(cl.last_error())
 
         run_e2e_async(3)
-        if index._lib.clann_search_wait(index.handle) != 0:
+        if index._lib.clann_search(index.handle, h_batches[0].data_ptr(), nq, h_ids.data_ptr(), h_dists.data_ptr(), h_counts.data_ptr()) != 0:
             raise RuntimeError(cl.last_error())
-        step_e2e()                                   # reference result of the synchronous call in h_outs[0]
         want = (h_ids.clone(), h_dists.clone(), h_counts.clone())
-        run_e2e_async(NSETS)
-        index._lib.clann_search_wait(index.handle)
+        run_e2e_async(NSETS, batch_of=lambda i: 0)
         for o in h_outs:
             if not (torch.equal(o[0], want[0]) and torch.equal(o[1], want[1]) and torch.equal(o[2], want[2])):
                 raise RuntimeError("clann_search_async returned results that differ from clann_search")
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        run_e2e_async(args.steps)
-        g1.record()
-        index._lib.clann_search_wait(index.handle)
-        barrier()
-        e2e_ms = g0.elapsed_time(g1)
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([e2e_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        e2e_ms /= args.steps
+        e2e_ms = timed(run_e2e_async, args.steps) / args.steps
         e2e_mode = ("clann_search_async + clann_search_wait: host buffers in and out, H2D / search / D2H of each step on its batch "
                     "stream, three batches in flight; results identical to clann_search (checked)")
     e2e_value = global_nq / (e2e_ms / 1000.0)
 
     # ---- correctness of what was timed: the pipelined batches return what the stream-ordered call returns
-    pipe_same = None
     if pipelined:
-        run_steps(3)
+        for i in range(3):
+            o = outs[i]
+            if index._lib.clann_search_device_async(index.handle, d_batches[1].data_ptr(), gnq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+                raise RuntimeError(cl.last_error())
+        index._lib.clann_search_flush(index.handle, cur_stream)
         torch.cuda.synchronize()
         a_ids, a_dists = outs[1][0].clone(), outs[1][1].clone()
         b_ids, b_dists = outs[2][0].clone(), outs[2][1].clone()
-        step_device()
+        step_device(1)
         torch.cuda.synchronize()
-        pipe_same = bool(torch.equal(a_ids, d_ids) and torch.equal(b_ids, d_ids) and torch.equal(a_dists, d_dists) and torch.equal(b_dists, d_dists))
-        if not pipe_same:
+        if not (torch.equal(a_ids, d_ids) and torch.equal(b_ids, d_ids) and torch.equal(a_dists, d_dists) and torch.equal(b_dists, d_dists)):
             raise RuntimeError("pipelined batches returned results that differ from the stream-ordered call")
-    # ---- recall@k against exact fp32 neighbours (utils/mod.rs:59-95)
-    step_device()
+
+    # ---- recall@k against exact fp32 neighbours (utils/mod.rs:59-95), on this rank's share of batch 0
+    step_device(0)
     torch.cuda.synchronize()
     ids = d_ids.cpu().numpy().view(np.uint32); dists = d_dists.cpu().numpy(); counts = d_counts.cpu().numpy()
-    nchk = min(nq, 2000)
+    nchk = min(gnq, 2000)
     with torch.no_grad():
         dd = torch.from_numpy(data).to(dev)
         ex = torch.empty((nchk, k), device=dev)
         chunk = max(8, min(250, int(2.5e8 // w["n"])))   # keep the similarity tile under ~1 GB
+        dq0 = d_batches[0]
         for s in range(0, nchk, chunk):
             e = min(s + chunk, nchk)
-            sim = d_q[s:e] @ dd.T
+            sim = dq0[s:e] @ dd.T
             ex[s:e] = torch.topk(sim, k, dim=1).values
         kth = (1.0 - ex[:, k - 1]).cpu().numpy()
         del dd
     hit = sum(int(np.sum(dists[i, :counts[i]] <= kth[i] + 1e-3)) for i in range(nchk))
     recall = hit / (nchk * k)
+    if args.dist == "planted" and not args.small and recall < 0.9:
+        raise RuntimeError(f"recall@{k} = {recall:.4f} < 0.9: the metric is defined at recall >= 0.9, refusing to report a throughput")
 
-    line = None
-    if rank == 0:
-        ctr = index.counters(nq) if single else searcher.counters(nq)
+    # ---- per-query work (this rank's share in sharded mode, summed over the ranks below)
+    if mode == "clusters":
+        ctr = index.counters(gnq)
+        tot = torch.tensor([float(ctr["candidates"].sum()), float(ctr["distance_computations"].sum()), float(ctr["clusters_visited"].sum())],
+                           dtype=torch.float64, device=dev)
+        import torch.distributed as dist
+        dist.all_reduce(tot)
+        cand, dc, vis = (float(x) for x in tot.tolist())
+        routed, still_open = searcher.stats()
+    else:
+        ctr = index.counters(gnq) if single else searcher.counters(gnq)
         cand = float(ctr["candidates"].sum()); dc = float(ctr["distance_computations"].sum()); vis = float(ctr["clusters_visited"].sum())
+        routed = still_open = None
+
+    # ---- N > 1: the replica arrangement for comparison (index replicated, every rank its own batch, no collective)
+    replicas = None
+    if world > 1 and mode == "clusters" and not args.no_replicas:
+        rindex, _, _ = build_index(False)
+        rq = torch.from_numpy(make_queries(data, nq, d, args.dist, 43 + 1000 * rank)[0]).to(dev)
+        r_outs = [(torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+                   torch.empty(nq, dtype=torch.int32, device=dev)) for _ in range(NSETS)]
+
+        def run_replica(steps):
+            for i in range(steps):
+                o = r_outs[i % NSETS]
+                if rindex._lib.clann_search_device_async(rindex.handle, rq.data_ptr(), nq, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr()) != 0:
+                    raise RuntimeError(cl.last_error())
+            rindex._lib.clann_search_flush(rindex.handle, cur_stream)
+
+        run_replica(args.warmup)
+        r_ms = timed(run_replica, args.steps) / args.steps
+        replicas = {"value": nq * world / (r_ms / 1000.0), "unit": UNIT, "ms_per_step": r_ms,
+                    "what": f"index replicated on {world} GPUs, {nq} queries per GPU per step, three batches in flight, no collective"}
+        rindex.close()
+
+    if rank == 0:
         sl = (d + 15) // 16 * 16
         rerank_bytes = dc * 2 * sl + vis * k * 4 * d
         filter_bytes = cand * 12
@@ -521,43 +593,55 @@ def main():
         roofline = None
         if probe_ms:
             ach = (rerank_bytes + filter_bytes) / (probe_ms / 1000.0) / 1e9
-            roofline = {"bound": "hbm", "kernel": "k_dense_sims + k_first_ranges + k_probe (rerank and anchors of first visits streamed, then one warp per query)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roofline = {"bound": "hbm", "kernel": "k_dense_sims + k_first_ranges + k_probe (rerank and anchors of first visits streamed, then one warp per query)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                        "traffic": MEASURED_TRAFFIC.get(args.workload if not args.small else "small"),
-                        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_probe launch, ncu --set full, "
-                                          "k_dense_sims + k_first_ranges + k_probe, profiles/r1g_first_ranges_dense_sims_probe_full_raw.csv (glove100 planted only)",
+                        "traffic": MEASURED_TRAFFIC.get(args.workload if not args.small else "small"), "traffic_source": TRAFFIC_SOURCE,
                         "kernel_ms": probe_ms, "prep_ms": prep_ms,
                         "kernel_ms_note": "k_dense_sims (the rerank arithmetic of every query's first visit, streamed) + k_first_ranges (its "
                                           "anchors) + k_probe: the kernels between the library's events, all counted against the same "
                                           "algorithmic bytes",
                         "algorithmic_bytes_per_launch": rerank_bytes + filter_bytes,
                         "rerank_gbs": rerank_bytes / (probe_ms / 1000.0) / 1e9, "filter_gbs": filter_bytes / (probe_ms / 1000.0) / 1e9}
+        # build roofline: the greedy k-center passes stream n x d fp32 once per centre
+        gmm_bytes = float(K) * w["n"] * d * 4
+        build_roofline = {"bound": "hbm", "kernel": "k_gmm_pass_v x K (one pass over the rows per centre; rows the triangle inequality rules out are not read)",
+                          "achieved": gmm_bytes / (build_ms2[0] / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": gmm_bytes / (build_ms2[0] / 1000.0) / 1e9 / peak,
+                          "note": "algorithmic bytes K x n x d x 4 over the whole clustering phase (events around run_gmm incl. host hand-offs)"}
         cpu = None
-        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N=1 only
+        if not args.no_cpu_baseline and world == 1 and args.workload in ("glove100", "glove25", "readme"):
             try:
-                ref = run_reference(w, data, queries, src, centers, assignment, radii, threads=1)
+                ref = run_reference(w, data, queries, src, centers, assignment, radii, n_clusters=12, per_cluster=24)
                 cpu = {"value": ref["qps_1thread"], "unit": UNIT, "cores": 1, "kind": ref["kind"], "sample": ref["sample"],
+                       "qps_allcores": ref["qps_allcores"], "cores_allcores": ref["cores"], "recall_at_k": ref["recall"],
                        "clusters_visited_per_query": ref["visited"], "distance_computations_per_query": ref["distcomp"],
                        "index_build_s_for_sample": ref["build_s"]}
             except Exception as e:  # the baseline is reported, never required for our own number
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if shard_clusters else "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i16",
             "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
             "pipeline": ("clann_search_device_async: three batches in flight on three internal streams; outputs identical to the "
                          "stream-ordered call (checked)") if pipelined else "none (stream-ordered calls)",
-            "data": "synthetic", "config": cfg_json, "recall_at_k": recall, "recall_queries_checked": nchk,
+            "data": "synthetic", "config": cfg_json, "parallelism": parallelism, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,
                     "d2h_bytes_per_step": global_nq * k * 8 + global_nq * 4,
                     "ms_per_step": e2e_ms, "call": e2e_mode,
                     "value_synchronous_call": global_nq / (e2e_sync_ms / 1000.0), "ms_per_step_synchronous_call": e2e_sync_ms},
-            "gpu_launches": int(launches_per_step * args.steps * (1 if (world == 1 or shard_clusters) else world)), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "build": {"wall_s": build_wall, "gmm_ms": build_ms[0], "hash_ms": build_ms[1], "sort_ms": build_ms[2], "device_ms": build_ms[3],
-                      "clusters": int(K)},
-            "per_query": {"clusters_visited": vis / nq, "candidates": cand / nq, "distance_computations": dc / nq},
+            "gpu_launches": int(max(launches_per_step, 9) * args.steps * (world if mode == "replicas" else 1)),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "build": {"wall_s": build_wall2, "gmm_ms": build_ms2[0], "hash_ms": build_ms2[1], "sort_ms": build_ms2[2], "device_ms": build_ms2[3],
+                      "clusters": int(K), "first_build_wall_s": build_wall, "first_build_device_ms": build_ms[3], "roofline": build_roofline,
+                      "note": "second (warm) build of the same index; the first pays module loading"
+                              if world == 1 else "per-rank build: the full clustering, then the tables of this rank's clusters only"},
+            "per_query": {"clusters_visited": vis / gnq, "candidates": cand / gnq, "distance_computations": dc / gnq},
         }
+        if mode == "clusters":
+            line["sharded"] = {"routed_to_rank0_round_one": routed, "open_after_round_one": still_open, "global_batch": gnq}
+            line["replicas"] = replicas
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
