@@ -173,57 +173,68 @@ def reference_sample(queries, src, assignment, n_centers, n_clusters, per_cluste
     return groups, desc
 
 
+def _reference_worker(tmp, wi):
+    """One CPU worker of the reference arm (a fresh process: no CUDA context, no inherited OpenMP pool): loads the shared arrays,
+    answers its deal of queries with the real PUFFINN headers, prints one JSON object."""
+    from oracle.pyoracle import RefLib
+    meta = json.load(open(os.path.join(tmp, "meta.json")))
+    data = np.load(os.path.join(tmp, "data.npy"), mmap_mode="r")
+    data = np.ascontiguousarray(data)
+    queries = np.load(os.path.join(tmp, "queries.npy"))
+    centers = np.load(os.path.join(tmp, "centers.npy"))
+    assignment = np.load(os.path.join(tmp, "assignment.npy"))
+    radii = np.load(os.path.join(tmp, "radii.npy"))
+    idx = np.load(os.path.join(tmp, f"deal_{wi}.npy"))
+    eng = RefLib().clann(data, meta["L"], meta["k"], meta["delta"], centers, assignment, radii, seed_base=1234)
+    for i in idx:                       # pass 1: builds what the queries visit (untimed; in the reference this is `build`)
+        eng.search(queries[i])
+    build_s = eng.build_seconds
+    ts = time.time()
+    out = []
+    for i in idx:                       # pass 2: the timed pass, every query once
+        ids, dd, _, ctr = eng.search(queries[i])
+        out.append((int(i), dd.tolist(), ctr["visited"], ctr["distance_computations"]))
+    print(json.dumps({"search_s": time.time() - ts, "build_s": build_s, "res": out}))
+
+
 def run_reference(w, data, queries, src, centers, assignment, radii, workers=None, n_clusters=50, per_cluster=24):
     """The reference's own CPU implementation of the path (oracle/_ref: the real PUFFINN headers under the CLANN loop of
-    index.rs:311-439) on a bounded sample. The sample's home clusters are dealt to `workers` forked processes; each builds the
-    PUFFINN indices its queries visit (lazily, in an untimed first pass — in the reference this is `build`), then answers its
-    queries ONE pass, one query at a time (collection.hpp:104-113 allows nothing else per index). Reported: q/s of one core
+    index.rs:311-439) on a bounded sample. The sample's home clusters are dealt to `workers` processes (one per host core, one
+    OpenMP thread each); each builds the PUFFINN indices its queries visit (lazily, in an untimed first pass), then answers its
+    queries in ONE pass, one query at a time (collection.hpp:104-113 allows nothing else per index). Reported: q/s of one core
     (queries / sum of the workers' search times) and of the whole host (queries / slowest worker), recall of the sample."""
+    import shutil
+    import tempfile
     from oracle.pyoracle import RefLib
     if not RefLib.available():
         raise RuntimeError("oracle/_ref/libpuffinn_ref.so is missing; build it with `make -C oracle` where /root/reference exists")
     groups, desc = reference_sample(queries, src, assignment, len(centers), n_clusters, per_cluster)
     ncores = os.cpu_count() or 1
     P = max(1, min(workers or ncores, len(groups)))
-    eng = RefLib().clann(data, w["L"], w["k"], w["delta"], centers, assignment, radii, seed_base=1234)
     k = w["k"]
     t0 = time.time()
-    deals = [np.concatenate(groups[i::P]) if len(groups[i::P]) else np.zeros(0, np.int64) for i in range(P)]
-    pipes, pids = [], []
-    for wi in range(P):
-        r, wfd = os.pipe()
-        pid = os.fork()
-        if pid == 0:
-            try:
-                os.close(r)
-                idx = deals[wi]
-                for i in idx:                       # pass 1: builds what the queries visit (untimed)
-                    eng.search(queries[i])
-                build_s = eng.build_seconds
-                ts = time.time()
-                out = []
-                for i in idx:                       # pass 2: the timed pass, every query once
-                    ids, dd, _, ctr = eng.search(queries[i])
-                    out.append((int(i), dd.tolist(), ctr["visited"], ctr["distance_computations"]))
-                search_s = time.time() - ts
-                os.write(wfd, json.dumps({"search_s": search_s, "build_s": build_s, "res": out}).encode())
-            finally:
-                os._exit(0)
-        os.close(wfd)
-        pipes.append(r)
-        pids.append(pid)
-    results = []
-    for r, pid in zip(pipes, pids):
-        buf = b""
-        while True:
-            chunk = os.read(r, 1 << 20)
-            if not chunk:
-                break
-            buf += chunk
-        os.close(r)
-        os.waitpid(pid, 0)
-        if buf:
-            results.append(json.loads(buf.decode()))
+    tmp = tempfile.mkdtemp(prefix="clann_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        np.save(os.path.join(tmp, "data.npy"), data)
+        np.save(os.path.join(tmp, "queries.npy"), queries)
+        np.save(os.path.join(tmp, "centers.npy"), np.asarray(centers, np.uint64))
+        np.save(os.path.join(tmp, "assignment.npy"), np.asarray(assignment, np.uint64))
+        np.save(os.path.join(tmp, "radii.npy"), np.asarray(radii, np.float32))
+        json.dump({"L": w["L"], "k": k, "delta": w["delta"]}, open(os.path.join(tmp, "meta.json"), "w"))
+        for wi in range(P):
+            deal = groups[wi::P]
+            np.save(os.path.join(tmp, f"deal_{wi}.npy"), np.concatenate(deal) if deal else np.zeros(0, np.int64))
+        env = dict(os.environ, OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+        procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", tmp, str(wi)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, env=env, text=True) for wi in range(P)]
+        results = []
+        for p in procs:
+            out, _ = p.communicate(timeout=900)
+            lines = [l for l in out.splitlines() if l.startswith("{")]
+            if lines:
+                results.append(json.loads(lines[-1]))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     n_sample = sum(len(x["res"]) for x in results)
     if n_sample == 0:
         raise RuntimeError("the reference workers returned nothing")
@@ -247,6 +258,9 @@ def run_reference(w, data, queries, src, centers, assignment, radii, workers=Non
 # ------------------------------------------------------------------------------------------------ our arm
 
 def main():
+    if len(sys.argv) >= 4 and sys.argv[1] == "--ref-worker":
+        _reference_worker(sys.argv[2], int(sys.argv[3]))
+        return 0
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -640,7 +654,8 @@ def main():
             "per_query": {"clusters_visited": vis / gnq, "candidates": cand / gnq, "distance_computations": dc / gnq},
         }
         if mode == "clusters":
-            line["sharded"] = {"routed_to_rank0_round_one": routed, "open_after_round_one": still_open, "global_batch": gnq}
+            line["sharded"] = {"routed_to_rank0_round_one": routed, "open_after_round_one": still_open, "global_batch": gnq,
+                               "phase_ms_rank0": getattr(searcher, "phase_ms", None)}
             line["replicas"] = replicas
         print(json.dumps(line))
     if world > 1:

@@ -86,7 +86,7 @@ def load() -> C.CDLL:
     L.clann_comm_init.restype, L.clann_comm_init.argtypes = _i32, [_vp, _i32, _i32, _vp]
     L.clann_set_collectives.restype, L.clann_set_collectives.argtypes = _i32, [_vp, ALLGATHER_FN, ALLREDUCE_MIN_FN, _vp]
     L.clann_search_sharded.restype, L.clann_search_sharded.argtypes = _i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]
-    L.clann_shard_stats.restype, L.clann_shard_stats.argtypes = _i32, [_vp, C.POINTER(_u64), C.POINTER(_u64)]
+    L.clann_shard_stats.restype, L.clann_shard_stats.argtypes = _i32, [_vp, C.POINTER(_u64), C.POINTER(_u64), _vp]
     L.clann_export.restype, L.clann_export.argtypes = _i32, [_vp, _i32, _u64, _vp, _u64, C.POINTER(_u64)]
     L.clann_last_search_profile.restype, L.clann_last_search_profile.argtypes = _i32, [_vp, _vp, _vp]
     L.clann_destroy.restype, L.clann_destroy.argtypes = None, [_vp]

@@ -484,6 +484,7 @@ struct clann_index {
         uint64_t nq = 0;
         uint32_t n0 = 0, n1 = 0;
         bool last_was_sharded = false;
+        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last call
     } sh;
 
     // host mirrors
@@ -1395,8 +1396,11 @@ struct clann_index {
             sh.q0.ensure(nq * d);
             sh.q1.ensure(nq * d);
             if (!sh.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&sh.h_counts), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            for (auto& e : sh.ev)
+                if (!e) CLANN_CUDA(cudaEventCreate(&e));
             sh.nq = nq;
         }
+        CLANN_CUDA(cudaEventRecord(sh.ev[0], s));
         SearchWs* saved = W;
         try {
             CLANN_CUDA(cudaMemsetAsync(sh.counts.p, 0, 2 * sizeof(uint32_t), s));
@@ -1412,6 +1416,7 @@ struct clann_index {
                 launch_center_order(p, b, s);
                 CLANN_CUDA(cudaMemcpyAsync(sh.first_all.p + lo, b.first, (hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
             }
+            CLANN_CUDA(cudaEventRecord(sh.ev[1], s));
             // in-place all-gather: every rank's slice sits at rank * chunk of the same buffer
             all_gather(sh.first_all.p + rank * chunk, sh.first_all.p, chunk * sizeof(uint32_t), s);
             launch_shard_select_owned(sh.first_all.p, d_owner.p, rank, nq, sh.list0.p, sh.counts.p, s);
@@ -1419,6 +1424,7 @@ struct clann_index {
             CLANN_CUDA(cudaStreamSynchronize(s));
             const uint32_t n0 = sh.h_counts[0];
             sh.n0 = n0;
+            CLANN_CUDA(cudaEventRecord(sh.ev[2], s));
             // ---- round one
             launch_fill_u64(sh.packed.p, nq, 0xff800000ffffffffull, s);  // {+inf, nothing consumed}
             launch_fill_u64(sh.top_local.p, nq * k, ~0ull, s);
@@ -1436,12 +1442,14 @@ struct clann_index {
                 launch_shard_collect(W->w_state.p, k, sh.list0.p, n0, sh.top_local.p, false, sh.counters.p, s);
             }
             // ---- agree on the bounds, select what is still open
+            CLANN_CUDA(cudaEventRecord(sh.ev[3], s));
             all_reduce_min_u64(sh.packed.p, nq, s);
             launch_shard_select_open(sh.packed.p, nq, sh.list1.p, sh.packed1.p, sh.counts.p + 1, s);
             CLANN_CUDA(cudaMemcpyAsync(sh.h_counts + 1, sh.counts.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             CLANN_CUDA(cudaStreamSynchronize(s));
             const uint32_t n1 = sh.h_counts[1];
             sh.n1 = n1;
+            CLANN_CUDA(cudaEventRecord(sh.ev[4], s));
             // ---- round two
             W = &wsv[1];
             if (n1) {
@@ -1454,8 +1462,10 @@ struct clann_index {
                 launch_shard_collect(W->w_state.p, k, sh.list1.p, n1, sh.top_local.p, true, sh.counters.p, s);
             }
             // ---- merge
+            CLANN_CUDA(cudaEventRecord(sh.ev[5], s));
             all_gather(sh.top_local.p, sh.top_all.p, nq * k * sizeof(unsigned long long), s);
             launch_shard_final_merge(sh.top_all.p, world, nq, k, d_ids, d_dists, d_counts, s);
+            CLANN_CUDA(cudaEventRecord(sh.ev[6], s));
             sh.last_was_sharded = true;
             last_nq = nq;
             last_launches = 0;
@@ -1785,11 +1795,16 @@ int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq
     });
 }
 
-int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two) {
+int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms) {
     return guarded([&] {
         if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
         if (routed_round_one) *routed_round_one = index->sh.n0;
         if (open_round_two) *open_round_two = index->sh.n1;
+        if (phase_ms) {
+            if (!index->sh.ev[6]) throw StatusError(CLANN_ERR_ARG, "no sharded search yet");
+            CLANN_CUDA(cudaEventSynchronize(index->sh.ev[6]));
+            for (int i = 0; i < 6; i++) CLANN_CUDA(cudaEventElapsedTime(&phase_ms[i], index->sh.ev[i], index->sh.ev[i + 1]));
+        }
     });
 }
 

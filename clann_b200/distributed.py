@@ -151,7 +151,9 @@ class ClusterShardedSearcher:
 
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
-        _check(self.lib.clann_shard_stats(self.index.handle, C.byref(a), C.byref(b)))
+        ms = (C.c_float * 6)()
+        _check(self.lib.clann_shard_stats(self.index.handle, C.byref(a), C.byref(b), ms))
+        self.phase_ms = dict(zip(("route_scoring", "route_exchange", "round_one", "bound_exchange", "round_two", "merge"), [float(x) for x in ms]))
         return int(a.value), int(b.value)
 
 

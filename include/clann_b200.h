@@ -128,8 +128,9 @@ int clann_comm_init(clann_index* index, int rank, int world, const uint8_t* uniq
 int clann_set_collectives(clann_index* index, clann_allgather_fn allgather, clann_allreduce_min_u64_fn allreduce_min, void* ctx);
 int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts,
                          void* stream);
-/* queries routed to this rank in round one / still open in round two of the last clann_search_sharded */
-int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two);
+/* queries routed to this rank in round one / still open in round two of the last clann_search_sharded; phase_ms[6] (may be NULL) =
+ * device time of its phases: route scoring, route all-gather + selection, round one, bound all-reduce + selection, round two, merge */
+int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms);
 
 /* Per-query counters of the last search, the same quantities the reference keeps (performance.hpp:72-86 plus the
  * cluster count): any pointer may be NULL. Arrays of nq. */
