@@ -477,10 +477,11 @@ struct clann_index {
     clann_allreduce_min_u64_fn user_allreduce_min = nullptr;
     void* user_ctx = nullptr;
     struct ShardBufs {
-        DevBuf<uint32_t> first_all, list0, list1, counts;
-        DevBuf<unsigned long long> packed, packed1, top_local, top_all, counters;
+        DevBuf<uint32_t> first_all, list0, list1, list2, counts;
+        DevBuf<unsigned long long> packed, packed1, packed2, top_local, top_all, counters;
         DevBuf<float> q0, q1;
-        uint32_t* h_counts = nullptr;  // pinned: {queries routed to this rank in round one, queries still open in round two}
+        uint32_t* h_counts = nullptr;  // pinned: {routed to this rank in round one, still open after it, of those: served by this rank}
+        uint32_t n2 = 0;
         uint64_t nq = 0;
         uint32_t n0 = 0, n1 = 0;
         bool last_was_sharded = false;
@@ -1100,23 +1101,22 @@ struct clann_index {
         W->ws_fs = want_fs;
         const uint32_t F = n_fsets();
         const uint32_t k = (uint32_t)cfg.k;
-        W->w_qnorm.ensure(nq);
-        W->w_q15.ensure(nq * g.sl);
-        W->w_codes.ensure((size_t)F * g.L * nq);
-        W->w_sketches.ensure((size_t)F * nq * kNumSketches);
-        W->w_cdist.ensure(nq * K);
-        W->w_exact_limit.ensure(nq);
-        W->w_first.ensure(nq);
-        W->w_qperm.ensure(nq);
+        // capacity in steps of 2048 queries: batches of slightly different sizes (the sharded search) reuse the allocations
+        const uint64_t cq = (nq + 2047) / 2048 * 2048;
+        W->w_qnorm.ensure(cq);
+        W->w_q15.ensure(cq * g.sl);
+        W->w_codes.ensure((size_t)F * g.L * cq);
+        W->w_sketches.ensure((size_t)F * cq * kNumSketches);
+        W->w_cdist.ensure(cq * K);
+        W->w_exact_limit.ensure(cq);
+        W->w_first.ensure(cq);
+        W->w_qperm.ensure(cq);
         if (nq > segment_sort_smem_capacity()) {
-            W->w_sort_k.ensure(nq);
-            W->w_sort_i.ensure(nq);
+            W->w_sort_k.ensure(cq);
+            W->w_sort_i.ensure(cq);
         }
-        {
-            std::vector<SortSegment> seg(1, SortSegment{0, 0, (uint32_t)nq, 0});
-            W->w_sort_seg.upload(seg, s);
-        }
-        W->w_state.ensure(nq * query_state_bytes(k));
+        W->w_sort_seg.ensure(1);
+        W->w_state.ensure(cq * query_state_bytes(k));
         {
             // one memo region (u16 per local id of the largest cluster) per resident probe warp; skipped beyond 1 GiB
             const uint32_t max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
@@ -1130,14 +1130,14 @@ struct clann_index {
             // dense first-visit similarities: one u16 per (query, row of the largest cluster); skipped beyond 2 GiB
             const uint32_t max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
             W->w_dense_stride = ((uint64_t)max_cluster + 63) & ~63ull;
-            const uint64_t need = W->w_dense_stride * nq;
+            const uint64_t need = W->w_dense_stride * cq;
             if (need > 0 && need * sizeof(uint16_t) <= (2ull << 30) && !puffinn_mode) W->w_dense.ensure(need);
             else W->w_dense_stride = 0;
-            const uint64_t words = nq * kMaxHashBits * g.L;
+            const uint64_t words = cq * kMaxHashBits * g.L;
             if (W->w_dense_stride && words * 4 <= (2ull << 30)) {
-                W->w_pre_anchor.ensure(nq * g.L);
+                W->w_pre_anchor.ensure(cq * g.L);
                 W->w_pre_range.ensure(words);
-                W->w_pre_lcp.ensure(nq * g.L);
+                W->w_pre_lcp.ensure(cq * g.L);
             }
             // first-visit candidate stream: room for 2 x the largest cluster in segments per query (a visit scans ~4 candidates
             // per cluster row on the planted shapes, p99 ~2x that), 12 bytes per segment; only what a visit needs is written
@@ -1147,11 +1147,11 @@ struct clann_index {
                 const int64_t knob = tune_get("first_stream_cap", 0);
                 if (knob > 0) cap = (uint64_t)knob;
                 cap = (cap + 31) & ~31ull;
-                if (nq * cap * 12 <= (6ull << 30)) {
-                    W->w_fs_idx.ensure(nq * cap * 4);
-                    W->w_fs_hd.ensure(nq * cap);
-                    W->w_fs_tab.ensure(nq * cap / 32);
-                    W->w_fs_meta.ensure(nq * kFsMeta);
+                if (cq * cap * 12 <= (6ull << 30)) {
+                    W->w_fs_idx.ensure(cq * cap * 4);
+                    W->w_fs_hd.ensure(cq * cap);
+                    W->w_fs_tab.ensure(cq * cap / 32);
+                    W->w_fs_meta.ensure(cq * kFsMeta);
                     W->w_fs_cap = (uint32_t)cap;
                 }
             }
@@ -1166,26 +1166,23 @@ struct clann_index {
             h_stats[0] = h_stats[1] = 0;
             CLANN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_stats_dev), h_stats, 0));
         }
-        W->w_cand.ensure(nq);
-        W->w_dc.ensure(nq);
-        W->w_vis.ensure(nq);
-        std::vector<RowTile> tiles;
-        for (uint32_t f = 0; f < F; f++)
-            for (uint64_t q0 = 0; q0 < nq; q0 += 32)
-                tiles.push_back(RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(32, nq - q0), f, 0, 0, 0});
-        W->w_tiles.upload(tiles, s);
-        W->w_ntiles = (uint32_t)tiles.size();
+        W->w_cand.ensure(cq);
+        W->w_dc.ensure(cq);
+        W->w_vis.ensure(cq);
+        // The tile lists of the hashing kernels and the sort segment are written by a kernel: a batch of a new size (the sub-batches of
+        // the sharded search change size with every call) costs no host-device synchronisation.
+        const uint32_t per_f = (uint32_t)((nq + 31) / 32), per_f_tc = (uint32_t)((nq + 127) / 128);
+        W->w_ntiles = per_f * F;
+        W->w_tiles.ensure(W->w_ntiles);
+        W->w_tiles_codes.ensure(W->w_ntiles);
         W->w_n_tc_tiles = 0;
         if (sketch_tc_supported(g.sl) && nq < (1ull << 31)) {
-            std::vector<SketchTcTile> tct;
-            for (uint32_t f = 0; f < F; f++)
-                for (uint64_t q0 = 0; q0 < nq; q0 += 128)
-                    tct.push_back(SketchTcTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)std::min<uint64_t>(128, nq - q0), f});
-            W->w_tc_tiles.upload(tct, s);
-            W->w_n_tc_tiles = (uint32_t)tct.size();
-            W->w_qslices.ensure(nq * 2 * sketch_tc_kp(g.sl));
-            CLANN_CUDA(cudaStreamSynchronize(s));  // the host vector goes out of scope
+            W->w_n_tc_tiles = per_f_tc * F;
+            W->w_tc_tiles.ensure(W->w_n_tc_tiles);
+            W->w_qslices.ensure(cq * 2 * sketch_tc_kp(g.sl));
         }
+        launch_query_tiles(nq, F, W->w_tiles.p, W->w_tiles_codes.p, W->w_n_tc_tiles ? W->w_tc_tiles.p : nullptr, W->w_sort_seg.p, s);
+        W->w_tiles_codes_nq = nq;
         W->ws_nq = nq;
     }
 
@@ -1272,7 +1269,7 @@ struct clann_index {
     }
 
     const RowTile* w_code_tiles(uint64_t nq, cudaStream_t s) {
-        if (W->w_tiles_codes_nq != nq || !W->w_tiles_codes.p) {
+        if (W->w_tiles_codes_nq != nq || !W->w_tiles_codes.p) {  // (ensure_workspace already wrote them for its nq)
             std::vector<RowTile> tiles;
             for (uint32_t f = 0; f < n_fsets(); f++)
                 for (uint64_t q0 = 0; q0 < nq; q0 += 32)
@@ -1387,7 +1384,9 @@ struct clann_index {
             sh.first_all.ensure(chunk * world);
             sh.list0.ensure(nq);
             sh.list1.ensure(nq);
-            sh.counts.ensure(2);
+            sh.list2.ensure(nq);
+            sh.packed2.ensure(nq);
+            sh.counts.ensure(4);
             sh.packed.ensure(nq);
             sh.packed1.ensure(nq);
             sh.top_local.ensure(nq * k);
@@ -1395,7 +1394,7 @@ struct clann_index {
             sh.counters.ensure(nq * 3);
             sh.q0.ensure(nq * d);
             sh.q1.ensure(nq * d);
-            if (!sh.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&sh.h_counts), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            if (!sh.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&sh.h_counts), 4 * sizeof(uint32_t), cudaHostAllocDefault));
             for (auto& e : sh.ev)
                 if (!e) CLANN_CUDA(cudaEventCreate(&e));
             sh.nq = nq;
@@ -1403,7 +1402,7 @@ struct clann_index {
         CLANN_CUDA(cudaEventRecord(sh.ev[0], s));
         SearchWs* saved = W;
         try {
-            CLANN_CUDA(cudaMemsetAsync(sh.counts.p, 0, 2 * sizeof(uint32_t), s));
+            CLANN_CUDA(cudaMemsetAsync(sh.counts.p, 0, 4 * sizeof(uint32_t), s));
             // ---- route: nearest centre of this rank's slice of the batch
             const uint64_t lo = std::min<uint64_t>(nq, rank * chunk), hi = std::min<uint64_t>(nq, lo + chunk);
             W = &wsv[2];
@@ -1451,15 +1450,36 @@ struct clann_index {
             sh.n1 = n1;
             CLANN_CUDA(cudaEventRecord(sh.ev[4], s));
             // ---- round two
-            W = &wsv[1];
+            uint32_t n2 = 0;
             if (n1) {
+                // every rank scores the open queries against the centres (cheap), but hashes and probes only those for which it
+                // owns a cluster the agreed bound does not prune
+                W = &wsv[2];
                 launch_shard_gather_rows(d_queries, sh.list1.p, n1, d, sh.q1.p, s);
-                search_begin(sh.q1.p, n1, s);
+                ensure_workspace(n1, s);
+                W->ws_tc_center = use_tc_center();
+                {
+                    SearchParams p = params();
+                    QueryBatch b = batch(sh.q1.p, n1, nullptr, nullptr, nullptr);
+                    launch_prep_queries(p, b, s);
+                    launch_center_order(p, b, s);
+                    launch_shard_select_mine(b.cdist, b.exact_limit, d_radii.p, d_owner.p, rank, K, sh.list1.p, sh.packed1.p, n1, sh.list2.p,
+                                             sh.packed2.p, sh.counts.p + 2, s);
+                }
+                CLANN_CUDA(cudaMemcpyAsync(sh.h_counts + 2, sh.counts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                CLANN_CUDA(cudaStreamSynchronize(s));
+                n2 = sh.h_counts[2];
+            }
+            sh.n2 = n2;
+            W = &wsv[1];
+            if (n2) {
+                launch_shard_gather_rows(d_queries, sh.list2.p, n2, d, sh.q1.p, s);
+                search_begin(sh.q1.p, n2, s);
                 SearchParams p = params();
-                QueryBatch b = batch(sh.q1.p, n1, nullptr, nullptr, nullptr);
-                b.shard_packed = sh.packed1.p;
+                QueryBatch b = batch(sh.q1.p, n2, nullptr, nullptr, nullptr);
+                b.shard_packed = sh.packed2.p;
                 launch_probe(p, b, 2, s);
-                launch_shard_collect(W->w_state.p, k, sh.list1.p, n1, sh.top_local.p, true, sh.counters.p, s);
+                launch_shard_collect(W->w_state.p, k, sh.list2.p, n2, sh.top_local.p, true, sh.counters.p, s);
             }
             // ---- merge
             CLANN_CUDA(cudaEventRecord(sh.ev[5], s));

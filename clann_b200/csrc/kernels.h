@@ -170,6 +170,8 @@ int64_t tune_get(const char* key, int64_t dflt);
 void tune_set(const char* key, int64_t value);
 
 uint64_t query_state_bytes(uint32_t k);
+void launch_query_tiles(uint64_t nq, uint32_t F, RowTile* sk_tiles, RowTile* code_tiles, SketchTcTile* tc_tiles, SortSegment* seg,
+                        cudaStream_t s);
 void launch_prep_queries(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 // Tensor-pipe centre scoring (kernels_tc.cu): approx[q*K + c] = 1 - dot_tf32(q, c) / (|q| |c|), within kCentreEps of the exact value.
 constexpr float kCentreEps = 0.004f;   // tf32 operands: |error| <= 2^-9 |q||c| on the dot, i.e. 0.00195 on the cosine; doubled
@@ -208,6 +210,9 @@ void launch_shard_select_owned(const uint32_t* first_all, const uint8_t* owner, 
                                cudaStream_t s);
 void launch_shard_select_open(const unsigned long long* packed, uint64_t nq, uint32_t* list, unsigned long long* packed_local,
                               uint32_t* count, cudaStream_t s);
+void launch_shard_select_mine(const float* cdist, const float* exact_limit, const float* radii, const uint8_t* owner, uint32_t rank,
+                              uint32_t K, const uint32_t* list_in, const unsigned long long* packed_in, uint32_t count_in,
+                              uint32_t* list_out, unsigned long long* packed_out, uint32_t* count_out, cudaStream_t s);
 void launch_shard_gather_rows(const float* all, const uint32_t* list, uint32_t count, uint32_t d, float* out, cudaStream_t s);
 void launch_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v, cudaStream_t s);
 void launch_shard_pack_bounds(const uint8_t* state, uint32_t k, const uint32_t* list, uint32_t count, unsigned long long* packed,

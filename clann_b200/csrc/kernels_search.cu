@@ -39,6 +39,33 @@ void tune_set(const char* key, int64_t value) {
     tune_table()[key] = value;
 }
 
+// Tile lists of the row-parallel hashing kernels for a query batch of nq rows and F function sets, and the one-segment descriptor of
+// the work-order sort — written on the device so that a new batch size needs no host round trip.
+__global__ void __launch_bounds__(256) k_query_tiles(uint64_t nq, uint32_t F, RowTile* __restrict__ sk_tiles, RowTile* __restrict__ code_tiles,
+                                                     SketchTcTile* __restrict__ tc_tiles, SortSegment* __restrict__ seg) {
+    const uint32_t per_f = (uint32_t)((nq + 31) / 32), per_f_tc = (uint32_t)((nq + 127) / 128);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && seg) *seg = SortSegment{0, 0, (uint32_t)nq, 0};
+    if (i < per_f * F) {
+        const uint32_t f = i / per_f;
+        const uint64_t q0 = (uint64_t)(i % per_f) * 32;
+        const uint32_t cnt = (uint32_t)(nq - q0 < 32 ? nq - q0 : 32);
+        sk_tiles[i] = RowTile{(uint32_t)q0, (uint32_t)(f * nq + q0), cnt, f, 0, 0, 0};     // sketches: out row = fset * nq + q
+        code_tiles[i] = RowTile{(uint32_t)q0, (uint32_t)q0, cnt, f, 0, 0, 0};              // codes: [fset][table][q]
+    }
+    if (tc_tiles && i < per_f_tc * F) {
+        const uint32_t f = i / per_f_tc;
+        const uint64_t q0 = (uint64_t)(i % per_f_tc) * 128;
+        tc_tiles[i] = SketchTcTile{(uint32_t)q0, (uint32_t)(f * nq + q0), (uint32_t)(nq - q0 < 128 ? nq - q0 : 128), f};
+    }
+}
+
+void launch_query_tiles(uint64_t nq, uint32_t F, RowTile* sk_tiles, RowTile* code_tiles, SketchTcTile* tc_tiles, SortSegment* seg,
+                        cudaStream_t s) {
+    const uint32_t n = (uint32_t)((nq + 31) / 32) * F;
+    k_query_tiles<<<(n + 255) / 256 + 1, 256, 0, s>>>(nq, F, sk_tiles, code_tiles, tc_tiles, seg);
+}
+
 uint64_t query_state_bytes(uint32_t k) { return sizeof(QueryStateHeader) + (uint64_t)k * 8; }
 
 // ------------------------------------------------------------------------------------------------ query prep
@@ -1053,6 +1080,31 @@ __global__ void __launch_bounds__(256) k_shard_select_open(const unsigned long l
     }
 }
 
+// Round two, second cut: of the open queries, those for which this rank owns at least one cluster the agreed bound does not prune
+// (distance to the centre - radius <= bound, index.rs:342-361 with the bound of round one). Only these are hashed and probed
+// here; the test ignores the order of the walk, so it keeps a superset of the queries the probe would actually serve.
+__global__ void __launch_bounds__(256) k_shard_select_mine(const float* __restrict__ cdist, const float* __restrict__ exact_limit,
+                                                           const float* __restrict__ radii, const uint8_t* __restrict__ owner,
+                                                           uint32_t rank, uint32_t K, const uint32_t* __restrict__ list_in,
+                                                           const unsigned long long* __restrict__ packed_in, uint32_t count_in,
+                                                           uint32_t* __restrict__ list_out, unsigned long long* __restrict__ packed_out,
+                                                           uint32_t* count_out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (warp >= count_in) return;
+    const unsigned long long pk = packed_in[warp];
+    const float bound = float_from_order_bits((uint32_t)(pk >> 32));
+    const float* cd = cdist + (uint64_t)warp * K;
+    // entries at or above exact_limit are lower bounds of the exact distance (tensor-pipe screen): testing them keeps a superset
+    (void)exact_limit;
+    bool any = false;
+    for (uint32_t c = lane; c < K; c += 32) any |= owner[c] == rank && !(cd[c] - radii[c] > bound);
+    if (__any_sync(0xffffffffu, any) && lane == 0) {
+        const uint32_t slot = atomicAdd(count_out, 1u);
+        list_out[slot] = list_in[warp];
+        packed_out[slot] = pk;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_shard_gather_rows(const float* __restrict__ all, const uint32_t* __restrict__ list, uint32_t count,
                                                            uint32_t d, float* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1162,6 +1214,13 @@ void launch_shard_select_owned(const uint32_t* first_all, const uint8_t* owner, 
 void launch_shard_select_open(const unsigned long long* packed, uint64_t nq, uint32_t* list, unsigned long long* packed_local,
                               uint32_t* count, cudaStream_t s) {
     if (nq) k_shard_select_open<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(packed, nq, list, packed_local, count);
+}
+void launch_shard_select_mine(const float* cdist, const float* exact_limit, const float* radii, const uint8_t* owner, uint32_t rank,
+                              uint32_t K, const uint32_t* list_in, const unsigned long long* packed_in, uint32_t count_in,
+                              uint32_t* list_out, unsigned long long* packed_out, uint32_t* count_out, cudaStream_t s) {
+    if (count_in)
+        k_shard_select_mine<<<(unsigned)(((uint64_t)count_in * 32 + 255) / 256), 256, 0, s>>>(cdist, exact_limit, radii, owner, rank, K, list_in,
+                                                                                          packed_in, count_in, list_out, packed_out, count_out);
 }
 void launch_shard_gather_rows(const float* all, const uint32_t* list, uint32_t count, uint32_t d, float* out, cudaStream_t s) {
     const uint64_t n = (uint64_t)count * d;
