@@ -104,6 +104,42 @@ def make_data(w, dist):
     return data, q, src
 
 
+def make_data_device(w, dist, dev, fp16):
+    """The same two distributions generated on the device (torch, fixed seeds: every rank of a job draws identical rows) for the
+    shapes that are too large to draw with numpy on the host in reasonable time (10M x 96, 100M x 96). Rows are normalised in
+    fp32 and, for the fp16 workload, rounded to half precision — the index is then built from exactly those half values."""
+    import torch
+    n, d, nq = w["n"], w["d"], w["nq"]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(42)
+    out = torch.empty((n, d), dtype=torch.float16 if fp16 else torch.float32, device=dev)
+    c0 = max(1, int(0.4 * np.sqrt(n)))
+    centers = torch.randn((c0, d), generator=gen, device=dev) if dist == "planted" else None
+    step = 2_000_000
+    for s0 in range(0, n, step):
+        m = min(step, n - s0)
+        x = torch.randn((m, d), generator=gen, device=dev)
+        if dist == "planted":
+            which = torch.randint(0, c0, (m,), generator=gen, device=dev)
+            x = centers[which] + 0.6 * x
+        x = x / x.norm(dim=1, keepdim=True)
+        out[s0:s0 + m] = x.to(out.dtype)
+    return out
+
+
+def make_queries_device(data_t, nq, dist, seed, dev):
+    import torch
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    n, d = data_t.shape
+    if dist == "planted":
+        src = torch.randint(0, n, (nq,), generator=gen, device=dev)
+        q = data_t[src].float() + 0.05 * torch.randn((nq, d), generator=gen, device=dev)
+    else:
+        q = torch.randn((nq, d), generator=gen, device=dev)
+    return (q / q.norm(dim=1, keepdim=True)).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
@@ -334,8 +370,14 @@ def main():
     from clann_b200.distributed import ClusterShardedSearcher, ShardedSearcher
 
     dev = torch.device("cuda", local_rank)
-    data, queries, src = make_data(w, args.dist)
     nq, k, d = w["nq"], w["k"], w["d"]
+    big = w["n"] >= 5_000_000 or w.get("fp16", False)   # rows generated (and kept) on the device
+    data_t = None
+    if big:
+        data_t = make_data_device(w, args.dist, dev, w.get("fp16", False))
+        data, queries, src = None, make_queries_device(data_t, nq, args.dist, 43, dev).cpu().numpy(), np.full(nq, -1)
+    else:
+        data, queries, src = make_data(w, args.dist)
     mode = "single" if world == 1 else args.shard
     gnq = nq * world if mode in ("clusters", "stepping") else nq      # queries every rank holds per step
     global_nq = nq * world if world > 1 else nq                        # queries the whole job answers per step
@@ -345,6 +387,8 @@ def main():
     for j in range(N_QUERY_BATCHES):
         if j == 0 and gnq == nq and mode != "replicas":
             batches.append(queries)
+        elif big:
+            batches.append(make_queries_device(data_t, gnq, args.dist, seed0 + 17 * j, dev).cpu().numpy())
         else:
             batches.append(make_queries(data, gnq, d, args.dist, seed0 + 17 * j)[0])
     parallelism = ("single GPU" if world == 1 else
@@ -357,7 +401,11 @@ def main():
     # ---- build (untimed setup of the search benchmark; reported on its own)
     def build_index(sharded):
         t0 = time.time()
-        ix = cb.init_with_config(data, cb.Config(w["L"], w["factor"], w["k"], w["delta"], "bench"))
+        conf = cb.Config(w["L"], w["factor"], w["k"], w["delta"], "bench")
+        if big:
+            ix = cb.ClusteredIndex.from_rows(conf, data_t.data_ptr(), w["n"], d, "f16" if w.get("fp16") else "f32", on_device=True)
+        else:
+            ix = cb.init_with_config(data, conf)
         ix.set_option("seed", 1234)
         if sharded:
             ix.set_option("shard_count", world)
@@ -367,7 +415,7 @@ def main():
         return ix, time.time() - t0, ix.export(cl.X_BUILD_MS, 0, np.float64).copy()
 
     index, build_wall, build_ms = build_index(mode in ("clusters", "stepping"))
-    if world == 1:   # a second, warm build: the first one pays module loading and the first cudaMallocs
+    if world == 1 and not big:   # a second, warm build: the first one pays module loading and the first cudaMallocs
         index.close()
         index, build_wall2, build_ms2 = build_index(False)
     else:
@@ -544,16 +592,21 @@ def main():
     ids = d_ids.cpu().numpy().view(np.uint32); dists = d_dists.cpu().numpy(); counts = d_counts.cpu().numpy()
     nchk = min(gnq, 2000)
     with torch.no_grad():
-        dd = torch.from_numpy(data).to(dev)
-        ex = torch.empty((nchk, k), device=dev)
-        chunk = max(8, min(250, int(2.5e8 // w["n"])))   # keep the similarity tile under ~1 GB
-        dq0 = d_batches[0]
-        for s in range(0, nchk, chunk):
-            e = min(s + chunk, nchk)
-            sim = dq0[s:e] @ dd.T
-            ex[s:e] = torch.topk(sim, k, dim=1).values
-        kth = (1.0 - ex[:, k - 1]).cpu().numpy()
-        del dd
+        dd = data_t if big else torch.from_numpy(data).to(dev)
+        dq0 = d_batches[0][:nchk]
+        best = torch.full((nchk, k), -2.0, device=dev)
+        rows_step = 2_000_000
+        qs = max(8, min(nchk, int(2.5e8 // min(w["n"], rows_step))))   # keep the similarity tile under ~1 GB
+        for r0 in range(0, w["n"], rows_step):   # running top-k over row chunks (the big shapes do not fit one tile)
+            blk = dd[r0:r0 + rows_step].float()
+            for s in range(0, nchk, qs):
+                e = min(s + qs, nchk)
+                sim = dq0[s:e] @ blk.T
+                cand = torch.cat([best[s:e], torch.topk(sim, min(k, sim.shape[1]), dim=1).values], dim=1)
+                best[s:e] = torch.topk(cand, k, dim=1).values
+        kth = (1.0 - best[:, k - 1]).cpu().numpy()
+        if not big:
+            del dd
     hit = sum(int(np.sum(dists[i, :counts[i]] <= kth[i] + 1e-3)) for i in range(nchk))
     recall = hit / (nchk * k)
     if args.dist == "planted" and not args.small and recall < 0.9:
@@ -577,7 +630,8 @@ def main():
     replicas = None
     if world > 1 and mode == "clusters" and not args.no_replicas:
         rindex, _, _ = build_index(False)
-        rq = torch.from_numpy(make_queries(data, nq, d, args.dist, 43 + 1000 * rank)[0]).to(dev)
+        rq = (make_queries_device(data_t, nq, args.dist, 43 + 1000 * rank, dev) if big else
+              torch.from_numpy(make_queries(data, nq, d, args.dist, 43 + 1000 * rank)[0]).to(dev))
         r_outs = [(torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
                    torch.empty(nq, dtype=torch.int32, device=dev)) for _ in range(NSETS)]
 

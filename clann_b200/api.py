@@ -156,6 +156,19 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class _Shape:
+    """Stand-in for AngularData when the rows never lived in a host array of this process (device-resident / fp16 ingest)."""
+
+    def __init__(self, n, d):
+        self.n, self.d = n, d
+
+    def num_points(self):
+        return self.n
+
+    def dimensions(self):
+        return self.d
+
+
 class ClusteredIndex:
     """ClusteredIndex<T> (src/core/index.rs:37-47), device resident behind the C ABI."""
 
@@ -171,6 +184,30 @@ class ClusteredIndex:
         n, d = data.data.shape if data.data.size else (data.data.shape[0], data.data.shape[1] if data.data.ndim == 2 else 0)
         _check(self._lib.clann_init_with_config(_ptr(data.data) if n else None, n, d, C.byref(cfg), C.byref(self._h)))
         self.built = False
+
+    @classmethod
+    def from_rows(cls, config: Config, rows, n: int, d: int, dtype: str = "f32", on_device: bool = False) -> "ClusteredIndex":
+        """clann_init_with_config_ex: rows as fp16 ("f16"; widened exactly on the device) and / or already on the device (`rows` is
+        then a device pointer as an int; otherwise a numpy array of the matching dtype)."""
+        self = cls.__new__(cls)
+        self.config = config
+        self.data = _Shape(n, d)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        cfg = _lib.ClannConfig(int(config.num_tables), float(np.float32(config.num_clusters_factor)), int(config.k),
+                               float(np.float32(config.delta)))
+        if on_device:
+            ptr = C.c_void_p(int(rows))
+        else:
+            arr = np.ascontiguousarray(rows, np.float16 if dtype == "f16" else np.float32)
+            if arr.shape != (n, d):
+                raise DataError("rows do not have the stated shape")
+            self._keep = arr
+            ptr = _ptr(arr)
+        _check(self._lib.clann_init_with_config_ex(ptr, n, d, C.byref(cfg), 1 if dtype == "f16" else 0, 1 if on_device else 0,
+                                                   C.byref(self._h)))
+        self.built = False
+        return self
 
     # -- options / parity hooks (no counterpart in the reference API; used by tests and the multi-GPU driver)
     def set_option(self, key: str, value: int) -> None:

@@ -462,6 +462,7 @@ struct clann_index {
     // configuration
     clann_config cfg{};
     uint64_t n = 0;
+    uint64_t n_rows = 0;  // rows of the PUFFINN-layer arrays on this rank: n, or the rows of the clusters this shard owns
     HashGeom g{};
     uint32_t K = 0;
     uint64_t seed = 0x5eedc1a7ull;
@@ -597,9 +598,12 @@ struct clann_index {
         return (uint32_t)k;
     }
 
-    void init(const float* data, uint64_t n_, uint32_t d, const clann_config& c) {
+    // dtype: 0 = f32, 1 = f16 (IEEE half; converted to f32 exactly on the device — the index is the one the reference would build
+    // from the same rows widened to f32). on_device: `data` is a device pointer (copied / converted device to device).
+    void init(const void* data, uint64_t n_, uint32_t d, const clann_config& c, int dtype = 0, bool on_device = false) {
         if (n_ == 0) throw StatusError(CLANN_ERR_DATA, "empty dataset");  // index.rs:72-74
         if (!data || d == 0) throw StatusError(CLANN_ERR_ARG, "null data or zero dimension");
+        if (dtype != 0 && dtype != 1) throw StatusError(CLANN_ERR_ARG, "dtype must be 0 (f32) or 1 (f16)");
         if (d > 1024) throw StatusError(CLANN_ERR_CONFIG, "dimension above 1024 is not supported");
         if (c.num_tables == 0) throw StatusError(CLANN_ERR_CONFIG, "num tables should be >0");  // collection.hpp:242-244
         if (c.k == 0) throw StatusError(CLANN_ERR_CONFIG, "k must be at least 1");
@@ -611,8 +615,29 @@ struct clann_index {
         n = n_;
         g = make_geom(d, (uint32_t)c.num_tables);
         K = puffinn_mode ? 1u : num_clusters(c.num_clusters_factor, n);
-        d_data.upload(data, (size_t)n * d);
-        for (auto& e : ev) CLANN_CUDA(cudaEventCreate(&e));
+        const size_t count = (size_t)n * d;
+        if (dtype == 0) {
+            d_data.alloc(count);
+            CLANN_CUDA(cudaMemcpy(d_data.p, data, count * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        } else {
+            d_data.alloc(count);
+            // widen in chunks through a bounded staging buffer (host input) or straight from the caller's device buffer
+            const size_t chunk = std::min<size_t>(count, (size_t)256 << 20);
+            DevBuf<uint16_t> stage;
+            if (!on_device) stage.alloc(chunk);
+            for (size_t off = 0; off < count; off += chunk) {
+                const size_t m = std::min(chunk, count - off);
+                const uint16_t* src = static_cast<const uint16_t*>(data) + off;
+                if (!on_device) {
+                    CLANN_CUDA(cudaMemcpy(stage.p, src, m * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                    src = stage.p;
+                }
+                launch_widen_f16(src, m, d_data.p + off, 0);
+            }
+            CLANN_CUDA(cudaDeviceSynchronize());
+        }
+        for (auto& e : ev)
+            if (!e) CLANN_CUDA(cudaEventCreate(&e));
     }
 
     void set_clustering(uint64_t K_, const uint64_t* centers, const uint64_t* assignment, const float* radii) {
@@ -682,6 +707,7 @@ struct clann_index {
         puffinn_mode = true;
         cfg = clann_config{ls.L, 1.0f, 10, 0.9f};
         n = ls.n;
+        n_rows = n;
         g = make_geom(ls.d, ls.L);
         K = 1;
         for (auto& e : ev)
@@ -970,6 +996,27 @@ struct clann_index {
         h_fset_of.resize(K);
         for (uint32_t c = 0; c < K; c++) h_fset_of[c] = per_cluster_functions ? c : 0;
         assign_owners();
+        n_rows = n;
+        if (shard_count > 1) {
+            // A shard keeps the PUFFINN layer (Q15 rows, sketches, tables) of ITS clusters only, packed back to back: the per-GPU
+            // footprint of that layer is 1/shard_count of the index (the fp32 rows, centres and radii stay replicated — greedy
+            // k-center and the final distances read them). Foreign clusters become empty in this rank's layout; they are never
+            // probed here (the sharded entry points stop at / skip them).
+            std::vector<uint32_t> perm = d_perm.download(n), local;
+            local.reserve(n / shard_count + 1024);
+            std::vector<uint64_t> off(K + 1, 0);
+            for (uint32_t c = 0; c < K; c++) {
+                if (h_owner[c] == shard_rank) local.insert(local.end(), perm.begin() + h_offsets[c], perm.begin() + h_offsets[c] + h_sizes[c]);
+                else h_sizes[c] = 0;
+                off[c + 1] = local.size();
+            }
+            h_offsets = off;
+            n_rows = local.size();
+            if (local.empty()) local.push_back(0);
+            d_perm.upload(local, s);
+            d_offsets.upload(h_offsets, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));
+        }
         d_brute.upload(h_brute, s);
         d_fset_of.upload(h_fset_of, s);
         d_owner.upload(h_owner, s);
@@ -990,8 +1037,8 @@ struct clann_index {
         prepare_functions(s);
 
         // PUFFINN layer: Q15 rows in cluster order (puffinn.rs:41-46 -> dataset.hpp:109-124)
-        d_q15.alloc((size_t)n * g.sl);
-        launch_store_q15(d_data.p, d_perm.p, n, g.d, g.sl, d_q15.p, s);
+        d_q15.alloc((size_t)std::max<uint64_t>(n_rows, 1) * g.sl);
+        launch_store_q15(d_data.p, d_perm.p, n_rows, g.d, g.sl, d_q15.p, s);
         std::vector<RowTile> tiles;
         std::vector<SortSegment> segs;
         uint32_t max_len = 0;
@@ -1009,12 +1056,12 @@ struct clann_index {
         }
         DevBuf<RowTile> d_tiles;
         d_tiles.upload(tiles, s);
-        d_sketches.alloc((size_t)n * kNumSketches);
+        d_sketches.alloc((size_t)std::max<uint64_t>(n_rows, 1) * kNumSketches);
         if (use_tc_sketch()) build_sketches_tc(s);
         else launch_sketch(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_planes.p, g.sl, d_sketches.p, s);
-        d_tbl_hash.alloc((size_t)g.L * n);
-        d_tbl_idx.alloc((size_t)g.L * n);
-        launch_codes(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_signbits.p, g, d_tbl_hash.p, n, 0, s);
+        d_tbl_hash.alloc((size_t)g.L * std::max<uint64_t>(n_rows, 1));
+        d_tbl_idx.alloc((size_t)g.L * std::max<uint64_t>(n_rows, 1));
+        launch_codes(d_q15.p, d_tiles.p, (uint32_t)tiles.size(), d_signbits.p, g, d_tbl_hash.p, n_rows, 0, s);
         CLANN_CUDA(cudaEventRecord(e2, s));
         // collection.hpp:299-302 -> prefixmap.hpp:169-247: one stable radix sort per (cluster, table)
         for (uint32_t c = 0; c < K; c++) {
@@ -1045,7 +1092,7 @@ struct clann_index {
             DevBuf<uint8_t> d_skip;
             d_skip.upload(skip, s);
             d_tbl_dir.alloc((size_t)g.L * K * kDirEntries);
-            launch_build_dir(d_tbl_hash.p, n, d_offsets.p, d_skip.p, K, g.L, d_tbl_dir.p, s);
+            launch_build_dir(d_tbl_hash.p, n_rows, d_offsets.p, d_skip.p, K, g.L, d_tbl_dir.p, s);
             CLANN_CUDA(cudaStreamSynchronize(s));
         }
         CLANN_CUDA(cudaEventRecord(e3, s));
@@ -1612,6 +1659,22 @@ int clann_init_with_config(const float* data, uint64_t n, uint32_t d, const clan
     });
 }
 
+int clann_init_with_config_ex(const void* data, uint64_t n, uint32_t d, const clann_config* config, int dtype, int on_device,
+                              clann_index** out) {
+    if (out) *out = nullptr;
+    return guarded([&] {
+        if (!config || !out) throw StatusError(CLANN_ERR_ARG, "null config or output pointer");
+        auto* ix = new clann_index();
+        try {
+            ix->init(data, n, d, *config, dtype, on_device != 0);
+        } catch (...) {
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
 int clann_set_option(clann_index* index, const char* key, int64_t value) {
     return guarded([&] {
         if (!index || !key) throw StatusError(CLANN_ERR_ARG, "null index or key");
@@ -1909,7 +1972,7 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
             }
             case CLANN_X_RADII: index->require_built(); emit(index->h_radii.data(), (uint64_t)K * 4); break;
             case CLANN_X_OFFSETS: index->require_built(); emit(index->h_offsets.data(), (uint64_t)(K + 1) * 8); break;
-            case CLANN_X_PERM: index->require_built(); emit_dev(index->d_perm.p, index->n * 4); break;
+            case CLANN_X_PERM: index->require_built(); emit_dev(index->d_perm.p, index->n_rows * 4); break;
             case CLANN_X_Q15:
                 need_cluster();
                 emit_dev(index->d_q15.p + index->h_offsets[arg] * index->g.sl, (uint64_t)index->h_sizes[arg] * index->g.sl * 2);

@@ -14,6 +14,7 @@ void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t
                      float* dist, uint32_t* assign, float* cc, cudaStream_t s);
 void launch_gmm_finish(const uint64_t* keys, uint32_t K, uint64_t n, const float* dist, const uint32_t* assign,
                        uint32_t* centers, float* radii, uint32_t* sizes, cudaStream_t s);
+void launch_widen_f16(const uint16_t* in, uint64_t count, float* out, cudaStream_t s);
 void launch_gather_rows(const float* data, const uint32_t* rows, uint32_t count, uint32_t d, float* out, cudaStream_t s);
 
 // ---- build: PUFFINN layer

@@ -1,6 +1,8 @@
 // Build-side kernels: greedy k-center (gmm.rs), Q15 store, SimHash sketches, FHT cross-polytope table codes,
 // segmented stable radix sort of the hash tables, Monte-Carlo collision estimates.
 // Citations are file:line into /root/reference (libpuffinn/include/puffinn unless a src/ path is given).
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace clann {
@@ -181,6 +183,23 @@ __global__ void k_gather_rows(const float* __restrict__ data, const uint32_t* __
         uint32_t r = (uint32_t)(i / d), j = (uint32_t)(i % d);
         out[i] = data[(uint64_t)rows[r] * d + j];
     }
+}
+
+// fp16 rows -> fp32 (exact): the ingest path of BASELINE.json's 100M x 96 fp16 configuration.
+__global__ void __launch_bounds__(256) k_widen_f16(const uint16_t* __restrict__ in, uint64_t count, float* __restrict__ out) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < count) {
+        const __half2 h = *reinterpret_cast<const __half2*>(in + i);
+        const float2 f = __half22float2(h);
+        out[i] = f.x;
+        out[i + 1] = f.y;
+    } else if (i < count) {
+        out[i] = __half2float(*reinterpret_cast<const __half*>(in + i));
+    }
+}
+
+void launch_widen_f16(const uint16_t* in, uint64_t count, float* out, cudaStream_t s) {
+    if (count) k_widen_f16<<<(unsigned)(((count + 1) / 2 + 255) / 256), 256, 0, s>>>(in, count, out);
 }
 
 // ------------------------------------------------------------------------------------------------ Q15 store

@@ -55,6 +55,12 @@ typedef enum {
  * memory; it is copied to the device. n == 0 -> CLANN_ERR_DATA ("empty dataset"). Uses the current CUDA device. */
 int clann_init_with_config(const float* data, uint64_t n, uint32_t d, const clann_config* config, clann_index** out);
 
+/* The same with the rows as IEEE half precision (dtype 1; BASELINE.json's "100M x 96 fp16" configuration) and / or already
+ * resident on the device (on_device != 0: `data` is a device pointer, copied device to device). fp16 rows are widened to f32
+ * exactly on the device: the index is the one the reference builds from the same rows widened to f32. dtype 0 = f32. */
+int clann_init_with_config_ex(const void* data, uint64_t n, uint32_t d, const clann_config* config, int dtype, int on_device,
+                              clann_index** out);
+
 /* Options, to be set between init and build. Unknown key -> CLANN_ERR_ARG.
  *   "seed"            seed of the function generator (the reference seeds from the wall clock, typedefs.hpp:17)
  *   "function_sets"   0 (default) = one hash/sketch function set shared by all clusters (query hashed once);

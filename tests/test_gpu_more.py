@@ -692,3 +692,35 @@ def test_cluster_sharded_search_two_ranks_in_process(big):
     assert worse <= 12, worse
     for ix in shards:
         ix.close()
+
+
+def test_fp16_and_device_resident_ingest():
+    """clann_init_with_config_ex (BASELINE.json's fp16 configuration): rows handed over as IEEE half — from host memory or
+    already on the device — build exactly the index that the same rows widened to f32 build: identical clustering, tables,
+    results, counters."""
+    import torch
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    data16 = util.planted(30_000, 96, 131).astype(np.float16)
+    wide = data16.astype(np.float32)
+    conf = cb.Config(24, 0.4, 20, 0.9, "fp16")
+    q = util.planted_queries(wide, 300, 132)
+    ref = cb.init_with_config(wide, conf)
+    ref.set_option("seed", 3)
+    ref.build()
+    want = ref.search_batch(q)
+    want_ctr = ref.counters(len(q))
+    want_tables = ref.export(cl.X_TABLE_HASHES, 1, np.uint32).copy()
+    d_rows = torch.from_numpy(data16).cuda()
+    for rows, on_device in ((data16, False), (d_rows.data_ptr(), True)):
+        ix = cb.ClusteredIndex.from_rows(conf, rows, 30_000, 96, "f16", on_device=on_device)
+        ix.set_option("seed", 3)
+        ix.build()
+        assert np.array_equal(ix.export(cl.X_ASSIGNMENT, 0, np.uint64), ref.export(cl.X_ASSIGNMENT, 0, np.uint64))
+        assert np.array_equal(ix.export(cl.X_TABLE_HASHES, 1, np.uint32), want_tables)
+        got = ix.search_batch(q)
+        ctr = ix.counters(len(q))
+        assert all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(got, want))
+        assert all(np.array_equal(ctr[key], want_ctr[key]) for key in ctr)
+        ix.close()
+    ref.close()
