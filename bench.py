@@ -325,6 +325,8 @@ def main():
         return 0
 
     w = workload(args)
+    if w.get("fp16") and args.queries == 0:
+        w["nq"] = max(1, w["nq"] // world)   # the sweep's batch is 100 000 queries for the whole job
     if args.queries > 0:
         w["nq"] = args.queries
         w["name"] += f" [batch overridden: {args.queries} queries per step]"
@@ -421,9 +423,10 @@ def main():
     else:
         build_wall2, build_ms2 = build_wall, build_ms
     K = index.num_clusters
-    centers = index.export(cl.X_CENTERS, 0, np.uint64).copy()
-    assignment = index.export(cl.X_ASSIGNMENT, 0, np.uint64).copy()
-    radii = index.export(cl.X_RADII, 0, np.float32).copy()
+    if not big:   # only the CPU baseline needs the clustering on the host
+        centers = index.export(cl.X_CENTERS, 0, np.uint64).copy()
+        assignment = index.export(cl.X_ASSIGNMENT, 0, np.uint64).copy()
+        radii = index.export(cl.X_RADII, 0, np.float32).copy()
 
     d_batches = [torch.from_numpy(b).to(dev) for b in batches]
     d_q = d_batches[0]
@@ -628,7 +631,7 @@ def main():
 
     # ---- N > 1: the replica arrangement for comparison (index replicated, every rank its own batch, no collective)
     replicas = None
-    if world > 1 and mode == "clusters" and not args.no_replicas:
+    if world > 1 and mode == "clusters" and not args.no_replicas and w["n"] <= 20_000_000:
         rindex, _, _ = build_index(False)
         rq = (make_queries_device(data_t, nq, args.dist, 43 + 1000 * rank, dev) if big else
               torch.from_numpy(make_queries(data, nq, d, args.dist, 43 + 1000 * rank)[0]).to(dev))
@@ -647,6 +650,21 @@ def main():
         replicas = {"value": nq * world / (r_ms / 1000.0), "unit": UNIT, "ms_per_step": r_ms,
                     "what": f"index replicated on {world} GPUs, {nq} queries per GPU per step, three batches in flight, no collective"}
         rindex.close()
+
+    sweep = None
+    if w.get("fp16") and not args.delta:
+        sweep = []
+        for dl in (0.8, 0.9, 0.95):
+            index.set_delta(dl)
+            for i in range(2):
+                step_device(i)
+            ms = timed(lambda steps: [step_device(i) for i in range(steps)], max(3, args.steps // 2)) / max(3, args.steps // 2)
+            step_device(0)
+            torch.cuda.synchronize()
+            dd_ = d_dists.cpu().numpy(); cc_ = d_counts.cpu().numpy()
+            hit_ = sum(int(np.sum(dd_[i, :cc_[i]] <= kth[i] + 1e-3)) for i in range(nchk))
+            sweep.append({"delta": dl, "value": global_nq / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "recall_at_k": hit_ / (nchk * k)})
+        index.set_delta(w["delta"])
 
     if rank == 0:
         sl = (d + 15) // 16 * 16
@@ -711,6 +729,8 @@ def main():
             line["sharded"] = {"routed_to_rank0_round_one": routed, "open_after_round_one": still_open, "global_batch": gnq,
                                "phase_ms_rank0": getattr(searcher, "phase_ms", None)}
             line["replicas"] = replicas
+        if sweep:
+            line["delta_sweep"] = sweep
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

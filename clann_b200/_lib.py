@@ -33,7 +33,7 @@ ALLGATHER_FN = C.CFUNCTYPE(_i32, _vp, _vp, _vp, _u64, _vp)
 ALLREDUCE_MIN_FN = C.CFUNCTYPE(_i32, _vp, _vp, _u64, _vp)
 
 EXPORTED_SYMBOLS = [
-    "clann_init_with_config", "clann_init_with_config_ex", "clann_set_option", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
+    "clann_init_with_config", "clann_init_with_config_ex", "clann_set_option", "clann_set_delta", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
     "clann_build", "clann_search", "clann_search_device", "clann_search_device_async", "clann_search_flush", "clann_search_async", "clann_search_wait", "clann_search_begin", "clann_search_step", "clann_state_bytes",
     "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
     "clann_comm_unique_id", "clann_comm_init", "clann_set_collectives", "clann_search_sharded", "clann_shard_stats",
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
     L.clann_init_with_config.argtypes = [_vp, _u64, _u32, C.POINTER(ClannConfig), C.POINTER(_vp)]
     L.clann_init_with_config_ex.restype = _i32
     L.clann_init_with_config_ex.argtypes = [_vp, _u64, _u32, C.POINTER(ClannConfig), _i32, _i32, C.POINTER(_vp)]
+    L.clann_set_delta.restype, L.clann_set_delta.argtypes = _i32, [_vp, _f32]
     L.clann_set_option.restype, L.clann_set_option.argtypes = _i32, [_vp, C.c_char_p, _i64]
     L.clann_tune.restype, L.clann_tune.argtypes = _i32, [C.c_char_p, _i64]
     L.clann_set_clustering.restype, L.clann_set_clustering.argtypes = _i32, [_vp, _u64, _vp, _vp, _vp]

@@ -213,6 +213,11 @@ class ClusteredIndex:
     def set_option(self, key: str, value: int) -> None:
         _check(self._lib.clann_set_option(self._h, key.encode(), int(value)))
 
+    def set_delta(self, delta: float) -> None:
+        """Config.delta of a built index (stop rule only; no rebuild)."""
+        _check(self._lib.clann_set_delta(self._h, float(np.float32(delta))))
+        self.config.delta = float(delta)
+
     def set_clustering(self, centers, assignment, radii) -> None:
         c = np.ascontiguousarray(centers, np.uint64)
         a = np.ascontiguousarray(assignment, np.uint64)

@@ -1693,6 +1693,15 @@ int clann_set_option(clann_index* index, const char* key, int64_t value) {
     });
 }
 
+int clann_set_delta(clann_index* index, float delta) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        if (!(delta > 0.0f && delta < 1.0f)) throw StatusError(CLANN_ERR_CONFIG, "delta must be in (0, 1)");
+        index->cfg.delta = delta;
+        if (index->built) index->ensure_stop_table(delta, 0);  // the tables and functions do not depend on delta (collection.hpp:927-943)
+    });
+}
+
 int clann_tune(const char* key, int64_t value) {
     return guarded([&] {
         if (!key) throw StatusError(CLANN_ERR_ARG, "null key");

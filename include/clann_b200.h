@@ -70,6 +70,10 @@ int clann_init_with_config_ex(const void* data, uint64_t n, uint32_t d, const cl
  *                     owner(c) == shard_rank (longest-processing-time assignment on cluster sizes), default 0 / 1  */
 int clann_set_option(clann_index* index, const char* key, int64_t value);
 
+/* Config.delta of a built index without rebuilding it (only the stop rule reads it, collection.hpp:927-943): the recall sweep of
+ * BASELINE.json's last configuration searches one index at delta = 0.8 / 0.9 / 0.95. */
+int clann_set_delta(clann_index* index, float delta);
+
 /* Parity mode: impose a clustering instead of running greedy k-center (centers[K] = point ids, assignment[n] = cluster
  * of every point, radii[K]); and import the function set (SimHash planes, FHT signs, collision estimates) of one
  * cluster from the bytes of puffinn::Index::serialize (collection.hpp:185-203). Importing implies function_sets = 1. */
