@@ -761,13 +761,28 @@ struct clann_index {
             h_radii.assign(K, 0.0f);
             return;
         }
-        d_dist.alloc(n);
-        d_assign.alloc(n);
+        // Sharded clustering, when a communicator exists at build time: every rank runs the K passes over ITS rows only
+        // (rows are replicated, so the newest centre's row is at hand everywhere) and the packed arg-max key of each pass is
+        // all-reduced (max, 8 bytes, in stream); the distances and assignments of the shares are all-gathered once at the end. The
+        // arg-max of the union is the max of the shares' arg-maxes under the same key, so the clustering is the single-GPU one.
+        const bool shard_gmm = shard_count > 1 && comm && !user_allgather && tune_get("shard_gmm", 1) != 0;
+        const uint64_t chunk = shard_gmm ? (n + shard_count - 1) / shard_count : n;
+        const uint64_t row0 = shard_gmm ? std::min<uint64_t>(n, (uint64_t)shard_rank * chunk) : 0;
+        const uint64_t row1 = shard_gmm ? std::min<uint64_t>(n, row0 + chunk) : n;
+        d_dist.alloc(shard_gmm ? chunk * shard_count : n);
+        d_assign.alloc(shard_gmm ? chunk * shard_count : n);
         d_keys.alloc(K);
         d_keys.zero(s);
         DevBuf<float> d_cc;
         d_cc.alloc(K);
-        for (uint32_t c = 0; c < K; c++) launch_gmm_pass(d_data.p, d_norms.p, n, g.d, c, d_keys.p, d_dist.p, d_assign.p, d_cc.p, s);
+        for (uint32_t c = 0; c < K; c++) {
+            launch_gmm_pass(d_data.p, d_norms.p, row0, row1, g.d, c, d_keys.p, d_dist.p, d_assign.p, d_cc.p, s);
+            if (shard_gmm) CLANN_NCCL(nccl_api().AllReduce(d_keys.p + c, d_keys.p + c, 1, ncclUint64, ncclMax, comm, s));
+        }
+        if (shard_gmm) {
+            CLANN_NCCL(nccl_api().AllGather(d_dist.p + shard_rank * chunk, d_dist.p, chunk, ncclFloat32, comm, s));
+            CLANN_NCCL(nccl_api().AllGather(d_assign.p + shard_rank * chunk, d_assign.p, chunk, ncclUint32, comm, s));
+        }
         d_centers.alloc(K);
         d_radii.alloc(K);
         d_radii.zero(s);

@@ -10,7 +10,8 @@ void launch_row_norms(const float* data, uint64_t n, uint32_t d, float* norms, c
 // One greedy k-center pass for centre number c (gmm.rs:40-53). keys[K]: packed arg-max of pass c is written to keys[c];
 // the centre of pass c (c > 0) is decoded from keys[c-1].
 // cc: scratch of K floats (distances from the pass's centre to the earlier ones, for the triangle-inequality filter); may be null.
-void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t d, uint32_t c, uint64_t* keys,
+// Processes rows [row0, row1) of the full arrays (a rank's share of a sharded clustering; 0, n otherwise).
+void launch_gmm_pass(const float* data, const float* norms, uint64_t row0, uint64_t row1, uint32_t d, uint32_t c, uint64_t* keys,
                      float* dist, uint32_t* assign, float* cc, cudaStream_t s);
 void launch_gmm_finish(const uint64_t* keys, uint32_t K, uint64_t n, const float* dist, const uint32_t* assign,
                        uint32_t* centers, float* radii, uint32_t* sizes, cudaStream_t s);

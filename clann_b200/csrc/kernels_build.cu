@@ -26,12 +26,12 @@ __device__ __forceinline__ uint32_t gmm_key_index(uint64_t key) { return 0xfffff
 
 // src/core/gmm.rs:40-53 — one pass: distances of all points to centre c, strict-< reassignment, arg-max of the updated
 // distances (which selects centre c+1). Memory-bound: streams n*d floats once.
-__global__ void __launch_bounds__(256) k_gmm_pass(const float* __restrict__ data, const float* __restrict__ norms, uint64_t n,
+__global__ void __launch_bounds__(256) k_gmm_pass(const float* __restrict__ data, const float* __restrict__ norms, uint64_t row0, uint64_t n,
                                                   uint32_t d, uint32_t c, uint64_t* __restrict__ keys, float* __restrict__ dist,
                                                   uint32_t* __restrict__ assign) {
     __shared__ uint64_t s_key[8];
     const uint32_t ci = (c == 0) ? 0u : gmm_key_index(keys[c - 1]);
-    uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    uint64_t row = row0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3);  // rows [row0, n) of the full arrays
     const bool valid = row < n;
     uint64_t r = valid ? row : n - 1;
     const float* x = data + r * d;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) k_gmm_centre_dists(const float* __restric
 // strict `new < old` (gmm.rs:49) is false and nothing changes for that row. Every comparison with a NaN (zero vectors) is
 // false, which keeps such rows on the evaluated path.
 template <bool PRUNE>
-__global__ void __launch_bounds__(256) k_gmm_pass_v(const float* __restrict__ data, const float* __restrict__ norms, uint64_t n,
+__global__ void __launch_bounds__(256) k_gmm_pass_v(const float* __restrict__ data, const float* __restrict__ norms, uint64_t row0, uint64_t n,
                                                     uint32_t d, uint32_t c, uint64_t* __restrict__ keys, float* __restrict__ dist,
                                                     uint32_t* __restrict__ assign, const float* __restrict__ cc) {
     extern __shared__ __align__(16) float s_y[];  // centre row
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_gmm_pass_v(const float* __restrict__ da
     const uint32_t ci = (c == 0) ? 0u : gmm_key_index(keys[c - 1]);
     for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) s_y[i] = data[(uint64_t)ci * d + i];
     __syncthreads();
-    const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint64_t row = row0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1);  // rows [row0, n) of the full arrays
     const uint32_t s = threadIdx.x & 1u;
     const bool valid = row < n;
     const uint64_t r = valid ? row : n - 1;
@@ -672,23 +672,29 @@ void launch_row_norms(const float* data, uint64_t n, uint32_t d, float* norms, c
     k_row_norms<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, n, d, norms);
 }
 
-void launch_gmm_pass(const float* data, const float* norms, uint64_t n, uint32_t d, uint32_t c, uint64_t* keys, float* dist,
+void launch_gmm_pass(const float* data, const float* norms, uint64_t row0, uint64_t row1, uint32_t d, uint32_t c, uint64_t* keys, float* dist,
                      uint32_t* assign, float* cc, cudaStream_t s) {
+    // rows [row0, row1) of the full arrays (a rank's share when the clustering is sharded; everything otherwise)
+    const uint64_t n = row1, rows = row1 > row0 ? row1 - row0 : 0;
+    if (rows == 0) {
+        if (c > 0 && cc && d % 4 == 0 && tune_get("gmm_vec", 1) != 0 && tune_get("gmm_prune", 1) != 0) return;
+        return;
+    }
     // knobs (never change a result): gmm_vec 0 = the 8-lanes-per-row kernel; gmm_prune 0 = evaluate every row in every pass
     if (d % 4 == 0 && d * sizeof(float) <= 40 * 1024 && tune_get("gmm_vec", 1) != 0) {
-        const uint64_t threads = n * 2;
+        const uint64_t threads = rows * 2;
         const unsigned grid = (unsigned)((threads + 255) / 256);
         const size_t smem = d * sizeof(float);
         if (c > 0 && cc && tune_get("gmm_prune", 1) != 0) {
             k_gmm_centre_dists<<<(c + 127) / 128, 128, 0, s>>>(data, norms, d, c, keys, cc);
-            k_gmm_pass_v<true><<<grid, 256, smem, s>>>(data, norms, n, d, c, keys, dist, assign, cc);
+            k_gmm_pass_v<true><<<grid, 256, smem, s>>>(data, norms, row0, n, d, c, keys, dist, assign, cc);
         } else {
-            k_gmm_pass_v<false><<<grid, 256, smem, s>>>(data, norms, n, d, c, keys, dist, assign, cc);
+            k_gmm_pass_v<false><<<grid, 256, smem, s>>>(data, norms, row0, n, d, c, keys, dist, assign, cc);
         }
         return;
     }
-    uint64_t threads = n * 8;
-    k_gmm_pass<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, norms, n, d, c, keys, dist, assign);
+    uint64_t threads = rows * 8;
+    k_gmm_pass<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(data, norms, row0, n, d, c, keys, dist, assign);
 }
 
 void launch_gmm_finish(const uint64_t* keys, uint32_t K, uint64_t n, const float* dist, const uint32_t* assign, uint32_t* centers,
