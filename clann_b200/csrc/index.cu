@@ -1882,6 +1882,12 @@ int clann_comm_init(clann_index* index, int rank, int world, const uint8_t* uniq
             index->comm = nullptr;
         }
         CLANN_NCCL(nccl_api().CommInitRank(&index->comm, world, id, rank));
+        // first collective now: NCCL sets up its channels lazily (~1 s), which must not land inside a build or a search
+        DevBuf<unsigned long long> warm;
+        warm.alloc(1);
+        warm.zero(0);
+        CLANN_NCCL(nccl_api().AllReduce(warm.p, warm.p, 1, ncclUint64, ncclMax, index->comm, 0));
+        CLANN_CUDA(cudaStreamSynchronize(0));
     });
 }
 
