@@ -1613,9 +1613,209 @@ __global__ void __launch_bounds__(256, 3) k_first_stream(SearchParams p, QueryBa
     if (lane == 0) meta[48] = lowest;
 }
 
+// The same stream produced by one CTA of four warps per query (knob first_stream = 2): every table has its own thread for the
+// anchor and for the range of each depth (no three-rounds-per-lane serialisation), the segments of a depth are spread over 128
+// threads, and — because a query is done four times sooner — the queries in flight at any time span a quarter of the clusters, so
+// that their sketches and tables stay in the L2.
+constexpr uint32_t kFsThreads = 128;
+
+__global__ void __launch_bounds__(kFsThreads, 8) k_first_stream_cta(SearchParams p, QueryBatch b) {
+    extern __shared__ __align__(16) uint8_t s_stream[];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_sel[4];  // {bin, remaining rank, S, stop flag}
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
+    const uint64_t w = blockIdx.x;
+    if (w >= b.nq) return;
+    const uint32_t q = b.qperm[w], c = b.first[w];
+    uint32_t* meta = b.fs_meta + (uint64_t)q * kFsMeta;
+    const uint32_t L = p.g.L;
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    if (p.brute[c] || nc > 65536u || nc > b.dense_stride) {
+        if (tid == 0) meta[48] = kMaxHashBits + 1;
+        return;
+    }
+    StreamSmem sm;
+    {
+        uint8_t* ptr = s_stream;
+        sm.lcp_up = reinterpret_cast<uint2*>(ptr); ptr += L * 8;
+        sm.lcp_dn = reinterpret_cast<uint2*>(ptr); ptr += L * 8;
+        sm.anchor = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.code = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.start = reinterpret_cast<uint32_t*>(ptr); ptr += L * 4;
+        sm.segbase = reinterpret_cast<uint32_t*>(ptr); ptr += (L + 1) * 4;
+        sm.hist = reinterpret_cast<uint32_t*>(ptr);  // [L] segments per table of the current depth
+    }
+    const uint32_t fsid = p.fset_of[c];
+    const uint32_t* codes = b.codes + (uint64_t)fsid * L * b.nq + q;
+    const uint64_t my_sketch = b.sketches[((uint64_t)fsid * b.nq + q) * kNumSketches + lane];
+    const uint32_t* stop = p.stop + (uint64_t)fsid * kMaxHashBits * kEstBins * p.stop_words;
+    const uint64_t* sk = p.sketches + off * kNumSketches;
+    // ---- anchors: one thread per table
+    for (uint32_t t = tid; t < L; t += kFsThreads) {
+        const uint32_t h = __ldg(codes + (uint64_t)t * b.nq);
+        uint32_t A;
+        uint2 up, dn;
+        table_anchor(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc, h, A, up, dn);
+        sm.code[t] = h;
+        sm.anchor[t] = A;
+        sm.lcp_up[t] = up;
+        sm.lcp_dn[t] = dn;
+    }
+    // ---- k-th largest dense similarity of the cluster (two byte passes over a block-wide histogram)
+    uint32_t kth16 = 0;
+    if (p.k > 0 && nc >= p.k) {
+        const uint32_t* v32 = reinterpret_cast<const uint32_t*>(b.dense + (uint64_t)q * b.dense_stride);
+        uint32_t prefix = 0, want = p.k;
+        for (int pass = 0; pass < 2; pass++) {
+            for (uint32_t i = tid; i < 256; i += kFsThreads) s_hist[i] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < (nc + 1) / 2; i += kFsThreads) {
+                const uint32_t wv = __ldg(v32 + i);
+                const uint32_t a = wv & 0xffffu, bb = wv >> 16;
+                if (pass == 0) {
+                    atomicAdd(&s_hist[a >> 8], 1u);
+                    if (2 * i + 1 < nc) atomicAdd(&s_hist[bb >> 8], 1u);
+                } else {
+                    if ((a >> 8) == prefix) atomicAdd(&s_hist[a & 0xffu], 1u);
+                    if (2 * i + 1 < nc && (bb >> 8) == prefix) atomicAdd(&s_hist[bb & 0xffu], 1u);
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) mine += s_hist[8 * lane + j];
+                uint32_t suf = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + o < 32) suf += t;
+                }
+                const uint32_t above = suf - mine;
+                if (above < want && want <= suf) {
+                    uint32_t acc = above;
+                    for (int j = 7; j >= 0; j--) {
+                        const uint32_t h = s_hist[8 * lane + j];
+                        if (acc + h >= want) {
+                            s_sel[0] = 8 * lane + j;
+                            s_sel[1] = want - acc;
+                            break;
+                        }
+                        acc += h;
+                    }
+                }
+            }
+            __syncthreads();
+            if (pass == 0) {
+                prefix = s_sel[0];
+                want = s_sel[1];
+            } else {
+                kth16 = (prefix << 8) | s_sel[0];
+            }
+            __syncthreads();
+        }
+    } else {
+        __syncthreads();
+    }
+    uint32_t bin = (uint32_t)__fdiv_rn(__fdiv_rn((float)kth16, 65536.0f), 0.005f);
+    bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
+
+    const uint64_t sbase = (uint64_t)q * b.fs_cap;
+    uint2* out_idx = reinterpret_cast<uint2*>(b.fs_idx) + sbase;
+    uint32_t* out_hd = b.fs_hd + sbase;
+    uint8_t* out_tab = b.fs_tab + (sbase >> 5);
+    uint32_t cum = 0, lowest = kMaxHashBits + 1;
+    uint32_t my_S = 0, my_off = 0;  // thread d-1 keeps the record of depth d
+    for (uint32_t depth = kMaxHashBits; depth > 0; depth--) {
+        for (uint32_t t = tid; t < L; t += kFsThreads) {
+            uint32_t nseg = 0;
+            sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc,
+                                      sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
+            sm.hist[t] = nseg;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t running = 0;
+            for (uint32_t t0 = 0; t0 < L; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                const uint32_t nseg = t < L ? sm.hist[t] : 0u;
+                uint32_t total;
+                const uint32_t ex = warp_excl_scan(nseg, total);
+                if (t < L) sm.segbase[t] = running + ex;
+                running += total;
+            }
+            if (lane == 0) {
+                sm.segbase[L] = running;
+                s_sel[2] = running;
+            }
+        }
+        __syncthreads();
+        const uint32_t S = s_sel[2];
+        const uint32_t S32 = (S + 31u) & ~31u;
+        if (S > (uint32_t)kRing && cum + S32 > b.fs_cap) break;
+        if (tid == depth - 1) {
+            my_S = S;
+            my_off = cum;
+        }
+        lowest = depth;
+        if (S <= (uint32_t)kRing) continue;
+        for (uint32_t s0 = 0; s0 < S; s0 += 2 * kFsThreads) {
+            uint32_t v[2][4], tb[2];
+            bool valid[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const uint32_t s = s0 + u * kFsThreads + tid;
+                valid[u] = s < S;
+                tb[u] = 0;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0;
+                if (valid[u]) {
+                    uint32_t lo = 0, len = L;  // upper_bound(segbase, s) - 1 over segbase[0..L)
+                    while (len > 0) {
+                        const uint32_t half = len >> 1, mid = lo + half;
+                        if (sm.segbase[mid] <= s) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                    }
+                    const uint32_t t = lo - 1;
+                    tb[u] = t;
+                    const uint32_t* seg = p.tbl_idx + table_base(off, nc, L, t) + sm.start[t] + 4 * (s - sm.segbase[t]);
+                    v[u][0] = __ldg(seg); v[u][1] = __ldg(seg + 1); v[u][2] = __ldg(seg + 2); v[u][3] = __ldg(seg + 3);
+                }
+            }
+            uint64_t sw[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) sw[u][j] = valid[u] ? __ldg(sk + ((uint64_t)v[u][j] << 5 | lane)) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!valid[u]) continue;
+                const uint32_t s = s0 + u * kFsThreads + tid;
+                const uint32_t h4 = (uint32_t)__popcll(sw[u][0] ^ my_sketch) | (uint32_t)__popcll(sw[u][1] ^ my_sketch) << 8 |
+                                    (uint32_t)__popcll(sw[u][2] ^ my_sketch) << 16 | (uint32_t)__popcll(sw[u][3] ^ my_sketch) << 24;
+                out_idx[cum + s] = make_uint2(v[u][0] | v[u][1] << 16, v[u][2] | v[u][3] << 16);
+                out_hd[cum + s] = h4;
+                if (lane == 0) out_tab[(cum + s) >> 5] = (uint8_t)tb[u];
+            }
+        }
+        cum += S32;
+        const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (L >> 5));
+        if ((word >> (L & 31)) & 1u) break;
+    }
+    if (tid < (uint32_t)kMaxHashBits) {
+        meta[tid] = my_S;
+        meta[kMaxHashBits + tid] = my_off;
+    }
+    if (tid == 0) meta[48] = lowest;
+}
+
 bool launch_first_stream(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
     if (b.nq == 0 || !b.fs_meta || !b.fs_idx || !b.fs_hd || !b.fs_tab || !b.dense || b.fs_cap < 64) return false;
     if (p.g.L > 255) return false;  // fs_tab holds the table index in a byte
+    if (tune_get("first_stream", 0) == 2) {  // one CTA of four warps per query
+        const size_t smem_cta = (size_t)p.g.L * (8 + 8 + 4 + 4 + 4 + 4 + 4) + 16;
+        k_first_stream_cta<<<(unsigned)b.nq, kFsThreads, smem_cta, s>>>(p, b);
+        return true;
+    }
     const uint32_t wb = stream_smem_bytes(p.g.L);
     const uint32_t warps = 8;
     const size_t smem = (size_t)warps * wb;

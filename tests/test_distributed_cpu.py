@@ -100,3 +100,60 @@ def test_stepping_matches_sequential_walk():
 def test_stepping_reports_non_convergence():
     with pytest.raises(RuntimeError, match="did not converge"):
         run_stepping(lambda: None, lambda: 1, max_steps=3)
+
+
+def _sharded_protocol_worker(rank, world, port, out):
+    """Host side of clann_search_sharded's exchanges under gloo: the packed (bound, consumed) words are min-reduced through the
+    order-preserving int64 view, the per-rank candidate lists are all-gathered and k-way merged."""
+    import torch
+    import torch.distributed as dist
+    from clann_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = np.random.default_rng(100)           # same draws on every rank
+    nq, k = 64, 5
+    owner = rng.integers(0, world, nq)         # which rank advanced each query in round one
+    bound = rng.random(nq).astype(np.float32)
+    bound[::7] = -1.0                          # finished queries
+    bound[3::11] = np.inf                      # heap not full yet
+    consumed = rng.integers(1, 9, nq)
+    mine = owner == rank
+    packed = np.full(nq, D.NOTHING, np.uint64)
+    packed[mine] = D.pack_bound(bound[mine], consumed[mine])
+    t = torch.from_numpy(packed.view(np.int64).copy())
+    key = D.u64_min_key(t)
+    dist.all_reduce(key, op=dist.ReduceOp.MIN)
+    agreed = torch.bitwise_xor(key, torch.tensor(-2 ** 63, dtype=torch.int64)).numpy().view(np.uint64)
+    want = D.pack_bound(bound, consumed)
+    assert np.array_equal(agreed, want)
+    # open queries = non-negative bound; decode what round two reads
+    open_q = (agreed >> np.uint64(32)).astype(np.uint32) >= 0x80000000
+    assert np.array_equal(open_q, bound >= 0)
+    assert np.array_equal((np.uint64(0xFFFFFFFF) - (agreed & np.uint64(0xFFFFFFFF))).astype(np.int64), consumed)
+    # merge: every rank contributes its own candidates of every query
+    allc = (D.order_bits(rng.random((world, nq, k)).astype(np.float32)).astype(np.uint64) << np.uint64(32)) | \
+        rng.integers(0, 1 << 20, (world, nq, k)).astype(np.uint64)
+    allc.sort(axis=2)
+    allc[:, ::5, 3:] = np.uint64(0xFFFFFFFFFFFFFFFF)   # short lists
+    local = torch.from_numpy(allc[rank].view(np.int64).copy())
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    lists = np.stack([g.numpy().view(np.uint64) for g in gathered])
+    merged = D.merge_topk(lists, k)
+    assert np.array_equal(merged, np.sort(allc.transpose(1, 0, 2).reshape(nq, -1), axis=1)[:, :k])
+    out.put((rank, True))
+    dist.destroy_process_group()
+
+
+def test_sharded_protocol_exchanges_under_gloo():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    world, port = 2, _free_port()
+    procs = [ctx.Process(target=_sharded_protocol_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs)
+    got = sorted(out.get(timeout=5) for _ in range(world))
+    assert got == [(0, True), (1, True)]

@@ -375,6 +375,8 @@ def test_probe_kernel_variants_agree(tmp_path):
                 ("no_tensor_centre_scoring", {"CLANN_TUNE_TC_CENTER": "0"}), ("no_tensor_sketches", {"CLANN_TUNE_TC_SKETCH": "0"}),
                 ("no_tensor_at_all", {"CLANN_TUNE_TC_CENTER": "0", "CLANN_TUNE_TC_SKETCH": "0"}),
                 ("first_stream", {"CLANN_TUNE_FIRST_STREAM": "1"}),
+                ("first_stream_cta", {"CLANN_TUNE_FIRST_STREAM": "2"}),
+                ("first_stream_cta_cut_short", {"CLANN_TUNE_FIRST_STREAM": "2", "CLANN_TUNE_FIRST_STREAM_CAP": "320"}),
                 ("first_stream_cut_short", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "256"}),   # most visits outlive it
                 ("first_stream_tiny", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "64"}),
                 ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "0"}),
@@ -724,3 +726,32 @@ def test_fp16_and_device_resident_ingest():
         assert all(np.array_equal(ctr[key], want_ctr[key]) for key in ctr)
         ix.close()
     ref.close()
+
+
+@pytest.mark.parametrize("name", ["puffinn_d25", "puffinn_d100"])
+def test_device_collision_estimates_agree_with_reference_table(name):
+    """k_cp_trials (the device Monte-Carlo of CrossPolytopeCollisionEstimates, crosspolytope.hpp:16-88: 201 cosine bins x 1000
+    repetitions) against the table the real reference drew for the same dimension (golden fixture). Both are 1000-repetition
+    estimates, so each entry carries ~1.6 % of sampling noise: like the reference's own statistical test (hash_test.hpp:101-124,
+    +-2 % on measured collision rates) the comparison is statistical — mean absolute difference below 2 %, no entry off by more
+    than 8 %, every row non-decreasing in the cosine up to noise, P[.][200] ~ 1 and P[0][.] = 1."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    from oracle.pyoracle import OracleLib
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    oi = OracleLib().index_import(g["stream"].tobytes())
+    ref_est = oi.functions().est.copy()           # (m + 2) x 201, drawn by the reference
+    oi.free()
+    data = g["data"]
+    ix = cb.init_with_config(data, cb.Config(int(g["L"]), 1.0, 10, 0.9, "est"))
+    ix.set_clustering([0], np.zeros(len(data), np.uint64), [2.0])
+    ix.set_option("seed", 11)
+    ix.build()
+    est = ix.export(cl.X_EST, 0, np.float32).reshape(ref_est.shape)
+    ix.close()
+    assert np.all(est[:, 200] >= 0.99) and np.all(est[0] == 1.0)   # cosine 1 (the reference's own draw reads 0.999 there); zero bits
+    diff = np.abs(est - ref_est)
+    assert diff.mean() < 0.02, diff.mean()
+    assert diff.max() < 0.08, diff.max()
+    assert np.all(np.diff(est, axis=1) > -0.06)
+    assert np.all((est >= 0) & (est <= 1))
