@@ -477,17 +477,7 @@ struct clann_index {
     clann_allgather_fn user_allgather = nullptr;
     clann_allreduce_min_u64_fn user_allreduce_min = nullptr;
     void* user_ctx = nullptr;
-    struct ShardBufs {
-        DevBuf<uint32_t> first_all, list0, list1, list2, counts;
-        DevBuf<unsigned long long> packed, packed1, packed2, top_local, top_all, counters;
-        DevBuf<float> q0, q1;
-        uint32_t* h_counts = nullptr;  // pinned: {routed to this rank in round one, still open after it, of those: served by this rank}
-        uint32_t n2 = 0;
-        uint64_t nq = 0;
-        uint32_t n0 = 0, n1 = 0;
-        bool last_was_sharded = false;
-        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last call
-    } sh;
+
 
     // host mirrors
     std::vector<uint32_t> h_centers, h_sizes, h_assign;
@@ -552,6 +542,26 @@ struct clann_index {
     static constexpr int kPipeMax = 4;
     SearchWs wsv[1 + kPipeMax];
     SearchWs* W = &wsv[0];
+    struct ShardLane {  // one sub-batch in flight: its buffers (sized for the sub-batch), its stream, its three workspaces
+        DevBuf<uint32_t> first_all, list0, list1, list2, counts;
+        DevBuf<unsigned long long> packed, packed1, packed2, top_local, top_all, counters;
+        DevBuf<float> q0, q1;
+        uint32_t* h_counts = nullptr;  // pinned: {routed to this rank in round one, still open after it, of those: served by this rank}
+        uint64_t nq = 0;               // size the buffers were made for
+        uint64_t q_lo = 0, q_n = 0;    // the sub-batch of the current call
+        uint32_t n0 = 0, n1 = 0, n2 = 0;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ready = nullptr, done = nullptr;
+        cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last call
+        SearchWs ws[3];                // route / open-query scoring, round one, round two
+    };
+    static constexpr int kShardLanes = 2;
+    ShardLane lanes[kShardLanes];
+    struct {
+        bool last_was_sharded = false;
+        int lanes_used = 0;
+        cudaEvent_t fork = nullptr;
+    } sh;
     // {clusters visited, queries} of the last finished batch, written by k_finish into mapped host memory and read without any
     // synchronisation: when queries walk many clusters (avg > 3: overlapping or unclustered data) the dense first-visit
     // precompute buys nothing and the 24-warp schedule of the gather path is the faster one
@@ -576,7 +586,15 @@ struct clann_index {
         for (auto& st : pipe_stream)
             if (st) cudaStreamDestroy(st);
         if (h_stats) cudaFreeHost(h_stats);
-        if (sh.h_counts) cudaFreeHost(sh.h_counts);
+        for (auto& ln : lanes) {
+            if (ln.h_counts) cudaFreeHost(ln.h_counts);
+            if (ln.stream) cudaStreamDestroy(ln.stream);
+            for (cudaEvent_t e : {ln.ready, ln.done})
+                if (e) cudaEventDestroy(e);
+            for (auto& e : ln.ev)
+                if (e) cudaEventDestroy(e);
+        }
+        if (sh.fork) cudaEventDestroy(sh.fork);
         if (comm) nccl_api().CommDestroy(comm);
     }
 
@@ -586,6 +604,11 @@ struct clann_index {
             w.ws_nq = 0;
             w.w_tiles_codes_nq = 0;
         }
+        for (auto& ln : lanes)
+            for (auto& w : ln.ws) {
+                w.ws_nq = 0;
+                w.w_tiles_codes_nq = 0;
+            }
         if (h_stats) h_stats[0] = h_stats[1] = 0;
     }
 
@@ -1435,119 +1458,171 @@ struct clann_index {
     //   merge   one all-gather of nq x k x (distance, id) and a k-way merge
     // No step moves more than a few megabytes; results have recall >= the single-GPU search (identical whenever the walk of a query
     // stays on one rank).
+    // The call splits the batch into two halves ("lanes") that run the phases above on their own streams, interleaved by the host:
+    // while one half waits for a count to come back, sits in a latency-bound round two or in a collective, the other half's round
+    // one keeps the SMs busy. Collectives are issued in the same order on every rank.
+    void lane_prepare(ShardLane& ln, uint64_t nq) {
+        const uint32_t world = shard_count, k = (uint32_t)cfg.k, d = g.d;
+        const uint64_t chunk = (nq + world - 1) / world;
+        if (ln.nq != nq) {
+            ln.first_all.ensure(chunk * world);
+            ln.list0.ensure(nq);
+            ln.list1.ensure(nq);
+            ln.list2.ensure(nq);
+            ln.packed2.ensure(nq);
+            ln.counts.ensure(4);
+            ln.packed.ensure(nq);
+            ln.packed1.ensure(nq);
+            ln.top_local.ensure(nq * k);
+            ln.top_all.ensure(nq * k * world);
+            ln.counters.ensure(nq * 3);
+            ln.q0.ensure(nq * d);
+            ln.q1.ensure(nq * d);
+            ln.nq = nq;
+        }
+        if (!ln.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ln.h_counts), 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        if (!ln.stream) CLANN_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        if (!ln.ready) CLANN_CUDA(cudaEventCreateWithFlags(&ln.ready, cudaEventDisableTiming));
+        if (!ln.done) CLANN_CUDA(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        for (auto& e : ln.ev)
+            if (!e) CLANN_CUDA(cudaEventCreate(&e));
+    }
+
+    // route: nearest centre of this rank's slice of the sub-batch, all-gather, selection of the queries that start here
+    void lane_route(ShardLane& ln, const float* d_queries) {
+        cudaStream_t s = ln.stream;
+        const uint32_t world = shard_count, rank = shard_rank, d = g.d;
+        const uint64_t nq = ln.q_n, chunk = (nq + world - 1) / world;
+        CLANN_CUDA(cudaEventRecord(ln.ev[0], s));
+        CLANN_CUDA(cudaMemsetAsync(ln.counts.p, 0, 4 * sizeof(uint32_t), s));
+        const uint64_t lo = std::min<uint64_t>(nq, rank * chunk), hi = std::min<uint64_t>(nq, lo + chunk);
+        W = &ln.ws[0];
+        if (hi > lo) {
+            ensure_workspace(hi - lo, s);
+            W->ws_tc_center = use_tc_center();
+            SearchParams p = params();
+            QueryBatch b = batch(d_queries + lo * d, hi - lo, nullptr, nullptr, nullptr);
+            launch_prep_queries(p, b, s);
+            launch_center_order(p, b, s);
+            CLANN_CUDA(cudaMemcpyAsync(ln.first_all.p + lo, b.first, (hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        }
+        CLANN_CUDA(cudaEventRecord(ln.ev[1], s));
+        // in-place all-gather: every rank's slice sits at rank * chunk of the same buffer
+        all_gather(ln.first_all.p + rank * chunk, ln.first_all.p, chunk * sizeof(uint32_t), s);
+        launch_shard_select_owned(ln.first_all.p, d_owner.p, rank, nq, ln.list0.p, ln.counts.p, s);
+        CLANN_CUDA(cudaMemcpyAsync(ln.h_counts, ln.counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaEventRecord(ln.ready, s));
+    }
+
+    // round one on the queries routed here, then the bound exchange and the selection of the queries still open
+    void lane_round_one(ShardLane& ln, const float* d_queries) {
+        cudaStream_t s = ln.stream;
+        const uint32_t k = (uint32_t)cfg.k, d = g.d;
+        const uint64_t nq = ln.q_n;
+        CLANN_CUDA(cudaEventSynchronize(ln.ready));
+        const uint32_t n0 = ln.n0 = ln.h_counts[0];
+        CLANN_CUDA(cudaEventRecord(ln.ev[2], s));
+        launch_fill_u64(ln.packed.p, nq, 0xff800000ffffffffull, s);  // {+inf, nothing consumed}
+        launch_fill_u64(ln.top_local.p, nq * k, ~0ull, s);
+        CLANN_CUDA(cudaMemsetAsync(ln.counters.p, 0, nq * 3 * sizeof(unsigned long long), s));
+        W = &ln.ws[1];
+        if (n0) {
+            launch_shard_gather_rows(d_queries, ln.list0.p, n0, d, ln.q0.p, s);
+            search_begin(ln.q0.p, n0, s);
+            SearchParams p = params();
+            QueryBatch b = batch(ln.q0.p, n0, nullptr, nullptr, nullptr);
+            b.first_is_own = true;  // by construction of list0
+            use_dense_sims(p, b, s);
+            launch_probe(p, b, 1, s);
+            launch_shard_pack_bounds(W->w_state.p, k, ln.list0.p, n0, ln.packed.p, s);
+            launch_shard_collect(W->w_state.p, k, ln.list0.p, n0, ln.top_local.p, false, ln.counters.p, s);
+        }
+        CLANN_CUDA(cudaEventRecord(ln.ev[3], s));
+        all_reduce_min_u64(ln.packed.p, nq, s);
+        launch_shard_select_open(ln.packed.p, nq, ln.list1.p, ln.packed1.p, ln.counts.p + 1, s);
+        CLANN_CUDA(cudaMemcpyAsync(ln.h_counts + 1, ln.counts.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CLANN_CUDA(cudaEventRecord(ln.ready, s));
+    }
+
+    // every rank scores the open queries against the centres (cheap), but will hash and probe only those for which it owns a
+    // cluster the agreed bound does not prune
+    void lane_score_open(ShardLane& ln, const float* d_queries) {
+        cudaStream_t s = ln.stream;
+        const uint32_t rank = shard_rank, d = g.d;
+        CLANN_CUDA(cudaEventSynchronize(ln.ready));
+        const uint32_t n1 = ln.n1 = ln.h_counts[1];
+        CLANN_CUDA(cudaEventRecord(ln.ev[4], s));
+        ln.h_counts[2] = 0;
+        if (n1) {
+            W = &ln.ws[0];
+            launch_shard_gather_rows(d_queries, ln.list1.p, n1, d, ln.q1.p, s);
+            ensure_workspace(n1, s);
+            W->ws_tc_center = use_tc_center();
+            SearchParams p = params();
+            QueryBatch b = batch(ln.q1.p, n1, nullptr, nullptr, nullptr);
+            launch_prep_queries(p, b, s);
+            launch_center_order(p, b, s);
+            launch_shard_select_mine(b.cdist, b.exact_limit, d_radii.p, d_owner.p, rank, K, ln.list1.p, ln.packed1.p, n1, ln.list2.p,
+                                     ln.packed2.p, ln.counts.p + 2, s);
+            CLANN_CUDA(cudaMemcpyAsync(ln.h_counts + 2, ln.counts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
+        CLANN_CUDA(cudaEventRecord(ln.ready, s));
+    }
+
+    // round two, the all-gather of the candidate lists and the k-way merge into the caller's output rows of this sub-batch
+    void lane_round_two(ShardLane& ln, const float* d_queries, uint32_t* d_ids, float* d_dists, uint32_t* d_counts) {
+        cudaStream_t s = ln.stream;
+        const uint32_t world = shard_count, k = (uint32_t)cfg.k, d = g.d;
+        const uint64_t nq = ln.q_n;
+        CLANN_CUDA(cudaEventSynchronize(ln.ready));
+        const uint32_t n2 = ln.n2 = ln.n1 ? ln.h_counts[2] : 0;
+        W = &ln.ws[2];
+        if (n2) {
+            launch_shard_gather_rows(d_queries, ln.list2.p, n2, d, ln.q1.p, s);
+            search_begin(ln.q1.p, n2, s);
+            SearchParams p = params();
+            QueryBatch b = batch(ln.q1.p, n2, nullptr, nullptr, nullptr);
+            b.shard_packed = ln.packed2.p;
+            launch_probe(p, b, 2, s);
+            launch_shard_collect(W->w_state.p, k, ln.list2.p, n2, ln.top_local.p, true, ln.counters.p, s);
+        }
+        CLANN_CUDA(cudaEventRecord(ln.ev[5], s));
+        all_gather(ln.top_local.p, ln.top_all.p, nq * k * sizeof(unsigned long long), s);
+        launch_shard_final_merge(ln.top_all.p, world, nq, k, d_ids, d_dists, d_counts, s);
+        CLANN_CUDA(cudaEventRecord(ln.ev[6], s));
+        CLANN_CUDA(cudaEventRecord(ln.done, s));
+    }
+
     void search_sharded(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
         require_built();
         if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded needs an index built with shard_count > 1");
         if (nq == 0) return;
         if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
-        const uint32_t world = shard_count, rank = shard_rank, k = (uint32_t)cfg.k, d = g.d;
-        const uint64_t chunk = (nq + world - 1) / world;
-        if (sh.nq != nq) {
-            sh.first_all.ensure(chunk * world);
-            sh.list0.ensure(nq);
-            sh.list1.ensure(nq);
-            sh.list2.ensure(nq);
-            sh.packed2.ensure(nq);
-            sh.counts.ensure(4);
-            sh.packed.ensure(nq);
-            sh.packed1.ensure(nq);
-            sh.top_local.ensure(nq * k);
-            sh.top_all.ensure(nq * k * world);
-            sh.counters.ensure(nq * 3);
-            sh.q0.ensure(nq * d);
-            sh.q1.ensure(nq * d);
-            if (!sh.h_counts) CLANN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&sh.h_counts), 4 * sizeof(uint32_t), cudaHostAllocDefault));
-            for (auto& e : sh.ev)
-                if (!e) CLANN_CUDA(cudaEventCreate(&e));
-            sh.nq = nq;
-        }
-        CLANN_CUDA(cudaEventRecord(sh.ev[0], s));
+        const uint32_t k = (uint32_t)cfg.k, d = g.d;
+        // knob shard_lanes (default 2): sub-batches in flight; small batches are not split
+        int nl = (int)tune_get("shard_lanes", 2);
+        nl = nl < 1 ? 1 : (nl > kShardLanes ? kShardLanes : nl);
+        if (nq < 2048ull * shard_count) nl = 1;
         SearchWs* saved = W;
         try {
-            CLANN_CUDA(cudaMemsetAsync(sh.counts.p, 0, 4 * sizeof(uint32_t), s));
-            // ---- route: nearest centre of this rank's slice of the batch
-            const uint64_t lo = std::min<uint64_t>(nq, rank * chunk), hi = std::min<uint64_t>(nq, lo + chunk);
-            W = &wsv[2];
-            if (hi > lo) {
-                ensure_workspace(hi - lo, s);
-                W->ws_tc_center = use_tc_center();
-                SearchParams p = params();
-                QueryBatch b = batch(d_queries + lo * d, hi - lo, nullptr, nullptr, nullptr);
-                launch_prep_queries(p, b, s);
-                launch_center_order(p, b, s);
-                CLANN_CUDA(cudaMemcpyAsync(sh.first_all.p + lo, b.first, (hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            if (!sh.fork) CLANN_CUDA(cudaEventCreateWithFlags(&sh.fork, cudaEventDisableTiming));
+            CLANN_CUDA(cudaEventRecord(sh.fork, s));
+            const uint64_t per = (nq + nl - 1) / nl;
+            for (int i = 0; i < nl; i++) {
+                ShardLane& ln = lanes[i];
+                ln.q_lo = std::min<uint64_t>(nq, (uint64_t)i * per);
+                ln.q_n = std::min<uint64_t>(per, nq - ln.q_lo);
+                lane_prepare(ln, per);
+                CLANN_CUDA(cudaStreamWaitEvent(ln.stream, sh.fork, 0));  // the caller's queries are ready
             }
-            CLANN_CUDA(cudaEventRecord(sh.ev[1], s));
-            // in-place all-gather: every rank's slice sits at rank * chunk of the same buffer
-            all_gather(sh.first_all.p + rank * chunk, sh.first_all.p, chunk * sizeof(uint32_t), s);
-            launch_shard_select_owned(sh.first_all.p, d_owner.p, rank, nq, sh.list0.p, sh.counts.p, s);
-            CLANN_CUDA(cudaMemcpyAsync(sh.h_counts, sh.counts.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CLANN_CUDA(cudaStreamSynchronize(s));
-            const uint32_t n0 = sh.h_counts[0];
-            sh.n0 = n0;
-            CLANN_CUDA(cudaEventRecord(sh.ev[2], s));
-            // ---- round one
-            launch_fill_u64(sh.packed.p, nq, 0xff800000ffffffffull, s);  // {+inf, nothing consumed}
-            launch_fill_u64(sh.top_local.p, nq * k, ~0ull, s);
-            CLANN_CUDA(cudaMemsetAsync(sh.counters.p, 0, nq * 3 * sizeof(unsigned long long), s));
-            W = &wsv[0];
-            if (n0) {
-                launch_shard_gather_rows(d_queries, sh.list0.p, n0, d, sh.q0.p, s);
-                search_begin(sh.q0.p, n0, s);
-                SearchParams p = params();
-                QueryBatch b = batch(sh.q0.p, n0, nullptr, nullptr, nullptr);
-                b.first_is_own = true;  // by construction of list0
-                use_dense_sims(p, b, s);
-                launch_probe(p, b, 1, s);
-                launch_shard_pack_bounds(W->w_state.p, k, sh.list0.p, n0, sh.packed.p, s);
-                launch_shard_collect(W->w_state.p, k, sh.list0.p, n0, sh.top_local.p, false, sh.counters.p, s);
-            }
-            // ---- agree on the bounds, select what is still open
-            CLANN_CUDA(cudaEventRecord(sh.ev[3], s));
-            all_reduce_min_u64(sh.packed.p, nq, s);
-            launch_shard_select_open(sh.packed.p, nq, sh.list1.p, sh.packed1.p, sh.counts.p + 1, s);
-            CLANN_CUDA(cudaMemcpyAsync(sh.h_counts + 1, sh.counts.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            CLANN_CUDA(cudaStreamSynchronize(s));
-            const uint32_t n1 = sh.h_counts[1];
-            sh.n1 = n1;
-            CLANN_CUDA(cudaEventRecord(sh.ev[4], s));
-            // ---- round two
-            uint32_t n2 = 0;
-            if (n1) {
-                // every rank scores the open queries against the centres (cheap), but hashes and probes only those for which it
-                // owns a cluster the agreed bound does not prune
-                W = &wsv[2];
-                launch_shard_gather_rows(d_queries, sh.list1.p, n1, d, sh.q1.p, s);
-                ensure_workspace(n1, s);
-                W->ws_tc_center = use_tc_center();
-                {
-                    SearchParams p = params();
-                    QueryBatch b = batch(sh.q1.p, n1, nullptr, nullptr, nullptr);
-                    launch_prep_queries(p, b, s);
-                    launch_center_order(p, b, s);
-                    launch_shard_select_mine(b.cdist, b.exact_limit, d_radii.p, d_owner.p, rank, K, sh.list1.p, sh.packed1.p, n1, sh.list2.p,
-                                             sh.packed2.p, sh.counts.p + 2, s);
-                }
-                CLANN_CUDA(cudaMemcpyAsync(sh.h_counts + 2, sh.counts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-                CLANN_CUDA(cudaStreamSynchronize(s));
-                n2 = sh.h_counts[2];
-            }
-            sh.n2 = n2;
-            W = &wsv[1];
-            if (n2) {
-                launch_shard_gather_rows(d_queries, sh.list2.p, n2, d, sh.q1.p, s);
-                search_begin(sh.q1.p, n2, s);
-                SearchParams p = params();
-                QueryBatch b = batch(sh.q1.p, n2, nullptr, nullptr, nullptr);
-                b.shard_packed = sh.packed2.p;
-                launch_probe(p, b, 2, s);
-                launch_shard_collect(W->w_state.p, k, sh.list2.p, n2, sh.top_local.p, true, sh.counters.p, s);
-            }
-            // ---- merge
-            CLANN_CUDA(cudaEventRecord(sh.ev[5], s));
-            all_gather(sh.top_local.p, sh.top_all.p, nq * k * sizeof(unsigned long long), s);
-            launch_shard_final_merge(sh.top_all.p, world, nq, k, d_ids, d_dists, d_counts, s);
-            CLANN_CUDA(cudaEventRecord(sh.ev[6], s));
+            for (int i = 0; i < nl; i++) lane_route(lanes[i], d_queries + lanes[i].q_lo * d);
+            for (int i = 0; i < nl; i++) lane_round_one(lanes[i], d_queries + lanes[i].q_lo * d);
+            for (int i = 0; i < nl; i++) lane_score_open(lanes[i], d_queries + lanes[i].q_lo * d);
+            for (int i = 0; i < nl; i++)
+                lane_round_two(lanes[i], d_queries + lanes[i].q_lo * d, d_ids + lanes[i].q_lo * k, d_dists + lanes[i].q_lo * k,
+                               d_counts + lanes[i].q_lo);
+            for (int i = 0; i < nl; i++) CLANN_CUDA(cudaStreamWaitEvent(s, lanes[i].done, 0));  // the caller's stream sees the results
+            sh.lanes_used = nl;
             sh.last_was_sharded = true;
             last_nq = nq;
             last_launches = 0;
@@ -1911,12 +1986,24 @@ int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq
 int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms) {
     return guarded([&] {
         if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
-        if (routed_round_one) *routed_round_one = index->sh.n0;
-        if (open_round_two) *open_round_two = index->sh.n1;
-        if (phase_ms) {
-            if (!index->sh.ev[6]) throw StatusError(CLANN_ERR_ARG, "no sharded search yet");
-            CLANN_CUDA(cudaEventSynchronize(index->sh.ev[6]));
-            for (int i = 0; i < 6; i++) CLANN_CUDA(cudaEventElapsedTime(&phase_ms[i], index->sh.ev[i], index->sh.ev[i + 1]));
+        uint64_t n0 = 0, n1 = 0;
+        for (int l = 0; l < index->sh.lanes_used; l++) {
+            n0 += index->lanes[l].n0;
+            n1 += index->lanes[l].n1;
+        }
+        if (routed_round_one) *routed_round_one = n0;
+        if (open_round_two) *open_round_two = n1;
+        if (phase_ms) {  // device time of the phases, summed over the sub-batches in flight (they overlap on the device)
+            if (index->sh.lanes_used == 0) throw StatusError(CLANN_ERR_ARG, "no sharded search yet");
+            for (int i = 0; i < 6; i++) phase_ms[i] = 0.0f;
+            for (int l = 0; l < index->sh.lanes_used; l++) {
+                CLANN_CUDA(cudaEventSynchronize(index->lanes[l].ev[6]));
+                for (int i = 0; i < 6; i++) {
+                    float ms = 0.0f;
+                    CLANN_CUDA(cudaEventElapsedTime(&ms, index->lanes[l].ev[i], index->lanes[l].ev[i + 1]));
+                    phase_ms[i] += ms;
+                }
+            }
         }
     });
 }
@@ -1928,11 +2015,16 @@ int clann_get_counters(clann_index* index, uint64_t nq, uint64_t* candidates, ui
         CLANN_CUDA(cudaDeviceSynchronize());
         if (index->sh.last_was_sharded) {
             // this rank's share of every query's counters (sum them over the ranks for the totals)
-            std::vector<unsigned long long> c = index->sh.counters.download(nq * 3);
-            for (uint64_t q = 0; q < nq; q++) {
-                if (candidates) candidates[q] = c[q * 3];
-                if (distance_computations) distance_computations[q] = c[q * 3 + 1];
-                if (clusters_visited) clusters_visited[q] = (uint32_t)c[q * 3 + 2];
+            for (int l = 0; l < index->sh.lanes_used; l++) {
+                const auto& ln = index->lanes[l];
+                if (ln.q_lo >= nq) break;
+                const uint64_t m = std::min<uint64_t>(ln.q_n, nq - ln.q_lo);
+                std::vector<unsigned long long> c = ln.counters.download(m * 3);
+                for (uint64_t q = 0; q < m; q++) {
+                    if (candidates) candidates[ln.q_lo + q] = c[q * 3];
+                    if (distance_computations) distance_computations[ln.q_lo + q] = c[q * 3 + 1];
+                    if (clusters_visited) clusters_visited[ln.q_lo + q] = (uint32_t)c[q * 3 + 2];
+                }
             }
             return;
         }
