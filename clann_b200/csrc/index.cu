@@ -507,6 +507,14 @@ struct clann_index {
     // the stream-ordered calls; the others rotate under clann_search_device_async so that consecutive batches overlap.
     struct SearchWs {
         uint64_t ws_nq = 0;
+        // side stream (high priority) for the first-visit anchors, which are latency-bound and independent of the dense similarities
+        cudaStream_t aux = nullptr;
+        cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+        ~SearchWs() {
+            if (aux) cudaStreamDestroy(aux);
+            if (ev_fork) cudaEventDestroy(ev_fork);
+            if (ev_join) cudaEventDestroy(ev_join);
+        }
         bool ws_tc_center = false;  // the batch in this workspace was scored by the tensor-pipe screen (cdist exact only below exact_limit)
         bool ws_fs = false;  // the workspace was sized with the first-visit stream buffers (knob first_stream)
         DevBuf<float> w_qnorm, w_cdist, w_exact_limit;
@@ -1397,18 +1405,16 @@ struct clann_index {
             if (queries > 0 && visited > 3 * queries) return false;  // the last finished batch walked > 3 clusters per query
         }
         b.dense = W->w_dense.p;
-        if (!launch_dense_sims(p, b, s)) {
+        if (!dense_sims_supported(p) || tune_get("order_longest_first", 0) != 0 || b.nq == 0 || p.max_cluster == 0) {
             b.dense = nullptr;
             return false;
         }
-        // knob: 0 off, 1 anchors + every depth's range, 2 anchors + samples only (default: same total time as 1 on the glove-100
-        // shape — 0.10 + 1.94 ms against 0.32 + 1.72 ms — with 13 MB instead of 94 MB of workspace per 10 000 queries)
         // knob first_stream (default 0): the whole first visit's candidate stream ahead of the probe (launch_first_stream); it
         // includes the anchors, so first_ranges is not launched then. Measured on B200 (glove-100 shape, 10 000 queries,
         // profiles/r2d_*): the probe falls from 1.89 to 1.35 ms (DRAM reads 2.85 -> 0.81 GB) but k_first_stream itself takes
-        // 1.22 ms at 24 warps per SM (latency-bound: 310 M L2 sectors, L2 hit rate 37 %), so the step is slower (3.04 vs
-        // 2.43 ms) and the stream stays opt-in until that kernel is restructured.
+        // 1.22 ms (0.82 ms as one CTA per query), so the step is slower and the stream stays opt-in.
         if (W->w_fs_cap && tune_get("first_stream", 0) != 0) {
+            launch_dense_sims(p, b, s);  // the stream's depth prediction reads the dense similarities
             b.fs_idx = W->w_fs_idx.p;
             b.fs_hd = W->w_fs_hd.p;
             b.fs_tab = W->w_fs_tab.p;
@@ -1418,15 +1424,41 @@ struct clann_index {
                 return true;
             }
             b.fs_idx = nullptr; b.fs_hd = nullptr; b.fs_tab = nullptr; b.fs_meta = nullptr;
+            last_pre_launches = 1;
+            return true;
         }
+        // knob first_ranges: 0 off, 1 anchors + every depth's range, 2 anchors + samples only (default: same total time as 1 on the
+        // glove-100 shape — 0.10 + 1.94 ms against 0.32 + 1.72 ms — with 13 MB instead of 94 MB of workspace per 10 000 queries)
         const int64_t fr = tune_get("first_ranges", 2);
         if (W->w_pre_range.p && fr != 0) {
             b.pre_anchor = W->w_pre_anchor.p;
             if (fr == 2) b.pre_lcp = W->w_pre_lcp.p;
             else b.pre_range = W->w_pre_range.p;
-            launch_first_ranges(p, b, s);
+            // k_first_ranges (840 000 independent searches, 13 % SM throughput, pure latency) does not depend on the dense similarities
+            // (ALU-bound): it runs beside them on a high-priority side stream (knob first_ranges_overlap)
+            if (tune_get("first_ranges_overlap", 1) != 0) {
+                if (!W->aux) {
+                    int lo = 0, hi = 0;
+                    CLANN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    CLANN_CUDA(cudaStreamCreateWithPriority(&W->aux, cudaStreamNonBlocking, hi));
+                    CLANN_CUDA(cudaEventCreateWithFlags(&W->ev_fork, cudaEventDisableTiming));
+                    CLANN_CUDA(cudaEventCreateWithFlags(&W->ev_join, cudaEventDisableTiming));
+                }
+                CLANN_CUDA(cudaEventRecord(W->ev_fork, s));          // query codes and work order are ready
+                CLANN_CUDA(cudaStreamWaitEvent(W->aux, W->ev_fork, 0));
+                launch_first_ranges(p, b, W->aux);
+                CLANN_CUDA(cudaEventRecord(W->ev_join, W->aux));
+                launch_dense_sims(p, b, s);
+                CLANN_CUDA(cudaStreamWaitEvent(s, W->ev_join, 0));   // the probe needs both
+            } else {
+                launch_dense_sims(p, b, s);
+                launch_first_ranges(p, b, s);
+            }
             last_pre_launches = 2;
-        } else last_pre_launches = 1;
+        } else {
+            launch_dense_sims(p, b, s);
+            last_pre_launches = 1;
+        }
         return true;
     }
 

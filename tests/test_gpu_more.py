@@ -379,6 +379,7 @@ def test_probe_kernel_variants_agree(tmp_path):
                 ("first_stream_cta_cut_short", {"CLANN_TUNE_FIRST_STREAM": "2", "CLANN_TUNE_FIRST_STREAM_CAP": "320"}),
                 ("first_stream_cut_short", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "256"}),   # most visits outlive it
                 ("first_stream_tiny", {"CLANN_TUNE_FIRST_STREAM": "1", "CLANN_TUNE_FIRST_STREAM_CAP": "64"}),
+                ("no_first_ranges_overlap", {"CLANN_TUNE_FIRST_RANGES_OVERLAP": "0"}),
                 ("warp_no_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "0"}),
                 ("warp_all_first_ranges", {"CLANN_TUNE_FIRST_RANGES": "1"}), ("warp_no_smem_memo", {"CLANN_TUNE_PROBE_SMEM_MEMO": "0"}), ("warp_nomemo", {"CLANN_TUNE_PROBE_NOMEMO": "1"}),
                 ("warp_small_grid", {"CLANN_TUNE_PROBE_WARPS": "4", "CLANN_TUNE_PROBE_CTAS": "1"}),
