@@ -464,6 +464,13 @@ def main():
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def run_steps(steps):
+        if mode == "clusters" and not args.no_pipeline:
+            # two whole batches in flight (clann_search_sharded_pair): the sharded counterpart of clann_search_device_async
+            for i in range(0, steps - 1, 2):
+                searcher.search_device_pair(d_batches[i % N_QUERY_BATCHES], d_batches[(i + 1) % N_QUERY_BATCHES], outs[0], outs[1])
+            if steps % 2:
+                step_device(steps - 1)
+            return
         if not pipelined:
             for i in range(steps):
                 step_device(i)
@@ -724,7 +731,9 @@ def main():
             "vs_baseline": None, "dtype": "i16",
             "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
             "pipeline": ("clann_search_device_async: three batches in flight on three internal streams; outputs identical to the "
-                         "stream-ordered call (checked)") if pipelined else "none (stream-ordered calls)",
+                         "stream-ordered call (checked)") if pipelined else
+                        ("clann_search_sharded_pair: two global batches in flight, their phases interleaved on two internal streams"
+                         if mode == "clusters" and not args.no_pipeline else "none (stream-ordered calls)"),
             "data": "synthetic", "config": cfg_json, "parallelism": parallelism, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,
                     "d2h_bytes_per_step": global_nq * k * 8 + global_nq * 4,

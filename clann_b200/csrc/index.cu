@@ -1436,7 +1436,9 @@ struct clann_index {
             else b.pre_range = W->w_pre_range.p;
             // k_first_ranges (840 000 independent searches, 13 % SM throughput, pure latency) does not depend on the dense similarities
             // (ALU-bound): it runs beside them on a high-priority side stream (knob first_ranges_overlap)
-            if (tune_get("first_ranges_overlap", 1) != 0) {
+            // Measured on B200 (glove-100 shape): the rerank kernels take 2.55 ms with the side stream against 2.48 ms without (the
+            // join costs more than the 0.09 ms it hides; three batches in flight gain 1 %), so it is off by default.
+            if (tune_get("first_ranges_overlap", 0) != 0) {
                 if (!W->aux) {
                     int lo = 0, hi = 0;
                     CLANN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1623,6 +1625,42 @@ struct clann_index {
         launch_shard_final_merge(ln.top_all.p, world, nq, k, d_ids, d_dists, d_counts, s);
         CLANN_CUDA(cudaEventRecord(ln.ev[6], s));
         CLANN_CUDA(cudaEventRecord(ln.done, s));
+    }
+
+    // Two WHOLE batches in flight (clann_search_sharded_pair): the same interleaving with one lane per batch — the next batch's
+    // round one fills the SMs while the current batch sits in its count read-backs, collectives and latency-bound round two. This is
+    // the batch pipelining of clann_search_device_async for the sharded search.
+    void search_sharded_pair(const float* const d_queries[2], uint64_t nq, uint32_t* const d_ids[2], float* const d_dists[2],
+                             uint32_t* const d_counts[2], cudaStream_t s) {
+        require_built();
+        if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded_pair needs an index built with shard_count > 1");
+        if (nq == 0) return;
+        if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
+        SearchWs* saved = W;
+        try {
+            if (!sh.fork) CLANN_CUDA(cudaEventCreateWithFlags(&sh.fork, cudaEventDisableTiming));
+            CLANN_CUDA(cudaEventRecord(sh.fork, s));
+            for (int i = 0; i < 2; i++) {
+                ShardLane& ln = lanes[i];
+                ln.q_lo = (uint64_t)i * nq;  // position in the concatenated counters
+                ln.q_n = nq;
+                lane_prepare(ln, nq);
+                CLANN_CUDA(cudaStreamWaitEvent(ln.stream, sh.fork, 0));
+            }
+            for (int i = 0; i < 2; i++) lane_route(lanes[i], d_queries[i]);
+            for (int i = 0; i < 2; i++) lane_round_one(lanes[i], d_queries[i]);
+            for (int i = 0; i < 2; i++) lane_score_open(lanes[i], d_queries[i]);
+            for (int i = 0; i < 2; i++) lane_round_two(lanes[i], d_queries[i], d_ids[i], d_dists[i], d_counts[i]);
+            for (int i = 0; i < 2; i++) CLANN_CUDA(cudaStreamWaitEvent(s, lanes[i].done, 0));
+            sh.lanes_used = 2;
+            sh.last_was_sharded = true;
+            last_nq = 2 * nq;
+            last_launches = 0;
+        } catch (...) {
+            W = saved;
+            throw;
+        }
+        W = saved;
     }
 
     void search_sharded(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
@@ -2014,6 +2052,19 @@ int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq
     return guarded([&] {
         if (!index || (nq && (!d_queries || !d_ids || !d_dists || !d_counts))) throw StatusError(CLANN_ERR_ARG, "null pointer");
         index->search_sharded(d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search_sharded_pair(clann_index* index, const float* d_queries_a, const float* d_queries_b, uint64_t nq, uint32_t* d_ids_a,
+                              float* d_dists_a, uint32_t* d_counts_a, uint32_t* d_ids_b, float* d_dists_b, uint32_t* d_counts_b, void* stream) {
+    return guarded([&] {
+        if (!index || (nq && (!d_queries_a || !d_queries_b || !d_ids_a || !d_dists_a || !d_counts_a || !d_ids_b || !d_dists_b || !d_counts_b)))
+            throw StatusError(CLANN_ERR_ARG, "null pointer");
+        const float* q[2] = {d_queries_a, d_queries_b};
+        uint32_t* ids[2] = {d_ids_a, d_ids_b};
+        float* dd[2] = {d_dists_a, d_dists_b};
+        uint32_t* cc[2] = {d_counts_a, d_counts_b};
+        index->search_sharded_pair(q, nq, ids, dd, cc, static_cast<cudaStream_t>(stream));
     });
 }
 

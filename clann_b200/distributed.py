@@ -149,6 +149,14 @@ class ClusterShardedSearcher:
         _check(self.lib.clann_search_sharded(self.index.handle, d_queries.data_ptr(), d_queries.shape[0], d_ids.data_ptr(),
                                              d_dists.data_ptr(), d_counts.data_ptr(), stream))
 
+    def search_device_pair(self, q_a, q_b, out_a, out_b) -> None:
+        """Two whole batches in flight (clann_search_sharded_pair); out_* = (ids, dists, counts) tensors."""
+        import torch
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _check(self.lib.clann_search_sharded_pair(self.index.handle, q_a.data_ptr(), q_b.data_ptr(), q_a.shape[0], out_a[0].data_ptr(),
+                                                  out_a[1].data_ptr(), out_a[2].data_ptr(), out_b[0].data_ptr(), out_b[1].data_ptr(),
+                                                  out_b[2].data_ptr(), stream))
+
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         ms = (C.c_float * 6)()

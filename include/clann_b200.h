@@ -138,6 +138,11 @@ int clann_comm_init(clann_index* index, int rank, int world, const uint8_t* uniq
 int clann_set_collectives(clann_index* index, clann_allgather_fn allgather, clann_allreduce_min_u64_fn allreduce_min, void* ctx);
 int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts,
                          void* stream);
+/* Two whole batches of nq queries each in flight: the phases of the two searches are interleaved on two internal streams, so
+ * that one batch's waits (count read-backs, collectives, the latency-bound second round) overlap the other's first round — the
+ * batch pipelining of clann_search_device_async for the sharded search. Results are those of two clann_search_sharded calls. */
+int clann_search_sharded_pair(clann_index* index, const float* d_queries_a, const float* d_queries_b, uint64_t nq, uint32_t* d_ids_a,
+                              float* d_dists_a, uint32_t* d_counts_a, uint32_t* d_ids_b, float* d_dists_b, uint32_t* d_counts_b, void* stream);
 /* queries routed to this rank in round one / still open in round two of the last clann_search_sharded; phase_ms[6] (may be NULL) =
  * device time of its phases: route scoring, route all-gather + selection, round one, bound all-reduce + selection, round two, merge */
 int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms);

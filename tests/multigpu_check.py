@@ -53,6 +53,19 @@ def main():
     for _ in range(2):
         searcher.search_device(dq, ids, dd, cc)
         torch.cuda.synchronize()
+    # two batches in flight return what two separate calls return
+    q2 = np.ascontiguousarray(q[::-1])
+    dq2 = torch.from_numpy(q2).to(dev)
+    outs_b = (torch.empty_like(ids), torch.empty_like(dd), torch.empty_like(cc))
+    want_b = (torch.empty_like(ids), torch.empty_like(dd), torch.empty_like(cc))
+    searcher.search_device(dq2, *want_b)
+    pair_a = (torch.empty_like(ids), torch.empty_like(dd), torch.empty_like(cc))
+    searcher.search_device_pair(dq, dq2, pair_a, outs_b)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(pair_a, (ids, dd, cc))), "pair: first batch differs"
+    assert all(torch.equal(x, y) for x, y in zip(outs_b, want_b)), "pair: second batch differs"
+    searcher.search_device(dq, ids, dd, cc)   # counters below are those of the single call
+    torch.cuda.synchronize()
     ids, dd, cc = ids.cpu().numpy().view(np.uint32), dd.cpu().numpy(), cc.cpu().numpy().view(np.uint32)
     # every rank holds the same merged result
     gathered = [torch.empty_like(torch.from_numpy(ids.view(np.int32))).to(dev) for _ in range(world)]
