@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--shard", default="clusters", choices=["clusters", "replicas", "stepping"],
                     help="N > 1: clusters (default) = clann_search_sharded; replicas = index replicated, queries sharded, no "
                          "collective; stepping = the exact hand-over protocol (clann_search_begin/step/merge/end)")
+    ap.add_argument("--sharded-in-flight", type=int, default=4, help="N > 1, clusters: global batches in flight per call (1..4)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the replica comparison run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -465,11 +466,12 @@ def main():
 
     def run_steps(steps):
         if mode == "clusters" and not args.no_pipeline:
-            # two whole batches in flight (clann_search_sharded_pair): the sharded counterpart of clann_search_device_async
-            for i in range(0, steps - 1, 2):
-                searcher.search_device_pair(d_batches[i % N_QUERY_BATCHES], d_batches[(i + 1) % N_QUERY_BATCHES], outs[0], outs[1])
-            if steps % 2:
-                step_device(steps - 1)
+            # several whole batches in flight (clann_search_sharded_multi): the sharded counterpart of clann_search_device_async
+            i = 0
+            while i < steps:
+                nb = min(args.sharded_in_flight, steps - i)
+                searcher.search_device_multi([d_batches[(i + j) % N_QUERY_BATCHES] for j in range(nb)], [outs[j] for j in range(nb)])
+                i += nb
             return
         if not pipelined:
             for i in range(steps):
@@ -732,7 +734,7 @@ def main():
             "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
             "pipeline": ("clann_search_device_async: three batches in flight on three internal streams; outputs identical to the "
                          "stream-ordered call (checked)") if pipelined else
-                        ("clann_search_sharded_pair: two global batches in flight, their phases interleaved on two internal streams"
+                        (f"clann_search_sharded_multi: {args.sharded_in_flight} global batches in flight, their phases interleaved on internal streams"
                          if mode == "clusters" and not args.no_pipeline else "none (stream-ordered calls)"),
             "data": "synthetic", "config": cfg_json, "parallelism": parallelism, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,

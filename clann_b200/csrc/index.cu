@@ -563,7 +563,7 @@ struct clann_index {
         cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last call
         SearchWs ws[3];                // route / open-query scoring, round one, round two
     };
-    static constexpr int kShardLanes = 2;
+    static constexpr int kShardLanes = 4;
     ShardLane lanes[kShardLanes];
     struct {
         bool last_was_sharded = false;
@@ -1630,31 +1630,32 @@ struct clann_index {
     // Two WHOLE batches in flight (clann_search_sharded_pair): the same interleaving with one lane per batch — the next batch's
     // round one fills the SMs while the current batch sits in its count read-backs, collectives and latency-bound round two. This is
     // the batch pipelining of clann_search_device_async for the sharded search.
-    void search_sharded_pair(const float* const d_queries[2], uint64_t nq, uint32_t* const d_ids[2], float* const d_dists[2],
-                             uint32_t* const d_counts[2], cudaStream_t s) {
+    void search_sharded_multi(int nb, const float* const* d_queries, uint64_t nq, uint32_t* const* d_ids, float* const* d_dists,
+                              uint32_t* const* d_counts, cudaStream_t s) {
         require_built();
-        if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded_pair needs an index built with shard_count > 1");
+        if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded_multi needs an index built with shard_count > 1");
+        if (nb < 1 || nb > kShardLanes) throw StatusError(CLANN_ERR_ARG, "1 to 4 batches in flight");
         if (nq == 0) return;
         if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
         SearchWs* saved = W;
         try {
             if (!sh.fork) CLANN_CUDA(cudaEventCreateWithFlags(&sh.fork, cudaEventDisableTiming));
             CLANN_CUDA(cudaEventRecord(sh.fork, s));
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < nb; i++) {
                 ShardLane& ln = lanes[i];
                 ln.q_lo = (uint64_t)i * nq;  // position in the concatenated counters
                 ln.q_n = nq;
                 lane_prepare(ln, nq);
                 CLANN_CUDA(cudaStreamWaitEvent(ln.stream, sh.fork, 0));
             }
-            for (int i = 0; i < 2; i++) lane_route(lanes[i], d_queries[i]);
-            for (int i = 0; i < 2; i++) lane_round_one(lanes[i], d_queries[i]);
-            for (int i = 0; i < 2; i++) lane_score_open(lanes[i], d_queries[i]);
-            for (int i = 0; i < 2; i++) lane_round_two(lanes[i], d_queries[i], d_ids[i], d_dists[i], d_counts[i]);
-            for (int i = 0; i < 2; i++) CLANN_CUDA(cudaStreamWaitEvent(s, lanes[i].done, 0));
-            sh.lanes_used = 2;
+            for (int i = 0; i < nb; i++) lane_route(lanes[i], d_queries[i]);
+            for (int i = 0; i < nb; i++) lane_round_one(lanes[i], d_queries[i]);
+            for (int i = 0; i < nb; i++) lane_score_open(lanes[i], d_queries[i]);
+            for (int i = 0; i < nb; i++) lane_round_two(lanes[i], d_queries[i], d_ids[i], d_dists[i], d_counts[i]);
+            for (int i = 0; i < nb; i++) CLANN_CUDA(cudaStreamWaitEvent(s, lanes[i].done, 0));
+            sh.lanes_used = nb;
             sh.last_was_sharded = true;
-            last_nq = 2 * nq;
+            last_nq = (uint64_t)nb * nq;
             last_launches = 0;
         } catch (...) {
             W = saved;
@@ -2064,7 +2065,17 @@ int clann_search_sharded_pair(clann_index* index, const float* d_queries_a, cons
         uint32_t* ids[2] = {d_ids_a, d_ids_b};
         float* dd[2] = {d_dists_a, d_dists_b};
         uint32_t* cc[2] = {d_counts_a, d_counts_b};
-        index->search_sharded_pair(q, nq, ids, dd, cc, static_cast<cudaStream_t>(stream));
+        index->search_sharded_multi(2, q, nq, ids, dd, cc, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search_sharded_multi(clann_index* index, int n_batches, const float* const* d_queries, uint64_t nq, uint32_t* const* d_ids,
+                               float* const* d_dists, uint32_t* const* d_counts, void* stream) {
+    return guarded([&] {
+        if (!index || !d_queries || !d_ids || !d_dists || !d_counts) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        for (int i = 0; i < n_batches && i < 4; i++)
+            if (nq && (!d_queries[i] || !d_ids[i] || !d_dists[i] || !d_counts[i])) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->search_sharded_multi(n_batches, d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
     });
 }
 

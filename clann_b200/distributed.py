@@ -157,6 +157,17 @@ class ClusterShardedSearcher:
                                                   out_a[1].data_ptr(), out_a[2].data_ptr(), out_b[0].data_ptr(), out_b[1].data_ptr(),
                                                   out_b[2].data_ptr(), stream))
 
+    def search_device_multi(self, queries, outs) -> None:
+        """1 to 4 whole batches in flight (clann_search_sharded_multi): queries = list of [nq, d] tensors, outs = list of
+        (ids, dists, counts) tensor triples."""
+        import torch
+        nb = len(queries)
+        arr = lambda ptrs: (C.c_void_p * nb)(*ptrs)  # noqa: E731
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _check(self.lib.clann_search_sharded_multi(self.index.handle, nb, arr([q.data_ptr() for q in queries]), queries[0].shape[0],
+                                                   arr([o[0].data_ptr() for o in outs]), arr([o[1].data_ptr() for o in outs]),
+                                                   arr([o[2].data_ptr() for o in outs]), stream))
+
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         ms = (C.c_float * 6)()

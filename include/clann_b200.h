@@ -143,6 +143,9 @@ int clann_search_sharded(clann_index* index, const float* d_queries, uint64_t nq
  * batch pipelining of clann_search_device_async for the sharded search. Results are those of two clann_search_sharded calls. */
 int clann_search_sharded_pair(clann_index* index, const float* d_queries_a, const float* d_queries_b, uint64_t nq, uint32_t* d_ids_a,
                               float* d_dists_a, uint32_t* d_counts_a, uint32_t* d_ids_b, float* d_dists_b, uint32_t* d_counts_b, void* stream);
+/* The same for 1 to 4 batches (host arrays of device pointers, one entry per batch). */
+int clann_search_sharded_multi(clann_index* index, int n_batches, const float* const* d_queries, uint64_t nq, uint32_t* const* d_ids,
+                               float* const* d_dists, uint32_t* const* d_counts, void* stream);
 /* queries routed to this rank in round one / still open in round two of the last clann_search_sharded; phase_ms[6] (may be NULL) =
  * device time of its phases: route scoring, route all-gather + selection, round one, bound all-reduce + selection, round two, merge */
 int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms);
