@@ -314,7 +314,7 @@ def main():
     ap.add_argument("--shard", default="clusters", choices=["clusters", "replicas", "stepping"],
                     help="N > 1: clusters (default) = clann_search_sharded; replicas = index replicated, queries sharded, no "
                          "collective; stepping = the exact hand-over protocol (clann_search_begin/step/merge/end)")
-    ap.add_argument("--sharded-in-flight", type=int, default=4, help="N > 1, clusters: global batches in flight per call (1..4)")
+    ap.add_argument("--sharded-in-flight", type=int, default=2, help="N > 1, clusters: global batches in flight per call (1..4)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the replica comparison run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
