@@ -1605,6 +1605,7 @@ __global__ void __launch_bounds__(256, 3) k_first_stream(SearchParams p, QueryBa
         // would the stop rule fire at the end of this depth (table index L, every table consumed) for the cluster's true k-th value?
         const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (L >> 5));
         if ((word >> (L & 31)) & 1u) break;
+        __syncwarp();  // sm.start of this depth must not be overwritten while another lane still reads it
     }
     if (lane < (uint32_t)kMaxHashBits) {
         meta[lane] = my_S;
@@ -1800,6 +1801,7 @@ __global__ void __launch_bounds__(kFsThreads, 8) k_first_stream_cta(SearchParams
         cum += S32;
         const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (L >> 5));
         if ((word >> (L & 31)) & 1u) break;
+        __syncthreads();  // sm.start of this depth is still being read by slower threads; the next depth overwrites it
     }
     if (tid < (uint32_t)kMaxHashBits) {
         meta[tid] = my_S;

@@ -665,6 +665,17 @@ def test_cluster_sharded_search_two_ranks_in_process(big):
                 torch.cuda.synchronize()
             outs[rank] = (ids.cpu().numpy().view(np.uint32), dd.cpu().numpy(), cc.cpu().numpy().view(np.uint32))
             per_rank[rank] = ix.counters(nq)
+            # two whole batches in flight (clann_search_sharded_multi): per batch the results of clann_search_sharded
+            dq2 = torch.flip(dq, dims=[0]).contiguous()
+            o2 = [(torch.empty_like(ids), torch.empty_like(dd), torch.empty_like(cc)) for _ in range(2)]
+            arr = lambda ps: (C.c_void_p * 2)(*ps)  # noqa: E731
+            rc = L.clann_search_sharded_multi(ix.handle, 2, arr([dq.data_ptr(), dq2.data_ptr()]), nq, arr([o[0].data_ptr() for o in o2]),
+                                              arr([o[1].data_ptr() for o in o2]), arr([o[2].data_ptr() for o in o2]), None)
+            assert rc == 0, cl.last_error()
+            torch.cuda.synchronize()
+            assert torch.equal(o2[0][0], ids) and torch.equal(o2[0][1], dd) and torch.equal(o2[0][2], cc)
+            assert torch.equal(o2[1][0], torch.flip(ids, dims=[0])) and torch.equal(o2[1][1], torch.flip(dd, dims=[0]))
+            assert torch.equal(o2[1][2], torch.flip(cc, dims=[0]))
         except Exception as e:  # noqa: BLE001
             errors.append((rank, repr(e)))
             transport.barrier.abort()
@@ -735,7 +746,7 @@ def test_device_collision_estimates_agree_with_reference_table(name):
     repetitions) against the table the real reference drew for the same dimension (golden fixture). Both are 1000-repetition
     estimates, so each entry carries ~1.6 % of sampling noise: like the reference's own statistical test (hash_test.hpp:101-124,
     +-2 % on measured collision rates) the comparison is statistical — mean absolute difference below 2 %, no entry off by more
-    than 8 %, every row non-decreasing in the cosine up to noise, P[.][200] ~ 1 and P[0][.] = 1."""
+    than 8 %, every row non-decreasing in the cosine up to noise (4.5 sigma of a difference), P[.][200] ~ 1 and P[0][.] = 1."""
     import clann_b200 as cb
     from clann_b200 import _lib as cl
     from oracle.pyoracle import OracleLib
@@ -754,5 +765,6 @@ def test_device_collision_estimates_agree_with_reference_table(name):
     diff = np.abs(est - ref_est)
     assert diff.mean() < 0.02, diff.mean()
     assert diff.max() < 0.08, diff.max()
-    assert np.all(np.diff(est, axis=1) > -0.06)
+    # adjacent entries are independent 1000-repetition estimates: their difference has sd <= 0.0224, so -0.10 is 4.5 sigma
+    assert np.diff(est, axis=1).min() > -0.10, np.diff(est, axis=1).min()
     assert np.all((est >= 0) & (est <= 1))
