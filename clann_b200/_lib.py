@@ -26,7 +26,7 @@ OK, ERR_DATA, ERR_CONFIG, ERR_CREATION, ERR_SEARCH, ERR_NOT_BUILT, ERR_BOUNDS, E
 # clann_export_what
 (X_NUM_CLUSTERS, X_CENTERS, X_ASSIGNMENT, X_RADII, X_OFFSETS, X_PERM, X_Q15, X_SKETCHES, X_TABLE_HASHES, X_TABLE_INDICES,
  X_BRUTE, X_NORMS, X_EST, X_QUERY_CODES, X_QUERY_SKETCHES, X_CLUSTER_ORDER, X_BUILD_MS, X_TABLE_DIR, X_REFERENCE_STREAM,
- X_QUERY_ANCHORS, X_QUERY_RANGES, X_STOP_POINTS) = range(22)
+ X_QUERY_ANCHORS, X_QUERY_RANGES, X_STOP_POINTS, X_VISIT_LOG) = range(23)
 
 # clann_allgather_fn / clann_allreduce_min_u64_fn (caller-supplied collectives of the cluster-sharded search)
 ALLGATHER_FN = C.CFUNCTYPE(_i32, _vp, _vp, _vp, _u64, _vp)

@@ -265,6 +265,12 @@ class ClusteredIndex:
         _check(self._lib.clann_get_counters(self._h, nq, _ptr(cand), _ptr(dc), _ptr(vis)))
         return dict(candidates=cand, distance_computations=dc, clusters_visited=vis)
 
+    def visit_log(self, nq: int) -> np.ndarray:
+        """The per-visit rows of the last batch (option "visit_log" set before the search): uint32 [nq, cap, 4] =
+        (cluster + 1, n_candidates, cluster_distance_computations, nanoseconds), zero rows beyond a query's visits."""
+        log = self.export(_lib.X_VISIT_LOG, 0, np.uint32)
+        return log.reshape(nq, -1, 4)
+
     def search_profile(self):
         ms = (C.c_float * 3)()
         launches = C.c_uint32(0)
@@ -495,13 +501,16 @@ def get_recall_values(dataset_distances: np.ndarray, run_distances: Sequence[Seq
 
 
 class RunMetrics:
-    """The run / query granularities of the reference's RunMetrics (src/utils/metrics/mod.rs:14-35,116-262) for one batch:
-    what the reference writes to sqlite (result_schema.sql: clann_results, clann_results_query) as plain rows. The
-    per-cluster granularity (cluster_n_candidates, cluster_timings, cluster_distance_computations) is summed on the device
-    into the per-query counters; per-query wall time is the batch time divided by the batch (queries run concurrently)."""
+    """The run / query / cluster granularities of the reference's RunMetrics (src/utils/metrics/mod.rs:14-35,116-262) for one
+    batch: what the reference writes to sqlite (result_schema.sql: search_metrics, search_metrics_query,
+    search_metrics_cluster) as plain rows. The cluster rows come from the device's per-visit log (CLANN_X_VISIT_LOG:
+    cluster_n_candidates = heap adds that returned true, cluster_distance_computations incl. the prune-test evaluation,
+    cluster time = nanoseconds of the visit on the device); per-query wall time is the batch time divided by the batch
+    (queries run concurrently)."""
 
     def __init__(self, config: "Config", dataset_len: int, total_search_time_s: float, counters: dict,
-                 run_distances=None, ground_truth_distances=None, indexing_duration_s: float = 0.0):
+                 run_distances=None, ground_truth_distances=None, indexing_duration_s: float = 0.0, visit_log=None):
+        self.visit_log = None if visit_log is None else np.asarray(visit_log, np.uint32)
         self.config, self.dataset_len = config, int(dataset_len)
         self.total_search_time_s = float(total_search_time_s)
         self.indexing_duration_s = float(indexing_duration_s)
@@ -529,11 +538,27 @@ class RunMetrics:
                      n_candidates=int(self.candidates[i]), clusters_visited=int(self.clusters_visited[i]),
                      recall=(self.recalls[i] / float(self.config.k)) if self.recalls else None) for i in range(nq)]
 
+    def cluster_rows(self) -> List[dict]:
+        """search_metrics_cluster (result_schema.sql:73-90, written by sqlite.rs:248-283): one row per visited cluster of every
+        query; cluster_idx is the visit's ordinal as in the reference's enumerate(), `cluster` the cluster's id (extra)."""
+        if self.visit_log is None:
+            raise ValueError("no per-visit log: run with granularity='cluster'")
+        rows = []
+        for q, per_query in enumerate(self.visit_log):
+            for v, (c1, added, dc, ns) in enumerate(per_query):
+                if c1 == 0:
+                    break
+                rows.append(dict(query_idx=q, cluster_idx=v, cluster=int(c1) - 1, n_candidates=int(added),
+                                 cluster_time_s=float(ns) * 1e-9, cluster_distance_computations=int(dc)))
+        return rows
+
     def to_json(self, granularity: str = "query") -> str:
         import json
         out = {"run": self.run_row()}
         if granularity in ("query", "cluster"):
             out["queries"] = self.query_rows()
+        if granularity == "cluster":
+            out["clusters"] = self.cluster_rows()
         return json.dumps(out)
 
     def write_csv(self, path: str) -> None:
@@ -546,16 +571,25 @@ class RunMetrics:
                                  ("query_idx", "query_time_s", "distance_computations", "n_candidates", "clusters_visited", "recall")) + "\n")
 
 
-def run_with_metrics(index: "ClusteredIndex", queries, ground_truth_distances=None) -> Tuple[Tuple[np.ndarray, np.ndarray, np.ndarray], RunMetrics]:
+def run_with_metrics(index: "ClusteredIndex", queries, ground_truth_distances=None, granularity: str = "query",
+                     max_visits: int = 64) -> Tuple[Tuple[np.ndarray, np.ndarray, np.ndarray], RunMetrics]:
     """One batch through clann_search with the reference's run metrics filled in (wall clock around the call, as
-    benches/distance_benches.rs:57-74 does around its query loop)."""
+    benches/distance_benches.rs:57-74 does around its query loop). granularity = "cluster" (MetricsGranularity::Cluster,
+    config.rs:9-13) also records the per-visit rows, up to max_visits per query."""
     import time
-    t0 = time.perf_counter()
-    ids, dists, counts = index.search_batch(queries)
-    dt = time.perf_counter() - t0
-    ctr = index.counters(len(counts))
+    if granularity not in ("run", "query", "cluster"):
+        raise ValueError("granularity must be 'run', 'query' or 'cluster'")
+    index.set_option("visit_log", max_visits if granularity == "cluster" else 0)
+    try:
+        t0 = time.perf_counter()
+        ids, dists, counts = index.search_batch(queries)
+        dt = time.perf_counter() - t0
+        ctr = index.counters(len(counts))
+        log = index.visit_log(len(counts)) if granularity == "cluster" else None
+    finally:
+        index.set_option("visit_log", 0)
     run = [dists[i, :counts[i]].tolist() for i in range(len(counts))] if ground_truth_distances is not None else None
-    return (ids, dists, counts), RunMetrics(index.config, index.data.num_points(), dt, ctr, run, ground_truth_distances)
+    return (ids, dists, counts), RunMetrics(index.config, index.data.num_points(), dt, ctr, run, ground_truth_distances, visit_log=log)
 
 
 def generate_random_unit_vectors(n: int, dimensions: int, seed: Optional[int] = None) -> np.ndarray:

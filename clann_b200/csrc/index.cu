@@ -488,6 +488,7 @@ struct clann_index {
     std::vector<FunctionSet> fsets;  // 1 (shared) or K
     std::vector<uint8_t> h_msd;
     double build_ms[4] = {0, 0, 0, 0};
+    uint32_t visit_log_cap = 0;  // option "visit_log"
 
     // device: dataset + CLANN layer
     DevBuf<float> d_data, d_norms, d_dist, d_radii, d_center_rows, d_center_norms;
@@ -517,6 +518,8 @@ struct clann_index {
         }
         bool ws_tc_center = false;  // the batch in this workspace was scored by the tensor-pipe screen (cdist exact only below exact_limit)
         bool ws_fs = false;  // the workspace was sized with the first-visit stream buffers (knob first_stream)
+        uint32_t ws_vlog = 0;  // rows per query of w_visit_log
+        DevBuf<uint32_t> w_visit_log;
         DevBuf<float> w_qnorm, w_cdist, w_exact_limit;
         DevBuf<int16_t> w_q15;
         DevBuf<uint32_t> w_codes, w_first, w_qperm, w_counter, w_vis, w_sort_k, w_sort_i;
@@ -1190,8 +1193,9 @@ struct clann_index {
 
     void ensure_workspace(uint64_t nq, cudaStream_t s) {
         const bool want_fs = tune_get("first_stream", 0) != 0;
-        if (nq == W->ws_nq && want_fs == W->ws_fs) return;
+        if (nq == W->ws_nq && want_fs == W->ws_fs && visit_log_cap == W->ws_vlog) return;
         W->ws_fs = want_fs;
+        W->ws_vlog = visit_log_cap;
         const uint32_t F = n_fsets();
         const uint32_t k = (uint32_t)cfg.k;
         // capacity in steps of 2048 queries: batches of slightly different sizes (the sharded search) reuse the allocations
@@ -1259,6 +1263,7 @@ struct clann_index {
             h_stats[0] = h_stats[1] = 0;
             CLANN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h_stats_dev), h_stats, 0));
         }
+        if (visit_log_cap) W->w_visit_log.ensure(cq * visit_log_cap * 4);
         W->w_cand.ensure(cq);
         W->w_dc.ensure(cq);
         W->w_vis.ensure(cq);
@@ -1308,6 +1313,8 @@ struct clann_index {
         b.fs_cap = W->w_fs_cap;
         b.first_is_own = false;
         b.shard_packed = nullptr;
+        b.visit_log = W->ws_vlog ? W->w_visit_log.p : nullptr;
+        b.visit_cap = W->ws_vlog;
         b.stats_dev = (d_ids && h_stats_dev) ? W->w_stats.p : nullptr;
         b.stats_host = h_stats_dev;
         b.out_ids = d_ids;
@@ -1356,6 +1363,7 @@ struct clann_index {
         // work order: stable sort of the queries by nearest cluster (same radix sort as the tables)
         launch_segment_sort(W->w_sort_seg.p, 1, (uint32_t)nq, b.first, b.qperm, W->w_sort_k.p, W->w_sort_i.p, s);
         launch_init_state(p, b, s);
+        if (b.visit_log) CLANN_CUDA(cudaMemsetAsync(b.visit_log, 0, nq * (uint64_t)b.visit_cap * 16, s));
         cur_queries = d_queries;
         last_nq = nq;
         last_launches = (use_tc_sketch() && W->w_n_tc_tiles && nq >= 64) ? 8 : 7;
@@ -1851,6 +1859,11 @@ int clann_set_option(clann_index* index, const char* key, int64_t value) {
         } else if (k == "shard_count") {
             if (value < 1 || value > 255) throw StatusError(CLANN_ERR_ARG, "shard_count must be in 1..255");
             index->shard_count = (uint32_t)value;
+        } else if (k == "visit_log") {
+            // rows of the per-visit log kept per query (0 = off): the cluster granularity of the reference's metrics. Not part of the index.
+            if (value < 0 || value > 65535) throw StatusError(CLANN_ERR_ARG, "visit_log must be in 0..65535");
+            index->visit_log_cap = (uint32_t)value;
+            return;
         } else throw StatusError(CLANN_ERR_ARG, "unknown option '" + k + "'");
         index->built = false;
     });
@@ -2326,6 +2339,14 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
                     outv[2 * q + 1] = (uint32_t)h->stop_point;
                 }
                 emit(outv.data(), outv.size() * 4);
+                break;
+            }
+            case CLANN_X_VISIT_LOG: {
+                index->require_built();
+                if (!index->W->ws_vlog || !index->W->w_visit_log.p)
+                    throw StatusError(CLANN_ERR_ARG, "no visit log: set option visit_log before the search");
+                std::vector<uint32_t> log = index->W->w_visit_log.download(index->last_nq * index->W->ws_vlog * 4);
+                emit(log.data(), log.size() * 4);
                 break;
             }
             default: throw StatusError(CLANN_ERR_ARG, "unknown export selector");

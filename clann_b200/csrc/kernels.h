@@ -156,6 +156,12 @@ struct QueryBatch {
     // shard_packed[q] = (order_bits(bound) << 32) | (0xffffffff - clusters consumed in round one), the input of round two
     bool first_is_own;
     const unsigned long long* shard_packed;
+    // per-visit log for the reference's cluster-granularity metrics (metrics/mod.rs:84-112, result_schema.sql:73-90), opt-in
+    // (clann_set_option "visit_log" = rows kept per query): visit_log[(q * visit_cap + v) * 4 + ..] = {cluster + 1, points_added
+    // (heap adds that returned true, index.rs:367-372,405-410), cluster_distance_computations (prune-test evaluation + PUFFINN's
+    // counter or the brute-force list length, index.rs:348,378,421), nanoseconds spent in the visit}; null = not recorded
+    uint32_t* visit_log;
+    uint32_t visit_cap;
     // outputs
     uint32_t* out_ids;      // [nq][k]
     float* out_dists;       // [nq][k]

@@ -920,6 +920,15 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
             }
             last_key = nk;
             visited++;
+            // cluster-granularity metrics (opt-in): the prune test above was an evaluation whenever the heap held something
+            // (the start values are parked in the log row itself, so nothing stays live across probe_cluster)
+            if (b.visit_log && lane == 0 && visited <= b.visit_cap) {
+                uint32_t* row = b.visit_log + ((uint64_t)q * b.visit_cap + (visited - 1)) * 4;
+                row[0] = c + 1;
+                row[2] = (uint32_t)ctr.distcomp - ((stop_at_foreign != 2 && heap_len > 0) ? 1u : 0u);  // index.rs:348
+                row[3] = (uint32_t)global_timer_ns();
+            }
+            uint32_t v_added = 0, v_brute = 0;
             const uint64_t off = p.offsets[c];
             const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
             if (p.brute[c]) {
@@ -947,8 +956,9 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                 warp_sort_desc(sm.mb, P);
                 for (uint32_t i = 0; i < loc_len; i++) {
                     unsigned long long key = ~sm.mb[i];
-                    topk_add(sm.heap, heap_len, p.k, float_from_order_bits((uint32_t)(key >> 32)), (uint32_t)key);
+                    v_added += topk_add(sm.heap, heap_len, p.k, float_from_order_bits((uint32_t)(key >> 32)), (uint32_t)key) ? 1u : 0u;
                 }
+                v_brute = loc_len;  // index.rs:378
             } else {
                 const uint32_t fs = p.fset_of[c];
                 const float max_sim = __fsub_rn(1.0f, __fdiv_rn(max_dist, 2.0f));  // puffinn_types.rs:77-79
@@ -1002,9 +1012,15 @@ __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b
                     for (uint32_t l = 0; l < lim; l++) {
                         float dl = __shfl_sync(0xffffffffu, dist, l);
                         uint32_t il = __shfl_sync(0xffffffffu, pid, l);
-                        topk_add(sm.heap, heap_len, p.k, dl, il);
+                        v_added += topk_add(sm.heap, heap_len, p.k, dl, il) ? 1u : 0u;
                     }
                 }
+            }
+            if (b.visit_log && lane == 0 && visited <= b.visit_cap) {
+                uint32_t* row = b.visit_log + ((uint64_t)q * b.visit_cap + (visited - 1)) * 4;
+                row[1] = v_added;
+                row[2] = (uint32_t)ctr.distcomp + v_brute - row[2];  // index.rs:378,421
+                row[3] = (uint32_t)global_timer_ns() - row[3];
             }
         }
         if (pos >= p.K) done = true;

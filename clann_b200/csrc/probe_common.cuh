@@ -109,13 +109,20 @@ __device__ __forceinline__ void warp_sort_desc(unsigned long long* keys, uint32_
 
 // heap.rs:23-36 — bounded max-heap on (distance, index): push while not full, else replace the maximum iff the new
 // distance is strictly smaller. Executed by the whole warp; `len` is warp-uniform.
-__device__ __forceinline__ void topk_add(unsigned long long* heap, uint32_t& len, uint32_t cap, float dist, uint32_t id) {
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// returns what TopKClosestHeap::add returns (heap.rs:23-36): true when the element entered the heap (warp-uniform)
+__device__ __forceinline__ bool topk_add(unsigned long long* heap, uint32_t& len, uint32_t cap, float dist, uint32_t id) {
     unsigned long long key = ((unsigned long long)float_order_bits(dist) << 32) | id;
     if (len < cap) {
         if (lane_id() == 0) heap[len] = key;
         len++;
         __syncwarp();
-        return;
+        return true;
     }
     unsigned long long best = 0;
     uint32_t where = 0;
@@ -128,11 +135,13 @@ __device__ __forceinline__ void topk_add(unsigned long long* heap, uint32_t& len
     }
     unsigned long long mx = warp_max_u64(best);
     // strict comparison on the distance only (heap.rs:27)
-    if ((uint32_t)(key >> 32) < (uint32_t)(mx >> 32)) {
+    const bool enters = (uint32_t)(key >> 32) < (uint32_t)(mx >> 32);
+    if (enters) {
         uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best == mx && lane_id() < len)) - 1;
         if (lane_id() == owner) heap[where] = key;
     }
     __syncwarp();
+    return enters || len == 0;  // k == 0: `else if let Some(max)` finds nothing and add() returns true
 }
 
 __device__ __forceinline__ unsigned long long topk_peek(const unsigned long long* heap, uint32_t len) {

@@ -185,8 +185,14 @@ typedef enum {
     CLANN_X_QUERY_ANCHORS = 19, /* u32[nq*L]       PrefixMapQuery anchors (prefixmap.hpp:36-57,250-260) */
     CLANN_X_QUERY_RANGES = 20,  /* u32[nq*24*L*2]  {start, end} returned by call it = 0..23 of get_next_range
                                    (prefixmap.hpp:267-304; depth 24 - it), layout [query][it][table][2] */
-    CLANN_X_STOP_POINTS = 21    /* u32[nq*2]       {depth, table index} at which the stop rule (collection.hpp:927-943) ended the
+    CLANN_X_STOP_POINTS = 21,   /* u32[nq*2]       {depth, table index} at which the stop rule (collection.hpp:927-943) ended the
                                    last PUFFINN visit of each query of the last batch; {0, 0} = the visit ran out of depths */
+    CLANN_X_VISIT_LOG = 22      /* u32[nq*cap*4]   the cluster granularity of the reference's RunMetrics (metrics/mod.rs:84-112,
+                                   result_schema.sql:73-90) for the last clann_search / clann_search_device batch, recorded when
+                                   clann_set_option(index, "visit_log", cap) was set before the search (cap rows per query, 0 =
+                                   off): row v of query q = {cluster + 1 (0 = no such visit), n_candidates (heap adds that
+                                   returned true, index.rs:367-372,405-410), cluster_distance_computations (index.rs:348,378,
+                                   421), nanoseconds the visit took on the device} */
 } clann_export_what;
 int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t cap, uint64_t* size);
 

@@ -948,8 +948,12 @@ int orc_clann_build_cluster(orc_clann* c, uint64_t ci, const orc_functions* fn) 
     return 0;
 }
 
-/* index.rs:311-439 */
-int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out, uint64_t* counters) {
+/* index.rs:311-439. visit_log (optional, visit_cap rows of 3): what the reference's RunMetrics records per visited cluster
+ * (index.rs:426-431 -> metrics/mod.rs:84-112 -> sqlite.rs:248-283): {cluster, points_added = heap adds that returned true,
+ * cluster_distance_computations = the prune-test evaluation (index.rs:348) + PUFFINN's counter or the brute-force list length}.
+ * The visit that ends the walk at the prune test pushes no n_candidates, so the zip of sqlite.rs:248-253 drops it: not logged. */
+int orc_clann_search_visits(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out, uint64_t* counters,
+                            uint64_t* visit_log, uint64_t visit_cap) {
     uint64_t K = c->K;
     cd_t* cd = (cd_t*)malloc(sizeof(cd_t) * K);
     for (uint64_t ci = 0; ci < K; ci++) { /* index.rs:592-600 */
@@ -976,9 +980,11 @@ int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out
     int err = 0;
     for (uint64_t oi = 0; oi < K; oi++) {
         uint64_t ci = cd[oi].ci;
+        uint64_t visit_dc = 0, points_added = 0;
         if (pq.len > 0) { /* index.rs:342-361 */
             hp_elem top = pq.e[hp_max(&pq)];
             max_dist = top.dist;
+            visit_dc = 1; /* index.rs:348 */
             float cmin = orc_distance_point(c->data + c->centers[ci] * c->d, c->norms[c->centers[ci]], q, c->d) - c->radii[ci];
             if (cmin > top.dist) break;
         }
@@ -991,7 +997,8 @@ int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out
                 hp_add(&loc, e);
             }
             qsort(loc.e, loc.len, sizeof(hp_elem), hp_cmp);
-            for (uint32_t j = 0; j < loc.len; j++) hp_add(&pq, loc.e[j]);
+            for (uint32_t j = 0; j < loc.len; j++) points_added += (uint64_t)hp_add(&pq, loc.e[j]);
+            visit_dc += loc.len; /* index.rs:378 */
             /* counters follow PUFFINN's own (performance.hpp:72-86): brute-force clusters add nothing */
         } else {
             if (!c->indices[ci]) { /* index.rs:386-388 IndexNotFound */
@@ -1004,11 +1011,17 @@ int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out
             int nr = orc_index_search(c->indices[ci], q, c->k, c->delta, max_sim, res, &tr);
             distcomp += tr.distance_computations;
             cands += tr.candidates;
+            visit_dc += tr.distance_computations; /* index.rs:421 */
             for (int j = 0; j < nr; j++) { /* index.rs:392-416 */
                 uint64_t p = c->members[ci][res[j]];
                 hp_elem e = {orc_distance_point(c->data + p * c->d, c->norms[p], q, c->d), p};
-                hp_add(&pq, e);
+                points_added += (uint64_t)hp_add(&pq, e);
             }
+        }
+        if (visit_log && visited <= visit_cap) {
+            visit_log[(visited - 1) * 3 + 0] = ci;
+            visit_log[(visited - 1) * 3 + 1] = points_added;
+            visit_log[(visited - 1) * 3 + 2] = visit_dc;
         }
     }
     qsort(pq.e, pq.len, sizeof(hp_elem), hp_cmp); /* heap.rs:42-48 */
@@ -1024,6 +1037,10 @@ int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out
     }
     free(cd); free(pq.e); free(loc.e); free(res);
     return r;
+}
+
+int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out, uint64_t* counters) {
+    return orc_clann_search_visits(c, q, out_ids, out_dists, order_out, counters, NULL, 0);
 }
 
 void orc_clann_free(orc_clann* c) {

@@ -97,6 +97,10 @@ int orc_clann_set_cluster_stream(orc_clann* c, uint64_t ci, const uint8_t* strea
 int orc_clann_build_cluster(orc_clann* c, uint64_t ci, const orc_functions* fn);
 int orc_clann_search(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out,
                      uint64_t* counters /*visited, distcomp, candidates*/);
+/* the same search with the reference's per-visit metric rows (metrics/mod.rs:84-112): visit_log[v*3 + ..] = {cluster,
+ * points_added, cluster_distance_computations} for the first visit_cap visits */
+int orc_clann_search_visits(orc_clann* c, const float* q, uint64_t* out_ids, float* out_dists, uint64_t* order_out,
+                            uint64_t* counters, uint64_t* visit_log, uint64_t visit_cap);
 void orc_clann_free(orc_clann* c);
 
 #ifdef __cplusplus

@@ -203,6 +203,7 @@ class OracleLib:
         L.orc_clann_set_cluster_stream.argtypes = [_vp, _u64, _vp, _u64]
         L.orc_clann_build_cluster.restype, L.orc_clann_build_cluster.argtypes = _i32, [_vp, _u64, _vp]
         L.orc_clann_search.restype, L.orc_clann_search.argtypes = _i32, [_vp, _vp, _vp, _vp, _vp, _vp]
+        L.orc_clann_search_visits.restype, L.orc_clann_search_visits.argtypes = _i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64]
         L.orc_clann_free.argtypes = [_vp]
 
     # L0 helpers -----------------------------------------------------------------------------------
@@ -325,6 +326,18 @@ class OracleClann:
             raise RuntimeError(f"oracle clann search failed ({c})")
         return ids[:c].copy(), dists[:c].copy(), order, dict(visited=int(counters[0]), distance_computations=int(counters[1]),
                                                             candidates=int(counters[2]))
+
+    def search_visits(self, q, cap=64):
+        """search() plus the per-visit rows of the reference's cluster-granularity metrics: uint64 [visits, 3] =
+        (cluster, points_added, cluster_distance_computations)."""
+        q = np.ascontiguousarray(q, np.float32)
+        ids, dists = np.zeros(max(self.k, 1), np.uint64), np.zeros(max(self.k, 1), np.float32)
+        order, counters = np.zeros(self.K, np.uint64), np.zeros(3, np.uint64)
+        log = np.zeros((cap, 3), np.uint64)
+        c = self.lib.lib.orc_clann_search_visits(self.h, _ptr(q), _ptr(ids), _ptr(dists), _ptr(order), _ptr(counters), _ptr(log), cap)
+        if c < 0:
+            raise RuntimeError(f"oracle clann search failed ({c})")
+        return ids[:c].copy(), dists[:c].copy(), log[: min(int(counters[0]), cap)].copy()
 
     def free(self):
         if self.h:

@@ -57,8 +57,11 @@ def compare_with_oracle(ix, data, q, k, delta, oracle, independent_builds=2, tra
     statistics; raises AssertionError on the first kind of difference."""
     from clann_b200 import _lib as cl
     nq = len(q)
+    ix.set_option("visit_log", 16)   # the cluster granularity of the reference's metrics, recorded by the probe
     ids, dists, counts = ix.search_batch(q)
     ctr = ix.counters(nq)
+    vlog = ix.visit_log(nq).copy()
+    ix.set_option("visit_log", 0)
     K = ix.num_clusters
     L = ix.config.num_tables
     order = ix.export(cl.X_CLUSTER_ORDER, 0, np.uint32).reshape(nq, K)
@@ -86,6 +89,13 @@ def compare_with_oracle(ix, data, q, k, delta, oracle, independent_builds=2, tra
     bad = []
     for i in range(nq):
         o_ids, o_d, o_order, o_ctr = orc.search(q[i])
+        # search_metrics_cluster rows (sqlite.rs:248-283): cluster, heap adds that returned true, distance computations incl. the
+        # prune-test evaluation — per visit, in visiting order
+        _, _, o_log = orc.search_visits(q[i], 16)
+        g_log = vlog[i][: len(o_log)]
+        assert np.array_equal(g_log[:, 0].astype(np.int64) - 1, o_log[:, 0].astype(np.int64)), (i, g_log, o_log)
+        assert np.array_equal(g_log[:, 1:3].astype(np.uint64), o_log[:, 1:3]), (i, g_log, o_log)
+        assert np.all(vlog[i][len(o_log):, 0] == 0) and np.all(g_log[:, 3] > 0)
         c = int(counts[i])
         g_ids, g_d = ids[i, :c], dists[i, :c]
         ok = (np.array_equal(order[i], o_order.astype(np.uint32))

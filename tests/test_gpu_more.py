@@ -197,12 +197,18 @@ def test_edge_cases_against_oracle(oracle):
         if not brute[ci]:
             orc.set_cluster_stream(ci, ix.export(cl.X_REFERENCE_STREAM, ci, np.uint8).tobytes())
     qs = np.concatenate([util.planted_queries(data, 20, 6), data[20:22], data[10:11] + 1e-3])
+    ix.set_option("visit_log", 8)
     ids, dists, counts = ix.search_batch(qs)
     ctr = ix.counters(len(qs))
+    vlog = ix.visit_log(len(qs))
     for i, q in enumerate(qs):
         o_ids, o_d, _, o_ctr = orc.search(q)
         assert util.same_ids_up_to_ties(ids[i, : counts[i]], dists[i, : counts[i]], o_ids.astype(np.uint32), o_d), i
         assert int(ctr["clusters_visited"][i]) == o_ctr["visited"] and int(ctr["distance_computations"][i]) == o_ctr["distance_computations"]
+        # per-visit metric rows incl. brute-force visits (index.rs:364-378: list length as distance computations)
+        _, _, o_log = orc.search_visits(q, 8)
+        assert np.array_equal(vlog[i][: len(o_log), 0].astype(np.int64) - 1, o_log[:, 0].astype(np.int64)), i
+        assert np.array_equal(vlog[i][: len(o_log), 1:3].astype(np.uint64), o_log[:, 1:3]), (i, vlog[i], o_log)
     ix.close(); orc.free()
     # (c) k larger than every cluster -> every cluster is brute force (index.rs:204-205), results exact
     data = util.planted(1200, 10, 7)
@@ -568,6 +574,11 @@ def test_serialize_and_init_from_file_round_trip(tmp_path):
     assert rec2.keys() == rec.keys() and all(rec2[k] == rec[k] for k in rec if k != "config") and json.loads(rec2["config"]) == cfg
 
 
+def _lib_x():
+    from clann_b200 import _lib
+    return _lib
+
+
 def test_run_with_metrics_on_device():
     """run_with_metrics (the run / query rows of the reference's RunMetrics): counters per query come from the device, recall
     from get_recall_values against exact distances, queries/s from the wall clock around the batched call."""
@@ -584,6 +595,24 @@ def test_run_with_metrics_on_device():
     assert [r["distance_computations"] for r in rows] == ctr["distance_computations"].tolist()
     assert [r["n_candidates"] for r in rows] == ctr["candidates"].tolist()
     assert m.run_row()["dataset_len"] == 15_000 and m.run_row()["dataset"] == "metrics"
+    # MetricsGranularity::Cluster: one row per visited cluster; results and counters are those of the plain call
+    (ids2, dists2, counts2), mc = cb.run_with_metrics(ix, q, gt, granularity="cluster")
+    assert np.array_equal(ids, ids2) and np.array_equal(dists.view(np.uint32), dists2.view(np.uint32))
+    crow = mc.cluster_rows()
+    vis = ix.counters(200)["clusters_visited"]
+    assert len(crow) == int(vis.sum())
+    per_q = np.zeros(200, np.int64)
+    dc_q = np.zeros(200, np.int64)
+    for r in crow:
+        assert r["cluster_idx"] == per_q[r["query_idx"]] and 0 <= r["cluster"] < ix.num_clusters and r["cluster_time_s"] > 0
+        per_q[r["query_idx"]] += 1
+        dc_q[r["query_idx"]] += r["cluster_distance_computations"]
+    assert np.array_equal(per_q, vis)
+    brute = ix.export(_lib_x().X_BRUTE, 0, np.uint8)
+    if not brute.any():  # PUFFINN's counter + one prune-test evaluation for every visit after the first (index.rs:348,421)
+        assert np.array_equal(dc_q, ctr["distance_computations"].astype(np.int64) + vis - 1)
+    import json
+    assert len(json.loads(mc.to_json("cluster"))["clusters"]) == len(crow)
 
 
 @pytest.mark.parametrize("shape", [(30_000, 64, "planted"), (12_000, 100, "uniform"), (9_000, 36, "planted")])

@@ -102,4 +102,13 @@ def test_clann_layer_restatements_agree(oracle, reflib):
         ri, rd, ro, rc = ref.search(q)
         oi, od, oo, oc = orc.search(q)
         assert list(ri) == list(oi) and np.array_equal(rd, od) and np.array_equal(ro, oo) and rc == oc
+        # per-visit rows (metrics/mod.rs:84-112): as many as visits, clusters in visiting order; the distance computations are
+        # PUFFINN's counter (pinned above against the real PUFFINN) + one prune-test evaluation per visit after the first
+        # + the list length of brute-force visits; a visit cannot add more points than the list it received (<= k)
+        vi, vd, log = orc.search_visits(q, 32)
+        assert list(vi) == list(oi) and np.array_equal(vd, od)
+        assert len(log) == oc["visited"] and np.array_equal(log[:, 0], oo[: len(log)])
+        brute_len = sum(min(5, int((a1 == c).sum())) for c in log[:, 0] if (a1 == c).sum() < 100)
+        assert int(log[:, 2].sum()) == oc["distance_computations"] + (len(log) - 1) + brute_len
+        assert np.all(log[:, 1] <= 5) and int(log[0, 1]) > 0
     ref.free(); orc.free()
