@@ -401,10 +401,13 @@ struct WarpSmem {
     uint32_t* code;            // [L] query code per table
     uint32_t* start;           // [L] range start of the current depth
     uint32_t* segbase;         // [L+1] exclusive prefix of 4-entry segment counts of the current depth
+    uint16_t* wstart;          // [kWinCap] table that holds segment 32 w of the current depth's stream (one entry per ring sweep)
     unsigned long long* mb;    // [P2K] MaxBuffer slots (maxbuffer.hpp:20): (sim16 << 32) | local id
     unsigned long long* heap;  // [k] TopKClosestHeap (src/core/heap.rs): (order_bits(dist) << 32) | point id
     unsigned long long* loc;   // [k] local heap of a brute-force cluster (index.rs:671)
 };
+
+constexpr uint32_t kWinCap = 64;  // ring sweeps per depth with a table hint (8 192 candidates); later sweeps search all tables
 
 __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t L, uint32_t k) {
     uint32_t p2k = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
@@ -413,6 +416,7 @@ __host__ __device__ inline uint32_t warp_smem_bytes(uint32_t L, uint32_t k) {
     b += L * 8 * 2;                                   // lcp_up, lcp_dn
     b += L * 4 * 2;                                   // code, start
     b += (L + 1) * 4;                                 // segbase
+    b += kWinCap * 2;                                 // wstart
     b = (b + 15) & ~15u;
     b += p2k * 8 + k * 8 * 2;
     return (b + 15) & ~15u;
@@ -431,6 +435,7 @@ __device__ __forceinline__ WarpSmem carve(uint8_t* base, uint32_t L, uint32_t k)
     w.segbase = reinterpret_cast<uint32_t*>(p); p += (L + 1) * 4;
     w.pass_sim = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
     w.unk = reinterpret_cast<uint16_t*>(p); p += kPassingCap * 2;
+    w.wstart = reinterpret_cast<uint16_t*>(p); p += kWinCap * 2;
     p = base + (((uint32_t)(p - base) + 15) & ~15u);
     w.mb = reinterpret_cast<unsigned long long*>(p); p += p2k * 8;
     w.heap = reinterpret_cast<unsigned long long*>(p); p += k * 8;
@@ -627,7 +632,14 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
                                           sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
             uint32_t total;
             uint32_t ex = warp_excl_scan(nseg, total);
-            if (t < L) sm.segbase[t] = running + ex;
+            if (t < L) {
+                const uint32_t sb = running + ex;
+                sm.segbase[t] = sb;
+                // every ring sweep starts at a multiple of 32 segments: note which table holds that segment
+                uint32_t w = (sb + 31u) >> 5, wend = (sb + nseg + 31u) >> 5;
+                wend = wend < kWinCap ? wend : kWinCap;
+                for (; w < wend; w++) sm.wstart[w] = (uint16_t)t;
+            }
             running += total;
         }
         if (lane == 0 && !streamed) sm.segbase[L] = running;
@@ -635,14 +647,21 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
         const uint32_t S = running;
         if (S <= kRing) continue;  // the initial ring fill swallows the whole stream (collection.hpp:802-810)
 
-        // segment number -> (table, position)
+        // segment number -> (table, position): the table is the last one whose prefix is <= s (upper_bound(segbase, s) - 1); the
+        // sweep's window [32 w, 32 w + 32) lies between the tables noted for w and w + 1, so the search is over that span only
         auto locate = [&](uint32_t s, uint32_t& t_out) -> uint64_t {
-            uint32_t lo = 0, len = L;  // upper_bound(segbase, s) - 1 over segbase[0..L)
-            while (len > 0) {
-                uint32_t half = len >> 1, mid = lo + half;
-                if (sm.segbase[mid] <= s) { lo = mid + 1; len -= half + 1; } else { len = half; }
+            const uint32_t w = s >> 5;
+            uint32_t lo = 0, hi = L - 1;
+            if (w < kWinCap) {
+                lo = sm.wstart[w];
+                if (w + 1 < kWinCap && ((w + 1) << 5) < S) hi = sm.wstart[w + 1];
             }
-            uint32_t t = lo - 1;
+            uint32_t a = lo + 1, len = hi - lo;  // upper_bound over segbase[lo + 1 .. hi]
+            while (len > 0) {
+                uint32_t half = len >> 1, mid = a + half;
+                if (sm.segbase[mid] <= s) { a = mid + 1; len -= half + 1; } else { len = half; }
+            }
+            uint32_t t = a - 1;
             t_out = t;
             return table_base(off, nc, L, t) + sm.start[t] + 4 * (s - sm.segbase[t]);
         };
@@ -745,12 +764,16 @@ __device__ uint32_t probe_cluster(const SearchParams& p, const WarpSmem& sm, uin
             if (streamed) {
                 if (pulled < S) table_idx = __ldg(fs.tab + ((soff + pulled) >> 5));
             } else if (pulled < S) {
-                uint32_t lo = 0, len = L;
-                while (len > 0) {
-                    uint32_t half = len >> 1, mid = lo + half;
-                    if (sm.segbase[mid] <= pulled) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                if ((pulled >> 5) < kWinCap) {
+                    table_idx = sm.wstart[pulled >> 5];  // pulled is a multiple of the ring size: the table noted for its sweep
+                } else {
+                    uint32_t lo = 0, len = L;
+                    while (len > 0) {
+                        uint32_t half = len >> 1, mid = lo + half;
+                        if (sm.segbase[mid] <= pulled) { lo = mid + 1; len -= half + 1; } else { len = half; }
+                    }
+                    table_idx = lo - 1;
                 }
-                table_idx = lo - 1;
             }
             float kth = __fdiv_rn((float)minval16, 65536.0f);
             float sim = kth < max_sim ? max_sim : kth;  // std::max(kth, max_sim)
@@ -2032,7 +2055,7 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, int stop
     uint32_t smem_memo_cap = 0;
     if (DENSE && tune_get("probe_smem_memo", 1) != 0) {
         const uint32_t cap = (p.max_cluster + 7u) & ~7u;
-        if (cap > 0 && (size_t)warps * (per_warp + cap * 2 + 16) * OCC <= 220 * 1024) {
+        if (cap > 0 && (size_t)warps * (per_warp + cap * 2 + 16) * OCC <= 224 * 1024) {  // 228 KB per SM - 1 KB per CTA, some slack
             smem_memo_cap = cap;
             per_warp += cap * 2 + 16;
         }
