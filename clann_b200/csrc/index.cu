@@ -487,7 +487,7 @@ struct clann_index {
     std::vector<uint32_t> h_fset_of;
     std::vector<FunctionSet> fsets;  // 1 (shared) or K
     std::vector<uint8_t> h_msd;
-    double build_ms[4] = {0, 0, 0, 0};
+    double build_ms[5] = {0, 0, 0, 0, 0};  // gmm phase, hashing, sort, total, the k-center passes alone
     uint32_t visit_log_cap = 0;  // option "visit_log"
 
     // device: dataset + CLANN layer
@@ -785,6 +785,7 @@ struct clann_index {
         // angulardata.rs:12-19
         d_norms.alloc(n);
         launch_row_norms(d_data.p, n, g.d, d_norms.p, s);
+        build_ms[4] = 0.0;
         if (clustering_imposed) return;
         if (n <= K) {  // gmm.rs:26-31: every point its own centre
             K = (uint32_t)n;
@@ -809,10 +810,14 @@ struct clann_index {
         d_keys.zero(s);
         DevBuf<float> d_cc;
         d_cc.alloc(K);
+        cudaEvent_t p0, p1;  // the K passes alone (build_ms[4]): what the build roofline is about
+        CLANN_CUDA(cudaEventCreate(&p0)); CLANN_CUDA(cudaEventCreate(&p1));
+        CLANN_CUDA(cudaEventRecord(p0, s));
         for (uint32_t c = 0; c < K; c++) {
             launch_gmm_pass(d_data.p, d_norms.p, row0, row1, g.d, c, d_keys.p, d_dist.p, d_assign.p, d_cc.p, s);
             if (shard_gmm) CLANN_NCCL(nccl_api().AllReduce(d_keys.p + c, d_keys.p + c, 1, ncclUint64, ncclMax, comm, s));
         }
+        CLANN_CUDA(cudaEventRecord(p1, s));
         if (shard_gmm) {
             CLANN_NCCL(nccl_api().AllGather(d_dist.p + shard_rank * chunk, d_dist.p, chunk, ncclFloat32, comm, s));
             CLANN_NCCL(nccl_api().AllGather(d_assign.p + shard_rank * chunk, d_assign.p, chunk, ncclUint32, comm, s));
@@ -824,6 +829,12 @@ struct clann_index {
         d_sizes.zero(s);
         launch_gmm_finish(d_keys.p, K, n, d_dist.p, d_assign.p, d_centers.p, d_radii.p, d_sizes.p, s);
         CLANN_CUDA(cudaStreamSynchronize(s));
+        {
+            float ms = 0.0f;
+            CLANN_CUDA(cudaEventElapsedTime(&ms, p0, p1));
+            build_ms[4] = ms;
+            cudaEventDestroy(p0); cudaEventDestroy(p1);
+        }
         h_centers = d_centers.download(K);
         h_radii = d_radii.download(K);
         h_assign = d_assign.download(n);
@@ -837,10 +848,21 @@ struct clann_index {
         for (uint64_t i = 0; i < n; i++) h_sizes[h_assign[i]]++;
         h_offsets.assign(K + 1, 0);
         for (uint32_t c = 0; c < K; c++) h_offsets[c + 1] = h_offsets[c] + h_sizes[c];
-        // stable partition by cluster id = the same radix sort the tables use, one segment of n keys
         DevBuf<uint32_t> keys, scratch_k, scratch_i;
         keys.upload(h_assign, s);
         d_perm.alloc(n);
+        // stable partition by cluster id: counting sort over warp-sized chunks of the rows (knob assign_partition, default 1) ...
+        if (tune_get("assign_partition", 1) != 0 && n < (1ull << 32)) {
+            uint64_t chunks = std::min<uint64_t>((n + 31) / 32, 4096);
+            while (chunks > 1 && chunks * K * sizeof(uint32_t) > (256ull << 20)) chunks >>= 1;
+            DevBuf<uint32_t> counts;
+            counts.alloc(chunks * K);
+            d_offsets.upload(h_offsets, s);
+            launch_assign_partition(keys.p, n, K, d_offsets.p, counts.p, (uint32_t)chunks, d_perm.p, s);
+            CLANN_CUDA(cudaStreamSynchronize(s));
+            return;
+        }
+        // ... or the same radix sort the tables use, one segment of n keys (one CTA)
         DevBuf<SortSegment> seg;
         std::vector<SortSegment> hs(1);
         hs[0] = SortSegment{0, 0, (uint32_t)n, 0};

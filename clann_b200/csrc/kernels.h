@@ -50,6 +50,10 @@ struct SortSegment {
 };
 // sorthash.hpp:133-194: stable LSD radix sort (3 byte passes) of every segment by its 24-bit key; payload = position in
 // the segment. keys are sorted in place, idx receives the payload. max_len = largest segment.
+// Stable partition of the rows by cluster id (index.rs:188-192): perm[offsets[c] + j] = j-th row (ascending) assigned to cluster c.
+// counts = scratch of n_chunks * K u32 (one private counter row per warp-sized chunk of the rows).
+void launch_assign_partition(const uint32_t* assign, uint64_t n, uint32_t K, const uint64_t* offsets, uint32_t* counts, uint32_t n_chunks,
+                             uint32_t* perm, cudaStream_t s);
 void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_len, uint32_t* keys, uint32_t* idx,
                          uint32_t* scratch_keys, uint32_t* scratch_idx, cudaStream_t s);
 uint32_t segment_sort_smem_capacity();  // segments up to this length are sorted entirely in shared memory

@@ -176,6 +176,68 @@ __global__ void k_gmm_finish(const uint64_t* __restrict__ keys, uint32_t K, uint
     }
 }
 
+// index.rs:188-192 — member lists in ascending point order = a stable partition of the rows by cluster id. One warp per chunk of
+// consecutive rows keeps a private row of K counters (counts[chunk * K + c], L2-resident): count, exclusive scan per cluster over
+// the chunks (starting at the cluster's offset), then the same walk again turns the counters into running write positions.
+// Within a 32-row tile the rows of one cluster are ranked by lane (match_any), so the order inside a cluster is the row order.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_assign_partition(const uint32_t* __restrict__ assign, uint64_t n, uint32_t K, uint64_t chunk_rows,
+                                                          uint32_t n_chunks, uint32_t* __restrict__ counts, uint32_t* __restrict__ perm) {
+    const uint32_t w = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31u;
+    if (w >= n_chunks) return;
+    const uint64_t lo = (uint64_t)w * chunk_rows, hi = lo + chunk_rows < n ? lo + chunk_rows : n;
+    uint32_t* mine = counts + (uint64_t)w * K;
+    for (uint64_t base = lo; base < hi; base += 32) {
+        const uint64_t i = base + lane;
+        const bool valid = i < hi;
+        const uint32_t c = valid ? assign[i] : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t leader = __ffs(peers) - 1u;
+        uint32_t start = 0;
+        if (valid && lane == leader) {
+            start = mine[c];
+            mine[c] = start + __popc(peers);
+        }
+        if (SCATTER) {
+            start = __shfl_sync(0xffffffffu, start, leader);
+            if (valid) perm[start + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
+        __syncwarp();  // the next tile's leader of the same cluster may be another lane
+    }
+}
+
+// one warp per cluster: counts[b * K + c] -> offsets[c] + (rows of cluster c in the chunks before b)
+__global__ void __launch_bounds__(256) k_assign_scan(uint32_t* __restrict__ counts, uint32_t K, uint32_t n_chunks,
+                                                     const uint64_t* __restrict__ offsets) {
+    const uint32_t c = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31u;
+    if (c >= K) return;
+    uint32_t running = (uint32_t)offsets[c];
+    for (uint32_t b0 = 0; b0 < n_chunks; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const uint32_t v = b < n_chunks ? counts[(uint64_t)b * K + c] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (b < n_chunks) counts[(uint64_t)b * K + c] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+void launch_assign_partition(const uint32_t* assign, uint64_t n, uint32_t K, const uint64_t* offsets, uint32_t* counts, uint32_t n_chunks,
+                             uint32_t* perm, cudaStream_t s) {
+    if (n == 0 || K == 0 || n_chunks == 0) return;
+    uint64_t chunk_rows = (n + n_chunks - 1) / n_chunks;
+    chunk_rows = (chunk_rows + 31) & ~31ull;
+    CLANN_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_chunks * K * sizeof(uint32_t), s));
+    const unsigned grid = (unsigned)(((uint64_t)n_chunks * 32 + 255) / 256);
+    k_assign_partition<false><<<grid, 256, 0, s>>>(assign, n, K, chunk_rows, n_chunks, counts, perm);
+    k_assign_scan<<<(unsigned)(((uint64_t)K * 32 + 255) / 256), 256, 0, s>>>(counts, K, n_chunks, offsets);
+    k_assign_partition<true><<<grid, 256, 0, s>>>(assign, n, K, chunk_rows, n_chunks, counts, perm);
+}
+
 __global__ void k_gather_rows(const float* __restrict__ data, const uint32_t* __restrict__ rows, uint32_t count, uint32_t d,
                               float* __restrict__ out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

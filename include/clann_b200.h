@@ -173,7 +173,8 @@ typedef enum {
     CLANN_X_QUERY_CODES = 13, /* u32[nq*L] table codes of the last search batch for the function set of cluster `arg` */
     CLANN_X_QUERY_SKETCHES = 14, /* u64[nq*32] likewise */
     CLANN_X_CLUSTER_ORDER = 15,  /* u32[nq*K] visiting order of the last search batch (index.rs:592-616) */
-    CLANN_X_BUILD_MS = 16,    /* f64[4] last build: gmm, hashing (store+sketch+codes), table sort, total (device ms) */
+    CLANN_X_BUILD_MS = 16,    /* f64[5] last build: gmm phase, hashing (store+sketch+codes), table sort, total, the K k-center
+                                 passes alone (device ms) */
     CLANN_X_TABLE_DIR = 17,   /* u32[L*4097] bucket directory of cluster `arg`: entry b of table t = first position whose top 12
                                  code bits are >= b, entry 4096 = cluster size (the role of PrefixMap::prefix_index,
                                  prefixmap.hpp:86,231-240, at 12 instead of 13 bits), table-major */

@@ -628,7 +628,7 @@ def test_gmm_kernel_variants_match_oracle(oracle, shape):
     data[40] = data[41]                 # duplicates: zero residual distance
     K = oracle.num_clusters(0.4, n)
     oc, oa, orad = oracle.gmm(data, K)
-    for knobs in ({"gmm_vec": 0}, {"gmm_prune": 0}, {}):
+    for knobs in ({"gmm_vec": 0}, {"gmm_prune": 0}, {"assign_partition": 0}, {}):
         for k_, v in knobs.items():
             cl.tune(k_, v)
         try:
@@ -637,6 +637,12 @@ def test_gmm_kernel_variants_match_oracle(oracle, shape):
             cen = ix.export(cl.X_CENTERS, 0, np.uint64)
             asg = ix.export(cl.X_ASSIGNMENT, 0, np.uint64)
             rad = ix.export(cl.X_RADII, 0, np.float32)
+            # member lists (index.rs:188-192): ascending point order inside every cluster, clusters back to back — by the
+            # chunked counting sort (default) and by the one-segment radix sort (assign_partition = 0)
+            perm = ix.export(cl.X_PERM, 0, np.uint32)
+            offs = ix.export(cl.X_OFFSETS, 0, np.uint64)
+            assert np.array_equal(perm, np.argsort(asg, kind="stable").astype(np.uint32)), knobs
+            assert np.array_equal(offs, np.concatenate([[0], np.cumsum(np.bincount(asg.astype(np.int64), minlength=K))]).astype(np.uint64))
             ix.close()
         finally:
             for k_ in knobs:
