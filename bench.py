@@ -315,6 +315,9 @@ def main():
                     help="N > 1: clusters (default) = clann_search_sharded; replicas = index replicated, queries sharded, no "
                          "collective; stepping = the exact hand-over protocol (clann_search_begin/step/merge/end)")
     ap.add_argument("--sharded-in-flight", type=int, default=2, help="N > 1, clusters: global batches in flight per call (1..4)")
+    ap.add_argument("--sharded-pipeline", choices=["stream", "multi"], default="stream",
+                    help="N > 1, clusters: stream = clann_search_sharded_submit/_flush (a software pipeline across the steps, four "
+                         "batches in staggered phases); multi = clann_search_sharded_multi (--sharded-in-flight batches per call, in step)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the replica comparison run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -465,8 +468,14 @@ def main():
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def run_steps(steps):
+        if mode == "clusters" and not args.no_pipeline and args.sharded_pipeline == "stream":
+            # one batch per step into the staggered pipeline: the sharded counterpart of clann_search_device_async / _flush
+            for i in range(steps):
+                searcher.submit(d_batches[i % N_QUERY_BATCHES], outs[i % NSETS])
+            searcher.flush()
+            return
         if mode == "clusters" and not args.no_pipeline:
-            # several whole batches in flight (clann_search_sharded_multi): the sharded counterpart of clann_search_device_async
+            # several whole batches in flight (clann_search_sharded_multi), all in the same phase
             i = 0
             while i < steps:
                 nb = min(args.sharded_in_flight, steps - i)
@@ -736,7 +745,10 @@ def main():
             "value_stream_ordered": global_nq / (ordered_ms / args.steps / 1000.0), "ms_per_step_stream_ordered": ordered_ms / args.steps,
             "pipeline": ("clann_search_device_async: three batches in flight on three internal streams; outputs identical to the "
                          "stream-ordered call (checked)") if pipelined else
-                        (f"clann_search_sharded_multi: {args.sharded_in_flight} global batches in flight, their phases interleaved on internal streams"
+                        (("clann_search_sharded_submit / _flush: one global batch per step into a software pipeline across the steps "
+                          "(route | round one | open-query scoring | round two + merge of four consecutive batches overlap)"
+                          if args.sharded_pipeline == "stream" else
+                          f"clann_search_sharded_multi: {args.sharded_in_flight} global batches in flight, their phases interleaved on internal streams")
                          if mode == "clusters" and not args.no_pipeline else "none (stream-ordered calls)"),
             "data": "synthetic", "config": cfg_json, "parallelism": parallelism, "recall_at_k": recall, "recall_queries_checked": nchk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": global_nq * d * 4,

@@ -47,6 +47,8 @@ extern "C" {
     pub fn clann_comm_unique_id(out: *mut u8, cap: u64) -> i32;
     pub fn clann_comm_init(index: *mut clann_index, rank: i32, world: i32, unique_id: *const u8) -> i32;
     pub fn clann_search_sharded(index: *mut clann_index, d_queries: *const f32, nq: u64, d_ids: *mut u32, d_dists: *mut f32, d_counts: *mut u32, stream: *mut c_void) -> i32;
+    pub fn clann_search_sharded_submit(index: *mut clann_index, d_queries: *const f32, nq: u64, d_ids: *mut u32, d_dists: *mut f32, d_counts: *mut u32, stream: *mut c_void) -> i32;
+    pub fn clann_search_sharded_flush(index: *mut clann_index, stream: *mut c_void) -> i32;
     pub fn clann_search_flush(index: *mut clann_index, stream: *mut c_void) -> i32;
 
     // legacy per-cluster ABI (c_binder.h:14-26)

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "clann_init_with_config", "clann_init_with_config_ex", "clann_set_option", "clann_set_delta", "clann_set_clustering", "clann_import_reference", "clann_set_functions",
     "clann_build", "clann_search", "clann_search_device", "clann_search_device_async", "clann_search_flush", "clann_search_async", "clann_search_wait", "clann_search_begin", "clann_search_step", "clann_state_bytes",
     "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
-    "clann_comm_unique_id", "clann_comm_init", "clann_set_collectives", "clann_search_sharded", "clann_search_sharded_pair", "clann_search_sharded_multi", "clann_shard_stats",
+    "clann_comm_unique_id", "clann_comm_init", "clann_set_collectives", "clann_search_sharded", "clann_search_sharded_pair", "clann_search_sharded_multi", "clann_search_sharded_submit", "clann_search_sharded_flush", "clann_shard_stats",
     "clann_last_search_profile", "clann_tune", "clann_last_error", "clann_destroy",
     "CPUFFINN_load_from_file", "CPUFFINN_index_create", "CPUFFINN_index_rebuild", "CPUFFINN_index_insert_cosine",
     "CPUFFINN_search_cosine", "CPUFFINN_get_distance_computations", "CPUFFINN_clear_distance_computations",
@@ -93,6 +93,10 @@ def load() -> C.CDLL:
     L.clann_search_sharded_pair.argtypes = [_vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.clann_search_sharded_multi.restype = _i32
     L.clann_search_sharded_multi.argtypes = [_vp, _i32, _vp, _u64, _vp, _vp, _vp, _vp]
+    L.clann_search_sharded_submit.restype = _i32
+    L.clann_search_sharded_submit.argtypes = [_vp, _vp, _u64, _vp, _vp, _vp, _vp]
+    L.clann_search_sharded_flush.restype = _i32
+    L.clann_search_sharded_flush.argtypes = [_vp, _vp]
     L.clann_shard_stats.restype, L.clann_shard_stats.argtypes = _i32, [_vp, C.POINTER(_u64), C.POINTER(_u64), _vp]
     L.clann_export.restype, L.clann_export.argtypes = _i32, [_vp, _i32, _u64, _vp, _u64, C.POINTER(_u64)]
     L.clann_last_search_profile.restype, L.clann_last_search_profile.argtypes = _i32, [_vp, _vp, _vp]

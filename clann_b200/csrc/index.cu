@@ -561,6 +561,14 @@ struct clann_index {
         uint64_t nq = 0;               // size the buffers were made for
         uint64_t q_lo = 0, q_n = 0;    // the sub-batch of the current call
         uint32_t n0 = 0, n1 = 0, n2 = 0;
+        // streaming mode (sharded_submit): the batch this lane carries and the phase it runs at the next tick (0 route, 1 round one,
+        // 2 scoring of the open queries, 3 round two + merge); phase < 0 = idle
+        int phase = -1;
+        const float* sq = nullptr;
+        uint32_t* s_ids = nullptr;
+        float* s_dists = nullptr;
+        uint32_t* s_counts = nullptr;
+        cudaEvent_t fork = nullptr;
         cudaStream_t stream = nullptr;
         cudaEvent_t ready = nullptr, done = nullptr;
         cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last call
@@ -572,6 +580,7 @@ struct clann_index {
         bool last_was_sharded = false;
         int lanes_used = 0;
         cudaEvent_t fork = nullptr;
+        uint64_t tick = 0;  // streaming mode: submissions so far
     } sh;
     // {clusters visited, queries} of the last finished batch, written by k_finish into mapped host memory and read without any
     // synchronisation: when queries walk many clusters (avg > 3: overlapping or unclustered data) the dense first-visit
@@ -1665,6 +1674,7 @@ struct clann_index {
         require_built();
         if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded_multi needs an index built with shard_count > 1");
         if (nb < 1 || nb > kShardLanes) throw StatusError(CLANN_ERR_ARG, "1 to 4 batches in flight");
+        require_no_stream_in_flight();
         if (nq == 0) return;
         if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
         SearchWs* saved = W;
@@ -1694,9 +1704,89 @@ struct clann_index {
         W = saved;
     }
 
+    // Streaming form (clann_search_sharded_submit / _flush): a software pipeline over consecutive calls. Every call ("tick") takes
+    // one new batch and moves each of the up to four batches in flight forward by ONE phase, newest first:
+    //     tick t:  route(t)  round one(t-1)  scoring of the open queries(t-2)  round two + merge(t-3)
+    // so that (i) the count a phase reads back was produced a whole tick earlier — the host no longer waits inside a batch, only for
+    // the previous tick's round one, after the next round one is already queued —, (ii) a collective that waits for a slower rank
+    // stalls only its own lane's stream, and (iii) the latency-bound round two of one batch runs in the shadow of the round one of a
+    // later batch instead of next to the round two of its twin (search_sharded_multi keeps its batches in the same phase). The
+    // collectives are issued in the same order on every rank as long as every rank makes the same sequence of calls. Results of a
+    // batch are complete (in stream order on the stream of the call that finishes it) after three more submissions or a flush.
+    void require_no_stream_in_flight() const {
+        for (const auto& ln : lanes)
+            if (ln.phase >= 0) throw StatusError(CLANN_ERR_SEARCH, "batches submitted with clann_search_sharded_submit are in flight: call clann_search_sharded_flush first");
+    }
+
+    void sharded_tick(cudaStream_t s) {
+        for (int age = 0; age < kShardLanes; age++) {
+            if ((uint64_t)age > sh.tick) break;
+            ShardLane& ln = lanes[(sh.tick - age) % kShardLanes];
+            switch (ln.phase) {
+                case 0: lane_route(ln, ln.sq); ln.phase = 1; break;
+                case 1: lane_round_one(ln, ln.sq); ln.phase = 2; break;
+                case 2: lane_score_open(ln, ln.sq); ln.phase = 3; break;
+                case 3:
+                    lane_round_two(ln, ln.sq, ln.s_ids, ln.s_dists, ln.s_counts);
+                    CLANN_CUDA(cudaStreamWaitEvent(s, ln.done, 0));  // the finishing call's stream sees the results
+                    ln.phase = -1;
+                    break;
+                default: break;
+            }
+        }
+        sh.tick++;
+    }
+
+    void sharded_submit(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
+        require_built();
+        if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded_submit needs an index built with shard_count > 1");
+        if (nq == 0 || nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch of 1 .. 2^32 - 1 queries");
+        SearchWs* saved = W;
+        try {
+            ShardLane& ln = lanes[sh.tick % kShardLanes];
+            if (ln.phase >= 0) throw StatusError(CLANN_ERR_SEARCH, "sharded pipeline out of step");  // cannot happen: a batch lives four ticks
+            lane_prepare(ln, nq);
+            if (!ln.fork) CLANN_CUDA(cudaEventCreateWithFlags(&ln.fork, cudaEventDisableTiming));
+            CLANN_CUDA(cudaEventRecord(ln.fork, s));
+            CLANN_CUDA(cudaStreamWaitEvent(ln.stream, ln.fork, 0));  // the caller's queries are ready
+            ln.q_lo = 0;
+            ln.q_n = nq;
+            ln.sq = d_queries;
+            ln.s_ids = d_ids;
+            ln.s_dists = d_dists;
+            ln.s_counts = d_counts;
+            ln.phase = 0;
+            sharded_tick(s);
+            sh.lanes_used = 0;  // per-batch counters / phase times are those of the blocking calls
+            sh.last_was_sharded = true;
+            last_nq = 0;
+        } catch (...) {
+            W = saved;
+            throw;
+        }
+        W = saved;
+    }
+
+    void sharded_flush(cudaStream_t s) {
+        SearchWs* saved = W;
+        try {
+            for (int i = 0; i < kShardLanes - 1; i++) {
+                bool any = false;
+                for (auto& ln : lanes) any = any || ln.phase >= 0;
+                if (!any) break;
+                sharded_tick(s);  // a tick without a new batch (its lane stays idle)
+            }
+        } catch (...) {
+            W = saved;
+            throw;
+        }
+        W = saved;
+    }
+
     void search_sharded(const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists, uint32_t* d_counts, cudaStream_t s) {
         require_built();
         if (shard_count < 2) throw StatusError(CLANN_ERR_CONFIG, "clann_search_sharded needs an index built with shard_count > 1");
+        require_no_stream_in_flight();
         if (nq == 0) return;
         if (nq >= (1ull << 32)) throw StatusError(CLANN_ERR_ARG, "batch too large");
         const uint32_t k = (uint32_t)cfg.k, d = g.d;
@@ -2111,6 +2201,21 @@ int clann_search_sharded_multi(clann_index* index, int n_batches, const float* c
         for (int i = 0; i < n_batches && i < 4; i++)
             if (nq && (!d_queries[i] || !d_ids[i] || !d_dists[i] || !d_counts[i])) throw StatusError(CLANN_ERR_ARG, "null pointer");
         index->search_sharded_multi(n_batches, d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search_sharded_submit(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
+                                uint32_t* d_counts, void* stream) {
+    return guarded([&] {
+        if (!index || !d_queries || !d_ids || !d_dists || !d_counts) throw StatusError(CLANN_ERR_ARG, "null pointer");
+        index->sharded_submit(d_queries, nq, d_ids, d_dists, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int clann_search_sharded_flush(clann_index* index, void* stream) {
+    return guarded([&] {
+        if (!index) throw StatusError(CLANN_ERR_ARG, "null index");
+        index->sharded_flush(static_cast<cudaStream_t>(stream));
     });
 }
 

@@ -168,6 +168,18 @@ class ClusterShardedSearcher:
                                                    arr([o[0].data_ptr() for o in outs]), arr([o[1].data_ptr() for o in outs]),
                                                    arr([o[2].data_ptr() for o in outs]), stream))
 
+    def submit(self, d_queries, out) -> None:
+        """Streaming form (clann_search_sharded_submit): one more batch into the software pipeline; out = (ids, dists, counts).
+        The batch's buffers must stay untouched until three more submits or flush(); every rank makes the same calls."""
+        import torch
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _check(self.lib.clann_search_sharded_submit(self.index.handle, d_queries.data_ptr(), d_queries.shape[0], out[0].data_ptr(),
+                                                    out[1].data_ptr(), out[2].data_ptr(), stream))
+
+    def flush(self) -> None:
+        import torch
+        _check(self.lib.clann_search_sharded_flush(self.index.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
     def stats(self):
         a, b = C.c_uint64(0), C.c_uint64(0)
         ms = (C.c_float * 6)()

@@ -146,6 +146,16 @@ int clann_search_sharded_pair(clann_index* index, const float* d_queries_a, cons
 /* The same for 1 to 4 batches (host arrays of device pointers, one entry per batch). */
 int clann_search_sharded_multi(clann_index* index, int n_batches, const float* const* d_queries, uint64_t nq, uint32_t* const* d_ids,
                                float* const* d_dists, uint32_t* const* d_counts, void* stream);
+/* Streaming form: a software pipeline across calls. Every call takes one new batch and advances each of the up to four batches in
+ * flight by one phase (route | round one | scoring of the open queries | round two + merge), newest first, each on its own
+ * internal stream: the latency-bound second round of one batch runs in the shadow of a later batch's first round, a count the host
+ * reads back was produced a whole call earlier, and a collective that waits for a slower rank stalls only its own batch. The
+ * query and output buffers of a batch must stay untouched until three more batches have been submitted or clann_search_sharded_flush
+ * has returned; its results are then complete in stream order on the stream of that call. Every rank must make the same sequence
+ * of submit / flush calls (the collectives are issued in call order). Results per batch are those of clann_search_sharded. */
+int clann_search_sharded_submit(clann_index* index, const float* d_queries, uint64_t nq, uint32_t* d_ids, float* d_dists,
+                                uint32_t* d_counts, void* stream);
+int clann_search_sharded_flush(clann_index* index, void* stream);
 /* queries routed to this rank in round one / still open in round two of the last clann_search_sharded; phase_ms[6] (may be NULL) =
  * device time of its phases: route scoring, route all-gather + selection, round one, bound all-reduce + selection, round two, merge */
 int clann_shard_stats(clann_index* index, uint64_t* routed_round_one, uint64_t* open_round_two, float* phase_ms);

@@ -64,6 +64,16 @@ def main():
     torch.cuda.synchronize()
     assert all(torch.equal(x, y) for x, y in zip(pair_a, (ids, dd, cc))), "pair: first batch differs"
     assert all(torch.equal(x, y) for x, y in zip(outs_b, want_b)), "pair: second batch differs"
+    # streaming form: seven batches through the staggered pipeline; every batch gets the results of the blocking call
+    seq = [dq, dq2, dq, dq, dq2, dq2, dq]
+    so = [(torch.empty_like(ids), torch.empty_like(dd), torch.empty_like(cc)) for _ in seq]
+    for x, o in zip(seq, so):
+        searcher.submit(x, o)
+    searcher.flush()
+    torch.cuda.synchronize()
+    for x, o in zip(seq, so):
+        want = (ids, dd, cc) if x is dq else want_b
+        assert all(torch.equal(a, b) for a, b in zip(o, want)), "stream: a batch differs from the blocking call"
     searcher.search_device(dq, ids, dd, cc)   # counters below are those of the single call
     torch.cuda.synchronize()
     ids, dd, cc = ids.cpu().numpy().view(np.uint32), dd.cpu().numpy(), cc.cpu().numpy().view(np.uint32)

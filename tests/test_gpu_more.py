@@ -711,6 +711,24 @@ def test_cluster_sharded_search_two_ranks_in_process(big):
             assert torch.equal(o2[0][0], ids) and torch.equal(o2[0][1], dd) and torch.equal(o2[0][2], cc)
             assert torch.equal(o2[1][0], torch.flip(ids, dims=[0])) and torch.equal(o2[1][1], torch.flip(dd, dims=[0]))
             assert torch.equal(o2[1][2], torch.flip(cc, dims=[0]))
+            # streaming form (clann_search_sharded_submit / _flush): six batches through the four-deep software pipeline, a batch of
+            # another size in between; every batch gets the results of the blocking call
+            dq3 = dq[: nq // 2].contiguous()
+            seq = [dq, dq2, dq3, dq, dq2, dq]
+            o3 = [(torch.empty((len(x), k), dtype=torch.int32, device=dev), torch.empty((len(x), k), dtype=torch.float32, device=dev),
+                   torch.empty(len(x), dtype=torch.int32, device=dev)) for x in seq]
+            for x, o in zip(seq, o3):
+                rc = L.clann_search_sharded_submit(ix.handle, x.data_ptr(), len(x), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), None)
+                assert rc == 0, cl.last_error()
+            # a blocking call while batches are in flight is refused
+            assert L.clann_search_sharded(ix.handle, dq.data_ptr(), nq, ids.data_ptr(), dd.data_ptr(), cc.data_ptr(), None) != 0
+            assert L.clann_search_sharded_flush(ix.handle, None) == 0, cl.last_error()
+            torch.cuda.synchronize()
+            want = {id(dq): (ids, dd, cc), id(dq2): tuple(torch.flip(t, dims=[0]) for t in (ids, dd, cc)),
+                    id(dq3): (ids[: nq // 2], dd[: nq // 2], cc[: nq // 2])}
+            for x, o in zip(seq, o3):
+                for got, exp in zip(o, want[id(x)]):
+                    assert torch.equal(got, exp)
         except Exception as e:  # noqa: BLE001
             errors.append((rank, repr(e)))
             transport.barrier.abort()
