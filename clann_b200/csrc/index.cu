@@ -1219,6 +1219,7 @@ struct clann_index {
         p.shard_rank = shard_rank;
         p.max_cluster = h_sizes.empty() ? 0u : *std::max_element(h_sizes.begin(), h_sizes.end());
         p.prefetch_rows = 0;
+        p.reserve_sms = 0;
         return p;
     }
 

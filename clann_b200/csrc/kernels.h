@@ -98,6 +98,7 @@ struct SearchParams {
     uint32_t shard_rank;
     uint32_t max_cluster;      // largest cluster size (sizes the per-CTA similarity memo)
     uint32_t prefetch_rows;    // probe kernel: bulk-prefetch the Q15 rows of a batch into the L2 before gathering them
+    uint32_t reserve_sms;      // probe kernel: CTAs that land on the last reserve_sms SMs exit at once (room for other streams' kernels)
 };
 
 constexpr uint32_t kFsMeta = 52;  // u32 words of stream metadata per query (QueryBatch::fs_meta)

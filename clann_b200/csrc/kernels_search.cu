@@ -827,6 +827,15 @@ template <int G, int OCC, bool DENSE, bool STREAM>
 __global__ void __launch_bounds__(256, OCC) k_probe(SearchParams p, QueryBatch b, uint32_t warp_bytes, int stop_at_foreign,
                                                     uint16_t* memo_base, uint64_t memo_stride, uint32_t smem_memo_cap) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
+    // The persistent grid fills every SM for the whole launch, so kernels of other streams (the other batches in flight of the
+    // sharded search: their collectives, selections, hashing) could only start in its last wave. With reserve_sms the CTAs that land
+    // on the last SMs leave at once — the work queue does not care who drains it — and those SMs stay free.
+    if (p.reserve_sms) {
+        uint32_t smid, nsmid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsmid));
+        if (smid + p.reserve_sms >= nsmid) return;
+    }
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     // per warp: [query row][WarpSmem][DENSE: memo of smem_memo_cap u16 + mbarrier]
     const uint32_t memo_extra = (DENSE && smem_memo_cap) ? smem_memo_cap * 2 + 16 : 0;
@@ -2081,6 +2090,11 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, int stop
     const uint64_t stride = b.memo_stride;
     SearchParams pp = p;
     pp.prefetch_rows = (uint32_t)tune_get("probe_prefetch_rows", 0);  // A/B knob (measured: 3.22 vs 3.12 ms, off by default)
+    // knob shard_reserve_sms: SMs the probe of a sharded search leaves to the other batches in flight (their NCCL kernels need whole SMs)
+    if (stop_at_foreign) {
+        const int64_t r = tune_get("shard_reserve_sms", 0);
+        pp.reserve_sms = (r > 0 && r < sm_count / 2) ? (uint32_t)r : 0u;
+    }
     k_probe<G, OCC, DENSE, STREAM><<<(unsigned)grid, warps * 32, smem, s>>>(pp, b, wb, stop_at_foreign, use, stride, smem_memo_cap);
 }
 
