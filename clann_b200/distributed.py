@@ -1,14 +1,18 @@
 """Multi-GPU search: one process per GPU, clusters sharded by owner, queries replicated.
 
-The reference's per-query loop (src/core/index.rs:331-432) is sequential over clusters: each visit needs the running top-k
-heap (the prune test :342-361 and max_sim :382-389). Sharding keeps that exact: every rank holds the full visiting order;
-in each step a rank advances every unfinished query through the consecutive clusters it owns and stops at the first
-foreign one; one all-gather of the per-query state (heap + position, 32 + 8k bytes) then hands each query to the owner
-of its next cluster. Results are therefore identical to the single-GPU search, and every (query, cluster) visit is done
-exactly once, by the GPU that holds the cluster.
+Two protocols, both implemented in libclann_b200.so; this module only drives them from Python:
 
-torch.distributed (NCCL over NVLink) is the plumbing for the one collective the path has; the kernels are in
-libclann_b200.so. The control loop below is backend-agnostic so it can be exercised on CPU with gloo (tests/).
+* ClusterShardedSearcher — the measured mode (clann_search_sharded and its multi-batch / streaming forms):
+  queries are routed to the owner of their nearest cluster, which runs the reference's loop (src/core/index.rs:331-432) for as long
+  as the walk stays in its own clusters; one all-reduce(min) of a per-query bound; a pruned second round on every rank; one
+  all-gather of the top-k lists and a k-way merge. The collectives are issued inside the library (NCCL, or two callbacks: see
+  InProcessTransport). torch.distributed only carries the 128-byte NCCL id at start-up.
+* ShardedSearcher — the exact stepping protocol: every rank holds the full visiting order; in each step a rank advances every
+  unfinished query through the consecutive clusters it owns and stops at the first foreign one; one all-gather of the per-query
+  state (heap + position, 32 + 8k bytes) hands each query to the owner of its next cluster. Bit-identical to the single-GPU search,
+  one collective per hand-over; the control loop below is backend-agnostic so it can be exercised on CPU with gloo (tests/).
+
+The small numpy helpers (order_bits, pack_bound, merge_topk) restate the device's exchange formats for the CPU tests.
 """
 from __future__ import annotations
 
