@@ -705,6 +705,78 @@ int orc_index_search(const orc_index* ix, const float* qf, uint32_t k, float rec
     return r;
 }
 
+/* collection.hpp:671-765 — search_maps_no_filter (filter_type 1) and search_maps_simple_filter (filter_type 2), driven by
+ * search_formatted_query (:543-601). No ring, no passing buffer, no max_sim: every entry of every non-empty range, in table
+ * order, goes to MaxBuffer::insert (after the sketch test of slot `range_idx % 32` in the Simple variant, whose threshold is
+ * refreshed after each range, :739-740); one stop test per depth with table_idx = last_tables = L. Neither variant touches the
+ * distance_computations / candidates counters (only :865,904,921 do). tr->stop_depth = hash_length (:704,758). */
+int orc_index_search_filter(const orc_index* ix, const float* qf, uint32_t k, float recall, float max_sim, int filter_type,
+                            uint32_t* out, orc_trace* tr) {
+    if (filter_type != 1 && filter_type != 2) return orc_index_search(ix, qf, k, recall, max_sim, out, tr);
+    const orc_functions* fn = &ix->fn;
+    uint32_t L = fn->L;
+    int16_t* q = (int16_t*)malloc(sizeof(int16_t) * fn->sl);
+    orc_store_q15(qf, fn->d, fn->sl, q);
+    orc_trace local;
+    if (!tr) {
+        memset(&local, 0, sizeof(local));
+        tr = &local;
+    }
+    tr->distance_computations = tr->candidates = tr->stop_depth = tr->stop_table = tr->n_batches = 0;
+    tr->passing_len = 0;
+    tr->kth = 0;
+    tr->max_sketch_diff = ORC_SKETCH_BITS;
+    if (ix->n < 100) { /* collection.hpp:550-555, before the switch on the filter type */
+        int r = search_bf(ix, q, k, out);
+        free(q);
+        return r;
+    }
+    uint32_t* codes = (uint32_t*)malloc(sizeof(uint32_t) * L);
+    uint64_t qs[ORC_NUM_SKETCHES];
+    orc_codes(fn, q, codes);
+    orc_sketch(fn, q, qs);
+    uint32_t max_diff = ORC_SKETCH_BITS;
+    maxbuffer mb;
+    mb_init(&mb, k);
+    size_t tl = (size_t)ix->n + 2 * ORC_SEGMENT;
+    pm_query* qo = (pm_query*)malloc(sizeof(pm_query) * L);
+    for (uint32_t t = 0; t < L; t++) {
+        uint32_t a = orc_anchor(ix, t, codes[t]);
+        qo[t].hash = codes[t];
+        qo[t].mask = 0xffffffffu;
+        qo[t].start = qo[t].end = a;
+    }
+    for (uint32_t depth = ORC_MAX_HASHBITS; depth > 0; depth--) {
+        uint32_t range_idx = 0; /* position among the non-empty ranges (fill_ranges skips the empty ones, :660) */
+        for (uint32_t t = 0; t < L; t++) {
+            uint32_t rs, re;
+            next_range(ix, t, &qo[t], &rs, &re);
+            if (rs == re) continue;
+            uint32_t slot = range_idx % ORC_NUM_SKETCHES;
+            for (uint32_t pos = rs; pos < re; pos++) {
+                uint32_t idx = ix->indices[t * tl + pos];
+                if (filter_type == 2 && !passes(qs, max_diff, ix->sketches[((size_t)idx << 5) | slot], slot)) continue;
+                mb_insert(&mb, idx, orc_similarity(q, ix->q15 + (size_t)idx * fn->sl, fn->sl));
+            }
+            if (filter_type == 2) max_diff = orc_max_sketch_diff(mb.minval);
+            range_idx++;
+        }
+        float fp = orc_failure_probability(fn, depth, L, L, mb.minval);
+        if (fp <= 1 - recall) {
+            tr->stop_depth = depth;
+            tr->stop_table = L;
+            break;
+        }
+    }
+    tr->kth = mb.minval;
+    tr->max_sketch_diff = max_diff;
+    mb_filter(&mb);
+    for (uint32_t i = 0; i < mb.inserted; i++) out[i] = mb.data[i].idx;
+    int r = (int)mb.inserted;
+    free(mb.data); free(q); free(codes); free(qo);
+    return r;
+}
+
 /* ------------------------------------------------------------------------------------------------ L3 (CLANN) */
 
 /* index.rs:78-80 */

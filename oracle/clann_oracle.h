@@ -77,6 +77,10 @@ uint32_t orc_anchor(const orc_index* ix, uint32_t t, uint32_t hash);
 void orc_query_ranges(const orc_index* ix, const uint32_t* codes, uint32_t* anchors, uint32_t* ranges);
 /* Index::search: returns count of ids (best first) */
 int orc_index_search(const orc_index* ix, const float* q, uint32_t k, float recall, float max_sim, uint32_t* out, orc_trace* tr);
+/* Index::search with FilterType::None (1) / FilterType::Simple (2), collection.hpp:671-765 (both ignore max_sim); 0 = the
+ * default path */
+int orc_index_search_filter(const orc_index* ix, const float* q, uint32_t k, float recall, float max_sim, int filter_type,
+                            uint32_t* out, orc_trace* tr);
 
 /* --- L3 (CLANN) */
 uint64_t orc_num_clusters(float factor, uint64_t n);

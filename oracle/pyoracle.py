@@ -134,7 +134,8 @@ class OracleIndex:
         self.lib.lib.orc_query_ranges(self.h, _ptr(codes), _ptr(anchors), _ptr(ranges))
         return anchors, ranges
 
-    def search(self, q, k, recall, max_sim=float("-inf"), trace=False):
+    def search(self, q, k, recall, max_sim=float("-inf"), trace=False, filter_type=0):
+        """filter_type: 0 = FilterType::Default, 1 = None, 2 = Simple (collection.hpp:22-34)."""
         q = np.ascontiguousarray(q, np.float32)
         out = np.zeros(max(k, 1), np.uint32)
         tr = OrcTrace()
@@ -144,7 +145,11 @@ class OracleIndex:
             batches = np.zeros(1 << 14, np.uint32)
             tr.passing, tr.passing_cap = _ptr(passing), passing.size
             tr.batch_sizes, tr.batch_cap = _ptr(batches), batches.size
-        cnt = self.lib.lib.orc_index_search(self.h, _ptr(q), k, float(recall), float(max_sim), _ptr(out), C.byref(tr))
+        if filter_type:
+            cnt = self.lib.lib.orc_index_search_filter(self.h, _ptr(q), k, float(recall), float(max_sim), int(filter_type), _ptr(out),
+                                                       C.byref(tr))
+        else:
+            cnt = self.lib.lib.orc_index_search(self.h, _ptr(q), k, float(recall), float(max_sim), _ptr(out), C.byref(tr))
         info = dict(distance_computations=tr.distance_computations, candidates=tr.candidates, stop_depth=tr.stop_depth,
                     stop_table=tr.stop_table, n_batches=tr.n_batches, kth=tr.kth, max_sketch_diff=tr.max_sketch_diff)
         if trace:
@@ -190,6 +195,8 @@ class OracleLib:
         L.orc_query_ranges.argtypes = [_vp, _vp, _vp, _vp]
         L.orc_index_search.restype = _i32
         L.orc_index_search.argtypes = [_vp, _vp, _u32, _f32, _f32, _vp, _vp]
+        L.orc_index_search_filter.restype = _i32
+        L.orc_index_search_filter.argtypes = [_vp, _vp, _u32, _f32, _f32, _i32, _vp, _vp]
         L.orc_num_clusters.restype, L.orc_num_clusters.argtypes = _u64, [_f32, _u64]
         L.orc_ndarray_dot.restype, L.orc_ndarray_dot.argtypes = _f32, [_vp, _vp, C.c_size_t]
         L.orc_distance_point.restype, L.orc_distance_point.argtypes = _f32, [_vp, _f32, _vp, _u32]
@@ -366,10 +373,15 @@ class RefIndex:
     def rebuild(self, L):
         return self.lib.lib.ref_index_rebuild(self.h, L)
 
-    def search(self, q, k, recall, max_sim=float("-inf")):
+    def search(self, q, k, recall, max_sim=float("-inf"), filter_type=0):
+        """filter_type: the reference's FilterType (collection.hpp:22-34): 0 = Default, 1 = None, 2 = Simple."""
         q = np.ascontiguousarray(q, np.float32)
         out, met = np.zeros(max(k, 1), np.uint32), np.zeros(4, np.uint32)
-        c = self.lib.lib.ref_index_search(self.h, _ptr(q), k, float(recall), float(max_sim), _ptr(out), out.size, _ptr(met))
+        if filter_type:
+            c = self.lib.lib.ref_index_search_filter(self.h, _ptr(q), k, float(recall), float(max_sim), int(filter_type), _ptr(out),
+                                                     out.size, _ptr(met))
+        else:
+            c = self.lib.lib.ref_index_search(self.h, _ptr(q), k, float(recall), float(max_sim), _ptr(out), out.size, _ptr(met))
         if c < 0:
             raise RuntimeError("reference search threw")
         return out[:c].copy(), dict(distance_computations=int(met[0]), candidates=int(met[1]), hash_length=int(met[2]),
@@ -455,6 +467,8 @@ class RefLib:
         L.ref_index_rebuild.restype, L.ref_index_rebuild.argtypes = _u64, [_vp, C.c_uint]
         L.ref_index_search.restype = _i32
         L.ref_index_search.argtypes = [_vp, _vp, C.c_uint, _f32, _f32, _vp, _i32, _vp]
+        L.ref_index_search_filter.restype = _i32
+        L.ref_index_search_filter.argtypes = [_vp, _vp, C.c_uint, _f32, _f32, _i32, _vp, _i32, _vp]
         L.ref_index_serialize.restype, L.ref_index_serialize.argtypes = _u64, [_vp, _vp, _u64]
         L.ref_index_deserialize.restype, L.ref_index_deserialize.argtypes = _vp, [_vp, _u64]
         L.ref_index_size.restype, L.ref_index_size.argtypes = _u32, [_vp]

@@ -201,6 +201,33 @@ int ref_index_search(void* h, const float* q, unsigned k, float recall, float ma
     return n;
 }
 
+// The same through Index::search's FilterType argument (collection.hpp:22-34,324-334): 0 = Default, 1 = None, 2 = Simple.
+int ref_index_search_filter(void* h, const float* q, unsigned k, float recall, float max_sim, int filter_type, uint32_t* out, int cap,
+                            uint32_t* metrics) {
+    auto* hh = static_cast<Handle*>(h);
+    puffinn::g_performance_metrics.clear();
+    const puffinn::FilterType ft = filter_type == 1   ? puffinn::FilterType::None
+                                   : filter_type == 2 ? puffinn::FilterType::Simple
+                                                      : puffinn::FilterType::Default;
+    std::vector<uint32_t> res;
+    try {
+        res = hh->index->search(std::vector<float>(q, q + hh->dim), k, recall, max_sim, ft);
+    } catch (...) {
+        return -1;
+    }
+    auto qm = puffinn::g_performance_metrics.get_query_metrics();
+    if (metrics) {
+        auto& m = qm.back();
+        metrics[0] = m.distance_computations;
+        metrics[1] = m.candidates;
+        metrics[2] = m.hash_length;
+        metrics[3] = m.considered_maps;
+    }
+    int n = std::min<int>(cap, (int)res.size());
+    for (int i = 0; i < n; i++) out[i] = res[i];
+    return n;
+}
+
 // Index::serialize (collection.hpp:185-203). Returns the stream size; copies min(size, cap) bytes.
 uint64_t ref_index_serialize(void* h, uint8_t* dst, uint64_t cap) {
     auto* hh = static_cast<Handle*>(h);

@@ -19,6 +19,8 @@ CASES = {
     "puffinn_d100": dict(n=300, d=100, L=6, seed=2100, nq=30),
 }
 SEARCHES = [(10, 0.9, float("-inf")), (1, 0.5, 0.6), (5, 0.95, 0.75)]
+# FilterType::None (1) / FilterType::Simple (2) of Index::search (collection.hpp:22-34,671-765): (k, recall)
+FILTER_SEARCHES = [(10, 0.9), (1, 0.5), (5, 0.95), (3, 0.2)]
 
 
 def main():
@@ -54,5 +56,37 @@ def main():
         ix.free()
 
 
+def filters():
+    """<name>_filters.npz: the reference's answers with FilterType::None / Simple on the index stored in <name>.npz (the stream is
+    loaded, not rebuilt, so the two fixtures describe the same index): ids best first, their count, and hash_length — the depth
+    at which the per-depth stop rule fired (0 = never)."""
+    R = RefLib()
+    for name in CASES:
+        g = np.load(os.path.join(HERE, name + ".npz"))
+        ix = R.index_from_stream(g["stream"].tobytes())
+        nq = len(g["queries"])
+        res_ids = np.full((2, len(FILTER_SEARCHES), nq, 10), 0xFFFFFFFF, np.uint32)
+        res_cnt = np.zeros((2, len(FILTER_SEARCHES), nq), np.uint32)
+        res_depth = np.zeros((2, len(FILTER_SEARCHES), nq), np.uint32)
+        for fi, ft in enumerate((1, 2)):
+            for si, (k, rec) in enumerate(FILTER_SEARCHES):
+                for qi, q in enumerate(g["queries"]):
+                    ids, m = ix.search(q, k, rec, filter_type=ft)
+                    res_ids[fi, si, qi, : len(ids)] = ids
+                    res_cnt[fi, si, qi] = len(ids)
+                    res_depth[fi, si, qi] = m["hash_length"]
+                    assert m["distance_computations"] == 0 and m["candidates"] == 0  # neither variant counts (only :865,904,921)
+        out = os.path.join(HERE, name + "_filters.npz")
+        np.savez_compressed(out, filter_types=np.array([1, 2]), searches=np.array(FILTER_SEARCHES, np.float64), res_ids=res_ids,
+                            res_cnt=res_cnt, res_depth=res_depth)
+        print(name + "_filters", os.path.getsize(out) // 1024, "KiB")
+        ix.free()
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["filters"]:
+        build()
+        filters()
+    else:
+        main()
+        filters()

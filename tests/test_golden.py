@@ -45,3 +45,19 @@ def test_oracle_reproduces_golden_queries(oracle, name):
             assert m["distance_computations"] == dc and m["candidates"] == cand and m["stop_depth"] == hl
             assert ((24 - hl) * L + m["stop_table"] if hl else 0) == maps
     oi.free()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden_filter_types(oracle, name):
+    """FilterType::None / FilterType::Simple (collection.hpp:671-765) on the same stored index: ids in the reference's order and
+    the depth its per-depth stop rule fired at (tests/golden/make_golden.py filters)."""
+    g, f = load(name), load(name + "_filters")
+    oi = oracle.index_import(g["stream"].tobytes())
+    for fi, ft in enumerate(f["filter_types"]):
+        for si, (k, rec) in enumerate(f["searches"]):
+            for qi, q in enumerate(g["queries"]):
+                ids, m = oi.search(q, int(k), float(rec), filter_type=int(ft))
+                cnt = int(f["res_cnt"][fi, si, qi])
+                assert np.array_equal(ids, f["res_ids"][fi, si, qi, :cnt]), (ft, si, qi)
+                assert m["stop_depth"] == int(f["res_depth"][fi, si, qi])
+    oi.free()

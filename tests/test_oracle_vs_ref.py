@@ -55,6 +55,33 @@ def test_index_build_and_search(oracle, reflib, n, d, L):
     ri.free(); oi.free(); ob.free()
 
 
+@pytest.mark.parametrize("n,d,L", [(1500, 33, 24), (900, 100, 10), (60, 25, 4)])
+def test_filter_type_none_and_simple(oracle, reflib, n, d, L):
+    """Index::search with FilterType::None / FilterType::Simple (collection.hpp:22-34,671-765): ids in order, the depth the
+    per-depth stop rule fired at (hash_length), considered_maps = (24 - depth + 1) L (:706-707,760-761), and counters that stay
+    at zero (neither variant calls add_candidates / add_distance_computations). n = 60 takes the brute-force path (:550-555)."""
+    rng = np.random.default_rng(n + L)
+    centres = rng.standard_normal((5, d)).astype(np.float32)
+    X = (centres[rng.integers(0, 5, n)] + 0.5 * rng.standard_normal((n, d))).astype(np.float32)
+    ri = reflib.index(d, X, L, seed=300 + d)
+    oi = oracle.index_import(ri.serialize())
+    Q = (X[rng.integers(0, n, 40)] + 0.15 * rng.standard_normal((40, d))).astype(np.float32)
+    depths = set()
+    for ft in (1, 2):
+        for k, rec in [(10, 0.9), (1, 0.5), (40, 0.95), (3, 0.2)]:
+            for q in Q:
+                r_ids, rm = ri.search(q, k, rec, filter_type=ft)
+                o_ids, om = oi.search(q, k, rec, filter_type=ft)
+                assert np.array_equal(r_ids, o_ids), (ft, k, rec)
+                assert rm["hash_length"] == om["stop_depth"]
+                assert rm["considered_maps"] == ((24 - om["stop_depth"] + 1) * L if om["stop_depth"] else 0)
+                assert rm["distance_computations"] == 0 and rm["candidates"] == 0
+                assert om["distance_computations"] == 0 and om["candidates"] == 0
+                depths.add(om["stop_depth"])
+    assert n < 100 or len(depths) > 2  # the cases stop at different depths
+    ri.free(); oi.free()
+
+
 def test_failure_probability_and_sketch_threshold(oracle, reflib):
     rng = np.random.default_rng(1)
     X = rng.standard_normal((200, 100)).astype(np.float32)
