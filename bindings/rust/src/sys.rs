@@ -60,4 +60,6 @@ extern "C" {
     pub fn CPUFFINN_clear_distance_computations();
     pub fn CPUFFINN_save_index(index: *mut c_void, file_name: *const c_char, index_id: c_int);
     pub fn CPUFFINN_load_from_file(file_name: *const c_char, dataset_name: *const c_char) -> *mut c_void;
+    // puffinn::Index::search with its FilterType argument (0 Default, 1 None, 2 Simple; collection.hpp:22-34)
+    pub fn clann_puffinn_search(index: *mut c_void, query: *const f32, k: u32, recall: f32, max_sim: f32, filter_type: c_int, out_ids: *mut u32, out_count: *mut u32, out_stop_depth: *mut u32) -> i32;
 }

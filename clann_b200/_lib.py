@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "clann_build", "clann_search", "clann_search_device", "clann_search_device_async", "clann_search_flush", "clann_search_async", "clann_search_wait", "clann_search_begin", "clann_search_step", "clann_state_bytes",
     "clann_state_ptr", "clann_search_merge", "clann_search_end", "clann_get_counters", "clann_export",
     "clann_comm_unique_id", "clann_comm_init", "clann_set_collectives", "clann_search_sharded", "clann_search_sharded_pair", "clann_search_sharded_multi", "clann_search_sharded_submit", "clann_search_sharded_flush", "clann_shard_stats",
-    "clann_last_search_profile", "clann_tune", "clann_last_error", "clann_destroy",
+    "clann_last_search_profile", "clann_tune", "clann_last_error", "clann_destroy", "clann_puffinn_search",
     "CPUFFINN_load_from_file", "CPUFFINN_index_create", "CPUFFINN_index_rebuild", "CPUFFINN_index_insert_cosine",
     "CPUFFINN_search_cosine", "CPUFFINN_get_distance_computations", "CPUFFINN_clear_distance_computations",
     "CPUFFINN_save_index",
@@ -111,6 +111,8 @@ def load() -> C.CDLL:
     L.CPUFFINN_get_distance_computations.restype, L.CPUFFINN_get_distance_computations.argtypes = C.c_uint, []
     L.CPUFFINN_clear_distance_computations.restype, L.CPUFFINN_clear_distance_computations.argtypes = None, []
     L.CPUFFINN_save_index.restype, L.CPUFFINN_save_index.argtypes = None, [_vp, C.c_char_p, _i32]
+    L.clann_puffinn_search.restype = _i32
+    L.clann_puffinn_search.argtypes = [_vp, _vp, _u32, _f32, _f32, _i32, _vp, _vp, _vp]
     _lib = L
     return L
 

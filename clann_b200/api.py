@@ -463,6 +463,22 @@ class PuffinnIndex:
         finally:
             C.CDLL(None).free(ptr)
 
+    FILTER_DEFAULT, FILTER_NONE, FILTER_SIMPLE = 0, 1, 2  # puffinn::FilterType (collection.hpp:22-34)
+
+    def search_filtered(self, query, k: int, recall: float, filter_type: int = 0, max_sim: float = float("-inf")) -> Tuple[List[int], int]:
+        """puffinn::Index::search(query, k, recall, max_sim, filter_type) (collection.hpp:324-334): the FilterType argument the
+        reference's FFI never passes. Returns (ids best first, prefix length at which the stop rule fired or 0)."""
+        L = _lib.load()
+        q = np.ascontiguousarray(query, np.float32)
+        if self.dim and q.size != self.dim:
+            raise PuffinnSearchError(f"query has {q.size} dimensions, the index {self.dim}")
+        ids = np.empty(max(k, 1), np.uint32)
+        cnt, depth = C.c_uint32(0), C.c_uint32(0)
+        st = L.clann_puffinn_search(self.raw, _ptr(q), k, float(recall), float(max_sim), int(filter_type), _ptr(ids), C.byref(cnt),
+                                    C.byref(depth))
+        if st != 0:
+            raise PuffinnSearchError(_lib.last_error())
+        return [int(v) for v in ids[: cnt.value]], int(depth.value)
 
     def save_to_file(self, file_path: str, index_id: int) -> None:
         """puffinn.rs:61-75 -> CPUFFINN_save_index: appends record "index_{id}" (the bytes of puffinn::Index::serialize,

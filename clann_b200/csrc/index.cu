@@ -2499,11 +2499,40 @@ struct CPUFFINN {
     unsigned num_maps = 0;
     bool loaded = false;  // came from CPUFFINN_load_from_file: the fp32 rows are not known, so it cannot be rebuilt here
     DevBuf<float> d_query;
-    DevBuf<uint32_t> d_out;  // [k] ids, then count, then distance computations
+    DevBuf<uint32_t> d_out;  // [k] ids, then count, distance computations, stop point
     ~CPUFFINN() { delete ix; }
 };
 
 static std::atomic<unsigned> g_legacy_distcomp{0};  // performance.hpp:65-80: counter of the last query, process-global
+
+// One query of a legacy handle: hash + sketch the query, one warp runs Index::search (collection.hpp:543-601) with the given
+// FilterType. Writes up to k ids (best first) and returns their number; *stop = (depth << 16 | table) where the stop rule fired.
+static uint32_t legacy_search(CPUFFINN* index, const float* query, uint32_t k, float recall, float max_sim, int filter_type,
+                              uint32_t* result, uint32_t* stop) {
+    clann_index* ix = index->ix;
+    ix->cfg.k = k;
+    cudaStream_t s = 0;
+    ix->ensure_workspace(1, s);
+    ix->ensure_stop_table(recall, s);
+    index->d_query.upload(query, (size_t)index->dim, s);
+    index->d_out.ensure((size_t)k + 3);
+    SearchParams p = ix->params();
+    QueryBatch b = ix->batch(index->d_query.p, 1, nullptr, nullptr, nullptr);
+    launch_prep_queries(p, b, s);
+    launch_sketch(b.q15, ix->W->w_tiles.p, ix->W->w_ntiles, ix->d_planes.p, ix->g.sl, b.sketches, s);
+    launch_codes(b.q15, ix->w_code_tiles(1, s), ix->W->w_ntiles, ix->d_signbits.p, ix->g, b.codes, 1, ix->g.L, s);
+    launch_puffinn_search(p, b, ix->d_stop.p, max_sim, filter_type, index->d_out.p, index->d_out.p + k, index->d_out.p + k + 1,
+                          index->d_out.p + k + 2, s);
+    std::vector<uint32_t> out(k + 3);
+    CLANN_CUDA(cudaMemcpyAsync(out.data(), index->d_out.p, sizeof(uint32_t) * (k + 3), cudaMemcpyDeviceToHost, s));
+    CLANN_CUDA(cudaStreamSynchronize(s));
+    CLANN_CUDA(cudaGetLastError());
+    const uint32_t cnt = out[k] < k ? out[k] : k;
+    for (uint32_t i = 0; i < cnt; i++) result[i] = out[i];
+    g_legacy_distcomp.store(out[k + 1]);
+    if (stop) *stop = out[k + 2];
+    return cnt;
+}
 
 extern "C" {
 
@@ -2585,26 +2614,7 @@ uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, 
         if (!result) return nullptr;
         for (unsigned i = 0; i < words; i++) result[i] = 0xFFFFFFFFu;  // EMPTY_RESULT_SENTINEL, c_binder.h:8
         if (k == 0) return result;
-        clann_index* ix = index->ix;
-        ix->cfg.k = k;
-        cudaStream_t s = 0;
-        ix->ensure_workspace(1, s);
-        ix->ensure_stop_table(recall, s);
-        index->d_query.upload(query, (size_t)dimension, s);
-        index->d_out.ensure((size_t)k + 2);
-        SearchParams p = ix->params();
-        QueryBatch b = ix->batch(index->d_query.p, 1, nullptr, nullptr, nullptr);
-        launch_prep_queries(p, b, s);
-        launch_sketch(b.q15, ix->W->w_tiles.p, ix->W->w_ntiles, ix->d_planes.p, ix->g.sl, b.sketches, s);
-        launch_codes(b.q15, ix->w_code_tiles(1, s), ix->W->w_ntiles, ix->d_signbits.p, ix->g, b.codes, 1, ix->g.L, s);
-        launch_puffinn_search(p, b, ix->d_stop.p, max_sim, index->d_out.p, index->d_out.p + k, index->d_out.p + k + 1, s);
-        std::vector<uint32_t> out(k + 2);
-        CLANN_CUDA(cudaMemcpyAsync(out.data(), index->d_out.p, sizeof(uint32_t) * (k + 2), cudaMemcpyDeviceToHost, s));
-        CLANN_CUDA(cudaStreamSynchronize(s));
-        CLANN_CUDA(cudaGetLastError());
-        const uint32_t cnt = out[k] < k ? out[k] : k;
-        for (uint32_t i = 0; i < cnt; i++) result[i] = out[i];
-        g_legacy_distcomp.store(out[k + 1]);
+        legacy_search(index, query, k, recall, max_sim, 0, result, nullptr);
         return result;
     } catch (const std::exception& e) {
         g_last_error = e.what();
@@ -2612,6 +2622,22 @@ uint32_t* CPUFFINN_search_cosine(CPUFFINN* index, float* query, unsigned int k, 
     } catch (...) {
         return nullptr;
     }
+}
+
+// Index::search with its FilterType argument (collection.hpp:22-34,324-334), which c_binder.cpp never passes: 0 = Default (what
+// CPUFFINN_search_cosine runs), 1 = None, 2 = Simple (:671-765). Caller-owned result buffer of k words.
+int clann_puffinn_search(CPUFFINN* index, const float* query, uint32_t k, float recall, float max_sim, int filter_type,
+                         uint32_t* out_ids, uint32_t* out_count, uint32_t* out_stop_depth) {
+    return guarded([&] {
+        if (!index || !query || !out_ids || !out_count) throw StatusError(CLANN_ERR_ARG, "null argument");
+        if (!index->ix) throw StatusError(CLANN_ERR_NOT_BUILT, "CPUFFINN_index_rebuild has not been called");
+        if (filter_type < 0 || filter_type > 2) throw StatusError(CLANN_ERR_ARG, "filter_type: 0 = Default, 1 = None, 2 = Simple");
+        if (k == 0) throw StatusError(CLANN_ERR_CONFIG, "k must be at least 1");
+        for (uint32_t i = 0; i < k; i++) out_ids[i] = 0xFFFFFFFFu;
+        uint32_t stop = 0;
+        *out_count = legacy_search(index, query, k, recall, max_sim, filter_type, out_ids, &stop);
+        if (out_stop_depth) *out_stop_depth = stop >> 16;
+    });
 }
 
 unsigned int CPUFFINN_get_distance_computations(void) { return g_legacy_distcomp.load(); }

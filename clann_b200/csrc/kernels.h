@@ -238,9 +238,11 @@ void launch_merge_states(const SearchParams& p, const QueryBatch& b, const uint8
 void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s);
 uint32_t probe_memo_slots();  // upper bound on the memo regions any probe launch uses on the current device
 
-// Single PUFFINN index query (legacy CPUFFINN_search_cosine): one cluster, explicit recall / max_sim, Q15 brute force
-// when n < 100 (collection.hpp:550-555). out_ids[k] local ids best first, out_count.
-void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim,
-                           uint32_t* out_ids, uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s);
+// Single PUFFINN index query (legacy CPUFFINN_search_cosine / clann_puffinn_search): one cluster, explicit recall / max_sim, Q15
+// brute force when n < 100 (collection.hpp:550-555). filter_type = the reference's FilterType (collection.hpp:22-34): 0 Default
+// (search_maps), 1 None, 2 Simple (:671-765; both ignore max_sim). out_ids[k] local ids best first, out_count, out_stop =
+// (depth << 16 | table index) where the stop rule fired, 0 = never.
+void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim, int filter_type,
+                           uint32_t* out_ids, uint32_t* out_count, uint32_t* out_distcomp, uint32_t* out_stop, cudaStream_t s);
 
 }  // namespace clann

@@ -813,6 +813,99 @@ __device__ uint32_t probe_bruteforce_q15(const SearchParams& p, const WarpSmem& 
     return inserted;
 }
 
+// FilterType::None (SIMPLE = false, collection.hpp:671-714) and FilterType::Simple (SIMPLE = true, :717-765) of one PUFFINN
+// query: no ring, no passing buffer, no tail, no max_sim. Every entry of every non-empty range of a depth, tables in order,
+// goes to MaxBuffer::insert — in the Simple variant after the sketch test of slot `range_idx % 32`, range_idx counting the
+// non-empty ranges (fill_ranges drops the empty ones, :660), with the threshold refreshed after each range (:739-740). One
+// stop test per depth with table_idx = last_tables = L. The warp takes a range 128 entries at a time (lane = four consecutive
+// entries, compacted in order), so the inserts happen in the reference's order; neither variant counts candidates or distance
+// computations (only :865,904,921 do). On return sm.mb[0..cnt) holds the best entries, best first.
+template <int G, bool SIMPLE>
+__device__ uint32_t probe_cluster_plain(const SearchParams& p, const WarpSmem& sm, uint32_t c, const uint32_t* __restrict__ codes,
+                                        uint64_t code_stride, uint64_t my_sketch, const uint32_t* __restrict__ stop,
+                                        const int16_t* qrow_smem, const int (&qreg)[8], bool qreg_valid, ProbeCounters& ctr) {
+    const uint32_t L = p.g.L, k = p.k;
+    const uint32_t lane = lane_id();
+    const uint64_t off = p.offsets[c];
+    const uint32_t nc = (uint32_t)(p.offsets[c + 1] - off);
+    const uint32_t P = next_pow2(2 * k) < 32 ? 32 : next_pow2(2 * k);
+    const int16_t* rows = p.q15 + off * p.g.sl;
+    const uint64_t* sk = p.sketches + off * kNumSketches;
+    uint32_t inserted = 0, minval16 = 0, max_diff = kSketchBits;
+
+    for (uint32_t t = lane; t < L; t += 32) {  // SearchBuffers ctor (collection.hpp:642-645)
+        const uint32_t h = codes[(uint64_t)t * code_stride];
+        uint32_t A;
+        uint2 up, dn;
+        table_anchor(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc, h, A, up, dn);
+        sm.code[t] = h;
+        sm.anchor[t] = A;
+        sm.lcp_up[t] = up;
+        sm.lcp_dn[t] = dn;
+    }
+    __syncwarp();
+
+    ctr.stop_point = 0;
+    for (uint32_t depth = kMaxHashBits; depth > 0; depth--) {
+        for (uint32_t t = lane; t < L; t += 32) {  // fill_ranges; segbase[t] = this range's length in 4-entry segments
+            uint32_t nseg = 0;
+            sm.start[t] = table_range(p.tbl_hash + table_base(off, nc, L, t), p.tbl_dir + ((uint64_t)c * L + t) * kDirEntries, nc,
+                                      sm.code[t], sm.anchor[t], sm.lcp_up[t], sm.lcp_dn[t], depth, nseg);
+            sm.segbase[t] = nseg;
+        }
+        __syncwarp();
+        uint32_t range_idx = 0;
+        for (uint32_t t = 0; t < L; t++) {
+            const uint32_t len = 4u * sm.segbase[t];
+            if (len == 0) continue;
+            const uint32_t slot = range_idx & (kNumSketches - 1);
+            const uint64_t qsk = __shfl_sync(0xffffffffu, my_sketch, slot);
+            const uint32_t* idx = p.tbl_idx + table_base(off, nc, L, t) + sm.start[t];
+            for (uint32_t e0 = 0; e0 < len; e0 += kFilterBuffer) {
+                const uint32_t e = e0 + 4 * lane;
+                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+                if (e < len) {  // len is a multiple of 4: a lane holds four entries or none
+                    v0 = __ldg(idx + e); v1 = __ldg(idx + e + 1); v2 = __ldg(idx + e + 2); v3 = __ldg(idx + e + 3);
+                    if (SIMPLE) {
+                        const uint64_t s0 = __ldg(sk + ((uint64_t)v0 << 5 | slot)), s1 = __ldg(sk + ((uint64_t)v1 << 5 | slot));
+                        const uint64_t s2 = __ldg(sk + ((uint64_t)v2 << 5 | slot)), s3 = __ldg(sk + ((uint64_t)v3 << 5 | slot));
+                        p0 = (uint32_t)__popcll(s0 ^ qsk) <= max_diff; p1 = (uint32_t)__popcll(s1 ^ qsk) <= max_diff;
+                        p2 = (uint32_t)__popcll(s2 ^ qsk) <= max_diff; p3 = (uint32_t)__popcll(s3 ^ qsk) <= max_diff;
+                    } else {
+                        p0 = p1 = p2 = p3 = 1;
+                    }
+                }
+                uint32_t total;
+                uint32_t pos = warp_excl_scan(p0 + p1 + p2 + p3, total);
+                if (p0) sm.pass_idx[pos++] = v0;
+                if (p1) sm.pass_idx[pos++] = v1;
+                if (p2) sm.pass_idx[pos++] = v2;
+                if (p3) sm.pass_idx[pos++] = v3;
+                __syncwarp();
+                if (total) {
+                    rerank<G>(sm, total, rows, p.g.sl, qrow_smem, qreg, qreg_valid, nullptr);
+                    maxbuffer_insert_list(sm.mb, P, k, inserted, minval16, sm.pass_idx, sm.pass_sim, total);
+                }
+                __syncwarp();
+            }
+            if (SIMPLE) max_diff = p.msd[minval16 < 65536u ? minval16 : 65535u];  // :739-740
+            range_idx++;
+        }
+        // stop rule (:697-713, :748-764): the k-th similarity alone, all L tables of this depth done
+        const float kth = __fdiv_rn((float)minval16, 65536.0f);
+        uint32_t bin = (uint32_t)__fdiv_rn(kth, 0.005f);
+        bin = bin > (uint32_t)(kEstBins - 1) ? (uint32_t)(kEstBins - 1) : bin;
+        const uint32_t word = __ldg(stop + ((uint64_t)(depth - 1) * kEstBins + bin) * p.stop_words + (L >> 5));
+        if ((word >> (L & 31)) & 1u) {
+            ctr.stop_point = depth << 16 | L;
+            break;
+        }
+        __syncwarp();
+    }
+    maxbuffer_filter(sm.mb, P, k, inserted, minval16);
+    return inserted;
+}
+
 // ------------------------------------------------------------------------------------------------ CLANN search loop
 
 // src/core/index.rs:311-439 — one warp per query (queries are pulled from a global counter, so cheap queries make room
@@ -1353,8 +1446,8 @@ __global__ void __launch_bounds__(128) k_finish(const uint8_t* __restrict__ stat
 // Legacy single-index query (c_binder.cpp:69-96 -> collection.hpp:324-334): one warp, cluster 0, explicit max_sim.
 template <int G>
 __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatch b, const uint32_t* stop, float max_sim,
-                                                       uint32_t warp_bytes, uint32_t* out_ids, uint32_t* out_count,
-                                                       uint32_t* out_distcomp) {
+                                                       int filter_type, uint32_t warp_bytes, uint32_t* out_ids, uint32_t* out_count,
+                                                       uint32_t* out_distcomp, uint32_t* out_stop) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t lane = lane_id();
     const WarpSmem sm = carve(s_dyn + p.g.sl * 2, p.g.L, p.k);
@@ -1376,12 +1469,18 @@ __global__ void __launch_bounds__(32) k_puffinn_search(SearchParams p, QueryBatc
         cnt = probe_bruteforce_q15<G>(p, sm, 0, qrow, qreg, qreg_valid);
     } else {
         const uint64_t my_sketch = b.sketches[lane];
-        cnt = probe_cluster<G>(p, sm, 0, b.codes, 1, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, nullptr, ctr);
+        if (filter_type == 1)  // FilterType::None
+            cnt = probe_cluster_plain<G, false>(p, sm, 0, b.codes, 1, my_sketch, stop, qrow, qreg, qreg_valid, ctr);
+        else if (filter_type == 2)  // FilterType::Simple
+            cnt = probe_cluster_plain<G, true>(p, sm, 0, b.codes, 1, my_sketch, stop, qrow, qreg, qreg_valid, ctr);
+        else
+            cnt = probe_cluster<G>(p, sm, 0, b.codes, 1, my_sketch, stop, max_sim, qrow, qreg, qreg_valid, nullptr, ctr);
     }
     for (uint32_t i = lane; i < cnt; i += 32) out_ids[i] = (uint32_t)sm.mb[i];
     if (lane == 0) {
         *out_count = cnt;
         *out_distcomp = (uint32_t)ctr.distcomp;
+        *out_stop = ctr.stop_point;
     }
 }
 
@@ -2163,8 +2262,8 @@ void launch_finish(const SearchParams& p, const QueryBatch& b, cudaStream_t s) {
 }
 
 template <int G>
-static void launch_puffinn_g(const SearchParams& p, const QueryBatch& b, const uint32_t* stop, float max_sim, uint32_t* out_ids,
-                             uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s) {
+static void launch_puffinn_g(const SearchParams& p, const QueryBatch& b, const uint32_t* stop, float max_sim, int filter_type,
+                             uint32_t* out_ids, uint32_t* out_count, uint32_t* out_distcomp, uint32_t* out_stop, cudaStream_t s) {
     const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
     size_t smem = (size_t)wb + p.g.sl * 2;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
@@ -2173,17 +2272,17 @@ static void launch_puffinn_g(const SearchParams& p, const QueryBatch& b, const u
         CLANN_CUDA(cudaFuncSetAttribute(k_puffinn_search<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_puffinn_search<G><<<1, 32, smem, s>>>(p, b, stop, max_sim, wb, out_ids, out_count, out_distcomp);
+    k_puffinn_search<G><<<1, 32, smem, s>>>(p, b, stop, max_sim, filter_type, wb, out_ids, out_count, out_distcomp, out_stop);
 }
 
-void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim, uint32_t* out_ids,
-                           uint32_t* out_count, uint32_t* out_distcomp, cudaStream_t s) {
+void launch_puffinn_search(const SearchParams& p, const QueryBatch& b, const uint32_t* stop_table, float max_sim, int filter_type,
+                           uint32_t* out_ids, uint32_t* out_count, uint32_t* out_distcomp, uint32_t* out_stop, cudaStream_t s) {
     switch (rerank_group(p.g.sl)) {
-        case 2: launch_puffinn_g<2>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
-        case 4: launch_puffinn_g<4>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
-        case 8: launch_puffinn_g<8>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
-        case 16: launch_puffinn_g<16>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
-        default: launch_puffinn_g<32>(p, b, stop_table, max_sim, out_ids, out_count, out_distcomp, s); break;
+        case 2: launch_puffinn_g<2>(p, b, stop_table, max_sim, filter_type, out_ids, out_count, out_distcomp, out_stop, s); break;
+        case 4: launch_puffinn_g<4>(p, b, stop_table, max_sim, filter_type, out_ids, out_count, out_distcomp, out_stop, s); break;
+        case 8: launch_puffinn_g<8>(p, b, stop_table, max_sim, filter_type, out_ids, out_count, out_distcomp, out_stop, s); break;
+        case 16: launch_puffinn_g<16>(p, b, stop_table, max_sim, filter_type, out_ids, out_count, out_distcomp, out_stop, s); break;
+        default: launch_puffinn_g<32>(p, b, stop_table, max_sim, filter_type, out_ids, out_count, out_distcomp, out_stop, s); break;
     }
 }
 

@@ -240,6 +240,15 @@ unsigned int CPUFFINN_get_distance_computations(void);                          
 void CPUFFINN_clear_distance_computations(void);                                             /* c_binder.cpp:102-104*/
 void CPUFFINN_save_index(CPUFFINN* index, const char* file_name, int index_number);          /* c_binder.cpp:106-146*/
 
+/* puffinn::Index::search with its FilterType argument (collection.hpp:22-34,324-334,568-594), which c_binder.cpp never passes and
+ * CLANN therefore never reaches: filter_type 0 = Default (search_maps; what CPUFFINN_search_cosine runs), 1 = None
+ * (search_maps_no_filter, :671-714), 2 = Simple (search_maps_simple_filter, :717-765); 1 and 2 ignore max_sim and count no
+ * distance computations, like the reference. `query` = the index's dimension floats (host). out_ids[k] (caller-owned, host,
+ * 0xFFFFFFFF-padded) best first, *out_count their number, *out_stop_depth (optional) = the prefix length at which the stop
+ * rule fired (performance.hpp hash_length), 0 = never. Returns a clann_status. */
+int clann_puffinn_search(CPUFFINN* index, const float* query, uint32_t k, float recall, float max_sim, int filter_type,
+                         uint32_t* out_ids, uint32_t* out_count, uint32_t* out_stop_depth);
+
 #ifdef __cplusplus
 }
 #endif

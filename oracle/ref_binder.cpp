@@ -190,11 +190,14 @@ int ref_index_search(void* h, const float* q, unsigned k, float recall, float ma
     }
     auto qm = puffinn::g_performance_metrics.get_query_metrics();
     if (metrics) {
-        auto& m = qm.back();
-        metrics[0] = m.distance_computations;
-        metrics[1] = m.candidates;
-        metrics[2] = m.hash_length;
-        metrics[3] = m.considered_maps;
+        metrics[0] = metrics[1] = metrics[2] = metrics[3] = 0;
+        if (!qm.empty()) {  // the brute-force path (collection.hpp:550-555) returns before new_query()
+            auto& m = qm.back();
+            metrics[0] = m.distance_computations;
+            metrics[1] = m.candidates;
+            metrics[2] = m.hash_length;
+            metrics[3] = m.considered_maps;
+        }
     }
     int n = std::min<int>(cap, (int)res.size());
     for (int i = 0; i < n; i++) out[i] = res[i];
@@ -217,11 +220,14 @@ int ref_index_search_filter(void* h, const float* q, unsigned k, float recall, f
     }
     auto qm = puffinn::g_performance_metrics.get_query_metrics();
     if (metrics) {
-        auto& m = qm.back();
-        metrics[0] = m.distance_computations;
-        metrics[1] = m.candidates;
-        metrics[2] = m.hash_length;
-        metrics[3] = m.considered_maps;
+        metrics[0] = metrics[1] = metrics[2] = metrics[3] = 0;
+        if (!qm.empty()) {  // the brute-force path (collection.hpp:550-555) returns before new_query()
+            auto& m = qm.back();
+            metrics[0] = m.distance_computations;
+            metrics[1] = m.candidates;
+            metrics[2] = m.hash_length;
+            metrics[3] = m.considered_maps;
+        }
     }
     int n = std::min<int>(cap, (int)res.size());
     for (int i = 0; i < n; i++) out[i] = res[i];

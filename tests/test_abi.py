@@ -69,6 +69,8 @@ def test_legacy_create_rejects_unknown_type(lib, capfd):
     assert lib.CPUFFINN_search_cosine(None, None, 3, 0.9, 0.0, 4) is None or not lib.CPUFFINN_search_cosine(None, None, 3, 0.9, 0.0, 4)
     lib.CPUFFINN_clear_distance_computations()
     assert lib.CPUFFINN_get_distance_computations() == 0
+    from clann_b200 import _lib
+    assert lib.clann_puffinn_search(None, None, 1, 0.9, 0.0, 1, None, None, None) == _lib.ERR_ARG
 
 
 def test_rust_binding_matches_header(lib):
