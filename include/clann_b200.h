@@ -211,6 +211,13 @@ int clann_export(clann_index* index, int what, uint64_t arg, void* dst, uint64_t
  * ms[1] = probe kernel (the roofline kernel), launches = kernels launched. Measured with CUDA events on the call's stream. */
 int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches);
 
+/* Schedule selection. The search picks between two probe schedules that return the same bits: dense first-visit
+ * similarities + first-visit anchors ahead of a 16-warp probe, or the 24-warp gather probe alone; likewise between the tensor-pipe
+ * centre screen and the all-exact centre kernel. The choice is made per call from {clusters visited, queries} of the last batch
+ * that FINISHED on this index (published by the device into mapped host memory without synchronisation): more than 3 clusters
+ * per query selects the gather probe, more than 8 the all-exact centre kernel. Results, counters and exports never depend on it;
+ * the time of a call can depend on what ran before it. clann_tune("dense_adaptive", 0) pins the first of each pair. */
+
 /* Process-global launch-parameter knob for A/B measurements of the probe kernels ("probe" 0 = one warp per query,
  * 1 = one CTA per query; "probe_occ", "probe_warps", "probe_ctas", "probe_nomemo", ...). Never changes a result. The
  * environment variable CLANN_TUNE_<KEY> seeds a key that was not set. Not part of the reference's interface. */
