@@ -4,8 +4,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace clann {
 
@@ -32,6 +35,22 @@ struct CudaError : std::runtime_error {
             throw ::clann::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
                                      ":" + std::to_string(__LINE__) + ")");                               \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to a (function, device) pair: the largest value set so far is remembered
+// per pair and under a lock, so that host threads driving the library side by side (two in-process ranks in the tests) or a
+// process that holds indices on several devices never launch with more shared memory than the attribute allows.
+inline void ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> largest;
+    int dev = 0;
+    CLANN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = largest[std::make_pair(kernel, dev)];
+    if (bytes > cur) {
+        CLANN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+}
 
 // One work tile for the row-parallel hashing kernels: up to 32 consecutive Q15 rows that share a function set.
 struct RowTile {

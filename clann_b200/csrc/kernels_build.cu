@@ -780,11 +780,7 @@ void launch_sketch(const int16_t* q15, const RowTile* tiles, uint32_t n_tiles, c
                    cudaStream_t s) {
     if (n_tiles == 0) return;
     size_t smem = (size_t)32 * sl * sizeof(int);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_sketch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) ensure_dynamic_smem((const void*)(k_sketch), smem);
     dim3 grid(n_tiles, kNumPlanes / 256);
     k_sketch<<<grid, 256, smem, s>>>(q15, tiles, planes, sl, sketches);
 }
@@ -797,11 +793,7 @@ static void launch_codes_m(const int16_t* q15, const RowTile* tiles, uint32_t n_
         if (tune_get("codes_fast", 1) != 0) {  // knob: 0 = the plain kernel (A/B)
             constexpr int N = 1 << M;
             const size_t fsmem = (size_t)32 * (N + 4) * 4 + (size_t)8 * g.fph * kRotations * N * 4;
-            static size_t configured = 0;
-            if (fsmem > 48 * 1024 && fsmem > configured) {
-                CLANN_CUDA(cudaFuncSetAttribute(k_codes_fast<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                configured = fsmem;
-            }
+            if (fsmem > 48 * 1024) ensure_dynamic_smem((const void*)(k_codes_fast<M>), fsmem);
             k_codes_fast<M><<<grid, 256, fsmem, s>>>(q15, tiles, signbits, g, codes, code_stride, fset_stride);
             return;
         }
@@ -835,11 +827,7 @@ void launch_segment_sort(const SortSegment* segs, uint32_t n_segs, uint32_t max_
     if (n_segs == 0) return;
     const uint32_t cap = (max_len <= kSortSmemCapSmall) ? kSortSmemCapSmall : kSortSmemCapLarge;
     size_t smem = ((size_t)kSortBookWords + (size_t)4 * cap) * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_segment_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dynamic_smem((const void*)(k_segment_sort), smem);
     k_segment_sort<<<n_segs, kSortThreads, smem, s>>>(segs, cap, keys, idx, scratch_keys, scratch_idx);
 }
 

@@ -1969,11 +1969,7 @@ bool launch_first_stream(const SearchParams& p, const QueryBatch& b, cudaStream_
     const uint32_t warps = 8;
     const size_t smem = (size_t)warps * wb;
     if (smem > 200 * 1024) return false;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_first_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) ensure_dynamic_smem((const void*)(k_first_stream), smem);
     k_first_stream<<<(unsigned)((b.nq + warps - 1) / warps), warps * 32, smem, s>>>(p, b, wb);
     return true;
 }
@@ -2079,11 +2075,7 @@ bool launch_dense_sims(const SearchParams& p, const QueryBatch& b, cudaStream_t 
     const size_t smem = (size_t)kDenseRows * (p.g.sl * 2 + 16) + (size_t)kDenseQueries * p.g.sl * sizeof(int);
     dim3 grid(p.K, (p.max_cluster + kDenseRows - 1) / kDenseRows);
     if (grid.y == 0) return false;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_dense_sims, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) ensure_dynamic_smem((const void*)(k_dense_sims), smem);
     k_dense_sims<<<grid, 256, smem, s>>>(p, b);
     return true;
 }
@@ -2108,21 +2100,13 @@ void launch_center_order(const SearchParams& p, const QueryBatch& b, cudaStream_
     size_t smem = (size_t)96 * stride * sizeof(float);
     if (p.g.d <= 256) {
         const size_t tsmem = ((size_t)32 * ((p.g.d + 3) & ~3u) + (size_t)p.g.d * 65) * sizeof(float);
-        static size_t tconfigured = 0;
-        if (tsmem > 48 * 1024 && tsmem > tconfigured) {
-            CLANN_CUDA(cudaFuncSetAttribute(k_center_dist_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-            tconfigured = tsmem;
-        }
+        if (tsmem > 48 * 1024) ensure_dynamic_smem((const void*)(k_center_dist_tiled), tsmem);
         const uint32_t nchunks = (p.K + 63) / 64;
         dim3 tgrid((unsigned)((b.nq + 31) / 32), nchunks < 8 ? nchunks : 8);
         k_center_dist_tiled<<<tgrid, 256, tsmem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms,
                                                                              p.K, p.g.d, b.cdist);
     } else if (smem <= 160 * 1024) {
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            CLANN_CUDA(cudaFuncSetAttribute(k_center_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        if (smem > 48 * 1024) ensure_dynamic_smem((const void*)(k_center_dist), smem);
         k_center_dist<<<(unsigned)((b.nq + 31) / 32), 256, smem, s>>>(b.queries, b.qnorm, b.nq, p.center_rows, p.center_norms, p.K,
                                                                      p.g.d, b.cdist);
     } else {
@@ -2170,11 +2154,7 @@ static void launch_probe_go(const SearchParams& p, const QueryBatch& b, int stop
     }
     size_t smem = (size_t)warps * per_warp;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_probe<G, OCC, DENSE, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dynamic_smem((const void*)(k_probe<G, OCC, DENSE, STREAM>), smem);
     int ctas_per_sm = 0;
     CLANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_probe<G, OCC, DENSE, STREAM>, warps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
@@ -2267,11 +2247,7 @@ static void launch_puffinn_g(const SearchParams& p, const QueryBatch& b, const u
     const uint32_t wb = warp_smem_bytes(p.g.L, p.k);
     size_t smem = (size_t)wb + p.g.sl * 2;
     if (smem > 227 * 1024) throw std::invalid_argument("num_tables / k too large for the probe kernel's shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_puffinn_search<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dynamic_smem((const void*)(k_puffinn_search<G>), smem);
     k_puffinn_search<G><<<1, 32, smem, s>>>(p, b, stop, max_sim, filter_type, wb, out_ids, out_count, out_distcomp, out_stop);
 }
 

@@ -412,11 +412,7 @@ void launch_sketch_tc(const void* tiles, uint32_t n_tiles, const uint8_t* row_sl
     const uint32_t KB = kp / tc::kKBlock;
     const size_t smem = 1024 + (size_t)KB * 2 * tc::kSliceBytes + (size_t)tc::kStages * 2 * tc::kSliceBytes +
                         (size_t)tc::kTileM * kNumSketches * 8 + (size_t)tc::kListCap * 4 + 128;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_sketch_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dynamic_smem((const void*)(k_sketch_tc), smem);
     // few row tiles (a query batch): split the plane tiles over blockIdx.y until the grid covers the GPU about twice
     int sms = 0, dev = 0;
     CLANN_CUDA(cudaGetDevice(&dev));
@@ -570,11 +566,7 @@ void launch_center_gemm_tc(const float* queries, const float* qnorm, uint64_t nq
     if (nq == 0 || K == 0) return;
     const CUtensorMap qm = f32_map(queries, nq, d), cm = f32_map(center_rows, K, d);
     const size_t smem = 1024 + (size_t)2 * tc::kGemmMaxKB * tc::kGemmTile + 64;
-    static bool configured = false;
-    if (!configured) {
-        CLANN_CUDA(cudaFuncSetAttribute(k_center_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void*)(k_center_gemm_tc), smem);
     dim3 grid((unsigned)((nq + tc::kTileM - 1) / tc::kTileM), (K + tc::kTileN - 1) / tc::kTileN);
     k_center_gemm_tc<<<grid, 192, smem, s>>>(qm, cm, nq, K, d, qnorm, center_norms, approx);
 }
