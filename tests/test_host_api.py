@@ -89,3 +89,25 @@ def test_record_container_round_trip(tmp_path):
         api._read_records(str(tmp_path / "x.clb2"))
     with pytest.raises(cb.api.ConfigError):
         api.init_from_file(np.zeros((4, 4), np.float32), str(tmp_path / "missing.clb2"))
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference under torchrun: rank 0 alone runs, the other ranks exit 0 without work and without output;
+    the data generators of the two arms are the same functions (same seeds, same shapes)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    sys.path.insert(0, root)
+    import argparse
+    import bench
+    w = bench.workload(argparse.Namespace(workload="glove100", small=True, rows=0, delta=0.0))
+    d1, q1, s1 = bench.make_data(w, "planted")
+    d2, q2, s2 = bench.make_data(w, "planted")
+    assert d1.shape == (w["n"], w["d"]) and q1.shape == (w["nq"], w["d"]) and d1.dtype == np.float32
+    assert np.array_equal(d1, d2) and np.array_equal(q1, q2) and np.array_equal(s1, s2)
+    assert np.allclose(np.linalg.norm(d1, axis=1), 1.0, atol=1e-5)
