@@ -5,7 +5,7 @@ from clann_b200 import _lib as cl
 class A: small=False; workload='glove100'
 w = bench.workload(A)
 data, q, src = bench.make_data(w, 'planted')
-for rep in range(3):
+for rep in range(4):
     t=time.time()
     ix = cb.init_with_config(data, cb.Config(w["L"], w["factor"], w["k"], w["delta"], "b"))
     ix.set_option("seed", 1234)
