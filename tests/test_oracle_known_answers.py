@@ -122,3 +122,78 @@ def test_num_clusters_rule(oracle):  # src/core/index.rs:78-80
     assert oracle.num_clusters(0.4, 10_000_000) == 1264
     assert oracle.num_clusters(0.4, 100_000_000) == 4000
     assert oracle.num_clusters(0.0001, 10) == 1
+
+
+def _unrolled_dot_f32(x, y):
+    """ndarray 0.16.1 numeric_util::unrolled_dot written a second time, step by step in numpy float32 (every product and every
+    sum rounded to f32, no FMA): eight partial sums over chunks of 8, (p0+p4)+(p1+p5)+(p2+p6)+(p3+p7), then the tail in order."""
+    f = np.float32
+    p = [f(0)] * 8
+    i = 0
+    while i + 8 <= len(x):
+        for j in range(8):
+            p[j] = f(p[j] + f(x[i + j] * y[i + j]))
+        i += 8
+    s = f(0)
+    for a, b in ((0, 4), (1, 5), (2, 6), (3, 7)):
+        s = f(s + f(p[a] + p[b]))
+    for j in range(i, len(x)):
+        s = f(s + f(x[j] * y[j]))
+    return s
+
+
+def test_ndarray_dot_and_distance_restatements_agree(oracle):
+    """The L3 arithmetic (angulardata.rs:12-43 over ndarray's dot) cannot be pinned against Rust here; this pins the C restatement
+    against an independent one of the published algorithm: bit-equal dots for every length 1..40 and the benchmarked dimensions,
+    and bit-equal distances (norm = sqrt(dot(x, x)), query norm = sequential sum of squares, 1 - dot / (|x| |q|))."""
+    rng = np.random.default_rng(77)
+    for d in list(range(1, 41)) + [96, 100, 128, 200]:
+        for _ in range(6):
+            x = (rng.standard_normal(d) * 10 ** rng.uniform(-2, 2)).astype(np.float32)
+            y = rng.standard_normal(d).astype(np.float32)
+            got = np.float32(oracle.lib.orc_ndarray_dot(x.ctypes.data, y.ctypes.data, d))
+            assert got.view(np.uint32) == _unrolled_dot_f32(x, y).view(np.uint32), d
+            f = np.float32
+            xn = f(np.sqrt(_unrolled_dot_f32(x, x)))
+            s = f(0)
+            for v in y:
+                s = f(s + f(v * v))
+            want = f(f(1) - f(_unrolled_dot_f32(x, y) / f(xn * f(np.sqrt(s)))))
+            assert np.float32(oracle.distance_point(x, y)).view(np.uint32) == want.view(np.uint32), d
+
+
+def test_gmm_restatements_agree(oracle):
+    """greedy_minimum_maximum (gmm.rs:21-62) over AngularData::distance (angulardata.rs:12-27) written a second time in numpy
+    float32 on top of the step-by-step dot above: first-max arg-max (gmm.rs:5-15), strict-< reassignment, radii by f32::max.
+    Small cases incl. duplicated rows (ties in the arg-max and in the reassignment) and n <= k."""
+    f = np.float32
+    rng = np.random.default_rng(5)
+    for n, d, K in [(120, 12, 7), (90, 25, 11), (64, 9, 5)]:
+        data = rng.standard_normal((n, d)).astype(np.float32)
+        data[n // 2] = data[3]          # duplicates: equal distances everywhere
+        data[n // 2 + 1] = data[3]
+        norms = [f(np.sqrt(_unrolled_dot_f32(r, r))) for r in data]
+
+        def dist_to(j):
+            return [f(f(1) - f(_unrolled_dot_f32(data[i], data[j]) / f(norms[i] * norms[j]))) for i in range(n)]
+
+        centers, assign = [0], [0] * n
+        dist = dist_to(0)
+        for idx in range(1, K):
+            far, m = 0, dist[0]
+            for i in range(1, n):
+                if dist[i] > m:
+                    far, m = i, dist[i]
+            centers.append(far)
+            nd = dist_to(far)
+            for i in range(n):
+                if nd[i] < dist[i]:
+                    assign[i], dist[i] = idx, nd[i]
+        radii = [f(0)] * K
+        for i in range(n):
+            radii[assign[i]] = max(radii[assign[i]], dist[i])
+        c, a, r = oracle.gmm(data, K)
+        assert list(c) == centers and list(a) == assign
+        assert np.array_equal(np.asarray(radii, np.float32).view(np.uint32), r.view(np.uint32))
+    c, a, r = oracle.gmm(rng.standard_normal((4, 6)).astype(np.float32), 9)   # gmm.rs:26-31
+    assert list(c) == [0, 1, 2, 3] and list(a) == [0, 1, 2, 3] and not r.any()
