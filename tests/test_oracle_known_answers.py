@@ -197,3 +197,83 @@ def test_gmm_restatements_agree(oracle):
         assert np.array_equal(np.asarray(radii, np.float32).view(np.uint32), r.view(np.uint32))
     c, a, r = oracle.gmm(rng.standard_normal((4, 6)).astype(np.float32), 9)   # gmm.rs:26-31
     assert list(c) == [0, 1, 2, 3] and list(a) == [0, 1, 2, 3] and not r.any()
+
+
+def _golden_index(oracle, name="puffinn_d100"):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return oracle.index_import(g["stream"].tobytes())
+
+
+def test_independent_hashes_use_every_bit(oracle):
+    """hash_source_test.hpp:13-45,76-91 ("Independent hashes", FHTCrossPolytopeHash, 24 bits): over random vectors every
+    concatenated hash is below 2^24 and every one of the 24 bits is set at least once — on the reference-drawn function set of
+    the golden index (d = 100: 3 functions of 8 bits per table)."""
+    oi = _golden_index(oracle)
+    rng = np.random.default_rng(3)
+    seen = 0
+    for v in rng.standard_normal((100, 100)).astype(np.float32):
+        codes = oi.codes(oracle.store_q15(v))
+        assert np.all(codes < (1 << 24))
+        seen |= int(np.bitwise_or.reduce(codes))
+    assert seen == (1 << 24) - 1
+    oi.free()
+
+
+def test_all_filtering_bits_used(oracle):
+    """filterer_test.hpp:44-70: the sketches of 20 random vectors set every one of the 64 bit positions at least once (and,
+    stronger, every position of every one of the 32 sketches takes both values)."""
+    oi = _golden_index(oracle)
+    rng = np.random.default_rng(4)
+    sk = np.stack([oi.sketch(oracle.store_q15(v)) for v in rng.standard_normal((20, 100)).astype(np.float32)])
+    assert int(np.bitwise_or.reduce(sk.ravel())) == 0xFFFFFFFFFFFFFFFF
+    assert np.all(np.bitwise_or.reduce(sk, axis=0) == np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert np.all(np.bitwise_and.reduce(sk, axis=0) == 0)
+    # filterer_test.hpp:12-42: a vector passes against itself at max_sketch_diff(1.0) = 0, its negation differs in every bit
+    v = rng.standard_normal(100).astype(np.float32)
+    a, b = oi.sketch(oracle.store_q15(v)), oi.sketch(oracle.store_q15(-v))
+    differing = sum(bin(int(x) ^ int(y)).count("1") for x, y in zip(a, b))
+    assert differing >= 32 * 64 - 32   # a plane whose rounded dot is exactly 0 gives the same bit (>= 0) to v and -v
+    oi.free()
+
+
+def test_fht_cross_polytope_collision_probability(oracle):
+    """hash_test.hpp:62-97,128-130 ("FHTCrossPolytope collision probability", d = 100): over 10 000 pairs of random unit vectors
+    the number of collisions of one 8-bit function stays within 2 % of the sum of the tabulated probabilities
+    (crosspolytope.hpp:116-118: estimates[bits][sim / eps]) — the table the stop rule is built on. Also "evenly distributed"
+    (:40-60) in its 8-bit form: no outcome of a function takes more than 3 % of the samples beyond its share."""
+    oi = _golden_index(oracle)
+    fn = oi.functions()
+    cfn = fn.c_struct()
+    import ctypes as C
+    rng = np.random.default_rng(6)
+    n_fn = fn.L * fn.fph
+    N = 10_000
+    A = oracle.store_q15(rng.standard_normal((N, 100)).astype(np.float32))
+    B = oracle.store_q15(rng.standard_normal((N, 100)).astype(np.float32))
+    prob_sum, actual = 0.0, 0
+    counts = np.zeros(1 << fn.bpf, np.int64)
+    for i in range(N):
+        f = i % n_fn
+        ha = oracle.lib.orc_fht_hash(C.byref(cfn), f, A[i].ctypes.data)
+        hb = oracle.lib.orc_fht_hash(C.byref(cfn), f, B[i].ctypes.data)
+        assert ha < (1 << fn.bpf) and hb < (1 << fn.bpf)
+        counts[ha] += 1
+        sim = np.float32(oracle.similarity(A[i], B[i]))
+        prob_sum += float(fn.est[fn.bpf][int(np.float32(sim / fn.eps))])
+        actual += int(ha == hb)
+    assert abs(prob_sum - actual) <= 0.02 * N, (prob_sum, actual)
+    assert np.all(np.abs(counts - N / counts.size) <= 0.03 * N)
+    # the same bound where collisions are frequent (random pairs collide 0.4 % of the time): correlated pairs, cosine ~0.6-0.95
+    M = 4000
+    X = rng.standard_normal((M, 100)).astype(np.float32)
+    Y = X + rng.uniform(0.3, 1.2, (M, 1)).astype(np.float32) * rng.standard_normal((M, 100)).astype(np.float32)
+    X15, Y15 = oracle.store_q15(X), oracle.store_q15(Y)
+    prob_sum, actual = 0.0, 0
+    for i in range(M):
+        f = i % n_fn
+        sim = np.float32(oracle.similarity(X15[i], Y15[i]))
+        prob_sum += float(fn.est[fn.bpf][int(np.float32(sim / fn.eps))])
+        actual += int(oracle.lib.orc_fht_hash(C.byref(cfn), f, X15[i].ctypes.data) == oracle.lib.orc_fht_hash(C.byref(cfn), f, Y15[i].ctypes.data))
+    assert actual > 0.05 * M and abs(prob_sum - actual) <= 0.02 * M, (prob_sum, actual)
+    oi.free()
