@@ -821,3 +821,28 @@ def test_device_collision_estimates_agree_with_reference_table(name):
     # adjacent entries are independent 1000-repetition estimates: their difference has sd <= 0.0224, so -0.10 is 4.5 sigma
     assert np.diff(est, axis=1).min() > -0.10, np.diff(est, axis=1).min()
     assert np.all((est >= 0) & (est <= 1))
+
+
+def test_device_drawn_functions_use_every_bit():
+    """The reference's own checks of a hash source and of the filter (hash_source_test.hpp:13-45,76-91, filterer_test.hpp:44-70,
+    hash_test.hpp:40-60), on a stand-alone device build (functions drawn by this library, not imported): every table code is below
+    2^24, every one of the 24 code bits and of the 32 x 64 sketch bits takes both values over random rows, and the 256 outcomes of
+    a table's first cross-polytope function are evenly distributed (+-3 % of the samples)."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    n, d, L = 4000, 100, 8
+    data = util.uniform_sphere(n, d, 91)
+    ix = cb.init_with_config(data, cb.Config(L, 1.0, 10, 0.9, "bits"))
+    ix.set_clustering([0], np.zeros(n, np.uint64), [2.0])
+    ix.set_option("seed", 77)
+    ix.build()
+    codes = ix.export(cl.X_TABLE_HASHES, 0, np.uint32).reshape(L, n)
+    assert np.all(codes < (1 << 24))
+    assert int(np.bitwise_or.reduce(codes.ravel())) == (1 << 24) - 1 and int(np.bitwise_and.reduce(codes.ravel())) == 0
+    sk = ix.export(cl.X_SKETCHES, 0, np.uint64).reshape(n, 32)
+    assert np.all(np.bitwise_or.reduce(sk, axis=0) == np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert np.all(np.bitwise_and.reduce(sk, axis=0) == 0)
+    for t in range(L):
+        first = np.bincount(codes[t] >> 16, minlength=256)   # the most significant of the three 8-bit function values
+        assert np.all(np.abs(first - n / 256) <= 0.03 * n), t
+    ix.close()
