@@ -846,3 +846,49 @@ def test_device_drawn_functions_use_every_bit():
         first = np.bincount(codes[t] >> 16, minlength=256)   # the most significant of the three 8-bit function values
         assert np.all(np.abs(first - n / 256) <= 0.03 * n), t
     ix.close()
+
+
+@pytest.mark.parametrize("d", [300, 1000])
+def test_wide_rows_take_the_fallback_paths(oracle, d):
+    """d > 256 (the documented limit is d <= 1024): storage rows wider than the register-resident query chunk, 512- / 1024-point
+    FHT, the CUDA-core sketch kernel, no dense first-visit precompute. Same comparison as smoke(): a stand-alone build on a shared
+    function set handed in from the host, every query against the oracle over the same functions — ids, distance bits, candidates,
+    distance computations, clusters visited."""
+    import clann_b200 as cb
+    from clann_b200 import _lib as cl
+    from oracle.pyoracle import Functions
+    n, L, k, delta, nq = 1500, 8, 10, 0.9, 24
+    rng = np.random.default_rng(d)
+    data = util.planted(n, d, 400 + d, n_centers=5)
+    queries = np.concatenate([util.planted_queries(data, nq - 4, 401 + d), util.uniform_sphere(4, d, 402 + d)]).astype(np.float32)
+    sl = (d + 15) // 16 * 16
+    m = int(np.ceil(np.log2(d)))
+    fph = (24 + m) // (m + 1)
+    planes = oracle.store_q15(rng.standard_normal((2048, d)).astype(np.float32), sl)
+    signs = (rng.integers(0, 2, (L * fph, 3 << m)) * 2 - 1).astype(np.int8)
+    index = cb.init_with_config(data, cb.Config(L, 0.2, k, delta, "wide"))
+    index.set_functions(None, planes, signs, None)
+    index.build()
+    ids, dists, counts = index.search_batch(queries)
+    ctr = index.counters(len(queries))
+    K = index.num_clusters
+    cen, asg = index.export(cl.X_CENTERS, 0, np.uint64), index.export(cl.X_ASSIGNMENT, 0, np.uint64)
+    rad, brute = index.export(cl.X_RADII, 0, np.float32), index.export(cl.X_BRUTE, 0, np.uint8)
+    assert not brute.all()
+    oc_, oa_, _ = oracle.gmm(data, K)
+    assert np.array_equal(cen, oc_) and np.array_equal(asg, oa_)
+    fn = Functions(d, L, planes, signs, index.export(cl.X_EST, int(np.argmin(brute)), np.float32))
+    oc = oracle.clann(data, k, delta, cen, asg, rad)
+    for ci in range(K):
+        if not brute[ci]:
+            oc.build_cluster(ci, fn)
+    for i in range(len(queries)):
+        o_ids, o_d, _, o_ctr = oc.search(queries[i])
+        c = int(counts[i])
+        assert c == len(o_ids) and sorted(ids[i, :c].tolist()) == sorted(int(x) for x in o_ids), i
+        assert np.array_equal(np.sort(dists[i, :c]), np.sort(o_d)), i
+        assert int(ctr["candidates"][i]) == o_ctr["candidates"], i
+        assert int(ctr["distance_computations"][i]) == o_ctr["distance_computations"], i
+        assert int(ctr["clusters_visited"][i]) == o_ctr["visited"], i
+    oc.free()
+    index.close()
