@@ -848,10 +848,12 @@ def test_device_drawn_functions_use_every_bit():
     ix.close()
 
 
-@pytest.mark.parametrize("d", [300, 1000])
-def test_wide_rows_take_the_fallback_paths(oracle, d):
-    """d > 256 (the documented limit is d <= 1024): storage rows wider than the register-resident query chunk, 512- / 1024-point
-    FHT, the CUDA-core sketch kernel, no dense first-visit precompute. Same comparison as smoke(): a stand-alone build on a shared
+@pytest.mark.parametrize("d", [2, 3, 7, 300, 1000])
+def test_unusual_row_widths(oracle, d):
+    """The ends of the supported range. d > 256 (the documented limit is d <= 1024): storage rows wider than the register-resident
+    query chunk, 512- / 1024-point FHT, the CUDA-core sketch kernel, no dense first-visit precompute. d = 2, 3, 7: 2- to 8-point
+    FHT with 12 / 8 / 6 functions per table and code bits cut off the last one (d = 7: 6 x 4 bits; d = 3: 8 x 3), one 16-element
+    storage row mostly padding, the 8-lanes-per-row k-center pass (d % 4 != 0). Same comparison as smoke(): a stand-alone build on a shared
     function set handed in from the host, every query against the oracle over the same functions — ids, distance bits, candidates,
     distance computations, clusters visited."""
     import clann_b200 as cb
