@@ -848,27 +848,21 @@ def test_device_drawn_functions_use_every_bit():
     ix.close()
 
 
-@pytest.mark.parametrize("d", [2, 3, 7, 300, 1000])
-def test_unusual_row_widths(oracle, d):
-    """The ends of the supported range. d > 256 (the documented limit is d <= 1024): storage rows wider than the register-resident
-    query chunk, 512- / 1024-point FHT, the CUDA-core sketch kernel, no dense first-visit precompute. d = 2, 3, 7: 2- to 8-point
-    FHT with 12 / 8 / 6 functions per table and code bits cut off the last one (d = 7: 6 x 4 bits; d = 3: 8 x 3), one 16-element
-    storage row mostly padding, the 8-lanes-per-row k-center pass (d % 4 != 0). Same comparison as smoke(): a stand-alone build on a shared
-    function set handed in from the host, every query against the oracle over the same functions — ids, distance bits, candidates,
-    distance computations, clusters visited."""
+def _standalone_vs_oracle(oracle, n, d, L, k, delta, factor, seed, n_centers=5, nq=24):
+    """Same comparison as smoke(): a stand-alone build on a shared function set handed in from the host, every query against the
+    oracle over the same functions — ids, distance bits, candidates, distance computations, clusters visited."""
     import clann_b200 as cb
     from clann_b200 import _lib as cl
     from oracle.pyoracle import Functions
-    n, L, k, delta, nq = 1500, 8, 10, 0.9, 24
-    rng = np.random.default_rng(d)
-    data = util.planted(n, d, 400 + d, n_centers=5)
-    queries = np.concatenate([util.planted_queries(data, nq - 4, 401 + d), util.uniform_sphere(4, d, 402 + d)]).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    data = util.planted(n, d, 400 + seed, n_centers=n_centers)
+    queries = np.concatenate([util.planted_queries(data, nq - 4, 401 + seed), util.uniform_sphere(4, d, 402 + seed)]).astype(np.float32)
     sl = (d + 15) // 16 * 16
     m = int(np.ceil(np.log2(d)))
     fph = (24 + m) // (m + 1)
     planes = oracle.store_q15(rng.standard_normal((2048, d)).astype(np.float32), sl)
     signs = (rng.integers(0, 2, (L * fph, 3 << m)) * 2 - 1).astype(np.int8)
-    index = cb.init_with_config(data, cb.Config(L, 0.2, k, delta, "wide"))
+    index = cb.init_with_config(data, cb.Config(L, factor, k, delta, "edge"))
     index.set_functions(None, planes, signs, None)
     index.build()
     ids, dists, counts = index.search_batch(queries)
@@ -894,3 +888,20 @@ def test_unusual_row_widths(oracle, d):
         assert int(ctr["clusters_visited"][i]) == o_ctr["visited"], i
     oc.free()
     index.close()
+
+
+@pytest.mark.parametrize("d", [2, 3, 7, 300, 1000])
+def test_unusual_row_widths(oracle, d):
+    """The ends of the supported range. d > 256 (the documented limit is d <= 1024): storage rows wider than the register-resident
+    query chunk, 512- / 1024-point FHT, the CUDA-core sketch kernel, no dense first-visit precompute. d = 2, 3, 7: 2- to 8-point
+    FHT with 12 / 8 / 6 functions per table and code bits cut off the last one (d = 7: 6 x 4 bits; d = 3: 8 x 3), one 16-element
+    storage row mostly padding, the 8-lanes-per-row k-center pass (d % 4 != 0)."""
+    _standalone_vs_oracle(oracle, n=1500, d=d, L=8, k=10, delta=0.9, factor=0.2, seed=d)
+
+
+@pytest.mark.parametrize("n,d,L,k,factor", [(6000, 32, 8, 1000, 0.04), (3000, 32, 8, 300, 0.05), (1200, 16, 1, 5, 0.1),
+                                            (1200, 16, 300, 5, 0.1)])
+def test_large_k_and_extreme_table_counts(oracle, n, d, L, k, factor):
+    """k = 300 / 1000 inside PUFFINN clusters (1 024- / 2 048-slot MaxBuffer per warp, fewer warps per CTA), a single table, and
+    300 tables (per-warp anchor / range arrays of 300 entries, ten-word stop masks)."""
+    _standalone_vs_oracle(oracle, n=n, d=d, L=L, k=k, delta=0.9, factor=factor, seed=n + L + k, n_centers=3, nq=16)
