@@ -905,3 +905,10 @@ def test_large_k_and_extreme_table_counts(oracle, n, d, L, k, factor):
     """k = 300 / 1000 inside PUFFINN clusters (1 024- / 2 048-slot MaxBuffer per warp, fewer warps per CTA), a single table, and
     300 tables (per-warp anchor / range arrays of 300 entries, ten-word stop masks)."""
     _standalone_vs_oracle(oracle, n=n, d=d, L=L, k=k, delta=0.9, factor=factor, seed=n + L + k, n_centers=3, nq=16)
+
+
+def test_cluster_beyond_65536_rows(oracle):
+    """One cluster of 70 000 rows (K = 1): local ids no longer fit 16 bits, so the opt-in u16 candidate streams and the dense
+    first-visit memo must step aside (kernels_search.cu: nc > 65536 guards) while the default probe, whose table indices are 32-bit,
+    answers as the oracle does — hundreds of thousands of candidates per query, long ranges at low depths."""
+    _standalone_vs_oracle(oracle, n=70_000, d=16, L=4, k=10, delta=0.9, factor=0.005, seed=70_014, n_centers=1, nq=12)
