@@ -218,8 +218,9 @@ int clann_last_search_profile(clann_index* index, float* ms, uint32_t* launches)
  * per query selects the gather probe, more than 8 the all-exact centre kernel. Results, counters and exports never depend on it;
  * the time of a call can depend on what ran before it. clann_tune("dense_adaptive", 0) pins the first of each pair. */
 
-/* Process-global launch-parameter knob for A/B measurements of the probe kernels ("probe" 0 = one warp per query,
- * 1 = one CTA per query; "probe_occ", "probe_warps", "probe_ctas", "probe_nomemo", ...). Never changes a result. The
+/* Process-global launch-parameter knob for A/B measurements of the kernels ("probe_occ", "probe_warps", "probe_ctas",
+ * "probe_nomemo", "dense_sims", "first_ranges", "first_stream", "tc_sketch", "tc_center", "pipeline_depth", ...; the full list
+ * is in INTEGRATION.md). Never changes a result. The
  * environment variable CLANN_TUNE_<KEY> seeds a key that was not set. Not part of the reference's interface. */
 int clann_tune(const char* key, int64_t value);
 
